@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — embedding-vectors/sec of the HPS lookup hot path on synthetic Criteo-shaped requests.
+
+A "step" is one request: batch 65536 x 26 slots (1 703 936 keys) against one dim-128 table
+(BASELINE.json configs[1]: DCN, 10 M rows, 90 % cache hit, one B200).  Rank r of N runs an independent
+replica on GPU r (the reference's multi-GPU mode is replicas: hps_backend/src/model_state.cpp:395-419),
+so scaling is weak and there is no data-path collective.
+
+  value     keys already resident in HBM -> hpsx_session_lookup_device_keys (misses still cross PCIe)
+  e2e       keys in pinned host memory   -> hpsx_session_lookup (H2D keys, D2H miss list, H2D miss rows
+            inside the timed region); vectors land in device memory like the reference's GPU output
+            buffer (hps_backend/src/hps.cc:639-642)
+  roofline  probe+gather kernel: algorithmic bytes / CUDA-event duration on the session stream
+  --impl reference   the CPU parameter-server path (C oracle port, all host threads) on the same requests
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 0xB2000000 + 2  # config id 2
+METRIC = "embedding_vectors_per_sec"
+UNIT = "vectors/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--batch", type=int, default=65536)
+    ap.add_argument("--slots", type=int, default=26)
+    ap.add_argument("--hit", type=float, default=0.90, help="fraction of keys drawn from the cached hot set")
+    ap.add_argument("--gpucacheper", type=float, default=0.2)
+    ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "ldg"), choices=["ldg", "tma"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_name(a) -> str:
+    return (f"DCN Criteo-shape: {a.slots} slots, {a.rows // 1_000_000}M-row table, dim {a.dim}, batch {a.batch}, "
+            f"{int(round(a.hit * 100))}% cache-hit")
+
+
+def make_requests(a, hot_keys: np.ndarray, cold_lo: int, count: int, seed: int):
+    """`count` key batches [batch*slots]: w.p. `hit` a key of the resident hot set, else uniform over the
+    rows that were not warmed into the cache."""
+    n = a.batch * a.slots
+    rng = np.random.default_rng(seed)
+    reqs = []
+    for _ in range(count):
+        is_hot = rng.random(n) < a.hit
+        k = rng.integers(cold_lo, a.rows, size=n, dtype=np.int64)
+        k[is_hot] = hot_keys[rng.integers(0, len(hot_keys), size=int(is_hot.sum()))]
+        reqs.append(k)
+    return reqs
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu = gpu
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(a, reqs, steps: int, warmup: int):
+    """The reference's CPU ParameterServer path (gpucache=false: hash-partitioned host maps + row copies,
+    docs/hierarchical_parameter_server.md:400-416) restated in oracle/hps_oracle.c, all host threads."""
+    from oracle import hps_oracle as O
+
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    table = O.CTable(a.dim, 0.0, num_partitions=max(8, min(cores, 64)))
+    table.fill_procedural(a.rows, SEED, cores)
+    build_s = time.perf_counter() - t0
+    n = a.batch * a.slots
+    out = np.empty((n, a.dim), dtype=np.float32)
+    for i in range(warmup):
+        table.lookup(reqs[i % len(reqs)], cores, out)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        table.lookup(reqs[i % len(reqs)], cores, out)
+    dt = time.perf_counter() - t0
+    return {"value": steps * n / dt, "ms_per_step": dt / steps * 1e3, "cores": cores, "build_s": build_s,
+            "sample": f"{steps} full requests of {n} keys ({a.rows} rows x dim {a.dim}, {warmup} warm-up), "
+                      f"{cores} threads, output in host memory"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = a.batch * a.slots
+    warm_rows = int(np.ceil(a.gpucacheper * a.rows))
+    hot = np.arange(0, warm_rows, dtype=np.int64)  # same key distribution as our arm's warmed set
+    reqs = make_requests(a, hot, warm_rows, 4, SEED)
+    r = cpu_reference_run(a, reqs, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "keys_per_step": n, "note": "CPU ParameterServer path, rank 0 only"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    import hugectr_backend_b200 as hb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the lookup path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = a.batch * a.slots
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+
+    # ---- server: host table + HBM cache ------------------------------------------------------------
+    t0 = time.perf_counter()
+    hps = hb.HPS(num_partitions=16)
+    hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
+                                 cache_size_percentage=a.gpucacheper, deployed_devices=[local]))
+    hps.load_table_procedural("dcn", 0, a.rows, SEED)
+    hps.create_embedding_cache("dcn")
+    setup_s = time.perf_counter() - t0
+    hot = hps.cache_keys("dcn", local, 0)
+    warm_rows = int(np.ceil(a.gpucacheper * a.rows))
+    reqs = make_requests(a, hot, warm_rows, 4, SEED + rank)
+    sess = hps.session("dcn", local)
+    sess.set_probe_variant(a.variant)
+    ext = torch.cuda.ExternalStream(sess.stream)
+
+    d_reqs = [torch.from_numpy(k).cuda() for k in reqs]
+    h_reqs = [torch.from_numpy(k).pin_memory() for k in reqs]
+    out = torch.empty((n, a.dim), device="cuda", dtype=torch.float32)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time from CUDA events on the session stream."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        w0 = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        e1.record(ext)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall
+
+    dev_step = lambda i: sess.lookup_device_keys([d_reqs[i % 4]], [out], [n])
+    e2e_step = lambda i: sess.lookup([h_reqs[i % 4].numpy()], [out], [n])
+
+    # ---- device-resident arm (value) ------------------------------------------------------------------
+    for i in range(a.warmup):
+        dev_step(i)
+    sess.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall = timed(dev_step, a.steps)
+    clocks = sampler.stop()
+    st = sess.stats()
+    value = world * a.steps * n / (ms / 1e3)
+
+    probe_ms = st.probe_kernel_ms / max(1, st.probe_kernel_launches)
+    hits_per, miss_per = st.hits / a.steps, st.misses / a.steps
+    # algorithmic bytes of one probe+gather launch: key read + row read + row write for a hit; key read +
+    # default-row write for a miss (its row arrives later through the merge kernel)
+    alg_bytes = hits_per * (8 + 8 * a.dim) + miss_per * (8 + 4 * a.dim)
+    achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": f"probe_gather_{a.variant}", "achieved": achieved, "peak": peak_gbs,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "share_of_step": probe_ms / (ms / a.steps)}
+
+    # ---- end-to-end arm: pinned host keys through the session C-ABI call ------------------------------
+    for i in range(a.warmup):
+        e2e_step(i)
+    sess.reset_stats()
+    ms_e, wall_e = timed(e2e_step, a.steps)
+    st_e = sess.stats()
+    e2e_value = world * a.steps * n / (ms_e / 1e3)
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": st_e.h2d_bytes / a.steps,
+           "d2h_bytes_per_step": st_e.d2h_bytes / a.steps, "ms_per_step": ms_e / a.steps,
+           "output": "device memory (Triton GPU output buffer contract)", "hit_rate": st_e.hits / max(1, st_e.keys),
+           "host_gather_ms_per_step": st_e.host_gather_ms / a.steps}
+
+    # ---- 100 % cache-hit pass: the "cache-hit HBM GB/s" half of the metric -----------------------------
+    rng = np.random.default_rng(SEED + 77 + rank)
+    hot_now = hps.cache_keys("dcn", local, 0)
+    hit_reqs = [torch.from_numpy(hot_now[rng.integers(0, len(hot_now), size=n)]).cuda() for _ in range(4)]
+    hit_step = lambda i: sess.lookup_device_keys([hit_reqs[i % 4]], [out], [n])
+    for i in range(a.warmup):
+        hit_step(i)
+    sess.reset_stats()
+    ms_h, _ = timed(hit_step, a.steps)
+    st_h = sess.stats()
+    probe_h = st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches)
+    hit_alg = (st_h.hits * (8 + 8 * a.dim) + st_h.misses * (8 + 4 * a.dim)) / a.steps
+    cache_hit = {"vectors_per_s": world * a.steps * n / (ms_h / 1e3), "ms_per_step": ms_h / a.steps,
+                 "kernel_ms": probe_h, "hbm_gbs": hit_alg / (probe_h / 1e3) / 1e9 if probe_h > 0 else 0.0,
+                 "hit_rate": st_h.hits / max(1, st_h.keys)}
+    cache_hit["frac_of_peak"] = cache_hit["hbm_gbs"] / peak_gbs
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu_baseline = None
+    if world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_run(a, reqs, a.cpu_steps, 1)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                        "ms_per_step": r["ms_per_step"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
+                   "gpucacheper": a.gpucacheper, "hit_rate_measured": st.hits / max(1, st.keys),
+                   "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
+                   "l2": "inputs exceed L2: 13.6 MB keys + 872 MB output + 2 GB cache slab per step, 4 rotating key batches",
+                   "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "cache_hit": cache_hit,
+        "gpu_launches": int(st.kernel_launches), "clocks": clocks,
+        "wall_ms_per_step": wall / a.steps * 1e3,
+        "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,
+                      "insert_phase_ms_per_step": st.insert_kernel_ms / a.steps,
+                      "h2d_bytes_per_step": st.h2d_bytes / a.steps},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,105 @@
+// Internal C++ objects behind the opaque handles of include/hpsx.h.
+//   hpsx_ps      ~ HugeCTR::HierParameterServerBase   (reference: hps_backend/src/backend.cpp:68-71)
+//   hpsx_cache   ~ HugeCTR::EmbeddingCacheBase        (hps_backend/src/model_state.cpp:404-412)
+//   hpsx_session ~ HugeCTR::LookupSessionBase         (hps_backend/src/model_instance_state.cpp:170-171)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hpsx.h"
+#include "host_ps.hpp"
+#include "kernels.h"
+#include "ps_config.hpp"
+
+namespace hpsx {
+
+constexpr size_t kStageChunkRows = 32768;  // rows per host->device miss chunk (16 MiB at dim 128)
+
+struct Model;
+
+}  // namespace hpsx
+
+// One HBM embedding cache: all tables of one model on one device.
+struct hpsx_cache {
+  hpsx::Model* model = nullptr;
+  int device = -1;
+  bool is_static = false;
+  std::vector<hpsx::DeviceTable> tables;
+  std::vector<size_t> slots;            // capacity of every table (ways * buckets)
+  std::atomic<uint32_t> epoch{1};       // one tick per lookup call; LRU stamps are epochs
+  // Probes (readers) run concurrently; a kernel that rewrites slots (insert) excludes them, so a
+  // row is never copied while it is being replaced.
+  std::shared_mutex rw;
+  // asynchronous insertion (hit_rate >= hit_rate_threshold): one workspace, jobs serialised
+  std::mutex async_mu;
+  std::condition_variable async_cv;
+  size_t async_pending = 0;
+  cudaStream_t async_stream = nullptr;
+  int64_t* async_d_keys = nullptr;
+  float* async_d_stage = nullptr;
+  float* async_h_stage = nullptr;
+  size_t async_rows = 0;  // capacity of the async staging buffers (rows of the widest table)
+  size_t max_dim = 0;
+  std::atomic<uint64_t> async_inserted{0};
+
+  ~hpsx_cache();
+};
+
+namespace hpsx {
+
+struct Model {
+  ModelConfig cfg;
+  float load_factor = 0.5f;
+  std::vector<std::unique_ptr<HostTable>> tables;
+  std::mutex mu;  // guards `caches`
+  std::map<int, std::unique_ptr<hpsx_cache>> caches;
+};
+
+}  // namespace hpsx
+
+struct hpsx_ps {
+  hpsx::VolatileDbConfig vdb;
+  std::unique_ptr<hpsx::ThreadPool> pool;
+  std::mutex mu;  // guards `models`
+  std::map<std::string, std::unique_ptr<hpsx::Model>> models;
+  std::vector<std::string> model_order;
+};
+
+struct hpsx_session {
+  hpsx_ps* ps = nullptr;
+  hpsx::Model* model = nullptr;
+  hpsx_cache* cache = nullptr;  // nullptr: CPU session
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  int probe_variant = hpsx::kProbeLdg;
+  int insert_mode = -1;
+
+  size_t cap_keys = 0;                 // sum over tables of max_batch * maxnum_catfeature
+  std::vector<size_t> cap_per_table;
+  int64_t* d_keys = nullptr;           // [cap_keys]
+  uint32_t* d_miss_pos = nullptr;      // [cap_keys]
+  int64_t* d_miss_keys = nullptr;      // [cap_keys]
+  uint32_t* d_counters = nullptr;      // [T] miss counts, [T..2T) inserted counts
+  uint32_t* h_counters = nullptr;      // pinned mirror
+  int64_t* h_miss_keys = nullptr;      // pinned [cap_keys]
+  float* h_stage[2] = {nullptr, nullptr};  // pinned [kStageChunkRows * max_dim]
+  float* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  uint32_t* d_src = nullptr;           // pooled path, lazily [cap_keys]
+  float* d_pool_stage = nullptr;       // pooled path: all miss rows of one call
+  size_t pool_stage_rows = 0;
+  size_t max_dim = 0;
+  std::vector<cudaEvent_t> ev;         // 2 per table: probe start / stop
+  hpsx_session_stats stats{};
+  std::mutex mu;  // one lookup at a time per session (Triton guarantees it; tests may not)
+
+  ~hpsx_session();
+};

@@ -1,0 +1,320 @@
+#include "host_ps.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+
+#include "hpsx_common.h"
+
+namespace hpsx {
+
+// ------------------------------------------------------------------------------------------------
+// ThreadPool
+// ------------------------------------------------------------------------------------------------
+size_t ThreadPool::default_concurrency() {
+  if (const char* env = std::getenv("HCTR_DEFAULT_CONCURRENCY")) {
+    const long v = std::atol(env);
+    if (v > 0) return static_cast<size_t>(v);
+  }
+  const unsigned hc = std::thread::hardware_concurrency();
+  return hc > 0 ? hc : 4;
+}
+
+ThreadPool::ThreadPool(size_t num_threads) {
+  if (num_threads == 0) num_threads = default_concurrency();
+  // the caller of parallel_for is one of the lanes, so spawn one fewer
+  for (size_t i = 1; i < num_threads; ++i) workers_.emplace_back([this] { worker_loop(); });
+}
+
+ThreadPool::~ThreadPool() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (auto& t : workers_) t.join();
+}
+
+void ThreadPool::run_batch(const std::shared_ptr<Batch>& b) {
+  while (true) {
+    const size_t t = b->next.fetch_add(1, std::memory_order_relaxed);
+    if (t >= b->num_tasks) break;
+    (*b->fn)(t);
+    if (b->done.fetch_add(1, std::memory_order_acq_rel) + 1 == b->num_tasks) {
+      std::lock_guard<std::mutex> lk(b->mu);
+      b->cv.notify_all();
+    }
+  }
+}
+
+void ThreadPool::worker_loop() {
+  while (true) {
+    std::shared_ptr<Batch> batch;
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [this] { return stop_ || !batches_.empty() || !jobs_.empty(); });
+      if (stop_ && batches_.empty() && jobs_.empty()) return;
+      // drop exhausted batches from the front
+      while (!batches_.empty() &&
+             batches_.front()->next.load(std::memory_order_relaxed) >= batches_.front()->num_tasks)
+        batches_.pop_front();
+      if (!batches_.empty()) {
+        batch = batches_.front();
+      } else if (!jobs_.empty()) {
+        job = std::move(jobs_.front());
+        jobs_.pop_front();
+      } else {
+        continue;
+      }
+    }
+    if (batch)
+      run_batch(batch);
+    else if (job)
+      job();
+  }
+}
+
+void ThreadPool::parallel_for(size_t num_tasks, const std::function<void(size_t)>& fn) {
+  if (num_tasks == 0) return;
+  if (num_tasks == 1 || workers_.empty()) {
+    for (size_t t = 0; t < num_tasks; ++t) fn(t);
+    return;
+  }
+  auto b = std::make_shared<Batch>();
+  b->fn = &fn;
+  b->num_tasks = num_tasks;
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    batches_.push_back(b);
+  }
+  cv_.notify_all();
+  run_batch(b);
+  std::unique_lock<std::mutex> lk(b->mu);
+  b->cv.wait(lk, [&] { return b->done.load(std::memory_order_acquire) == b->num_tasks; });
+}
+
+void ThreadPool::post(std::function<void()> job) {
+  if (workers_.empty()) {
+    job();
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    jobs_.push_back(std::move(job));
+  }
+  cv_.notify_one();
+}
+
+// ------------------------------------------------------------------------------------------------
+// HostTable
+// ------------------------------------------------------------------------------------------------
+HostTable::HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate)
+    : dim_(dim), default_value_(default_value) {
+  if (dim == 0) throw std::invalid_argument("embedding vector size must be > 0");
+  if (num_partitions == 0) num_partitions = 1;
+  if (allocation_rate == 0) allocation_rate = 256ull << 20;
+  const size_t row_bytes = dim * sizeof(float);
+  size_t rows_per_slab = std::max<size_t>(1, allocation_rate / row_bytes);
+  slab_shift_ = 0;
+  while ((2ull << slab_shift_) <= rows_per_slab) ++slab_shift_;
+  slab_mask_ = (1ull << slab_shift_) - 1;
+  for (size_t p = 0; p < num_partitions; ++p) {
+    parts_.emplace_back(new Partition());
+    parts_.back()->slots.assign(1024, Slot{kEmpty, 0});
+  }
+}
+
+HostTable::~HostTable() {
+  for (auto& p : parts_)
+    for (float* s : p->slabs) std::free(s);
+}
+
+uint64_t HostTable::alloc_row(Partition& p) {
+  const uint64_t row = p.rows_used++;
+  if ((row >> slab_shift_) >= p.slabs.size()) {
+    void* mem = nullptr;
+    const size_t bytes = (static_cast<size_t>(1) << slab_shift_) * dim_ * sizeof(float);
+    if (posix_memalign(&mem, 4096, bytes) != 0 || mem == nullptr) throw std::bad_alloc();
+    p.slabs.push_back(static_cast<float*>(mem));
+  }
+  return row;
+}
+
+void HostTable::grow(Partition& p) {
+  std::vector<Slot> old;
+  old.swap(p.slots);
+  p.slots.assign(old.size() * 2, Slot{kEmpty, 0});
+  const size_t mask = p.slots.size() - 1;
+  for (const Slot& s : old) {
+    if (s.key == kEmpty) continue;
+    size_t i = mix64(static_cast<uint64_t>(s.key)) & mask;
+    while (p.slots[i].key != kEmpty) i = (i + 1) & mask;
+    p.slots[i] = s;
+  }
+}
+
+float* HostTable::upsert(Partition& p, int64_t key, uint64_t h) {
+  if (key == kEmpty) {
+    if (!p.has_sentinel) {
+      p.sentinel_row = alloc_row(p);
+      p.has_sentinel = true;
+      rows_.fetch_add(1, std::memory_order_relaxed);
+    }
+    return row_ptr(p, p.sentinel_row);
+  }
+  if ((p.count + 1) * 2 > p.slots.size()) grow(p);
+  const size_t mask = p.slots.size() - 1;
+  size_t i = h & mask;
+  while (true) {
+    Slot& s = p.slots[i];
+    if (s.key == key) return row_ptr(p, s.row);
+    if (s.key == kEmpty) {
+      s.key = key;
+      s.row = alloc_row(p);
+      ++p.count;
+      rows_.fetch_add(1, std::memory_order_relaxed);
+      return row_ptr(p, s.row);
+    }
+    i = (i + 1) & mask;
+  }
+}
+
+const float* HostTable::find(const Partition& p, int64_t key, uint64_t h) const {
+  if (key == kEmpty) return p.has_sentinel ? row_ptr(p, p.sentinel_row) : nullptr;
+  const size_t mask = p.slots.size() - 1;
+  size_t i = h & mask;
+  while (true) {
+    const Slot& s = p.slots[i];
+    if (s.key == key) return row_ptr(p, s.row);
+    if (s.key == kEmpty) return nullptr;
+    i = (i + 1) & mask;
+  }
+}
+
+void HostTable::note_loaded(const int64_t* keys, size_t n) {
+  load_order_.insert(load_order_.end(), keys, keys + n);
+}
+
+void HostTable::warm_keys(size_t count, std::vector<int64_t>& out) const {
+  std::shared_lock<std::shared_mutex> lk(rw_);
+  out.clear();
+  out.reserve(count);
+  for (size_t k = 0; k < procedural_rows_ && out.size() < count; ++k)
+    out.push_back(static_cast<int64_t>(k));
+  for (size_t i = 0; i < load_order_.size() && out.size() < count; ++i) out.push_back(load_order_[i]);
+}
+
+void HostTable::reserve(size_t rows) {
+  std::unique_lock<std::shared_mutex> lk(rw_);
+  const size_t per_part = rows / parts_.size() + rows / (parts_.size() * 8) + 64;
+  for (auto& pp : parts_) {
+    Partition& p = *pp;
+    while ((p.count + per_part) * 2 > p.slots.size()) grow(p);
+  }
+}
+
+void HostTable::insert(const int64_t* keys, const float* vectors, size_t n, ThreadPool& pool) {
+  std::unique_lock<std::shared_mutex> lk(rw_);
+  note_loaded(keys, n);
+  const size_t P = parts_.size();
+  // every partition task scans the whole batch and takes its own keys: no locks, no sorting
+  pool.parallel_for(P, [&](size_t p) {
+    Partition& part = *parts_[p];
+    for (size_t i = 0; i < n; ++i) {
+      const uint64_t h = mix64(static_cast<uint64_t>(keys[i]));
+      if (partition_of(h) != p) continue;
+      float* dst = upsert(part, keys[i], h);
+      std::memcpy(dst, vectors + i * dim_, dim_ * sizeof(float));
+    }
+  });
+}
+
+void HostTable::fill_procedural(size_t n, uint64_t seed, ThreadPool& pool) {
+  std::unique_lock<std::shared_mutex> lk(rw_);
+  procedural_rows_ = std::max(procedural_rows_, n);
+  const size_t P = parts_.size();
+  {
+    const size_t per_part = n / P + n / (P * 8) + 64;
+    for (auto& pp : parts_)
+      while ((pp->count + per_part) * 2 > pp->slots.size()) grow(*pp);
+  }
+  // pass 1 (one task per partition: the maps are not concurrent): claim a row for every key
+  std::vector<float*> dst(n);
+  pool.parallel_for(P, [&](size_t p) {
+    Partition& part = *parts_[p];
+    for (size_t k = 0; k < n; ++k) {
+      const int64_t key = static_cast<int64_t>(k);
+      const uint64_t h = mix64(static_cast<uint64_t>(key));
+      if (partition_of(h) != p) continue;
+      dst[k] = upsert(part, key, h);
+    }
+  });
+  // pass 2 (all threads): generate the rows
+  constexpr size_t kRowsPerTask = 4096;
+  pool.parallel_for((n + kRowsPerTask - 1) / kRowsPerTask, [&](size_t task) {
+    const size_t e = std::min(n, (task + 1) * kRowsPerTask);
+    for (size_t k = task * kRowsPerTask; k < e; ++k)
+      for (size_t j = 0; j < dim_; ++j)
+        dst[k][j] = synth_value(static_cast<int64_t>(k), static_cast<uint32_t>(j), seed);
+  });
+}
+
+size_t HostTable::fetch_range(const int64_t* keys, size_t begin, size_t end, float* out,
+                              size_t stride) const {
+  constexpr size_t kBatch = 16;
+  const size_t row_bytes = dim_ * sizeof(float);
+  size_t absent = 0;
+  uint64_t hs[kBatch];
+  const float* rows[kBatch];
+  for (size_t b0 = begin; b0 < end; b0 += kBatch) {
+    const size_t nb = std::min(kBatch, end - b0);
+    // stage 1: hash, prefetch the home slot of every key
+    for (size_t j = 0; j < nb; ++j) {
+      hs[j] = mix64(static_cast<uint64_t>(keys[b0 + j]));
+      const Partition& p = *parts_[partition_of(hs[j])];
+      __builtin_prefetch(&p.slots[hs[j] & (p.slots.size() - 1)], 0, 0);
+    }
+    // stage 2: resolve, prefetch the rows
+    for (size_t j = 0; j < nb; ++j) {
+      const Partition& p = *parts_[partition_of(hs[j])];
+      rows[j] = find(p, keys[b0 + j], hs[j]);
+      if (rows[j]) {
+        const char* r = reinterpret_cast<const char*>(rows[j]);
+        for (size_t off = 0; off < row_bytes; off += 64) __builtin_prefetch(r + off, 0, 0);
+      }
+    }
+    // stage 3: copy
+    for (size_t j = 0; j < nb; ++j) {
+      float* dst = out + (b0 + j) * stride;
+      if (rows[j]) {
+        std::memcpy(dst, rows[j], row_bytes);
+      } else {
+        for (size_t d = 0; d < dim_; ++d) dst[d] = default_value_;
+        ++absent;
+      }
+    }
+  }
+  return absent;
+}
+
+size_t HostTable::fetch(const int64_t* keys, size_t n, float* out, size_t stride,
+                        ThreadPool& pool) const {
+  std::shared_lock<std::shared_mutex> lk(rw_);
+  if (n == 0) return 0;
+  constexpr size_t kMinChunk = 2048;
+  const size_t max_tasks = pool.size() * 4;
+  const size_t tasks = std::max<size_t>(1, std::min(max_tasks, (n + kMinChunk - 1) / kMinChunk));
+  if (tasks == 1) return fetch_range(keys, 0, n, out, stride);
+  const size_t chunk = (n + tasks - 1) / tasks;
+  std::atomic<size_t> absent{0};
+  pool.parallel_for(tasks, [&](size_t t) {
+    const size_t b = t * chunk;
+    const size_t e = std::min(n, b + chunk);
+    if (b < e) absent.fetch_add(fetch_range(keys, b, e, out, stride), std::memory_order_relaxed);
+  });
+  return absent.load();
+}
+
+}  // namespace hpsx

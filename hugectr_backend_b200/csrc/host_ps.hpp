@@ -1,0 +1,122 @@
+// Host-DRAM parameter server: the volatile database of the HPS (hash_map / parallel_hash_map
+// backend) behind the HBM cache.  Serves cache misses and the gpucache=false CPU path.
+//
+// Behaviour restated from the reference documentation (docs/hierarchical_parameter_server.md:67-78,
+// 244-246, 400-416): tables are hash-partitioned into `num_partitions` flat hash maps, values live in
+// `allocation_rate`-sized slabs, a key that is in no database gets default_value_for_each_table.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace hpsx {
+
+// Fixed pool; size follows the reference (HCTR_DEFAULT_CONCURRENCY, else hardware_concurrency:
+// src/thread_pool.cpp:25-41).  parallel_for is re-entrant from several caller threads.
+class ThreadPool {
+ public:
+  explicit ThreadPool(size_t num_threads);
+  ~ThreadPool();
+  size_t size() const { return workers_.size() + 1; }  // workers + the calling thread
+  // Runs fn(task) for task in [0, num_tasks); the caller participates; returns when all are done.
+  void parallel_for(size_t num_tasks, const std::function<void(size_t)>& fn);
+  // Fire-and-forget job (asynchronous cache insertion).
+  void post(std::function<void()> job);
+  static size_t default_concurrency();
+
+ private:
+  struct Batch {
+    const std::function<void(size_t)>* fn;
+    size_t num_tasks;
+    std::atomic<size_t> next{0};
+    std::atomic<size_t> done{0};
+    std::mutex mu;
+    std::condition_variable cv;
+  };
+  void worker_loop();
+  static void run_batch(const std::shared_ptr<Batch>& b);
+
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::shared_ptr<Batch>> batches_;
+  std::deque<std::function<void()>> jobs_;
+  bool stop_ = false;
+};
+
+// One embedding table in host DRAM.
+class HostTable {
+ public:
+  HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate);
+  ~HostTable();
+  HostTable(const HostTable&) = delete;
+  HostTable& operator=(const HostTable&) = delete;
+
+  size_t dim() const { return dim_; }
+  float default_value() const { return default_value_; }
+  size_t rows() const { return rows_.load(std::memory_order_relaxed); }
+  size_t num_partitions() const { return parts_.size(); }
+
+  // Insert or overwrite `n` rows (key file + vector file contents).
+  void insert(const int64_t* keys, const float* vectors, size_t n, ThreadPool& pool);
+  // keys [0,n) with synthetic rows, see hpsx_common.h synth_value().
+  void fill_procedural(size_t n, uint64_t seed, ThreadPool& pool);
+
+  // out[i*stride .. +dim) = row(keys[i]) or default.  Returns the number of absent keys.
+  // Multi-threaded over key ranges; software-prefetched probe + row gather.
+  size_t fetch(const int64_t* keys, size_t n, float* out, size_t stride, ThreadPool& pool) const;
+  // Single-threaded variant used from worker threads that already fan out themselves.
+  size_t fetch_range(const int64_t* keys, size_t begin, size_t end, float* out, size_t stride) const;
+
+  // The first min(count, rows) keys in load order (cache warm-up, a9).
+  void warm_keys(size_t count, std::vector<int64_t>& out) const;
+  // Pre-size the partition maps for `rows` more rows (avoids rehashing during bulk loads).
+  void reserve(size_t rows);
+
+ private:
+  struct Slot {
+    int64_t key;
+    uint64_t row;  // index into this partition's slabs
+  };
+  struct Partition {
+    std::vector<Slot> slots;  // open addressing, power-of-two capacity
+    size_t count = 0;
+    std::vector<float*> slabs;
+    size_t rows_used = 0;
+    bool has_sentinel = false;  // row of the key that doubles as the empty marker
+    uint64_t sentinel_row = 0;
+    std::mutex mu;
+  };
+
+  static constexpr int64_t kEmpty = INT64_MIN;
+  size_t partition_of(uint64_t h) const { return ((h >> 32) * parts_.size()) >> 32; }
+  float* row_ptr(const Partition& p, uint64_t row) const {
+    return p.slabs[row >> slab_shift_] + (row & slab_mask_) * dim_;
+  }
+  // returns the row pointer of `key` in partition `p`, inserting a fresh row if absent
+  float* upsert(Partition& p, int64_t key, uint64_t h);
+  const float* find(const Partition& p, int64_t key, uint64_t h) const;
+  void grow(Partition& p);
+  uint64_t alloc_row(Partition& p);
+  void note_loaded(const int64_t* keys, size_t n);
+
+  size_t dim_;
+  float default_value_;
+  std::vector<std::unique_ptr<Partition>> parts_;
+  size_t slab_shift_;  // rows per slab = 1 << slab_shift_
+  uint64_t slab_mask_;
+  std::atomic<size_t> rows_{0};
+  mutable std::shared_mutex rw_;  // fetch: shared; insert/fill: exclusive
+  std::vector<int64_t> load_order_;   // keys in the order insert() first saw them
+  size_t procedural_rows_ = 0;        // fill_procedural(n): keys [0,n) precede load_order_
+};
+
+}  // namespace hpsx

@@ -1,0 +1,1120 @@
+// libhpsx.so — C ABI of the HPS engine (include/hpsx.h): host orchestration of the lookup hot path.
+//
+//   keys (host) --H2D--> probe+gather kernel --> out (device, possibly the Triton output buffer)
+//                              | miss list (warp-compacted)
+//                              v
+//        D2H miss keys -> host parameter server gather (pinned, chunked, double-buffered)
+//                      -> H2D rows -> merge+insert kernel (writes `out` and the cache slot)
+//
+// The reference performs the same stages inside libhuge_ctr_hps.so behind
+// LookupSessionBase::lookup (call site hps_backend/src/model_instance_state.cpp:194-195).
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "engine.hpp"
+
+using namespace hpsx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, std::string msg) {
+  g_err = std::move(msg);
+  return code;
+}
+
+#define HPSX_CU(call)                                                                         \
+  do {                                                                                        \
+    const cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(HPSX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
+  } while (0)
+
+#define HPSX_GUARD_BEGIN try {
+#define HPSX_GUARD_END                                         \
+  }                                                            \
+  catch (const std::bad_alloc&) {                              \
+    return fail(HPSX_ERR_INTERNAL, "out of host memory");      \
+  }                                                            \
+  catch (const std::exception& e) {                            \
+    return fail(HPSX_ERR_INTERNAL, e.what());                  \
+  }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+Model* find_model(hpsx_ps* ps, const char* name) {
+  if (!ps || !name) return nullptr;
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->models.find(name);
+  return it == ps->models.end() ? nullptr : it->second.get();
+}
+
+size_t resolve_partitions(size_t requested) {
+  if (requested > 0) return requested;
+  // docs/hierarchical_parameter_server.md:410-412: min(number of cores, 16)
+  return std::max<size_t>(1, std::min<size_t>(ThreadPool::default_concurrency(), 16));
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse model files: <dir>/key (int64 | uint32) + <dir>/emb_vector (fp32 row-major)
+// (docs/architecture.md:185-218; writer samples/hps-triton-ensemble/01_model_training.ipynb:498-505)
+// ------------------------------------------------------------------------------------------------
+int load_sparse_dir(hpsx_ps* ps, HostTable* table, const std::string& dir) {
+  const std::string key_path = dir + "/key";
+  const std::string vec_path = dir + "/emb_vector";
+  struct stat ks {}, vs {};
+  if (stat(key_path.c_str(), &ks) != 0)
+    return fail(HPSX_ERR_IO, "cannot stat sparse key file '" + key_path + "'");
+  if (stat(vec_path.c_str(), &vs) != 0)
+    return fail(HPSX_ERR_IO, "cannot stat sparse vector file '" + vec_path + "'");
+  const size_t row_bytes = table->dim() * sizeof(float);
+  if (static_cast<size_t>(vs.st_size) % row_bytes != 0)
+    return fail(HPSX_ERR_IO, "'" + vec_path + "' is not a whole number of " +
+                                 std::to_string(table->dim()) + "-float rows");
+  const size_t rows = static_cast<size_t>(vs.st_size) / row_bytes;
+  if (rows == 0) {
+    if (ks.st_size != 0) return fail(HPSX_ERR_IO, "'" + key_path + "' has keys but no vectors");
+    return HPSX_OK;
+  }
+  size_t key_bytes = 0;
+  if (static_cast<size_t>(ks.st_size) == rows * 8)
+    key_bytes = 8;
+  else if (static_cast<size_t>(ks.st_size) == rows * 4)
+    key_bytes = 4;
+  else
+    return fail(HPSX_ERR_IO, "'" + key_path + "' (" + std::to_string(ks.st_size) +
+                                 " B) does not match " + std::to_string(rows) + " rows of '" +
+                                 vec_path + "'");
+  FILE* kf = std::fopen(key_path.c_str(), "rb");
+  FILE* vf = std::fopen(vec_path.c_str(), "rb");
+  if (!kf || !vf) {
+    if (kf) std::fclose(kf);
+    if (vf) std::fclose(vf);
+    return fail(HPSX_ERR_IO, "cannot open sparse files under '" + dir + "'");
+  }
+  table->reserve(rows);
+  constexpr size_t kChunk = 1 << 18;
+  std::vector<int64_t> keys(std::min(rows, kChunk));
+  std::vector<uint32_t> keys32(key_bytes == 4 ? keys.size() : 0);
+  std::vector<float> vecs(keys.size() * table->dim());
+  int rc = HPSX_OK;
+  for (size_t done = 0; done < rows && rc == HPSX_OK;) {
+    const size_t n = std::min(kChunk, rows - done);
+    size_t got;
+    if (key_bytes == 8) {
+      got = std::fread(keys.data(), 8, n, kf);
+    } else {
+      got = std::fread(keys32.data(), 4, n, kf);
+      for (size_t i = 0; i < got; ++i) keys[i] = static_cast<int64_t>(keys32[i]);
+    }
+    if (got != n || std::fread(vecs.data(), row_bytes, n, vf) != n) {
+      rc = fail(HPSX_ERR_IO, "short read in sparse files under '" + dir + "'");
+      break;
+    }
+    table->insert(keys.data(), vecs.data(), n, *ps->pool);
+    done += n;
+  }
+  std::fclose(kf);
+  std::fclose(vf);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cache construction + warm-up
+// ------------------------------------------------------------------------------------------------
+int insert_rows_from_host(hpsx_ps* ps, hpsx_cache* c, size_t t, const int64_t* keys, size_t n,
+                          cudaStream_t stream, int64_t* d_keys, float* h_stage, float* d_stage,
+                          size_t chunk_rows, uint32_t* d_inserted) {
+  // caller holds c->rw exclusively and has the device selected
+  const HostTable& ht = *c->model->tables[t];
+  const size_t dim = ht.dim();
+  for (size_t off = 0; off < n; off += chunk_rows) {
+    const size_t m = std::min(chunk_rows, n - off);
+    ht.fetch(keys + off, m, h_stage, dim, *ps->pool);
+    HPSX_CU(cudaMemcpyAsync(d_keys, keys + off, m * sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    HPSX_CU(cudaMemcpyAsync(d_stage, h_stage, m * dim * sizeof(float), cudaMemcpyHostToDevice,
+                            stream));
+    const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+    HPSX_CU(launch_insert_merge(c->tables[t], d_keys, nullptr, d_stage, m, nullptr, true, epoch,
+                                d_inserted, stream));
+    HPSX_CU(cudaStreamSynchronize(stream));  // h_stage / d_keys are reused by the next chunk
+  }
+  return HPSX_OK;
+}
+
+int build_cache(hpsx_ps* ps, Model* model, int device, std::unique_ptr<hpsx_cache>* out) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(HPSX_ERR_CUDA, "model '" + model->cfg.model_name + "' is deployed on device " +
+                                   std::to_string(device) + " but only " + std::to_string(ndev) +
+                                   " CUDA device(s) are usable");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice(" + std::to_string(device) + ") failed");
+
+  std::unique_ptr<hpsx_cache> c(new hpsx_cache());
+  c->model = model;
+  c->device = device;
+  c->is_static = model->cfg.embedding_cache_type == CacheType::Static;
+  const size_t T = model->tables.size();
+  c->tables.resize(T);
+  c->slots.resize(T);
+  for (size_t t = 0; t < T; ++t) c->max_dim = std::max(c->max_dim, model->tables[t]->dim());
+
+  cudaStream_t stream = nullptr;
+  HPSX_CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  HPSX_CU(cudaStreamCreateWithFlags(&c->async_stream, cudaStreamNonBlocking));
+  const size_t chunk = kStageChunkRows;
+  int64_t* d_keys = nullptr;
+  float *h_stage = nullptr, *d_stage = nullptr;
+  uint32_t* d_inserted = nullptr;
+  HPSX_CU(cudaMalloc(&d_keys, chunk * sizeof(int64_t)));
+  HPSX_CU(cudaMalloc(&d_stage, chunk * c->max_dim * sizeof(float)));
+  HPSX_CU(cudaMallocHost(&h_stage, chunk * c->max_dim * sizeof(float)));
+  HPSX_CU(cudaMalloc(&d_inserted, sizeof(uint32_t)));
+  // the asynchronous-insert workspace reuses these buffers after warm-up
+  c->async_d_keys = d_keys;
+  c->async_d_stage = d_stage;
+  c->async_h_stage = h_stage;
+  c->async_rows = chunk;
+
+  int rc = HPSX_OK;
+  std::vector<int64_t> warm;
+  for (size_t t = 0; t < T && rc == HPSX_OK; ++t) {
+    const HostTable& ht = *model->tables[t];
+    const size_t rows = ht.rows();
+    double pct = c->is_static ? 1.0 : static_cast<double>(model->cfg.cache_size_percentage);
+    pct = std::min(1.0, std::max(0.0, pct));
+    const size_t warm_rows = std::min(rows, static_cast<size_t>(std::ceil(pct * static_cast<double>(rows))));
+    const double lf = model->load_factor > 0.f ? model->load_factor : 0.5;
+    const size_t want_slots = static_cast<size_t>(std::ceil(static_cast<double>(warm_rows) / lf));
+    const size_t buckets = std::max<size_t>(1, (want_slots + kWays - 1) / kWays);
+    if (buckets > 0xFFFFFFFFull / kWays)
+      return fail(HPSX_ERR_UNSUPPORTED, "embedding cache of table " + std::to_string(t) +
+                                            " needs more than 2^32 slots");
+    DeviceTable& dt = c->tables[t];
+    dt.num_buckets = static_cast<uint32_t>(buckets);
+    dt.dim = static_cast<uint32_t>(ht.dim());
+    dt.default_value = ht.default_value();
+    c->slots[t] = buckets * kWays;
+    HPSX_CU(cudaMalloc(&dt.buckets, buckets * sizeof(Bucket)));
+    HPSX_CU(cudaMalloc(&dt.values, buckets * kWays * ht.dim() * sizeof(float)));
+    HPSX_CU(launch_table_clear(dt, stream));
+    HPSX_CU(cudaStreamSynchronize(stream));
+    if (warm_rows > 0) {
+      ht.warm_keys(warm_rows, warm);
+      std::unique_lock<std::shared_mutex> lk(c->rw);
+      rc = insert_rows_from_host(ps, c.get(), t, warm.data(), warm.size(), stream, d_keys, h_stage,
+                                 d_stage, chunk, nullptr);
+    }
+  }
+  cudaFree(d_inserted);
+  cudaStreamDestroy(stream);
+  if (rc != HPSX_OK) return rc;
+  *out = std::move(c);
+  return HPSX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// session helpers
+// ------------------------------------------------------------------------------------------------
+int check_tables(hpsx_session* s, const size_t* n_per_table, size_t num_tables) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  const size_t T = s->model->tables.size();
+  if (num_tables > T)
+    return fail(HPSX_ERR_INVALID_ARG, "lookup names " + std::to_string(num_tables) +
+                                          " tables but model '" + s->model->cfg.model_name +
+                                          "' has " + std::to_string(T));
+  if (num_tables > 0 && !n_per_table) return fail(HPSX_ERR_INVALID_ARG, "null num_keys_per_table");
+  for (size_t t = 0; t < num_tables; ++t) {
+    if (n_per_table[t] > s->cap_per_table[t])
+      return fail(HPSX_ERR_INVALID_ARG,
+                  "table " + std::to_string(t) + ": " + std::to_string(n_per_table[t]) +
+                      " keys exceed max_batch_size * maxnum_catfeature_query_per_table_per_sample = " +
+                      std::to_string(s->cap_per_table[t]));
+  }
+  return HPSX_OK;
+}
+
+struct AsyncJob {
+  hpsx_ps* ps;
+  hpsx_cache* cache;
+  size_t table;
+  std::vector<int64_t> keys;
+};
+
+void run_async_insert(AsyncJob job) {
+  hpsx_cache* c = job.cache;
+  {
+    DeviceGuard guard(c->device);
+    std::lock_guard<std::mutex> ws(c->async_mu);  // one job owns the workspace
+    std::unique_lock<std::shared_mutex> lk(c->rw);
+    // dedup on the host: the same missing key often repeats inside one request
+    std::sort(job.keys.begin(), job.keys.end());
+    job.keys.erase(std::unique(job.keys.begin(), job.keys.end()), job.keys.end());
+    uint32_t* d_ins = nullptr;
+    if (cudaMalloc(&d_ins, sizeof(uint32_t)) == cudaSuccess) {
+      cudaMemsetAsync(d_ins, 0, sizeof(uint32_t), c->async_stream);
+      insert_rows_from_host(job.ps, c, job.table, job.keys.data(), job.keys.size(), c->async_stream,
+                            c->async_d_keys, c->async_h_stage, c->async_d_stage, c->async_rows,
+                            d_ins);
+      uint32_t h = 0;
+      cudaMemcpy(&h, d_ins, sizeof(h), cudaMemcpyDeviceToHost);
+      c->async_inserted.fetch_add(h, std::memory_order_relaxed);
+      cudaFree(d_ins);
+    }
+  }
+  std::lock_guard<std::mutex> lk(c->async_mu);
+  --c->async_pending;
+  c->async_cv.notify_all();
+}
+
+// Resolve the misses of one table after its probe.  `d_out` may be nullptr (pooled path: rows are
+// only staged).  Caller holds s->mu; the stream is idle (probe results are on the host).
+int resolve_misses(hpsx_session* s, size_t t, size_t key_off, size_t n, uint32_t m, float* d_out,
+                   bool sync_insert, float* d_all_stage) {
+  hpsx_cache* c = s->cache;
+  const HostTable& ht = *s->model->tables[t];
+  const size_t dim = ht.dim();
+  int64_t* h_keys = s->h_miss_keys + key_off;
+  HPSX_CU(cudaMemcpyAsync(h_keys, s->d_miss_keys + key_off, m * sizeof(int64_t),
+                          cudaMemcpyDeviceToHost, s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  s->stats.d2h_bytes += m * sizeof(int64_t);
+  s->stats.misses += m;
+
+  if (!sync_insert) {
+    // asynchronous insertion: this response already carries the default vector for the misses
+    // (written by the probe kernel); a worker fetches + inserts later (docs/architecture.md:65-67)
+    s->stats.default_filled += m;
+    AsyncJob job{s->ps, c, t, std::vector<int64_t>(h_keys, h_keys + m)};
+    {
+      std::lock_guard<std::mutex> lk(c->async_mu);
+      ++c->async_pending;
+    }
+    s->ps->pool->post([job]() mutable { run_async_insert(std::move(job)); });
+    return HPSX_OK;
+  }
+
+  std::unique_lock<std::shared_mutex> lk(c->rw);
+  const bool insert = !c->is_static;
+  const uint32_t epoch = c->epoch.load(std::memory_order_relaxed);
+  uint32_t* d_inserted = s->d_counters + s->model->tables.size() + t;
+  (void)n;
+  size_t chunk_idx = 0;
+  for (size_t off = 0; off < m; off += kStageChunkRows, ++chunk_idx) {
+    const size_t mc = std::min<size_t>(kStageChunkRows, m - off);
+    const int b = static_cast<int>(chunk_idx & 1);
+    // the copy + kernel that last used this buffer pair must be done before the host refills it
+    HPSX_CU(cudaEventSynchronize(s->stage_free[b]));
+    const double t0 = now_ms();
+    const size_t absent = ht.fetch(h_keys + off, mc, s->h_stage[b], dim, *s->ps->pool);
+    s->stats.host_gather_ms += now_ms() - t0;
+    s->stats.default_filled += absent;
+    float* d_rows = d_all_stage ? d_all_stage + off * dim : s->d_stage[b];
+    HPSX_CU(cudaMemcpyAsync(d_rows, s->h_stage[b], mc * dim * sizeof(float), cudaMemcpyHostToDevice,
+                            s->stream));
+    s->stats.h2d_bytes += mc * dim * sizeof(float);
+    HPSX_CU(launch_insert_merge(c->tables[t], s->d_miss_keys + key_off + off,
+                                s->d_miss_pos + key_off + off, d_rows, mc, d_out, insert, epoch,
+                                d_inserted, s->stream));
+    ++s->stats.kernel_launches;
+    HPSX_CU(cudaEventRecord(s->stage_free[b], s->stream));
+  }
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  return HPSX_OK;
+}
+
+bool decide_sync(const hpsx_session* s, size_t n, uint32_t m) {
+  if (s->insert_mode == 0) return false;
+  if (s->insert_mode > 0) return true;
+  // [UPSTREAM] hit_rate < hit_rate_threshold -> synchronous insertion
+  const double hit_rate = 1.0 - static_cast<double>(m) / static_cast<double>(n);
+  return hit_rate < static_cast<double>(s->model->cfg.hit_rate_threshold);
+}
+
+int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
+               float* const* out_per_table, const size_t* n_per_table, size_t num_tables) {
+  hpsx_cache* c = s->cache;
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  const size_t T = s->model->tables.size();
+  const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  size_t total = 0;
+  for (size_t t = 0; t < num_tables; ++t) total += n_per_table[t];
+  ++s->stats.lookups;
+  s->stats.keys += total;
+  if (total == 0) return HPSX_OK;
+
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  std::vector<size_t> off(num_tables + 1, 0);
+  {
+    std::shared_lock<std::shared_mutex> lk(c->rw);
+    for (size_t t = 0; t < num_tables; ++t) {
+      const size_t n = n_per_table[t];
+      off[t + 1] = off[t] + n;
+      if (n == 0) continue;
+      if (!keys_per_table[t] || !out_per_table[t])
+        return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
+      const int64_t* d_keys;
+      if (keys_on_device) {
+        d_keys = static_cast<const int64_t*>(keys_per_table[t]);
+      } else {
+        HPSX_CU(cudaMemcpyAsync(s->d_keys + off[t], keys_per_table[t], n * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, s->stream));
+        s->stats.h2d_bytes += n * sizeof(int64_t);
+        d_keys = s->d_keys + off[t];
+      }
+      HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
+      HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
+                                  s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
+                                  s->probe_variant, s->stream));
+      HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
+      ++s->stats.kernel_launches;
+    }
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+  }
+  s->stats.d2h_bytes += T * sizeof(uint32_t);
+  for (size_t t = 0; t < num_tables; ++t) {
+    if (n_per_table[t] == 0) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]) == cudaSuccess) {
+      s->stats.probe_kernel_ms += ms;
+      ++s->stats.probe_kernel_launches;
+      s->stats.probe_kernel_keys += n_per_table[t];
+    }
+  }
+
+  bool any_sync = false;
+  for (size_t t = 0; t < num_tables; ++t) {
+    const uint32_t m = s->h_counters[t];
+    const size_t n = n_per_table[t];
+    s->stats.hits += n - m;
+    if (m == 0) continue;
+    const bool sync = decide_sync(s, n, m);
+    any_sync |= sync;
+    cudaEvent_t e0 = s->ev[2 * t], e1 = s->ev[2 * t + 1];
+    if (sync) HPSX_CU(cudaEventRecord(e0, s->stream));
+    const int rc = resolve_misses(s, t, off[t], n, m, out_per_table[t], sync, nullptr);
+    if (rc != HPSX_OK) return rc;
+    if (sync) {
+      HPSX_CU(cudaEventRecord(e1, s->stream));
+      HPSX_CU(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    }
+  }
+  if (any_sync) {
+    HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, T * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    for (size_t t = 0; t < num_tables; ++t) s->stats.inserted += s->h_counters[T + t];
+  }
+  return HPSX_OK;
+}
+
+int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool keys_on_device,
+                      size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
+  hpsx_cache* c = s->cache;
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  const size_t T = s->model->tables.size();
+  const size_t n = num_bags * hotness;
+  const size_t dim = s->model->tables[table]->dim();
+  ++s->stats.lookups;
+  s->stats.keys += n;
+  if (n == 0) return HPSX_OK;
+  if (!keys || !d_pooled) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
+  if (!s->d_src) HPSX_CU(cudaMalloc(&s->d_src, s->cap_keys * sizeof(uint32_t)));
+  const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  const int64_t* d_keys = keys;
+  {
+    std::shared_lock<std::shared_mutex> lk(c->rw);
+    if (!keys_on_device) {
+      HPSX_CU(cudaMemcpyAsync(s->d_keys, keys, n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+      s->stats.h2d_bytes += n * sizeof(int64_t);
+      d_keys = s->d_keys;
+    }
+    HPSX_CU(launch_probe_index(c->tables[table], d_keys, n, epoch, !c->is_static, s->d_src,
+                               s->d_counters + table, s->d_miss_pos, s->d_miss_keys, s->stream));
+    ++s->stats.kernel_launches;
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+  }
+  s->stats.d2h_bytes += T * sizeof(uint32_t);
+  const uint32_t m = s->h_counters[table];
+  s->stats.hits += n - m;
+  if (m > 0) {
+    // the pooled sum needs every row: misses are always resolved before pooling
+    if (s->pool_stage_rows < m) {
+      if (s->d_pool_stage) cudaFree(s->d_pool_stage);
+      s->d_pool_stage = nullptr;
+      s->pool_stage_rows = 0;
+      HPSX_CU(cudaMalloc(&s->d_pool_stage, static_cast<size_t>(m) * s->max_dim * sizeof(float)));
+      s->pool_stage_rows = m;
+    }
+    const int rc = resolve_misses(s, table, 0, n, m, nullptr, true, s->d_pool_stage);
+    if (rc != HPSX_OK) return rc;
+    HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, T * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
+  }
+  {
+    std::shared_lock<std::shared_mutex> lk(c->rw);
+    HPSX_CU(cudaEventRecord(s->ev[2 * table], s->stream));
+    HPSX_CU(launch_pooled_gather(c->tables[table], s->d_src, s->d_pool_stage, num_bags, hotness,
+                                 combiner == HPSX_COMBINER_MEAN, d_pooled, s->stream));
+    HPSX_CU(cudaEventRecord(s->ev[2 * table + 1], s->stream));
+    ++s->stats.kernel_launches;
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+  }
+  if (m > 0) s->stats.inserted += s->h_counters[T + table];
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev[2 * table], s->ev[2 * table + 1]) == cudaSuccess) {
+    s->stats.probe_kernel_ms += ms;
+    ++s->stats.probe_kernel_launches;
+    s->stats.probe_kernel_keys += n;
+  }
+  (void)dim;
+  return HPSX_OK;
+}
+
+}  // namespace
+
+hpsx_cache::~hpsx_cache() {
+  if (device >= 0) {
+    DeviceGuard guard(device);
+    {
+      std::unique_lock<std::mutex> lk(async_mu);
+      async_cv.wait(lk, [this] { return async_pending == 0; });
+    }
+    for (auto& t : tables) {
+      if (t.buckets) cudaFree(t.buckets);
+      if (t.values) cudaFree(t.values);
+    }
+    if (async_d_keys) cudaFree(async_d_keys);
+    if (async_d_stage) cudaFree(async_d_stage);
+    if (async_h_stage) cudaFreeHost(async_h_stage);
+    if (async_stream) cudaStreamDestroy(async_stream);
+  }
+}
+
+hpsx_session::~hpsx_session() {
+  if (device >= 0 && cache) {
+    DeviceGuard guard(device);
+    if (stream) cudaStreamSynchronize(stream);
+    cudaFree(d_keys);
+    cudaFree(d_miss_pos);
+    cudaFree(d_miss_keys);
+    cudaFree(d_counters);
+    cudaFree(d_src);
+    cudaFree(d_pool_stage);
+    if (h_counters) cudaFreeHost(h_counters);
+    if (h_miss_keys) cudaFreeHost(h_miss_keys);
+    for (int b = 0; b < 2; ++b) {
+      if (h_stage[b]) cudaFreeHost(h_stage[b]);
+      cudaFree(d_stage[b]);
+      if (stage_free[b]) cudaEventDestroy(stage_free[b]);
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+}
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int hpsx_abi_version(void) { return HPSX_ABI_VERSION; }
+const char* hpsx_last_error(void) { return g_err.c_str(); }
+
+int hpsx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int hpsx_ps_create(const hpsx_volatile_params* vdb, hpsx_ps** out) {
+  HPSX_GUARD_BEGIN
+  if (!out) return fail(HPSX_ERR_INVALID_ARG, "null output handle");
+  std::unique_ptr<hpsx_ps> ps(new hpsx_ps());
+  size_t threads = 0;
+  if (vdb) {
+    ps->vdb.num_partitions = vdb->num_partitions;
+    if (vdb->allocation_rate) ps->vdb.allocation_rate = vdb->allocation_rate;
+    if (vdb->initial_cache_rate > 0) ps->vdb.initial_cache_rate = vdb->initial_cache_rate;
+    threads = vdb->num_threads;
+  }
+  ps->vdb.num_partitions = resolve_partitions(ps->vdb.num_partitions);
+  ps->pool.reset(new ThreadPool(threads));
+  *out = ps.release();
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_destroy(hpsx_ps* ps) {
+  HPSX_GUARD_BEGIN
+  if (!ps) return HPSX_OK;
+  // caches wait for their asynchronous jobs, which run on the pool: destroy them first
+  for (auto& kv : ps->models) kv.second->caches.clear();
+  delete ps;
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_num_models(const hpsx_ps* ps, size_t* out) {
+  if (!ps || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = ps->model_order.size();
+  return HPSX_OK;
+}
+
+int hpsx_ps_model_name(const hpsx_ps* ps, size_t index, const char** out) {
+  if (!ps || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (index >= ps->model_order.size()) return fail(HPSX_ERR_NOT_FOUND, "model index out of range");
+  *out = ps->model_order[index].c_str();
+  return HPSX_OK;
+}
+
+int hpsx_ps_has_model(const hpsx_ps* ps, const char* model_name) {
+  return find_model(const_cast<hpsx_ps*>(ps), model_name) != nullptr ? 1 : 0;
+}
+
+static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor) {
+  const size_t T = cfg.embedding_vecsize_per_table.size();
+  if (cfg.model_name.empty()) return fail(HPSX_ERR_INVALID_ARG, "model name is empty");
+  if (T == 0) return fail(HPSX_ERR_INVALID_ARG, "model '" + cfg.model_name + "' has no tables");
+  if (cfg.maxnum_catfeature_query_per_table_per_sample.size() != T ||
+      cfg.default_value_for_each_table.size() != T)
+    return fail(HPSX_ERR_INVALID_ARG, "model '" + cfg.model_name + "': per-table lists differ in length");
+  if (cfg.embedding_cache_type == CacheType::UVM)
+    return fail(HPSX_ERR_UNSUPPORTED, "embedding_cache_type 'uvm' is not supported");
+  std::unique_ptr<Model> m(new Model());
+  m->cfg = cfg;
+  m->load_factor = load_factor > 0.f ? load_factor : 0.5f;
+  for (size_t t = 0; t < T; ++t) {
+    if (cfg.embedding_vecsize_per_table[t] == 0)
+      return fail(HPSX_ERR_INVALID_ARG, "embedding_vecsize_per_table must be > 0");
+    m->tables.emplace_back(new HostTable(cfg.embedding_vecsize_per_table[t],
+                                         cfg.default_value_for_each_table[t], ps->vdb.num_partitions,
+                                         ps->vdb.allocation_rate));
+  }
+  for (size_t t = 0; t < T && t < cfg.sparse_files.size(); ++t) {
+    if (cfg.sparse_files[t].empty()) continue;
+    const int rc = load_sparse_dir(ps, m->tables[t].get(), cfg.sparse_files[t]);
+    if (rc != HPSX_OK) return rc;
+  }
+  std::lock_guard<std::mutex> lk(ps->mu);
+  if (ps->models.count(cfg.model_name))
+    return fail(HPSX_ERR_INVALID_ARG, "model '" + cfg.model_name + "' is already registered");
+  ps->model_order.push_back(cfg.model_name);
+  ps->models[cfg.model_name] = std::move(m);
+  return HPSX_OK;
+}
+
+int hpsx_ps_add_model(hpsx_ps* ps, const hpsx_model_params* p) {
+  HPSX_GUARD_BEGIN
+  if (!ps || !p || !p->model_name) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (p->num_tables == 0 || !p->embedding_vecsize_per_table ||
+      !p->maxnum_catfeature_query_per_table_per_sample || !p->default_value_for_each_table)
+    return fail(HPSX_ERR_INVALID_ARG, "per-table parameter arrays are required");
+  ModelConfig cfg;
+  cfg.model_name = p->model_name;
+  cfg.max_batch_size = p->max_batch_size;
+  for (size_t t = 0; t < p->num_tables; ++t) {
+    cfg.sparse_files.push_back(p->sparse_files && p->sparse_files[t] ? p->sparse_files[t] : "");
+    if (p->table_names && p->table_names[t]) cfg.embedding_table_names.push_back(p->table_names[t]);
+    cfg.embedding_vecsize_per_table.push_back(p->embedding_vecsize_per_table[t]);
+    cfg.maxnum_catfeature_query_per_table_per_sample.push_back(
+        p->maxnum_catfeature_query_per_table_per_sample[t]);
+    cfg.default_value_for_each_table.push_back(p->default_value_for_each_table[t]);
+  }
+  cfg.use_gpu_embedding_cache = p->use_gpu_embedding_cache != 0;
+  cfg.hit_rate_threshold = p->hit_rate_threshold;
+  cfg.cache_size_percentage = p->cache_size_percentage;
+  cfg.number_of_worker_buffers_in_pool = p->number_of_worker_buffers_in_pool;
+  for (size_t i = 0; i < p->num_deployed_devices; ++i)
+    cfg.deployed_devices.push_back(p->deployed_devices[i]);
+  if (cfg.deployed_devices.empty()) cfg.deployed_devices.push_back(0);
+  cfg.device_id = cfg.deployed_devices.back();
+  cfg.embedding_cache_type = p->embedding_cache_type == HPSX_CACHE_STATIC ? CacheType::Static
+                                                                          : CacheType::Dynamic;
+  return add_model_cfg(ps, cfg, p->cache_load_factor);
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_create_from_json(const char* ps_json_path, hpsx_ps** out) {
+  HPSX_GUARD_BEGIN
+  if (!ps_json_path || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  PsConfig cfg;
+  const ParseResult pr = parse_ps_config_file(ps_json_path, &cfg);
+  if (!pr.ok) return fail(HPSX_ERR_INVALID_ARG, pr.message);
+  switch (cfg.volatile_db.type) {
+    case DatabaseType::HashMap:
+    case DatabaseType::ParallelHashMap:
+      break;
+    default:
+      return fail(HPSX_ERR_UNSUPPORTED,
+                  std::string("volatile_db.type '") + to_string(cfg.volatile_db.type) +
+                      "' is not supported: this engine serves the hash_map / parallel_hash_map "
+                      "host database only");
+  }
+  if (cfg.persistent_db.type != DatabaseType::Disabled)
+    return fail(HPSX_ERR_UNSUPPORTED, "persistent_db is not supported (type must be 'disabled')");
+  hpsx_volatile_params vp{};
+  vp.num_partitions = cfg.volatile_db.num_partitions;
+  vp.allocation_rate = cfg.volatile_db.allocation_rate;
+  vp.initial_cache_rate = cfg.volatile_db.initial_cache_rate;
+  hpsx_ps* ps = nullptr;
+  int rc = hpsx_ps_create(&vp, &ps);
+  if (rc != HPSX_OK) return rc;
+  ps->vdb = cfg.volatile_db;
+  ps->vdb.num_partitions = resolve_partitions(cfg.volatile_db.num_partitions);
+  for (const ModelConfig& m : cfg.models) {
+    rc = add_model_cfg(ps, m, 0.f);
+    if (rc == HPSX_OK && m.use_gpu_embedding_cache && m.init_ec)
+      rc = hpsx_ps_create_embedding_cache_per_model(ps, m.model_name.c_str());
+    if (rc != HPSX_OK) {
+      const std::string keep = g_err;
+      hpsx_ps_destroy(ps);
+      return fail(rc, keep);
+    }
+  }
+  *out = ps;
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_load_table(hpsx_ps* ps, const char* model, size_t table, const int64_t* h_keys,
+                       const float* h_vectors, size_t num_rows) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (num_rows > 0 && (!h_keys || !h_vectors)) return fail(HPSX_ERR_INVALID_ARG, "null rows");
+  m->tables[table]->insert(h_keys, h_vectors, num_rows, *ps->pool);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_load_table_procedural(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
+                                  uint64_t seed) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  m->tables[table]->fill_procedural(num_rows, seed, *ps->pool);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_t* out) {
+  Model* m = find_model(const_cast<hpsx_ps*>(ps), model);
+  if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, "unknown model");
+  if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  *out = m->tables[table]->rows();
+  return HPSX_OK;
+}
+
+int hpsx_ps_lookup(hpsx_ps* ps, const char* model, size_t table, const int64_t* h_keys, size_t n,
+                   float* h_vectors) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (n > 0 && (!h_keys || !h_vectors)) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
+  const HostTable& ht = *m->tables[table];
+  ht.fetch(h_keys, n, h_vectors, ht.dim(), *ps->pool);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_create_embedding_cache_per_model(hpsx_ps* ps, const char* model) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  if (!m->cfg.use_gpu_embedding_cache)
+    return fail(HPSX_ERR_INVALID_ARG, "model '" + m->cfg.model_name + "' has gpucache = false");
+  for (int dev : m->cfg.deployed_devices) {
+    {
+      std::lock_guard<std::mutex> lk(m->mu);
+      if (m->caches.count(dev)) continue;
+    }
+    std::unique_ptr<hpsx_cache> c;
+    const int rc = build_cache(ps, m, dev, &c);
+    if (rc != HPSX_OK) return rc;
+    std::lock_guard<std::mutex> lk(m->mu);
+    m->caches[dev] = std::move(c);
+  }
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_get_embedding_cache(hpsx_ps* ps, const char* model, int device, hpsx_cache** out) {
+  Model* m = find_model(ps, model);
+  if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  std::lock_guard<std::mutex> lk(m->mu);
+  auto it = m->caches.find(device);
+  if (it == m->caches.end()) {
+    *out = nullptr;
+    return fail(HPSX_ERR_NOT_FOUND, "model '" + m->cfg.model_name + "' has no embedding cache on device " +
+                                        std::to_string(device));
+  }
+  *out = it->second.get();
+  return HPSX_OK;
+}
+
+int hpsx_ps_destroy_embedding_cache_per_model(hpsx_ps* ps, const char* model) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  std::map<int, std::unique_ptr<hpsx_cache>> doomed;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    doomed.swap(m->caches);
+  }
+  doomed.clear();
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_cache_num_tables(const hpsx_cache* cache, size_t* out) {
+  if (!cache || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = cache->tables.size();
+  return HPSX_OK;
+}
+
+int hpsx_cache_device(const hpsx_cache* cache, int* out) {
+  if (!cache || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = cache->device;
+  return HPSX_OK;
+}
+
+int hpsx_cache_capacity(const hpsx_cache* cache, size_t table, size_t* slots) {
+  if (!cache || !slots) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (table >= cache->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  *slots = cache->slots[table];
+  return HPSX_OK;
+}
+
+int hpsx_cache_resident(hpsx_cache* cache, size_t table, size_t* keys) {
+  if (!cache || !keys) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (table >= cache->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  DeviceGuard guard(cache->device);
+  std::shared_lock<std::shared_mutex> lk(cache->rw);
+  unsigned long long* d = nullptr;
+  HPSX_CU(cudaMalloc(&d, sizeof(unsigned long long)));
+  cudaError_t e = launch_count_resident(cache->tables[table], d, nullptr);
+  unsigned long long h = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  HPSX_CU(e);
+  *keys = static_cast<size_t>(h);
+  return HPSX_OK;
+}
+
+int hpsx_cache_dump_keys(hpsx_cache* cache, size_t table, int64_t* h_keys, size_t cap, size_t* n) {
+  if (!cache || !n || (cap > 0 && !h_keys)) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (table >= cache->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  DeviceGuard guard(cache->device);
+  std::shared_lock<std::shared_mutex> lk(cache->rw);
+  unsigned long long* d_count = nullptr;
+  int64_t* d_keys = nullptr;
+  HPSX_CU(cudaMalloc(&d_count, sizeof(unsigned long long)));
+  cudaError_t e = cudaMalloc(&d_keys, std::max<size_t>(cap, 1) * sizeof(int64_t));
+  unsigned long long h = 0;
+  if (e == cudaSuccess) e = launch_dump_keys(cache->tables[table], d_keys, cap, d_count, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost);
+  const size_t got = std::min<size_t>(static_cast<size_t>(h), cap);
+  if (e == cudaSuccess && got > 0)
+    e = cudaMemcpy(h_keys, d_keys, got * sizeof(int64_t), cudaMemcpyDeviceToHost);
+  cudaFree(d_count);
+  if (d_keys) cudaFree(d_keys);
+  HPSX_CU(e);
+  *n = got;
+  return HPSX_OK;
+}
+
+int hpsx_cache_drain_async(hpsx_cache* cache) {
+  if (!cache) return fail(HPSX_ERR_INVALID_ARG, "null cache");
+  std::unique_lock<std::mutex> lk(cache->async_mu);
+  cache->async_cv.wait(lk, [cache] { return cache->async_pending == 0; });
+  return HPSX_OK;
+}
+
+int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session** out) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  std::unique_ptr<hpsx_session> s(new hpsx_session());
+  s->ps = ps;
+  s->model = m;
+  const size_t T = m->tables.size();
+  s->cap_per_table.resize(T);
+  for (size_t t = 0; t < T; ++t) {
+    s->cap_per_table[t] =
+        m->cfg.max_batch_size * m->cfg.maxnum_catfeature_query_per_table_per_sample[t];
+    s->cap_keys += s->cap_per_table[t];
+    s->max_dim = std::max(s->max_dim, m->tables[t]->dim());
+  }
+  if (!m->cfg.use_gpu_embedding_cache || device < 0) {
+    // CPU session: vectors are returned in host memory (hps_backend/src/hps.cc:640-642)
+    *out = s.release();
+    return HPSX_OK;
+  }
+  hpsx_cache* c = nullptr;
+  int rc = hpsx_ps_get_embedding_cache(ps, model, device, &c);
+  if (rc != HPSX_OK) return rc;
+  s->cache = c;
+  s->device = device;
+  if (const char* env = std::getenv("HPSX_PROBE"))
+    s->probe_variant = std::strcmp(env, "tma") == 0 ? kProbeTma : kProbeLdg;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+  const size_t cap = std::max<size_t>(s->cap_keys, 1);
+  HPSX_CU(cudaMalloc(&s->d_keys, cap * sizeof(int64_t)));
+  HPSX_CU(cudaMalloc(&s->d_miss_pos, cap * sizeof(uint32_t)));
+  HPSX_CU(cudaMalloc(&s->d_miss_keys, cap * sizeof(int64_t)));
+  HPSX_CU(cudaMalloc(&s->d_counters, 2 * T * sizeof(uint32_t)));
+  HPSX_CU(cudaMallocHost(&s->h_counters, 2 * T * sizeof(uint32_t)));
+  HPSX_CU(cudaMallocHost(&s->h_miss_keys, cap * sizeof(int64_t)));
+  const size_t chunk_rows = std::min<size_t>(kStageChunkRows, cap);
+  for (int b = 0; b < 2; ++b) {
+    HPSX_CU(cudaMallocHost(&s->h_stage[b], kStageChunkRows * s->max_dim * sizeof(float)));
+    HPSX_CU(cudaMalloc(&s->d_stage[b], kStageChunkRows * s->max_dim * sizeof(float)));
+    HPSX_CU(cudaEventCreateWithFlags(&s->stage_free[b], cudaEventDisableTiming));
+  }
+  (void)chunk_rows;
+  s->ev.resize(2 * T);
+  for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
+  *out = s.release();
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_session_destroy(hpsx_session* s) {
+  HPSX_GUARD_BEGIN
+  delete s;
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_session_device(const hpsx_session* s, int* out) {
+  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = s->device;
+  return HPSX_OK;
+}
+
+int hpsx_session_stream(const hpsx_session* s, void** out) {
+  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = s->stream;
+  return HPSX_OK;
+}
+
+int hpsx_session_lookup(hpsx_session* s, const void* const* h_keys_per_table,
+                        float* const* vectors_per_table, const size_t* num_keys_per_table,
+                        size_t num_tables) {
+  HPSX_GUARD_BEGIN
+  int rc = check_tables(s, num_keys_per_table, num_tables);
+  if (rc != HPSX_OK) return rc;
+  if (num_tables > 0 && (!h_keys_per_table || !vectors_per_table))
+    return fail(HPSX_ERR_INVALID_ARG, "null pointer arrays");
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (!s->cache) {
+    ++s->stats.lookups;
+    for (size_t t = 0; t < num_tables; ++t) {
+      const size_t n = num_keys_per_table[t];
+      if (n == 0) continue;
+      if (!h_keys_per_table[t] || !vectors_per_table[t])
+        return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
+      const HostTable& ht = *s->model->tables[t];
+      const double t0 = now_ms();
+      const size_t absent = ht.fetch(static_cast<const int64_t*>(h_keys_per_table[t]), n,
+                                     vectors_per_table[t], ht.dim(), *s->ps->pool);
+      s->stats.host_gather_ms += now_ms() - t0;
+      s->stats.keys += n;
+      s->stats.misses += n;
+      s->stats.default_filled += absent;
+    }
+    return HPSX_OK;
+  }
+  return gpu_lookup(s, h_keys_per_table, false, vectors_per_table, num_keys_per_table, num_tables);
+  HPSX_GUARD_END
+}
+
+int hpsx_session_lookup_device_keys(hpsx_session* s, const int64_t* const* d_keys_per_table,
+                                    float* const* d_vectors_per_table,
+                                    const size_t* num_keys_per_table, size_t num_tables) {
+  HPSX_GUARD_BEGIN
+  int rc = check_tables(s, num_keys_per_table, num_tables);
+  if (rc != HPSX_OK) return rc;
+  if (!s->cache)
+    return fail(HPSX_ERR_UNSUPPORTED, "device keys need a GPU session (gpucache = true)");
+  if (num_tables > 0 && (!d_keys_per_table || !d_vectors_per_table))
+    return fail(HPSX_ERR_INVALID_ARG, "null pointer arrays");
+  std::lock_guard<std::mutex> lk(s->mu);
+  return gpu_lookup(s, reinterpret_cast<const void* const*>(d_keys_per_table), true,
+                    d_vectors_per_table, num_keys_per_table, num_tables);
+  HPSX_GUARD_END
+}
+
+static int pooled_common(hpsx_session* s, size_t table, const int64_t* keys, bool on_device,
+                         size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (!s->cache)
+    return fail(HPSX_ERR_UNSUPPORTED, "pooled lookup needs a GPU session (gpucache = true)");
+  if (table >= s->model->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (combiner != HPSX_COMBINER_SUM && combiner != HPSX_COMBINER_MEAN)
+    return fail(HPSX_ERR_INVALID_ARG, "unknown combiner");
+  if (hotness == 0 && num_bags > 0) return fail(HPSX_ERR_INVALID_ARG, "hotness must be > 0");
+  if (num_bags * hotness > s->cap_per_table[table])
+    return fail(HPSX_ERR_INVALID_ARG, "pooled lookup exceeds the table's key capacity");
+  std::lock_guard<std::mutex> lk(s->mu);
+  return gpu_lookup_pooled(s, table, keys, on_device, num_bags, hotness, combiner, d_pooled);
+}
+
+int hpsx_session_lookup_pooled(hpsx_session* s, size_t table, const int64_t* h_keys, size_t num_bags,
+                               size_t hotness, int combiner, float* d_pooled) {
+  HPSX_GUARD_BEGIN
+  return pooled_common(s, table, h_keys, false, num_bags, hotness, combiner, d_pooled);
+  HPSX_GUARD_END
+}
+
+int hpsx_session_lookup_pooled_device_keys(hpsx_session* s, size_t table, const int64_t* d_keys,
+                                           size_t num_bags, size_t hotness, int combiner,
+                                           float* d_pooled) {
+  HPSX_GUARD_BEGIN
+  return pooled_common(s, table, d_keys, true, num_bags, hotness, combiner, d_pooled);
+  HPSX_GUARD_END
+}
+
+int hpsx_session_get_stats(const hpsx_session* s, hpsx_session_stats* out) {
+  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = s->stats;
+  return HPSX_OK;
+}
+
+int hpsx_session_reset_stats(hpsx_session* s) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  std::lock_guard<std::mutex> lk(s->mu);
+  s->stats = hpsx_session_stats{};
+  return HPSX_OK;
+}
+
+int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  s->insert_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  return HPSX_OK;
+}
+
+int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (variant != kProbeLdg && variant != kProbeTma)
+    return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
+  s->probe_variant = variant;
+  return HPSX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone device primitives
+// ------------------------------------------------------------------------------------------------
+int hpsx_unique(int device, const int64_t* d_keys, size_t n, int64_t* d_unique, uint32_t* d_inverse,
+                size_t* h_num_unique, void* stream) {
+  HPSX_GUARD_BEGIN
+  if (!h_num_unique) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *h_num_unique = 0;
+  if (n == 0) return HPSX_OK;
+  if (!d_keys || !d_unique || !d_inverse) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (n > (1ull << 31)) return fail(HPSX_ERR_UNSUPPORTED, "too many keys for one dedup call");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  size_t cap = 64;
+  while (cap < 2 * n) cap <<= 1;
+  int64_t* ws_keys = nullptr;
+  uint32_t *ws_ids = nullptr, *d_counter = nullptr;
+  HPSX_CU(cudaMalloc(&ws_keys, cap * sizeof(int64_t)));
+  cudaError_t e = cudaMalloc(&ws_ids, cap * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_counter, 4 * sizeof(uint32_t));
+  if (e == cudaSuccess)
+    e = launch_unique(d_keys, n, ws_keys, ws_ids, cap, d_unique, d_inverse, d_counter, st);
+  uint32_t h[4] = {0, 0, 0, 0};
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h, d_counter, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(ws_keys);
+  if (ws_ids) cudaFree(ws_ids);
+  if (d_counter) cudaFree(d_counter);
+  HPSX_CU(e);
+  *h_num_unique = h[0];
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+uint32_t hpsx_owner(int64_t key, uint32_t num_shards) { return owner_of(key, num_shards); }
+
+int hpsx_route_keys(int device, const int64_t* d_keys, size_t n, uint32_t num_shards,
+                    int64_t* d_routed_keys, uint32_t* d_perm, uint32_t* d_counts, uint32_t* h_counts,
+                    void* stream) {
+  HPSX_GUARD_BEGIN
+  if (num_shards == 0 || num_shards > 64) return fail(HPSX_ERR_INVALID_ARG, "num_shards must be in [1,64]");
+  if (!d_counts) return fail(HPSX_ERR_INVALID_ARG, "null d_counts");
+  if (n > 0 && (!d_keys || !d_routed_keys || !d_perm)) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (n > 0xFFFFFFFFull) return fail(HPSX_ERR_UNSUPPORTED, "too many keys for one routing call");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint32_t* d_cursor = nullptr;
+  HPSX_CU(cudaMalloc(&d_cursor, num_shards * sizeof(uint32_t)));
+  cudaError_t e = launch_route_keys(d_keys, n, num_shards, d_routed_keys, d_perm, d_counts, d_cursor, st);
+  if (e == cudaSuccess && h_counts)
+    e = cudaMemcpyAsync(h_counts, d_counts, num_shards * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_cursor);
+  HPSX_CU(e);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_scatter_rows(int device, const float* d_rows, const uint32_t* d_perm, size_t n, size_t d,
+                      float* d_out, void* stream) {
+  HPSX_GUARD_BEGIN
+  if (n == 0) return HPSX_OK;
+  if (!d_rows || !d_perm || !d_out || d == 0) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(launch_scatter_rows(d_rows, d_perm, n, d, d_out, static_cast<cudaStream_t>(stream)));
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,990 @@
+// sm_100a kernels of the HPS lookup hot path.
+//
+// None of this is a contraction: every kernel is HBM-bound integer hashing + row copies, so the
+// design rules are coalescing, 16-B vector accesses, many independent loads in flight per warp,
+// bulk-async (TMA engine) row staging where rows are >= 16 B, and warp ballot/prefix compaction.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+
+namespace hpsx {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kBlock = 256;  // 8 warps; one warp owns one tile of 32 keys
+
+// ------------------------------------------------------------------------------------------------
+// vector load/store helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float2* p, const float2& v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float* p, const float& v) { __stcs(p, v); }
+
+template <typename VecT>
+__device__ __forceinline__ VecT splat(float x);
+template <>
+__device__ __forceinline__ float4 splat<float4>(float x) {
+  return make_float4(x, x, x, x);
+}
+template <>
+__device__ __forceinline__ float2 splat<float2>(float x) {
+  return make_float2(x, x);
+}
+template <>
+__device__ __forceinline__ float splat<float>(float x) {
+  return x;
+}
+
+__device__ __forceinline__ void vadd(float4& a, const float4& b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+__device__ __forceinline__ void vadd(float2& a, const float2& b) {
+  a.x += b.x;
+  a.y += b.y;
+}
+__device__ __forceinline__ void vadd(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void vdiv(float4& a, float d) {
+  a.x = __fdiv_rn(a.x, d);
+  a.y = __fdiv_rn(a.y, d);
+  a.z = __fdiv_rn(a.z, d);
+  a.w = __fdiv_rn(a.w, d);
+}
+__device__ __forceinline__ void vdiv(float2& a, float d) {
+  a.x = __fdiv_rn(a.x, d);
+  a.y = __fdiv_rn(a.y, d);
+}
+__device__ __forceinline__ void vdiv(float& a, float d) { a = __fdiv_rn(a, d); }
+
+// ------------------------------------------------------------------------------------------------
+// probe: one thread, one key, one 64-B bucket (two DRAM sectors, four LDG.128 through L2 only)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t probe_bucket(Bucket* __restrict__ buckets, uint32_t num_buckets,
+                                                 int64_t key, uint32_t epoch, bool touch) {
+  if (key == kEmptyKey) return kMissSlot;
+  const uint32_t b = bucket_of(key, num_buckets);
+  const longlong2* kp = reinterpret_cast<const longlong2*>(buckets[b].keys);
+  const longlong2 k01 = __ldcg(kp + 0);
+  const longlong2 k23 = __ldcg(kp + 1);
+  const longlong2 k45 = __ldcg(kp + 2);
+  const longlong2 k67 = __ldcg(kp + 3);
+  int way = -1;
+  way = (k01.x == key) ? 0 : way;
+  way = (k01.y == key) ? 1 : way;
+  way = (k23.x == key) ? 2 : way;
+  way = (k23.y == key) ? 3 : way;
+  way = (k45.x == key) ? 4 : way;
+  way = (k45.y == key) ? 5 : way;
+  way = (k67.x == key) ? 6 : way;
+  way = (k67.y == key) ? 7 : way;
+  if (way < 0) return kMissSlot;
+  if (touch) buckets[b].stamp[way] = epoch;  // LRU touch: 4-B store into the line's third sector
+  return b * kWays + static_cast<uint32_t>(way);
+}
+
+struct ProbeArgs {
+  Bucket* buckets;
+  const float* values;
+  uint32_t num_buckets;
+  uint32_t dim;
+  float default_value;
+  const int64_t* keys;
+  size_t n;
+  float* out;
+  uint32_t epoch;
+  int touch;
+  uint32_t* miss_count;
+  uint32_t* miss_pos;
+  int64_t* miss_keys;
+  uint32_t* src;  // probe_index only
+};
+
+// Append the misses of one warp tile to the global miss list: ballot -> popc prefix -> one atomic.
+__device__ __forceinline__ uint32_t warp_claim_misses(bool is_miss, uint32_t lane,
+                                                      uint32_t* miss_count, unsigned* mask_out) {
+  const unsigned mask = __ballot_sync(kFull, is_miss);
+  *mask_out = mask;
+  uint32_t base = 0;
+  if (mask != 0u) {
+    if (lane == 0) base = atomicAdd(miss_count, static_cast<uint32_t>(__popc(mask)));
+    base = __shfl_sync(kFull, base, 0);
+  }
+  return base;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (+K3,K6) LDG variant.  Warp = tile of 32 keys.  Phase 1: lane-per-key probe.  Phase 2: the
+// warp copies the 32 rows cooperatively, kUnroll independent 16-B loads per lane in flight, output
+// addresses contiguous across the whole tile (rows of consecutive keys are adjacent in `out`).
+// kV = vectors per row when known at compile time (0: runtime).
+// ------------------------------------------------------------------------------------------------
+template <typename VecT, int kV, int kUnroll>
+__global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t tile = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t tile_base = tile * 32;
+  if (tile_base >= a.n) return;
+  const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), a.n - tile_base));
+  const uint32_t V = kV > 0 ? static_cast<uint32_t>(kV)
+                            : a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+
+  const bool valid = lane < nk;
+  const int64_t key = valid ? a.keys[tile_base + lane] : kEmptyKey;
+  uint32_t slot = kMissSlot;
+  if (valid) slot = probe_bucket(a.buckets, a.num_buckets, key, a.epoch, a.touch != 0);
+  const bool is_miss = valid && slot == kMissSlot;
+  unsigned miss_mask;
+  const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+
+  const VecT* __restrict__ vals = reinterpret_cast<const VecT*>(a.values);
+  VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + tile_base * V;
+  const VecT defv = splat<VecT>(a.default_value);
+  const uint32_t total = nk * V;
+  for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
+    VecT buf[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      const uint32_t kk = min(i / V, 31u);
+      const uint32_t s = __shfl_sync(kFull, slot, kk);
+      const uint32_t v = i - kk * V;
+      buf[u] = defv;
+      if (i < total && s != kMissSlot) buf[u] = ld_stream(vals + static_cast<size_t>(s) * V + v);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      if (i < total) st_stream(outv + i, buf[u]);
+    }
+  }
+
+  if (is_miss) {
+    const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
+    a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+    a.miss_keys[r] = key;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 TMA variant: rows are staged global -> shared with cp.async.bulk (UBLKCP, the TMA engine's
+// 1-D path) and leave with ONE bulk store per tile, because the 32 output rows of a tile are
+// contiguous.  No row data passes through registers.  Ring of kStages tiles per warp-group-free
+// CTA: every warp owns its own ring slot sequence, so there is no CTA-wide barrier on the hot path.
+// Requires dim*4 % 16 == 0 and 16-B aligned `out`.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr int kTmaTileKeys = 32;
+
+// Dynamic smem: [warp][stage][32 rows * row_bytes] then one mbarrier per (warp, stage).
+// Schedule per warp: iteration t issues the loads of tile t into stage t % kStages, then retires
+// tile t-1 (wait for its bytes, one bulk store).  The previous user of stage t % kStages is tile
+// t-kStages, whose store was committed in iteration t-kStages+1, i.e. it is the (kStages-1)-th most
+// recent bulk group at the top of iteration t: wait_group.read <kStages-2> frees it.
+template <int kWarps, int kStages>
+__global__ void __launch_bounds__(kWarps * 32) probe_gather_tma_kernel(const ProbeArgs a,
+                                                                       uint32_t tiles_per_warp) {
+  static_assert(kStages >= 2, "need a ring");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t row_bytes = a.dim * 4u;
+  const uint32_t tile_bytes = kTmaTileKeys * row_bytes;
+  unsigned char* ring = smem_raw + static_cast<size_t>(warp) * kStages * tile_bytes;
+  uint64_t* bars =
+      reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(kWarps) * kStages * tile_bytes) +
+      warp * kStages;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const size_t warp_global = static_cast<size_t>(blockIdx.x) * kWarps + warp;
+  const size_t first_tile = warp_global * tiles_per_warp;
+  const size_t num_tiles = (a.n + kTmaTileKeys - 1) / kTmaTileKeys;
+  const float4 defv = make_float4(a.default_value, a.default_value, a.default_value, a.default_value);
+  const unsigned char* vals = reinterpret_cast<const unsigned char*>(a.values);
+  unsigned char* outb = reinterpret_cast<unsigned char*>(a.out);
+
+  uint32_t phase_bits = 0;  // bit s = parity to wait for on stage s
+  uint32_t pend_nk = 0;
+  size_t pend_base = 0;
+  int pend_stage = -1;
+  for (uint32_t t = 0; t <= tiles_per_warp; ++t) {
+    const size_t tile = first_tile + t;
+    const bool have = t < tiles_per_warp && tile < num_tiles;
+    const int stage = static_cast<int>(t % kStages);
+    uint32_t nk = 0;
+    const size_t tile_base = tile * kTmaTileKeys;
+    if (have) {
+      nk = static_cast<uint32_t>(min(static_cast<size_t>(kTmaTileKeys), a.n - tile_base));
+      const bool valid = lane < nk;
+      const int64_t key = valid ? a.keys[tile_base + lane] : kEmptyKey;
+      uint32_t slot = kMissSlot;
+      if (valid) slot = probe_bucket(a.buckets, a.num_buckets, key, a.epoch, a.touch != 0);
+      const bool is_miss = valid && slot == kMissSlot;
+      unsigned miss_mask;
+      const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+      unsigned char* stage_buf = ring + static_cast<size_t>(stage) * tile_bytes;
+      const unsigned hit_mask = __ballot_sync(kFull, valid && !is_miss);
+      // the bulk store that last read this stage must have finished reading shared memory
+      if (lane == 0) {
+        bulk_wait_read<kStages - 2>();
+        mbar_expect_tx(&bars[stage], static_cast<uint32_t>(__popc(hit_mask)) * row_bytes);
+      }
+      __syncwarp();
+      if (valid && !is_miss) {
+        bulk_g2s(stage_buf + lane * row_bytes, vals + static_cast<size_t>(slot) * row_bytes,
+                 row_bytes, &bars[stage]);
+      }
+      if (miss_mask != 0u) {
+        // default vectors for the missing rows, written by the whole warp through the generic proxy
+        const uint32_t vec_per_row = row_bytes / 16u;
+        for (uint32_t m = miss_mask; m != 0u; m &= m - 1u) {
+          const uint32_t kk = __ffs(m) - 1u;
+          float4* dst = reinterpret_cast<float4*>(stage_buf + kk * row_bytes);
+          for (uint32_t v = lane; v < vec_per_row; v += 32u) dst[v] = defv;
+        }
+        if (is_miss) {
+          const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
+          a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+          a.miss_keys[r] = key;
+        }
+        fence_proxy_async_smem();  // generic-proxy default rows -> visible to the later bulk store
+      }
+    }
+    // retire the previous tile
+    if (pend_stage >= 0) {
+      mbar_wait(&bars[pend_stage], (phase_bits >> pend_stage) & 1u);
+      phase_bits ^= 1u << pend_stage;
+      __syncwarp();
+      if (lane == 0) {
+        bulk_s2g(outb + pend_base * row_bytes, ring + static_cast<size_t>(pend_stage) * tile_bytes,
+                 pend_nk * row_bytes);
+        bulk_commit();
+      }
+      pend_stage = -1;
+    }
+    if (have) {
+      pend_stage = stage;
+      pend_nk = nk;
+      pend_base = tile_base;
+    }
+  }
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the last bulk store's reads
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// probe only (pooled path): record where each key's row lives.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) probe_index_kernel(const ProbeArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const bool valid = idx < a.n;  // warp tiles are aligned, the whole warp runs the ballot
+  const int64_t key = valid ? a.keys[idx] : kEmptyKey;
+  uint32_t slot = kMissSlot;
+  if (valid) slot = probe_bucket(a.buckets, a.num_buckets, key, a.epoch, a.touch != 0);
+  const bool is_miss = valid && slot == kMissSlot;
+  unsigned miss_mask;
+  const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+  if (is_miss) {
+    const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
+    a.miss_pos[r] = static_cast<uint32_t>(idx);
+    a.miss_keys[r] = key;
+    slot = kSrcMissBit | r;
+  }
+  if (valid) a.src[idx] = slot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4+K5 fused merge + insert.  One warp per missing key.
+// ------------------------------------------------------------------------------------------------
+struct InsertArgs {
+  Bucket* buckets;
+  float* values;
+  uint32_t num_buckets;
+  uint32_t dim;
+  const int64_t* miss_keys;
+  const uint32_t* miss_pos;
+  const float* stage;
+  size_t m;
+  float* out;
+  int insert;
+  uint32_t epoch;
+  uint32_t* inserted;
+};
+
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  for (size_t i = warp; i < a.m; i += nwarps) {
+    const int64_t key = a.miss_keys[i];
+    const VecT* src = reinterpret_cast<const VecT*>(a.stage) + i * V;
+    VecT* dst_out =
+        a.out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
+    VecT* dst_slab = nullptr;
+    Bucket* B = nullptr;
+    if (a.insert && key != kEmptyKey) {
+      const uint32_t b = bucket_of(key, a.num_buckets);
+      B = &a.buckets[b];
+      if (lane == 0) {
+        while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
+        __threadfence();
+      }
+      __syncwarp();
+      int64_t k = kEmptyKey;
+      uint32_t st = a.epoch;
+      if (lane < kWays) {
+        k = __ldcg(reinterpret_cast<const long long*>(&B->keys[lane]));
+        st = __ldcg(&B->stamp[lane]);
+      }
+      const unsigned present = __ballot_sync(kFull, lane < kWays && k == key);
+      int way = -1;
+      if (present != 0u) {
+        if (lane == 0) B->stamp[__ffs(present) - 1] = a.epoch;  // already cached: refresh LRU only
+      } else {
+        const unsigned empties = __ballot_sync(kFull, lane < kWays && k == kEmptyKey);
+        if (empties != 0u) {
+          way = __ffs(empties) - 1;
+        } else {
+          // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted
+          const uint32_t age = lane < kWays ? a.epoch - st : 0u;
+          unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
+#pragma unroll
+          for (int off = 4; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
+            packed = o > packed ? o : packed;
+          }
+          packed = __shfl_sync(kFull, packed, 0);
+          if ((packed >> 8) != 0ull) way = 255 - static_cast<int>(packed & 255ull);
+        }
+        if (way >= 0) {
+          dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+          if (lane == 0) {
+            B->keys[way] = key;
+            B->stamp[way] = a.epoch;
+          }
+        }
+      }
+    }
+    for (uint32_t v = lane; v < V; v += 32u) {
+      const VecT x = src[v];
+      if (dst_out) dst_out[v] = x;
+      if (dst_slab) dst_slab[v] = x;
+    }
+    if (B != nullptr) {
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        atomicExch(&B->lock, 0u);
+        if (dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8 pooled gather + reduce.  A group of `kGroup` lanes owns one bag; fp32 adds in ascending j.
+// ------------------------------------------------------------------------------------------------
+template <typename VecT, int kGroup>
+__global__ void __launch_bounds__(kBlock) pooled_gather_kernel(
+    const float* __restrict__ values, const float* __restrict__ stage,
+    const uint32_t* __restrict__ src, size_t num_bags, uint32_t hotness, uint32_t dim, int mean,
+    float* __restrict__ out) {
+  constexpr uint32_t kBagsPerWarp = 32 / kGroup;
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t bag = warp * kBagsPerWarp + lane / kGroup;
+  const uint32_t v0 = lane % kGroup;
+  if (bag >= num_bags) return;
+  const uint32_t V = dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  const VecT* vals = reinterpret_cast<const VecT*>(values);
+  const VecT* stg = reinterpret_cast<const VecT*>(stage);
+  const uint32_t* s = src + bag * hotness;
+  for (uint32_t v = v0; v < V; v += kGroup) {
+    VecT acc = splat<VecT>(0.f);
+    uint32_t j = 0;
+    for (; j + 4 <= hotness; j += 4) {
+      VecT r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t sj = s[j + u];
+        const VecT* row = (sj & kSrcMissBit)
+                              ? stg + static_cast<size_t>(sj & ~kSrcMissBit) * V
+                              : vals + static_cast<size_t>(sj) * V;
+        r[u] = ld_stream(row + v);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) vadd(acc, r[u]);
+    }
+    for (; j < hotness; ++j) {
+      const uint32_t sj = s[j];
+      const VecT* row = (sj & kSrcMissBit) ? stg + static_cast<size_t>(sj & ~kSrcMissBit) * V
+                                           : vals + static_cast<size_t>(sj) * V;
+      vadd(acc, ld_stream(row + v));
+    }
+    if (mean) vdiv(acc, static_cast<float>(hotness));
+    st_stream(reinterpret_cast<VecT*>(out) + bag * V + v, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table maintenance
+// ------------------------------------------------------------------------------------------------
+__global__ void table_clear_kernel(Bucket* buckets, uint32_t num_buckets) {
+  // 8 threads per bucket, 16 B each
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t b = i >> 3;
+  if (b >= num_buckets) return;
+  const uint32_t part = i & 7u;
+  uint4* p = reinterpret_cast<uint4*>(&buckets[b]) + part;
+  if (part < 4) {
+    const unsigned long long e = static_cast<unsigned long long>(kEmptyKey);
+    *p = make_uint4(static_cast<uint32_t>(e), static_cast<uint32_t>(e >> 32),
+                    static_cast<uint32_t>(e), static_cast<uint32_t>(e >> 32));
+  } else {
+    *p = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+__global__ void count_resident_kernel(const Bucket* buckets, uint32_t num_buckets,
+                                      unsigned long long* count) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  bool used = false;
+  if ((i >> 3) < num_buckets) used = buckets[i >> 3].keys[i & 7u] != kEmptyKey;
+  const unsigned m = __ballot_sync(kFull, used);
+  if ((threadIdx.x & 31u) == 0 && m != 0u) atomicAdd(count, static_cast<unsigned long long>(__popc(m)));
+}
+
+__global__ void dump_keys_kernel(const Bucket* buckets, uint32_t num_buckets, int64_t* out,
+                                 unsigned long long cap, unsigned long long* count) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if ((i >> 3) >= num_buckets) return;
+  const int64_t k = buckets[i >> 3].keys[i & 7u];
+  if (k == kEmptyKey) return;
+  const unsigned long long r = atomicAdd(count, 1ull);
+  if (r < cap) out[r] = k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 dedup: open-addressing scratch table, CAS claim, warp-aggregated id allocation.
+// counter[0] = #unique, counter[1] = sentinel-key flag, counter[2] = sentinel-key id.
+// ------------------------------------------------------------------------------------------------
+__global__ void fill_empty_kernel(int64_t* ws_keys, size_t cap) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < cap) ws_keys[i] = kEmptyKey;
+}
+
+__global__ void __launch_bounds__(kBlock) unique_claim_kernel(const int64_t* __restrict__ keys,
+                                                              size_t n, int64_t* ws_keys,
+                                                              uint32_t* ws_ids, size_t mask,
+                                                              int64_t* unique, uint32_t* counter) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool won = false;
+  bool sentinel = false;
+  size_t slot = 0;
+  int64_t key = 0;
+  if (i < n) {
+    key = keys[i];
+    if (key == kEmptyKey) {
+      sentinel = true;
+      won = atomicCAS(&counter[1], 0u, 1u) == 0u;
+    } else {
+      slot = mix64(static_cast<uint64_t>(key)) & mask;
+      while (true) {
+        const unsigned long long prev =
+            atomicCAS(reinterpret_cast<unsigned long long*>(&ws_keys[slot]),
+                      static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+        if (prev == static_cast<unsigned long long>(kEmptyKey)) {
+          won = true;
+          break;
+        }
+        if (prev == static_cast<unsigned long long>(key)) break;
+        slot = (slot + 1) & mask;
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(kFull, won);
+  if (m == 0u) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(&counter[0], static_cast<uint32_t>(__popc(m)));
+  base = __shfl_sync(kFull, base, 0);
+  if (won) {
+    const uint32_t id = base + __popc(m & ((1u << lane) - 1u));
+    unique[id] = key;
+    if (sentinel)
+      counter[2] = id;
+    else
+      ws_ids[slot] = id;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) unique_resolve_kernel(const int64_t* __restrict__ keys,
+                                                                size_t n,
+                                                                const int64_t* __restrict__ ws_keys,
+                                                                const uint32_t* __restrict__ ws_ids,
+                                                                size_t mask, uint32_t* inverse,
+                                                                const uint32_t* counter) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int64_t key = keys[i];
+  if (key == kEmptyKey) {
+    inverse[i] = counter[2];
+    return;
+  }
+  size_t slot = mix64(static_cast<uint64_t>(key)) & mask;
+  while (ws_keys[slot] != key) slot = (slot + 1) & mask;
+  inverse[i] = ws_ids[slot];
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU key routing: histogram by owner, then scatter into per-owner contiguous ranges.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxShards = 64;
+constexpr int kRouteChunk = 2048;  // keys per CTA
+
+__global__ void __launch_bounds__(kBlock) route_hist_kernel(const int64_t* __restrict__ keys,
+                                                            size_t n, uint32_t shards,
+                                                            uint32_t* counts) {
+  __shared__ uint32_t h[kMaxShards];
+  if (threadIdx.x < kMaxShards) h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = static_cast<size_t>(blockIdx.x) * kRouteChunk;
+  for (uint32_t j = threadIdx.x; j < kRouteChunk; j += kBlock) {
+    const size_t i = base + j;
+    if (i < n) atomicAdd(&h[owner_of(keys[i], shards)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < shards && h[threadIdx.x] != 0u) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kBlock) route_scatter_kernel(const int64_t* __restrict__ keys,
+                                                               size_t n, uint32_t shards,
+                                                               const uint32_t* __restrict__ counts,
+                                                               uint32_t* cursor, int64_t* routed,
+                                                               uint32_t* perm) {
+  __shared__ uint32_t h[kMaxShards];
+  __shared__ uint32_t start[kMaxShards];
+  if (threadIdx.x < kMaxShards) h[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t base = static_cast<size_t>(blockIdx.x) * kRouteChunk;
+  for (uint32_t j = threadIdx.x; j < kRouteChunk; j += kBlock) {
+    const size_t i = base + j;
+    if (i < n) atomicAdd(&h[owner_of(keys[i], shards)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < shards) {
+    uint32_t prefix = 0;
+    for (uint32_t g = 0; g < threadIdx.x; ++g) prefix += counts[g];
+    const uint32_t mine = h[threadIdx.x];
+    start[threadIdx.x] = prefix + (mine ? atomicAdd(&cursor[threadIdx.x], mine) : 0u);
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxShards) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t j = threadIdx.x; j < kRouteChunk; j += kBlock) {
+    const size_t i = base + j;
+    if (i < n) {
+      const int64_t k = keys[i];
+      const uint32_t o = owner_of(k, shards);
+      const uint32_t p = start[o] + atomicAdd(&h[o], 1u);
+      routed[p] = k;
+      perm[p] = static_cast<uint32_t>(i);
+    }
+  }
+}
+
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) scatter_rows_kernel(const float* __restrict__ rows,
+                                                              const uint32_t* __restrict__ perm,
+                                                              size_t n, uint32_t V, float* out) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const size_t row = i / V;
+  if (row >= n) return;
+  const uint32_t v = static_cast<uint32_t>(i - row * V);
+  const VecT x = ld_stream(reinterpret_cast<const VecT*>(rows) + i);
+  st_stream(reinterpret_cast<VecT*>(out) + static_cast<size_t>(perm[row]) * V + v, x);
+}
+
+__global__ void __launch_bounds__(kBlock) synth_rows_kernel(const int64_t* __restrict__ keys, size_t n,
+                                                            uint32_t dim, uint64_t seed, float* rows) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  const size_t row = i / dim;
+  if (row >= n) return;
+  const uint32_t j = static_cast<uint32_t>(i - row * dim);
+  rows[i] = synth_value(keys[row], j, seed);
+}
+
+// widest vector (bytes) usable for rows of `dim` floats given the pointer alignments involved
+inline int vec_bytes(uint32_t dim, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) |
+                      reinterpret_cast<uintptr_t>(p2) | (static_cast<uintptr_t>(dim) * 4u);
+  if ((a & 15u) == 0) return 16;
+  if ((a & 7u) == 0) return 8;
+  return 4;
+}
+
+inline unsigned grid_for(size_t threads) {
+  return static_cast<unsigned>((threads + kBlock - 1) / kBlock);
+}
+
+template <typename VecT>
+cudaError_t launch_probe_ldg_vec(const ProbeArgs& a, cudaStream_t stream) {
+  const unsigned grid = grid_for(a.n);
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  switch (V) {
+    case 32:
+      probe_gather_ldg_kernel<VecT, 32, 8><<<grid, kBlock, 0, stream>>>(a);
+      break;
+    case 16:
+      probe_gather_ldg_kernel<VecT, 16, 8><<<grid, kBlock, 0, stream>>>(a);
+      break;
+    case 8:
+      probe_gather_ldg_kernel<VecT, 8, 8><<<grid, kBlock, 0, stream>>>(a);
+      break;
+    case 4:
+      probe_gather_ldg_kernel<VecT, 4, 4><<<grid, kBlock, 0, stream>>>(a);
+      break;
+    default:
+      probe_gather_ldg_kernel<VecT, 0, 4><<<grid, kBlock, 0, stream>>>(a);
+      break;
+  }
+  return cudaGetLastError();
+}
+
+template <int kWarps, int kStages>
+cudaError_t launch_probe_tma_cfg(const ProbeArgs& a, uint32_t tiles_per_warp, cudaStream_t stream) {
+  const uint32_t row_bytes = a.dim * 4u;
+  const size_t smem = static_cast<size_t>(kWarps) * kStages * kTmaTileKeys * row_bytes +
+                      kWarps * kStages * sizeof(uint64_t);
+  if (smem > 224 * 1024) return cudaErrorNotSupported;
+  static size_t attr_smem = 0;  // largest size this instantiation was configured for
+  if (smem > attr_smem) {
+    const cudaError_t e =
+        cudaFuncSetAttribute(probe_gather_tma_kernel<kWarps, kStages>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  const size_t num_tiles = (a.n + kTmaTileKeys - 1) / kTmaTileKeys;
+  const size_t warps = (num_tiles + tiles_per_warp - 1) / tiles_per_warp;
+  const unsigned grid = static_cast<unsigned>((warps + kWarps - 1) / kWarps);
+  probe_gather_tma_kernel<kWarps, kStages><<<grid, kWarps * 32, smem, stream>>>(a, tiles_per_warp);
+  return cudaGetLastError();
+}
+
+// HPSX_TMA_CFG="<warps>x<stages>x<tiles_per_warp>" selects the ring shape (tuning knob).
+cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
+  static int cfg_w = 0, cfg_s = 0, cfg_t = 0;
+  if (cfg_w == 0) {
+    cfg_w = 4;
+    cfg_s = 3;
+    cfg_t = 8;
+    if (const char* env = getenv("HPSX_TMA_CFG")) {
+      int w = 0, s = 0, t = 0;
+      if (sscanf(env, "%dx%dx%d", &w, &s, &t) == 3 && w > 0 && s > 1 && t > 0) {
+        cfg_w = w;
+        cfg_s = s;
+        cfg_t = t;
+      }
+    }
+  }
+  const uint32_t tpw = static_cast<uint32_t>(cfg_t);
+  const uint32_t row_bytes = a.dim * 4u;
+  // rows too large for the configured ring fall back to fewer warps/stages, then to LDG
+  if (cfg_w == 8 && cfg_s == 3 && 8u * 3u * 32u * row_bytes <= 200u * 1024u)
+    return launch_probe_tma_cfg<8, 3>(a, tpw, stream);
+  if (cfg_w == 8 && cfg_s == 2 && 8u * 2u * 32u * row_bytes <= 200u * 1024u)
+    return launch_probe_tma_cfg<8, 2>(a, tpw, stream);
+  if (cfg_w == 6 && cfg_s == 2 && 6u * 2u * 32u * row_bytes <= 200u * 1024u)
+    return launch_probe_tma_cfg<6, 2>(a, tpw, stream);
+  if (cfg_w == 4 && cfg_s == 2) return launch_probe_tma_cfg<4, 2>(a, tpw, stream);
+  if (cfg_w == 2 && cfg_s == 3) return launch_probe_tma_cfg<2, 3>(a, tpw, stream);
+  if (cfg_w == 2 && cfg_s == 2) return launch_probe_tma_cfg<2, 2>(a, tpw, stream);
+  if (4u * 3u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<4, 3>(a, tpw, stream);
+  if (2u * 2u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<2, 2>(a, tpw, stream);
+  return cudaErrorNotSupported;
+}
+
+}  // namespace
+
+cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
+                                uint32_t epoch, bool touch, uint32_t* d_miss_count,
+                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int variant,
+                                cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ProbeArgs a{};
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.dim = t.dim;
+  a.default_value = t.default_value;
+  a.keys = d_keys;
+  a.n = n;
+  a.out = d_out;
+  a.epoch = epoch;
+  a.touch = touch ? 1 : 0;
+  a.miss_count = d_miss_count;
+  a.miss_pos = d_miss_pos;
+  a.miss_keys = d_miss_keys;
+  a.src = nullptr;
+  const int vb = vec_bytes(t.dim, d_out, t.values);
+  if (variant == kProbeTma && vb == 16) {
+    const cudaError_t e = launch_probe_tma(a, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  if (vb == 16) return launch_probe_ldg_vec<float4>(a, stream);
+  if (vb == 8) return launch_probe_ldg_vec<float2>(a, stream);
+  return launch_probe_ldg_vec<float>(a, stream);
+}
+
+cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size_t n, uint32_t epoch,
+                               bool touch, uint32_t* d_src, uint32_t* d_miss_count,
+                               uint32_t* d_miss_pos, int64_t* d_miss_keys, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  ProbeArgs a{};
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.dim = t.dim;
+  a.default_value = t.default_value;
+  a.keys = d_keys;
+  a.n = n;
+  a.out = nullptr;
+  a.epoch = epoch;
+  a.touch = touch ? 1 : 0;
+  a.miss_count = d_miss_count;
+  a.miss_pos = d_miss_pos;
+  a.miss_keys = d_miss_keys;
+  a.src = d_src;
+  probe_index_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys,
+                                const uint32_t* d_miss_pos, const float* d_stage, size_t m,
+                                float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
+                                cudaStream_t stream) {
+  if (m == 0) return cudaSuccess;
+  InsertArgs a{};
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.dim = t.dim;
+  a.miss_keys = d_miss_keys;
+  a.miss_pos = d_miss_pos;
+  a.stage = d_stage;
+  a.m = m;
+  a.out = d_out;
+  a.insert = insert ? 1 : 0;
+  a.epoch = epoch;
+  a.inserted = d_inserted;
+  const size_t warps = m;
+  const unsigned grid = static_cast<unsigned>(
+      min(static_cast<size_t>(148 * 32), (warps * 32 + kBlock - 1) / kBlock));
+  const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
+  if (vb == 16)
+    insert_merge_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 8)
+    insert_merge_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+  else
+    insert_merge_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+namespace {
+template <typename VecT>
+cudaError_t launch_pooled_vec(const DeviceTable& t, const uint32_t* d_src, const float* d_stage,
+                              size_t num_bags, size_t hotness, bool mean, float* d_pooled,
+                              cudaStream_t stream) {
+  const uint32_t V = t.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  const uint32_t h = static_cast<uint32_t>(hotness);
+#define HPSX_POOLED(G)                                                                          \
+  do {                                                                                          \
+    const size_t warps = (num_bags + (32 / G) - 1) / (32 / G);                                  \
+    pooled_gather_kernel<VecT, G><<<grid_for(warps * 32), kBlock, 0, stream>>>(                 \
+        t.values, d_stage, d_src, num_bags, h, t.dim, mean ? 1 : 0, d_pooled);                  \
+  } while (0)
+  if (V >= 32)
+    HPSX_POOLED(32);
+  else if (V >= 16)
+    HPSX_POOLED(16);
+  else if (V >= 8)
+    HPSX_POOLED(8);
+  else if (V >= 4)
+    HPSX_POOLED(4);
+  else if (V >= 2)
+    HPSX_POOLED(2);
+  else
+    HPSX_POOLED(1);
+#undef HPSX_POOLED
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t launch_pooled_gather(const DeviceTable& t, const uint32_t* d_src, const float* d_stage,
+                                 size_t num_bags, size_t hotness, bool mean, float* d_pooled,
+                                 cudaStream_t stream) {
+  if (num_bags == 0) return cudaSuccess;
+  const int vb = vec_bytes(t.dim, d_pooled, d_stage, t.values);
+  if (vb == 16)
+    return launch_pooled_vec<float4>(t, d_src, d_stage, num_bags, hotness, mean, d_pooled, stream);
+  if (vb == 8)
+    return launch_pooled_vec<float2>(t, d_src, d_stage, num_bags, hotness, mean, d_pooled, stream);
+  return launch_pooled_vec<float>(t, d_src, d_stage, num_bags, hotness, mean, d_pooled, stream);
+}
+
+cudaError_t launch_table_clear(const DeviceTable& t, cudaStream_t stream) {
+  if (t.num_buckets == 0) return cudaSuccess;
+  table_clear_kernel<<<grid_for(static_cast<size_t>(t.num_buckets) * 8), kBlock, 0, stream>>>(
+      t.buckets, t.num_buckets);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_count_resident(const DeviceTable& t, unsigned long long* d_count,
+                                  cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  count_resident_kernel<<<grid_for(static_cast<size_t>(t.num_buckets) * 8), kBlock, 0, stream>>>(
+      t.buckets, t.num_buckets, d_count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dump_keys(const DeviceTable& t, int64_t* d_keys, unsigned long long cap,
+                             unsigned long long* d_count, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
+  if (e != cudaSuccess) return e;
+  dump_keys_kernel<<<grid_for(static_cast<size_t>(t.num_buckets) * 8), kBlock, 0, stream>>>(
+      t.buckets, t.num_buckets, d_keys, cap, d_count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unique(const int64_t* d_keys, size_t n, int64_t* ws_keys, uint32_t* ws_ids,
+                          size_t cap, int64_t* d_unique, uint32_t* d_inverse, uint32_t* d_counter,
+                          cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(d_counter, 0, 4 * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  fill_empty_kernel<<<grid_for(cap), kBlock, 0, stream>>>(ws_keys, cap);
+  unique_claim_kernel<<<grid_for(n), kBlock, 0, stream>>>(d_keys, n, ws_keys, ws_ids, cap - 1,
+                                                          d_unique, d_counter);
+  unique_resolve_kernel<<<grid_for(n), kBlock, 0, stream>>>(d_keys, n, ws_keys, ws_ids, cap - 1,
+                                                            d_inverse, d_counter);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_route_keys(const int64_t* d_keys, size_t n, uint32_t num_shards,
+                              int64_t* d_routed_keys, uint32_t* d_perm, uint32_t* d_counts,
+                              uint32_t* d_cursor, cudaStream_t stream) {
+  if (num_shards == 0 || num_shards > kMaxShards) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(d_counts, 0, num_shards * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(d_cursor, 0, num_shards * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  if (n == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((n + kRouteChunk - 1) / kRouteChunk);
+  route_hist_kernel<<<grid, kBlock, 0, stream>>>(d_keys, n, num_shards, d_counts);
+  route_scatter_kernel<<<grid, kBlock, 0, stream>>>(d_keys, n, num_shards, d_counts, d_cursor,
+                                                    d_routed_keys, d_perm);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, size_t n, size_t dim,
+                                float* d_out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const int vb = vec_bytes(static_cast<uint32_t>(dim), d_rows, d_out);
+  if (vb == 16) {
+    const uint32_t V = static_cast<uint32_t>(dim / 4);
+    scatter_rows_kernel<float4><<<grid_for(n * V), kBlock, 0, stream>>>(d_rows, d_perm, n, V, d_out);
+  } else if (vb == 8) {
+    const uint32_t V = static_cast<uint32_t>(dim / 2);
+    scatter_rows_kernel<float2><<<grid_for(n * V), kBlock, 0, stream>>>(d_rows, d_perm, n, V, d_out);
+  } else {
+    const uint32_t V = static_cast<uint32_t>(dim);
+    scatter_rows_kernel<float><<<grid_for(n * V), kBlock, 0, stream>>>(d_rows, d_perm, n, V, d_out);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_synth_rows(const int64_t* d_keys, size_t n, size_t dim, uint64_t seed,
+                              float* d_rows, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  synth_rows_kernel<<<grid_for(n * dim), kBlock, 0, stream>>>(d_keys, n, static_cast<uint32_t>(dim),
+                                                              seed, d_rows);
+  return cudaGetLastError();
+}
+
+}  // namespace hpsx

@@ -1,0 +1,80 @@
+// Launchers of the sm_100a kernels of the HPS lookup path.  Host C++ only sees this header.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "hpsx_common.h"
+
+namespace hpsx {
+
+// One table of the HBM embedding cache as the kernels see it.
+struct DeviceTable {
+  Bucket* buckets = nullptr;   // [num_buckets]
+  float* values = nullptr;     // [num_buckets * kWays, dim] row-major, 512-B aligned base
+  uint32_t num_buckets = 0;
+  uint32_t dim = 0;            // floats per row
+  float default_value = 0.f;
+};
+
+constexpr uint32_t kMissSlot = 0xFFFFFFFFu;
+constexpr uint32_t kSrcMissBit = 0x80000000u;  // pooled path: src index refers to the miss stage
+
+enum ProbeVariant : int {
+  kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers
+  kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
+};
+
+// K2+K3+K6 fused: probe the cache for keys[0..n), copy hit rows to out[i*dim..),
+// write the default vector for misses, touch LRU stamps, and append (position,key) of every miss to
+// the miss list (warp ballot + prefix, one atomic per warp tile).
+// `miss_count` must be zeroed by the caller (stream-ordered).  `touch`=false for static caches.
+cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
+                                uint32_t epoch, bool touch, uint32_t* d_miss_count,
+                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int variant,
+                                cudaStream_t stream);
+
+// Probe only (pooled path): d_src[i] = slot index on hit, kSrcMissBit | miss-list index on miss.
+cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size_t n, uint32_t epoch,
+                               bool touch, uint32_t* d_src, uint32_t* d_miss_count,
+                               uint32_t* d_miss_pos, int64_t* d_miss_keys, cudaStream_t stream);
+
+// K4+K5 fused: for every miss i in [0,m): row = stage[i*dim..); if d_out: out[pos[i]*dim..) = row
+// (merge); if `insert`: put (key,row) into the cache — skip when present, else first empty way, else
+// the way with the oldest stamp that was not touched in this epoch.  One warp per miss, per-bucket lock.
+cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys,
+                                const uint32_t* d_miss_pos, const float* d_stage, size_t m,
+                                float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
+                                cudaStream_t stream);
+
+// a8: pooled[b*dim..) = sum_{j<hotness} row(src[b*hotness+j]) (mean: / hotness), ascending j, fp32.
+// Rows come from the cache slab or (kSrcMissBit) from the staged miss rows.
+cudaError_t launch_pooled_gather(const DeviceTable& t, const uint32_t* d_src, const float* d_stage,
+                                 size_t num_bags, size_t hotness, bool mean, float* d_pooled,
+                                 cudaStream_t stream);
+
+cudaError_t launch_table_clear(const DeviceTable& t, cudaStream_t stream);
+cudaError_t launch_count_resident(const DeviceTable& t, unsigned long long* d_count,
+                                  cudaStream_t stream);
+cudaError_t launch_dump_keys(const DeviceTable& t, int64_t* d_keys, unsigned long long cap,
+                             unsigned long long* d_count, cudaStream_t stream);
+
+// K1: dedup.  Workspace: ws_keys[cap] (int64), ws_ids[cap] (u32), cap = power of two >= 2n.
+// d_counter[0] receives the number of unique keys; d_counter[1] is scratch for the sentinel key.
+cudaError_t launch_unique(const int64_t* d_keys, size_t n, int64_t* ws_keys, uint32_t* ws_ids,
+                          size_t cap, int64_t* d_unique, uint32_t* d_inverse, uint32_t* d_counter,
+                          cudaStream_t stream);
+
+// Multi-GPU routing: bucket keys by owner_of(key, num_shards).  d_counts[num_shards] zeroed inside;
+// d_cursor[num_shards] is scratch.
+cudaError_t launch_route_keys(const int64_t* d_keys, size_t n, uint32_t num_shards,
+                              int64_t* d_routed_keys, uint32_t* d_perm, uint32_t* d_counts,
+                              uint32_t* d_cursor, cudaStream_t stream);
+cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, size_t n, size_t dim,
+                                float* d_out, cudaStream_t stream);
+
+// Synthetic rows generated on the device (model-parallel shards too large for host memory).
+cudaError_t launch_synth_rows(const int64_t* d_keys, size_t n, size_t dim, uint64_t seed,
+                              float* d_rows, cudaStream_t stream);
+
+}  // namespace hpsx

@@ -1,0 +1,287 @@
+"""Host-side mirror of the interfaces the reference glue uses for the lookup path.
+
+``HPS``            ~ ``HugeCTR::HierParameterServerBase``  (reference: hps_backend/src/backend.cpp:68-71)
+``LookupSession``  ~ ``HugeCTR::LookupSessionBase``        (hps_backend/src/model_instance_state.cpp:170-195)
+
+Every method is one call into ``libhpsx.so``; arrays are passed by address (numpy for host memory,
+torch CUDA tensors or raw integer addresses for device memory).  Nothing is computed in Python.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+
+def _addr(x) -> int:
+    """Address of a numpy array, a torch tensor or a raw pointer."""
+    if x is None:
+        return 0
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        if not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr()
+    raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+@dataclass
+class ModelParams:
+    """~ ``HugeCTR::InferenceParams`` as filled from ps.json (hps_backend/src/backend.cpp:318-523)."""
+    model_name: str
+    max_batch_size: int
+    embedding_vecsize_per_table: Sequence[int]
+    maxnum_catfeature_query_per_table_per_sample: Sequence[int]
+    default_value_for_each_table: Optional[Sequence[float]] = None
+    sparse_files: Optional[Sequence[str]] = None
+    use_gpu_embedding_cache: bool = True
+    hit_rate_threshold: float = 1.0
+    cache_size_percentage: float = 1.0
+    number_of_worker_buffers_in_pool: int = 1
+    deployed_devices: Sequence[int] = field(default_factory=lambda: [0])
+    embedding_cache_type: str = "dynamic"
+    cache_load_factor: float = 0.0
+
+
+@dataclass
+class SessionStats:
+    lookups: int
+    keys: int
+    hits: int
+    misses: int
+    inserted: int
+    default_filled: int
+    h2d_bytes: int
+    d2h_bytes: int
+    kernel_launches: int
+    probe_kernel_ms: float
+    probe_kernel_launches: int
+    probe_kernel_keys: int
+    insert_kernel_ms: float
+    host_gather_ms: float
+
+
+class HPS:
+    """The parameter server: host database + per-(model, device) HBM embedding caches."""
+
+    def __init__(self, ps_json: Optional[str] = None, num_partitions: int = 0, num_threads: int = 0,
+                 allocation_rate: int = 0):
+        self._L = N.lib()
+        h = ctypes.c_void_p()
+        if ps_json is not None:
+            N.check(self._L.hpsx_ps_create_from_json(ps_json.encode(), ctypes.byref(h)))
+        else:
+            vp = N.VolatileParamsC(num_partitions, allocation_rate, 1.0, num_threads)
+            N.check(self._L.hpsx_ps_create(ctypes.byref(vp), ctypes.byref(h)))
+        self._h = h
+        self._dims = {}
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.hpsx_ps_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- models -------------------------------------------------------------------------------
+    def model_names(self) -> List[str]:
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_ps_num_models(self._h, ctypes.byref(n)))
+        out = []
+        for i in range(n.value):
+            s = ctypes.c_char_p()
+            N.check(self._L.hpsx_ps_model_name(self._h, i, ctypes.byref(s)))
+            out.append(s.value.decode())
+        return out
+
+    def has_model(self, name: str) -> bool:
+        return bool(self._L.hpsx_ps_has_model(self._h, name.encode()))
+
+    def add_model(self, p: ModelParams) -> None:
+        T = len(p.embedding_vecsize_per_table)
+        defaults = list(p.default_value_for_each_table) if p.default_value_for_each_table is not None else [0.0] * T
+        c = N.ModelParamsC()
+        c.model_name = p.model_name.encode()
+        c.max_batch_size = p.max_batch_size
+        c.num_tables = T
+        keep = []
+        if p.sparse_files:
+            arr = (ctypes.c_char_p * T)(*[s.encode() if s else None for s in p.sparse_files])
+            keep.append(arr)
+            c.sparse_files = arr
+        vec = (ctypes.c_size_t * T)(*[int(v) for v in p.embedding_vecsize_per_table])
+        mq = (ctypes.c_size_t * T)(*[int(v) for v in p.maxnum_catfeature_query_per_table_per_sample])
+        dv = (ctypes.c_float * T)(*[float(v) for v in defaults])
+        dev = (ctypes.c_int * len(p.deployed_devices))(*[int(d) for d in p.deployed_devices])
+        c.embedding_vecsize_per_table = vec
+        c.maxnum_catfeature_query_per_table_per_sample = mq
+        c.default_value_for_each_table = dv
+        c.use_gpu_embedding_cache = 1 if p.use_gpu_embedding_cache else 0
+        c.hit_rate_threshold = p.hit_rate_threshold
+        c.cache_size_percentage = p.cache_size_percentage
+        c.number_of_worker_buffers_in_pool = p.number_of_worker_buffers_in_pool
+        c.deployed_devices = dev
+        c.num_deployed_devices = len(p.deployed_devices)
+        c.embedding_cache_type = 1 if p.embedding_cache_type.lower() == "static" else 0
+        c.cache_load_factor = p.cache_load_factor
+        N.check(self._L.hpsx_ps_add_model(self._h, ctypes.byref(c)))
+        self._dims[p.model_name] = [int(v) for v in p.embedding_vecsize_per_table]
+
+    def load_table(self, model: str, table: int, keys: np.ndarray, vectors: np.ndarray) -> None:
+        keys = np.ascontiguousarray(keys, dtype=np.int64).ravel()
+        vectors = np.ascontiguousarray(vectors, dtype=np.float32)
+        N.check(self._L.hpsx_ps_load_table(self._h, model.encode(), table, _addr(keys), _addr(vectors), len(keys)))
+
+    def load_table_procedural(self, model: str, table: int, rows: int, seed: int) -> None:
+        N.check(self._L.hpsx_ps_load_table_procedural(self._h, model.encode(), table, rows, seed & ((1 << 64) - 1)))
+
+    def table_rows(self, model: str, table: int) -> int:
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_ps_table_rows(self._h, model.encode(), table, ctypes.byref(n)))
+        return n.value
+
+    def lookup(self, keys: np.ndarray, model: str, table: int, dim: Optional[int] = None) -> np.ndarray:
+        """CPU parameter-server lookup (gpucache = false path).  ~ ``HPS.lookup(key, model_name, table_id)``."""
+        keys = np.ascontiguousarray(keys, dtype=np.int64).ravel()
+        if dim is None:
+            dim = self._dims[model][table]
+        out = np.empty((len(keys), dim), dtype=np.float32)
+        N.check(self._L.hpsx_ps_lookup(self._h, model.encode(), table, _addr(keys), len(keys), _addr(out)))
+        return out
+
+    # -- embedding caches -----------------------------------------------------------------------
+    def create_embedding_cache(self, model: str) -> None:
+        N.check(self._L.hpsx_ps_create_embedding_cache_per_model(self._h, model.encode()))
+
+    def destroy_embedding_cache(self, model: str) -> None:
+        N.check(self._L.hpsx_ps_destroy_embedding_cache_per_model(self._h, model.encode()))
+
+    def _cache(self, model: str, device: int) -> ctypes.c_void_p:
+        c = ctypes.c_void_p()
+        N.check(self._L.hpsx_ps_get_embedding_cache(self._h, model.encode(), device, ctypes.byref(c)))
+        return c
+
+    def cache_capacity(self, model: str, device: int, table: int) -> int:
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_cache_capacity(self._cache(model, device), table, ctypes.byref(n)))
+        return n.value
+
+    def cache_resident(self, model: str, device: int, table: int) -> int:
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_cache_resident(self._cache(model, device), table, ctypes.byref(n)))
+        return n.value
+
+    def cache_keys(self, model: str, device: int, table: int) -> np.ndarray:
+        cap = self.cache_capacity(model, device, table)
+        out = np.empty(cap, dtype=np.int64)
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_cache_dump_keys(self._cache(model, device), table, _addr(out), cap, ctypes.byref(n)))
+        return out[: n.value].copy()
+
+    def drain_async(self, model: str, device: int) -> None:
+        N.check(self._L.hpsx_cache_drain_async(self._cache(model, device)))
+
+    def session(self, model: str, device: int = 0) -> "LookupSession":
+        return LookupSession(self, model, device)
+
+
+class LookupSession:
+    """One lookup workspace + stream (one per Triton model instance)."""
+
+    def __init__(self, hps: HPS, model: str, device: int):
+        self._L = N.lib()
+        self._hps = hps  # keep the server alive
+        h = ctypes.c_void_p()
+        N.check(self._L.hpsx_session_create(hps._h, model.encode(), device, ctypes.byref(h)))
+        self._h = h
+        d = ctypes.c_int()
+        N.check(self._L.hpsx_session_device(h, ctypes.byref(d)))
+        self.device = d.value
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.hpsx_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    @property
+    def stream(self) -> int:
+        p = ctypes.c_void_p()
+        N.check(self._L.hpsx_session_stream(self._h, ctypes.byref(p)))
+        return p.value or 0
+
+    def _arrays(self, keys_per_table, out_per_table, counts):
+        T = len(counts)
+        k = (ctypes.c_void_p * T)(*[_addr(x) for x in keys_per_table])
+        o = (ctypes.c_void_p * T)(*[_addr(x) for x in out_per_table])
+        n = (ctypes.c_size_t * T)(*[int(c) for c in counts])
+        return k, o, n, T
+
+    def lookup(self, h_keys_per_table, vectors_per_table, num_keys_per_table) -> None:
+        """~ ``LookupSessionBase::lookup(h_keys_per_table, d_vectors_per_table, num_keys_per_table)``."""
+        k, o, n, T = self._arrays(h_keys_per_table, vectors_per_table, num_keys_per_table)
+        N.check(self._L.hpsx_session_lookup(self._h, k, o, n, T))
+
+    def lookup_device_keys(self, d_keys_per_table, d_vectors_per_table, num_keys_per_table) -> None:
+        k, o, n, T = self._arrays(d_keys_per_table, d_vectors_per_table, num_keys_per_table)
+        N.check(self._L.hpsx_session_lookup_device_keys(self._h, k, o, n, T))
+
+    def lookup_pooled(self, table: int, keys, num_bags: int, hotness: int, d_pooled, combiner: str = "sum",
+                      device_keys: bool = False) -> None:
+        comb = 1 if combiner == "mean" else 0
+        fn = self._L.hpsx_session_lookup_pooled_device_keys if device_keys else self._L.hpsx_session_lookup_pooled
+        N.check(fn(self._h, table, _addr(keys), num_bags, hotness, comb, _addr(d_pooled)))
+
+    def stats(self) -> SessionStats:
+        s = N.SessionStatsC()
+        N.check(self._L.hpsx_session_get_stats(self._h, ctypes.byref(s)))
+        return SessionStats(*[getattr(s, f[0]) for f in N.SessionStatsC._fields_])
+
+    def reset_stats(self) -> None:
+        N.check(self._L.hpsx_session_reset_stats(self._h))
+
+    def set_insert_mode(self, mode: int) -> None:
+        N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
+
+    def set_probe_variant(self, variant: str) -> None:
+        N.check(self._L.hpsx_session_set_probe_variant(self._h, 1 if variant == "tma" else 0))
+
+
+# -- stand-alone device primitives ---------------------------------------------------------------
+def unique(device: int, d_keys, n: int, d_unique, d_inverse, stream: int = 0) -> int:
+    u = ctypes.c_size_t()
+    N.check(N.lib().hpsx_unique(device, _addr(d_keys), n, _addr(d_unique), _addr(d_inverse), ctypes.byref(u), stream))
+    return u.value
+
+
+def owner(key: int, num_shards: int) -> int:
+    return int(N.lib().hpsx_owner(int(key), int(num_shards)))
+
+
+def route_keys(device: int, d_keys, n: int, num_shards: int, d_routed, d_perm, d_counts, stream: int = 0) -> np.ndarray:
+    h = np.zeros(num_shards, dtype=np.uint32)
+    N.check(N.lib().hpsx_route_keys(device, _addr(d_keys), n, num_shards, _addr(d_routed), _addr(d_perm),
+                                    _addr(d_counts), _addr(h), stream))
+    return h
+
+
+def scatter_rows(device: int, d_rows, d_perm, n: int, dim: int, d_out, stream: int = 0) -> None:
+    N.check(N.lib().hpsx_scatter_rows(device, _addr(d_rows), _addr(d_perm), n, dim, _addr(d_out), stream))

@@ -1,0 +1,236 @@
+/*
+ * hpsx.h — C ABI of the B200-native Hierarchical Parameter Server engine (libhpsx.so).
+ *
+ * This is the thin FFI between the C++ host code of the Triton `hps` backend
+ * (libtriton_hps.so, see include/triton_hps_backend.h) and the hand-written sm_100a
+ * CUDA kernels.  Every entry point replaces one call the reference glue makes into the
+ * un-vendored libhuge_ctr_hps.so; the reference call site is cited next to each function
+ * (paths relative to /root/reference/hps_backend unless noted).
+ *
+ * Conventions
+ *   - plain C types only: pointers, sizes, opaque handles.  No C++/torch types.
+ *   - every function returns HPSX_OK (0) or a negative hpsx_status; the message for the
+ *     last failure on the calling thread is available from hpsx_last_error().
+ *   - "h_" pointers are host memory, "d_" pointers are device memory on the handle's GPU.
+ *   - keys are int64 ("supportlonglong": true, src/backend.cpp:124-126); vectors are fp32.
+ *   - nothing here falls back to a CPU implementation of a GPU path: if no CUDA device is
+ *     usable the GPU entry points fail with HPSX_ERR_CUDA.
+ */
+#ifndef HPSX_H_
+#define HPSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPSX_ABI_VERSION 1
+
+typedef enum hpsx_status {
+  HPSX_OK = 0,
+  HPSX_ERR_INVALID_ARG = -1, /* maps to TRITONSERVER_ERROR_INVALID_ARG */
+  HPSX_ERR_NOT_FOUND = -2,   /* unknown model / table / device */
+  HPSX_ERR_UNSUPPORTED = -3, /* maps to TRITONSERVER_ERROR_UNSUPPORTED */
+  HPSX_ERR_CUDA = -4,        /* CUDA runtime failure (reference throws: include/hps_buffer.hpp:79-87) */
+  HPSX_ERR_IO = -5,          /* sparse model files unreadable */
+  HPSX_ERR_INTERNAL = -6
+} hpsx_status;
+
+/* Opaque handles.  hpsx_ps      ~ HugeCTR::HierParameterServerBase   (src/backend.cpp:68-71)
+ *                  hpsx_cache   ~ HugeCTR::EmbeddingCacheBase        (src/model_state.cpp:404-412)
+ *                  hpsx_session ~ HugeCTR::LookupSessionBase         (src/model_instance_state.cpp:170-171) */
+typedef struct hpsx_ps hpsx_ps;
+typedef struct hpsx_cache hpsx_cache;
+typedef struct hpsx_session hpsx_session;
+
+typedef enum hpsx_cache_type {
+  HPSX_CACHE_DYNAMIC = 0, /* LRU set-associative cache with insertion (default, src/backend.cpp:489-490) */
+  HPSX_CACHE_STATIC = 1   /* loaded once, never replaced (src/backend.cpp:483-484) */
+} hpsx_cache_type;
+
+typedef enum hpsx_combiner { HPSX_COMBINER_SUM = 0, HPSX_COMBINER_MEAN = 1 } hpsx_combiner;
+
+/* ~ HugeCTR::InferenceParams as filled by HPSBackend::ParseParameterServer (src/backend.cpp:318-523).
+ * Arrays have `num_tables` entries and are copied by the callee. */
+typedef struct hpsx_model_params {
+  const char* model_name;                  /* "model"                       :325-328 */
+  size_t max_batch_size;                   /* "max_batch_size"              :341-344 */
+  size_t num_tables;                       /* = len(sparse_files)           :353-358 */
+  const char* const* sparse_files;         /* may be NULL when tables are loaded from memory / procedurally */
+  const char* const* table_names;          /* "embedding_table_names"       :462-467 (NULL -> sparse_embedding<i>) */
+  const size_t* embedding_vecsize_per_table;                  /* :454-460 */
+  const size_t* maxnum_catfeature_query_per_table_per_sample; /* :443-452 */
+  const float* default_value_for_each_table;                  /* :427-433 */
+  int use_gpu_embedding_cache;             /* "gpucache"                    :364-369 */
+  float hit_rate_threshold;                /* "hit_rate_threshold"          :372-377 */
+  float cache_size_percentage;             /* "gpucacheper"                 :380-385 */
+  size_t number_of_worker_buffers_in_pool; /* "num_of_worker_buffer_in_pool":397-402 */
+  const int* deployed_devices;             /* "deployed_device_list"        :418-425 */
+  size_t num_deployed_devices;
+  int embedding_cache_type;                /* hpsx_cache_type               :479-492 */
+  /* engine extensions (not in the reference config; 0 selects the default) */
+  float cache_load_factor;                 /* slots = gpucacheper*rows/load_factor, default 0.5 */
+} hpsx_model_params;
+
+/* ~ HugeCTR::VolatileDatabaseParams, hash_map / parallel_hash_map only (src/backend.cpp:129-216). */
+typedef struct hpsx_volatile_params {
+  size_t num_partitions;     /* "num_partitions" :155-159; 0 -> min(cores,16) (docs/hierarchical_parameter_server.md:410-412) */
+  size_t allocation_rate;    /* "allocation_rate" :161-165; 0 -> 256 MiB */
+  double initial_cache_rate; /* "initial_cache_rate" :194-198; <=0 -> 1.0 */
+  size_t num_threads;        /* worker pool; 0 -> HCTR_DEFAULT_CONCURRENCY or hardware_concurrency (src/thread_pool.cpp:25-41) */
+} hpsx_volatile_params;
+
+/* Counters of one lookup session, cumulative since creation / last reset. */
+typedef struct hpsx_session_stats {
+  uint64_t lookups;            /* hpsx_session_lookup* calls */
+  uint64_t keys;               /* key occurrences delivered */
+  uint64_t hits;               /* served from the HBM cache */
+  uint64_t misses;             /* went to the host parameter server */
+  uint64_t inserted;           /* rows written into the cache */
+  uint64_t default_filled;     /* rows answered with default_value (async mode / absent keys) */
+  uint64_t h2d_bytes;          /* bytes copied host->device on behalf of lookups */
+  uint64_t d2h_bytes;          /* bytes copied device->host on behalf of lookups */
+  uint64_t kernel_launches;    /* CUDA kernels launched by this session */
+  double probe_kernel_ms;      /* CUDA-event time of the probe+gather kernels (sum) */
+  uint64_t probe_kernel_launches;
+  uint64_t probe_kernel_keys;  /* keys those launches processed */
+  double insert_kernel_ms;     /* CUDA-event time of the merge+insert kernels (sum) */
+  double host_gather_ms;       /* wall time spent in the host parameter-server gather */
+} hpsx_session_stats;
+
+/* ---------------------------------------------------------------------------------------------
+ * library
+ * ------------------------------------------------------------------------------------------- */
+int hpsx_abi_version(void);
+/* Message of the last failing call on this thread ("" if none).  Valid until the next call. */
+const char* hpsx_last_error(void);
+/* Number of CUDA devices the engine can use (0 on a CPU-only box, never an error). */
+int hpsx_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * parameter server  (~ HierParameterServerBase)
+ * ------------------------------------------------------------------------------------------- */
+/* ~ HierParameterServerBase::create(ps_json_path)                         src/backend.cpp:68-69
+ * Parses ps.json, loads every model's sparse files into the host (volatile) database and, for
+ * gpucache models with init_ec, creates their embedding caches on deployed_device_list. */
+int hpsx_ps_create_from_json(const char* ps_json_path, hpsx_ps** out);
+/* Programmatic creation without a file (tests, bench). `vdb` may be NULL for defaults. */
+int hpsx_ps_create(const hpsx_volatile_params* vdb, hpsx_ps** out);
+int hpsx_ps_destroy(hpsx_ps* ps);
+
+/* ~ get_hps_model_configuration_map()                                     src/backend.cpp:70-71 */
+int hpsx_ps_num_models(const hpsx_ps* ps, size_t* out);
+int hpsx_ps_model_name(const hpsx_ps* ps, size_t index, const char** out);
+int hpsx_ps_has_model(const hpsx_ps* ps, const char* model_name);
+
+/* ~ update_database_per_model(InferenceParams)                            src/model_state.cpp:389
+ * Registers the model and (when sparse_files != NULL) loads `<dir>/key` + `<dir>/emb_vector`
+ * (docs/architecture.md:185-218) of every table into the host database. */
+int hpsx_ps_add_model(hpsx_ps* ps, const hpsx_model_params* params);
+/* Insert/overwrite rows of one table from host arrays (key file + vector file contents). */
+int hpsx_ps_load_table(hpsx_ps* ps, const char* model, size_t table, const int64_t* h_keys,
+                       const float* h_vectors, size_t num_rows);
+/* Fill one table with keys [0,num_rows) and procedural rows
+ *   row(k)[j] = bitcast_f32(0x3F800000 | (splitmix64(k*131 + j + seed) >> 41)) - 1.5
+ *  — the synthetic table of the benchmark configs; no files needed. */
+int hpsx_ps_load_table_procedural(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
+                                  uint64_t seed);
+int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_t* out);
+
+/* ~ HierParameterServerBase::lookup(h_keys, n, h_vectors, model, table)   (CPU path, gpucache=false;
+ * semantics docs/hierarchical_parameter_server.md:67-78,244-246): volatile-db fetch, absent keys get
+ * default_value_for_each_table[table]. `h_vectors` is [n, vecsize] row-major. */
+int hpsx_ps_lookup(hpsx_ps* ps, const char* model, size_t table, const int64_t* h_keys, size_t n,
+                   float* h_vectors);
+
+/* ---------------------------------------------------------------------------------------------
+ * embedding cache  (~ EmbeddingCacheBase, one per (model, device))
+ * ------------------------------------------------------------------------------------------- */
+/* ~ create_embedding_cache_per_model(InferenceParams)                     src/model_state.cpp:391
+ * Allocates the HBM hash table + value slab of every table on every deployed device and warms it
+ * with the first `gpucacheper` fraction of each table's rows. */
+int hpsx_ps_create_embedding_cache_per_model(hpsx_ps* ps, const char* model);
+/* ~ get_embedding_cache(model, device) — NULL/NOT_FOUND when absent        src/model_state.cpp:379,411 */
+int hpsx_ps_get_embedding_cache(hpsx_ps* ps, const char* model, int device, hpsx_cache** out);
+/* ~ destory_embedding_cache_per_model(model)                              src/model_state.cpp:111 */
+int hpsx_ps_destroy_embedding_cache_per_model(hpsx_ps* ps, const char* model);
+/* ~ get_cache_config().num_emb_table_                                     src/model_instance_state.cpp:107-109 */
+int hpsx_cache_num_tables(const hpsx_cache* cache, size_t* out);
+int hpsx_cache_device(const hpsx_cache* cache, int* out);
+/* Slots allocated / keys resident in one table's HBM cache (resident is counted on the device). */
+int hpsx_cache_capacity(const hpsx_cache* cache, size_t table, size_t* slots);
+int hpsx_cache_resident(hpsx_cache* cache, size_t table, size_t* keys);
+/* Copy the resident keys of one table to host (order unspecified). `cap` entries available. */
+int hpsx_cache_dump_keys(hpsx_cache* cache, size_t table, int64_t* h_keys, size_t cap, size_t* n);
+
+/* ---------------------------------------------------------------------------------------------
+ * lookup session  (~ LookupSessionBase, one per model instance)
+ * ------------------------------------------------------------------------------------------- */
+/* ~ LookupSessionBase::create(inference_params, embedding_cache)          src/model_instance_state.cpp:170-171
+ * `device` < 0 or a model with gpucache=false gives a CPU session (vectors returned in host memory,
+ * src/hps.cc:640-642). */
+int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session** out);
+int hpsx_session_destroy(hpsx_session* s);
+int hpsx_session_device(const hpsx_session* s, int* out);
+/* The CUDA stream (cudaStream_t) the session launches on, for callers that time with events. */
+int hpsx_session_stream(const hpsx_session* s, void** out);
+
+/* ~ LookupSessionBase::lookup(h_keys_per_table, d_vectors_per_table, num_keys_per_table)
+ *                                                                          src/model_instance_state.cpp:194-195
+ * For every table t: vectors_per_table[t][i*d_t .. (i+1)*d_t) = row_t(keys_per_table[t][i]) or the
+ * table's default value.  Blocks until the vectors are complete.  With a GPU session the vector
+ * pointers are device memory (they may be the Triton output buffer itself); with a CPU session
+ * they are host memory. */
+int hpsx_session_lookup(hpsx_session* s, const void* const* h_keys_per_table,
+                        float* const* vectors_per_table, const size_t* num_keys_per_table,
+                        size_t num_tables);
+/* Same, keys already resident in device memory (the engine-ABI arm of bench.py). */
+int hpsx_session_lookup_device_keys(hpsx_session* s, const int64_t* const* d_keys_per_table,
+                                    float* const* d_vectors_per_table,
+                                    const size_t* num_keys_per_table, size_t num_tables);
+/* Fused slot-wise gather + reduce (north-star stage a8): keys of table `table` laid out
+ * [num_bags, hotness]; d_pooled[b*d .. ) = sum_j row(key[b,j]) (MEAN: divided by hotness), fp32,
+ * accumulated in ascending j.  Misses are resolved (sync insert) before pooling. */
+int hpsx_session_lookup_pooled(hpsx_session* s, size_t table, const int64_t* h_keys,
+                               size_t num_bags, size_t hotness, int combiner, float* d_pooled);
+int hpsx_session_lookup_pooled_device_keys(hpsx_session* s, size_t table, const int64_t* d_keys,
+                                           size_t num_bags, size_t hotness, int combiner,
+                                           float* d_pooled);
+
+int hpsx_session_get_stats(const hpsx_session* s, hpsx_session_stats* out);
+int hpsx_session_reset_stats(hpsx_session* s);
+/* Force the insertion mode of subsequent lookups: <0 use hit_rate_threshold (default), 0 always
+ * asynchronous (misses answered with the default vector), 1 always synchronous. */
+int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
+/* Select the probe+gather kernel: 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
+ * staging through shared memory.  The environment variable HPSX_PROBE=ldg|tma sets the default. */
+int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
+/* Block until background (asynchronous) insertions queued by this session's cache are done. */
+int hpsx_cache_drain_async(hpsx_cache* cache);
+
+/* ---------------------------------------------------------------------------------------------
+ * stand-alone device primitives (testable without a parameter server)
+ * ------------------------------------------------------------------------------------------- */
+/* K1: dedup `n` device keys.  d_unique[0..*h_num_unique) holds each distinct key
+ * once (order unspecified), d_inverse[i] is the index into d_unique of d_keys[i].  `stream` is a
+ * cudaStream_t (NULL = default stream); the call synchronises that stream before returning. */
+int hpsx_unique(int device, const int64_t* d_keys, size_t n, int64_t* d_unique, uint32_t* d_inverse,
+                size_t* h_num_unique, void* stream);
+/* Shard routing of the model-parallel mode: owner(key) in [0, num_shards). */
+uint32_t hpsx_owner(int64_t key, uint32_t num_shards);
+/* Bucket `n` device keys by owner: d_counts[num_shards] (u32), d_perm[n] = original positions grouped
+ * by owner (stable within a CTA-tile, unspecified across), d_routed_keys[n] = keys in that order.
+ * h_counts receives the counts.  Synchronises `stream`. */
+int hpsx_route_keys(int device, const int64_t* d_keys, size_t n, uint32_t num_shards,
+                    int64_t* d_routed_keys, uint32_t* d_perm, uint32_t* d_counts, uint32_t* h_counts,
+                    void* stream);
+/* out[perm[i]*d .. ) = rows[i*d .. ) — return path of routed lookups (inverse permutation). */
+int hpsx_scatter_rows(int device, const float* d_rows, const uint32_t* d_perm, size_t n, size_t d,
+                      float* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPSX_H_ */

@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+def _native_built() -> bool:
+    return os.path.exists(os.path.join(ROOT, "hugectr_backend_b200", "lib", "libhpsx.so"))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_native():
+    """Build the native libraries once per test session when they are missing (CPU box: nvcc cross-compiles)."""
+    if not _native_built():
+        import __graft_entry__ as g
+
+        g.build()
+    from oracle import hps_oracle
+
+    hps_oracle.build_c_oracle()
+    yield
+
+
+@pytest.fixture(scope="session")
+def cuda_device():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible — there is no CPU fallback for the GPU path")
+    torch.cuda.set_device(0)
+    return 0
