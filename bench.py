@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=26)
     ap.add_argument("--hit", type=float, default=0.90, help="fraction of keys drawn from the cached hot set")
     ap.add_argument("--gpucacheper", type=float, default=0.2)
+    ap.add_argument("--load-factor", type=float, default=0.8,
+                    help="cache slots = gpucacheper*rows/load_factor (8-way buckets; little slack so that few cold keys stay resident)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
     ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "ldg"), choices=["ldg", "tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -194,13 +197,15 @@ def run_ours(a):
     t0 = time.perf_counter()
     hps = hb.HPS(num_partitions=16)
     hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
-                                 cache_size_percentage=a.gpucacheper, deployed_devices=[local]))
+                                 cache_size_percentage=a.gpucacheper, deployed_devices=[local],
+                                 cache_load_factor=a.load_factor))
     hps.load_table_procedural("dcn", 0, a.rows, SEED)
     hps.create_embedding_cache("dcn")
     setup_s = time.perf_counter() - t0
     hot = hps.cache_keys("dcn", local, 0)
     warm_rows = int(np.ceil(a.gpucacheper * a.rows))
-    reqs = make_requests(a, hot, warm_rows, 4, SEED + rank)
+    R = a.distinct if a.distinct > 0 else min(32, a.steps + a.warmup)
+    reqs = make_requests(a, hot, warm_rows, R, SEED + rank)
     sess = hps.session("dcn", local)
     sess.set_probe_variant(a.variant)
     ext = torch.cuda.ExternalStream(sess.stream)
@@ -233,12 +238,13 @@ def run_ours(a):
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall
 
-    dev_step = lambda i: sess.lookup_device_keys([d_reqs[i % 4]], [out], [n])
-    e2e_step = lambda i: sess.lookup([h_reqs[i % 4].numpy()], [out], [n])
+    h_np = [t.numpy() for t in h_reqs]
+    dev_step = lambda i: sess.lookup_device_keys([d_reqs[i % R]], [out], [n])
+    e2e_step = lambda i: sess.lookup([h_np[i % R]], [out], [n])
 
     # ---- device-resident arm (value) ------------------------------------------------------------------
     for i in range(a.warmup):
-        dev_step(i)
+        dev_step(a.steps + i)
     sess.reset_stats()
     sampler = ClockSampler(local)
     sampler.start()
@@ -260,7 +266,7 @@ def run_ours(a):
 
     # ---- end-to-end arm: pinned host keys through the session C-ABI call ------------------------------
     for i in range(a.warmup):
-        e2e_step(i)
+        e2e_step(a.steps + i)
     sess.reset_stats()
     ms_e, wall_e = timed(e2e_step, a.steps)
     st_e = sess.stats()
@@ -305,7 +311,8 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
                    "gpucacheper": a.gpucacheper, "hit_rate_measured": st.hits / max(1, st.keys),
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
-                   "l2": "inputs exceed L2: 13.6 MB keys + 872 MB output + 2 GB cache slab per step, 4 rotating key batches",
+                   "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches",
+                   "load_factor": a.load_factor,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "cache_hit": cache_hit,
         "gpu_launches": int(st.kernel_launches), "clocks": clocks,

@@ -86,6 +86,10 @@ SYMBOLS = {
     "hpsx_ps_load_table": (_int, [_vp, _cp, _sz, _vp, _vp, _sz]),
     "hpsx_ps_load_table_procedural": (_int, [_vp, _cp, _sz, _sz, ctypes.c_uint64]),
     "hpsx_ps_table_rows": (_int, [_vp, _cp, _sz, c_size_p]),
+    "hpsx_ps_get_model_params": (_int, [_vp, _cp, ctypes.POINTER(ModelParamsC)]),
+    "hpsx_ps_sync_models_from_json": (_int, [_vp, _cp, c_size_p]),
+    "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),
+    "hpsx_session_lookup_ex": (_int, [_vp, _vpp, _int, _vpp, _int, c_size_p, _sz]),
     "hpsx_ps_lookup": (_int, [_vp, _cp, _sz, _vp, _sz, _vp]),
     "hpsx_ps_create_embedding_cache_per_model": (_int, [_vp, _cp]),
     "hpsx_ps_get_embedding_cache": (_int, [_vp, _cp, _int, _vpp]),

@@ -21,7 +21,9 @@
 
 namespace hpsx {
 
-constexpr size_t kStageChunkRows = 32768;  // rows per host->device miss chunk (16 MiB at dim 128)
+constexpr size_t kStageChunkRows = 32768;    // most rows per host->device miss chunk (16 MiB at dim 128)
+constexpr size_t kMinStageChunkRows = 2048;  // smaller chunks cost more in launch + pool wake-ups than they hide
+constexpr int kNumStages = 3;                // pinned/device stage pairs rotating through the miss pipeline
 
 struct Model;
 
@@ -58,6 +60,9 @@ namespace hpsx {
 struct Model {
   ModelConfig cfg;
   float load_factor = 0.5f;
+  // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
+  std::vector<const char*> c_sparse_files, c_table_names;
+  std::vector<std::string> table_names;
   std::vector<std::unique_ptr<HostTable>> tables;
   std::mutex mu;  // guards `caches`
   std::map<int, std::unique_ptr<hpsx_cache>> caches;
@@ -89,11 +94,13 @@ struct hpsx_session {
   int64_t* d_miss_keys = nullptr;      // [cap_keys]
   uint32_t* d_counters = nullptr;      // [T] miss counts, [T..2T) inserted counts
   uint32_t* h_counters = nullptr;      // pinned mirror
-  int64_t* h_miss_keys = nullptr;      // pinned [cap_keys]
-  float* h_stage[2] = {nullptr, nullptr};  // pinned [kStageChunkRows * max_dim]
-  float* d_stage[2] = {nullptr, nullptr};
-  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  int64_t* h_miss_keys = nullptr;      // mapped pinned [cap_keys]: the probe kernels mirror miss keys here
+  int64_t* hd_miss_keys = nullptr;     // device-visible address of h_miss_keys
+  float* h_stage[hpsx::kNumStages] = {};  // pinned [<= kStageChunkRows * max_dim]
+  float* d_stage[hpsx::kNumStages] = {};
+  cudaEvent_t stage_free[hpsx::kNumStages] = {};
   uint32_t* d_src = nullptr;           // pooled path, lazily [cap_keys]
+  float* d_result = nullptr;           // host-output lookups of a GPU session: [sum_t cap_t * dim_t], lazy
   float* d_pool_stage = nullptr;       // pooled path: all miss rows of one call
   size_t pool_stage_rows = 0;
   size_t max_dim = 0;

@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -76,6 +77,15 @@ size_t resolve_partitions(size_t requested) {
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// HPSX_TRACE=1: one stderr line per lookup with the host-side timeline (debugging aid only).
+bool trace_on() {
+  static const bool on = [] {
+    const char* e = std::getenv("HPSX_TRACE");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -291,43 +301,29 @@ void run_async_insert(AsyncJob job) {
   c->async_cv.notify_all();
 }
 
-// Resolve the misses of one table after its probe.  `d_out` may be nullptr (pooled path: rows are
-// only staged).  Caller holds s->mu; the stream is idle (probe results are on the host).
-int resolve_misses(hpsx_session* s, size_t t, size_t key_off, size_t n, uint32_t m, float* d_out,
-                   bool sync_insert, float* d_all_stage) {
+// Stream the rows of the `m` missing keys of table `t` host -> device.  The keys are already on the
+// host: the probe kernel mirrored them into the mapped pinned buffer s->h_miss_keys + key_off.
+// Per chunk: thread-pool gather from the host database into a pinned stage, cudaMemcpyAsync H2D, then
+// (when `d_out` or `insert`) the fused merge+insert kernel.  Three stages rotate, so the gather of
+// chunk i+1 overlaps the copy and kernel of chunk i; nothing here waits for the stream except to
+// reuse a stage.  With `d_all_stage` the rows land at d_all_stage + i*dim and stay there for the
+// caller (pooled path).  The first kernel that rewrites cache slots takes `wlock` (exclusive) and
+// keeps it; the caller synchronises the stream before releasing it.
+int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, float* d_out, bool insert,
+                     uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock) {
   hpsx_cache* c = s->cache;
   const HostTable& ht = *s->model->tables[t];
   const size_t dim = ht.dim();
-  int64_t* h_keys = s->h_miss_keys + key_off;
-  HPSX_CU(cudaMemcpyAsync(h_keys, s->d_miss_keys + key_off, m * sizeof(int64_t),
-                          cudaMemcpyDeviceToHost, s->stream));
-  HPSX_CU(cudaStreamSynchronize(s->stream));
-  s->stats.d2h_bytes += m * sizeof(int64_t);
-  s->stats.misses += m;
-
-  if (!sync_insert) {
-    // asynchronous insertion: this response already carries the default vector for the misses
-    // (written by the probe kernel); a worker fetches + inserts later (docs/architecture.md:65-67)
-    s->stats.default_filled += m;
-    AsyncJob job{s->ps, c, t, std::vector<int64_t>(h_keys, h_keys + m)};
-    {
-      std::lock_guard<std::mutex> lk(c->async_mu);
-      ++c->async_pending;
-    }
-    s->ps->pool->post([job]() mutable { run_async_insert(std::move(job)); });
-    return HPSX_OK;
-  }
-
-  std::unique_lock<std::shared_mutex> lk(c->rw);
-  const bool insert = !c->is_static;
-  const uint32_t epoch = c->epoch.load(std::memory_order_relaxed);
+  const int64_t* h_keys = s->h_miss_keys + key_off;
   uint32_t* d_inserted = s->d_counters + s->model->tables.size() + t;
-  (void)n;
-  size_t chunk_idx = 0;
-  for (size_t off = 0; off < m; off += kStageChunkRows, ++chunk_idx) {
-    const size_t mc = std::min<size_t>(kStageChunkRows, m - off);
-    const int b = static_cast<int>(chunk_idx & 1);
-    // the copy + kernel that last used this buffer pair must be done before the host refills it
+  s->stats.misses += m;
+  size_t chunk = (static_cast<size_t>(m) + 3) / 4;
+  chunk = std::min<size_t>(kStageChunkRows, std::max<size_t>(kMinStageChunkRows, chunk));
+  size_t ci = 0;
+  for (size_t off = 0; off < m; off += chunk, ++ci) {
+    const size_t mc = std::min<size_t>(chunk, m - off);
+    const int b = static_cast<int>(ci % kNumStages);
+    // the copy (+ kernel) that last used this stage must be done before the host refills it
     HPSX_CU(cudaEventSynchronize(s->stage_free[b]));
     const double t0 = now_ms();
     const size_t absent = ht.fetch(h_keys + off, mc, s->h_stage[b], dim, *s->ps->pool);
@@ -337,14 +333,31 @@ int resolve_misses(hpsx_session* s, size_t t, size_t key_off, size_t n, uint32_t
     HPSX_CU(cudaMemcpyAsync(d_rows, s->h_stage[b], mc * dim * sizeof(float), cudaMemcpyHostToDevice,
                             s->stream));
     s->stats.h2d_bytes += mc * dim * sizeof(float);
-    HPSX_CU(launch_insert_merge(c->tables[t], s->d_miss_keys + key_off + off,
-                                s->d_miss_pos + key_off + off, d_rows, mc, d_out, insert, epoch,
-                                d_inserted, s->stream));
-    ++s->stats.kernel_launches;
+    if (d_out != nullptr || insert) {
+      if (insert && wlock != nullptr && !wlock->owns_lock()) wlock->lock();
+      HPSX_CU(launch_insert_merge(c->tables[t], s->d_miss_keys + key_off + off,
+                                  s->d_miss_pos + key_off + off, d_rows, mc, d_out, insert, epoch,
+                                  d_inserted, s->stream));
+      ++s->stats.kernel_launches;
+    }
     HPSX_CU(cudaEventRecord(s->stage_free[b], s->stream));
   }
-  HPSX_CU(cudaStreamSynchronize(s->stream));
   return HPSX_OK;
+}
+
+// Asynchronous insertion: this response already carries the default vector for the misses (written
+// by the probe kernel); a pool worker fetches + inserts later (docs/architecture.md:65-67).
+void post_async_insert(hpsx_session* s, size_t t, size_t key_off, uint32_t m) {
+  hpsx_cache* c = s->cache;
+  s->stats.misses += m;
+  s->stats.default_filled += m;
+  const int64_t* h_keys = s->h_miss_keys + key_off;
+  AsyncJob job{s->ps, c, t, std::vector<int64_t>(h_keys, h_keys + m)};
+  {
+    std::lock_guard<std::mutex> lk(c->async_mu);
+    ++c->async_pending;
+  }
+  s->ps->pool->post([job]() mutable { run_async_insert(std::move(job)); });
 }
 
 bool decide_sync(const hpsx_session* s, size_t n, uint32_t m) {
@@ -353,6 +366,15 @@ bool decide_sync(const hpsx_session* s, size_t n, uint32_t m) {
   // [UPSTREAM] hit_rate < hit_rate_threshold -> synchronous insertion
   const double hit_rate = 1.0 - static_cast<double>(m) / static_cast<double>(n);
   return hit_rate < static_cast<double>(s->model->cfg.hit_rate_threshold);
+}
+
+void account_probe_time(hpsx_session* s, size_t t, size_t n) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]) == cudaSuccess) {
+    s->stats.probe_kernel_ms += ms;
+    ++s->stats.probe_kernel_launches;
+    s->stats.probe_kernel_keys += n;
+  }
 }
 
 int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
@@ -367,8 +389,9 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
   ++s->stats.lookups;
   s->stats.keys += total;
   if (total == 0) return HPSX_OK;
+  const double tr0 = now_ms();
 
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
   std::vector<size_t> off(num_tables + 1, 0);
   {
     std::shared_lock<std::shared_mutex> lk(c->rw);
@@ -390,50 +413,54 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
       HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
       HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
-                                  s->probe_variant, s->stream));
+                                  s->hd_miss_keys + off[t], s->probe_variant, s->stream));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
     }
     HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
                             cudaMemcpyDeviceToHost, s->stream));
+    // one synchronisation: miss counts (copied) and miss keys (written by the kernel straight into
+    // mapped pinned memory) are both on the host after it
     HPSX_CU(cudaStreamSynchronize(s->stream));
   }
   s->stats.d2h_bytes += T * sizeof(uint32_t);
-  for (size_t t = 0; t < num_tables; ++t) {
-    if (n_per_table[t] == 0) continue;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]) == cudaSuccess) {
-      s->stats.probe_kernel_ms += ms;
-      ++s->stats.probe_kernel_launches;
-      s->stats.probe_kernel_keys += n_per_table[t];
-    }
-  }
+  for (size_t t = 0; t < num_tables; ++t)
+    if (n_per_table[t] != 0) account_probe_time(s, t, n_per_table[t]);
 
+  const double tr1 = now_ms();
+  const double gather0 = s->stats.host_gather_ms;
   bool any_sync = false;
+  std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
+  cudaEvent_t e0 = s->ev[0], e1 = s->ev[1];
   for (size_t t = 0; t < num_tables; ++t) {
     const uint32_t m = s->h_counters[t];
     const size_t n = n_per_table[t];
     s->stats.hits += n - m;
     if (m == 0) continue;
-    const bool sync = decide_sync(s, n, m);
-    any_sync |= sync;
-    cudaEvent_t e0 = s->ev[2 * t], e1 = s->ev[2 * t + 1];
-    if (sync) HPSX_CU(cudaEventRecord(e0, s->stream));
-    const int rc = resolve_misses(s, t, off[t], n, m, out_per_table[t], sync, nullptr);
-    if (rc != HPSX_OK) return rc;
-    if (sync) {
-      HPSX_CU(cudaEventRecord(e1, s->stream));
-      HPSX_CU(cudaEventSynchronize(e1));
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    s->stats.d2h_bytes += static_cast<uint64_t>(m) * sizeof(int64_t);  // zero-copy miss-key mirror
+    if (!decide_sync(s, n, m)) {
+      post_async_insert(s, t, off[t], m);
+      continue;
     }
+    if (!any_sync) HPSX_CU(cudaEventRecord(e0, s->stream));
+    any_sync = true;
+    const int rc = stream_miss_rows(s, t, off[t], m, out_per_table[t], !c->is_static, epoch, nullptr,
+                                    &wlock);
+    if (rc != HPSX_OK) return rc;
   }
+  const double tr2 = now_ms();
   if (any_sync) {
-    HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, T * sizeof(uint32_t),
-                            cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaEventRecord(e1, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
-    for (size_t t = 0; t < num_tables; ++t) s->stats.inserted += s->h_counters[T + t];
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) s->stats.insert_kernel_ms += ms;
   }
+  if (trace_on())
+    std::fprintf(stderr,
+                 "[hpsx] lookup n=%zu probe+sync %.3f ms | miss loop %.3f ms (host gather %.3f) | "
+                 "final sync %.3f ms | misses[0]=%u\n",
+                 total, tr1 - tr0, tr2 - tr1, s->stats.host_gather_ms - gather0, now_ms() - tr2,
+                 s->h_counters[0]);
   return HPSX_OK;
 }
 
@@ -444,16 +471,19 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   const size_t T = s->model->tables.size();
   const size_t n = num_bags * hotness;
-  const size_t dim = s->model->tables[table]->dim();
   ++s->stats.lookups;
   s->stats.keys += n;
   if (n == 0) return HPSX_OK;
   if (!keys || !d_pooled) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
   if (!s->d_src) HPSX_CU(cudaMalloc(&s->d_src, s->cap_keys * sizeof(uint32_t)));
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
   const int64_t* d_keys = keys;
+  uint32_t m = 0;
   {
+    // The slot indices recorded by the probe stay valid only while no kernel rewrites cache slots:
+    // the shared lock is held from the probe until the pooled gather has finished, and the rows of
+    // the misses are inserted only afterwards.
     std::shared_lock<std::shared_mutex> lk(c->rw);
     if (!keys_on_device) {
       HPSX_CU(cudaMemcpyAsync(s->d_keys, keys, n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
@@ -461,31 +491,28 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
       d_keys = s->d_keys;
     }
     HPSX_CU(launch_probe_index(c->tables[table], d_keys, n, epoch, !c->is_static, s->d_src,
-                               s->d_counters + table, s->d_miss_pos, s->d_miss_keys, s->stream));
+                               s->d_counters + table, s->d_miss_pos, s->d_miss_keys, s->hd_miss_keys,
+                               s->stream));
     ++s->stats.kernel_launches;
     HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
                             cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
-  }
-  s->stats.d2h_bytes += T * sizeof(uint32_t);
-  const uint32_t m = s->h_counters[table];
-  s->stats.hits += n - m;
-  if (m > 0) {
-    // the pooled sum needs every row: misses are always resolved before pooling
-    if (s->pool_stage_rows < m) {
-      if (s->d_pool_stage) cudaFree(s->d_pool_stage);
-      s->d_pool_stage = nullptr;
-      s->pool_stage_rows = 0;
-      HPSX_CU(cudaMalloc(&s->d_pool_stage, static_cast<size_t>(m) * s->max_dim * sizeof(float)));
-      s->pool_stage_rows = m;
+    s->stats.d2h_bytes += T * sizeof(uint32_t);
+    m = s->h_counters[table];
+    s->stats.hits += n - m;
+    if (m > 0) {
+      // the pooled sum needs every row: misses are always fetched before pooling
+      s->stats.d2h_bytes += static_cast<uint64_t>(m) * sizeof(int64_t);
+      if (s->pool_stage_rows < m) {
+        if (s->d_pool_stage) cudaFree(s->d_pool_stage);
+        s->d_pool_stage = nullptr;
+        s->pool_stage_rows = 0;
+        HPSX_CU(cudaMalloc(&s->d_pool_stage, static_cast<size_t>(m) * s->max_dim * sizeof(float)));
+        s->pool_stage_rows = m;
+      }
+      const int rc = stream_miss_rows(s, table, 0, m, nullptr, false, epoch, s->d_pool_stage, nullptr);
+      if (rc != HPSX_OK) return rc;
     }
-    const int rc = resolve_misses(s, table, 0, n, m, nullptr, true, s->d_pool_stage);
-    if (rc != HPSX_OK) return rc;
-    HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, T * sizeof(uint32_t),
-                            cudaMemcpyDeviceToHost, s->stream));
-  }
-  {
-    std::shared_lock<std::shared_mutex> lk(c->rw);
     HPSX_CU(cudaEventRecord(s->ev[2 * table], s->stream));
     HPSX_CU(launch_pooled_gather(c->tables[table], s->d_src, s->d_pool_stage, num_bags, hotness,
                                  combiner == HPSX_COMBINER_MEAN, d_pooled, s->stream));
@@ -493,14 +520,14 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
     ++s->stats.kernel_launches;
     HPSX_CU(cudaStreamSynchronize(s->stream));
   }
-  if (m > 0) s->stats.inserted += s->h_counters[T + table];
-  float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, s->ev[2 * table], s->ev[2 * table + 1]) == cudaSuccess) {
-    s->stats.probe_kernel_ms += ms;
-    ++s->stats.probe_kernel_launches;
-    s->stats.probe_kernel_keys += n;
+  account_probe_time(s, table, n);
+  if (m > 0 && !c->is_static) {
+    std::unique_lock<std::shared_mutex> wlock(c->rw);
+    HPSX_CU(launch_insert_merge(c->tables[table], s->d_miss_keys, s->d_miss_pos, s->d_pool_stage, m,
+                                nullptr, true, epoch, s->d_counters + T + table, s->stream));
+    ++s->stats.kernel_launches;
+    HPSX_CU(cudaStreamSynchronize(s->stream));
   }
-  (void)dim;
   return HPSX_OK;
 }
 
@@ -533,10 +560,11 @@ hpsx_session::~hpsx_session() {
     cudaFree(d_miss_keys);
     cudaFree(d_counters);
     cudaFree(d_src);
+    cudaFree(d_result);
     cudaFree(d_pool_stage);
     if (h_counters) cudaFreeHost(h_counters);
     if (h_miss_keys) cudaFreeHost(h_miss_keys);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < hpsx::kNumStages; ++b) {
       if (h_stage[b]) cudaFreeHost(h_stage[b]);
       cudaFree(d_stage[b]);
       if (stage_free[b]) cudaEventDestroy(stage_free[b]);
@@ -631,6 +659,16 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
     if (cfg.sparse_files[t].empty()) continue;
     const int rc = load_sparse_dir(ps, m->tables[t].get(), cfg.sparse_files[t]);
     if (rc != HPSX_OK) return rc;
+  }
+  for (size_t t = 0; t < T; ++t) {
+    m->table_names.push_back(t < cfg.embedding_table_names.size()
+                                 ? cfg.embedding_table_names[t]
+                                 : "sparse_embedding" + std::to_string(t));  // docs default name
+  }
+  m->cfg.sparse_files.resize(T);
+  for (size_t t = 0; t < T; ++t) {
+    m->c_sparse_files.push_back(m->cfg.sparse_files[t].c_str());
+    m->c_table_names.push_back(m->table_names[t].c_str());
   }
   std::lock_guard<std::mutex> lk(ps->mu);
   if (ps->models.count(cfg.model_name))
@@ -741,6 +779,58 @@ int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_
   if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, "unknown model");
   if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
   *out = m->tables[table]->rows();
+  return HPSX_OK;
+}
+
+int hpsx_ps_get_model_params(hpsx_ps* ps, const char* model, hpsx_model_params* out) {
+  Model* m = find_model(ps, model);
+  if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  const ModelConfig& c = m->cfg;
+  *out = hpsx_model_params{};
+  out->model_name = c.model_name.c_str();
+  out->max_batch_size = c.max_batch_size;
+  out->num_tables = m->tables.size();
+  out->sparse_files = m->c_sparse_files.data();
+  out->table_names = m->c_table_names.data();
+  out->embedding_vecsize_per_table = c.embedding_vecsize_per_table.data();
+  out->maxnum_catfeature_query_per_table_per_sample = c.maxnum_catfeature_query_per_table_per_sample.data();
+  out->default_value_for_each_table = c.default_value_for_each_table.data();
+  out->use_gpu_embedding_cache = c.use_gpu_embedding_cache ? 1 : 0;
+  out->hit_rate_threshold = c.hit_rate_threshold;
+  out->cache_size_percentage = c.cache_size_percentage;
+  out->number_of_worker_buffers_in_pool = c.number_of_worker_buffers_in_pool;
+  out->deployed_devices = c.deployed_devices.data();
+  out->num_deployed_devices = c.deployed_devices.size();
+  out->embedding_cache_type = c.embedding_cache_type == CacheType::Static ? HPSX_CACHE_STATIC : HPSX_CACHE_DYNAMIC;
+  out->cache_load_factor = m->load_factor;
+  return HPSX_OK;
+}
+
+int hpsx_ps_sync_models_from_json(hpsx_ps* ps, const char* ps_json_path, size_t* num_added) {
+  HPSX_GUARD_BEGIN
+  if (!ps || !ps_json_path) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (num_added) *num_added = 0;
+  PsConfig cfg;
+  const ParseResult pr = parse_ps_config_file(ps_json_path, &cfg);
+  if (!pr.ok) return fail(HPSX_ERR_INVALID_ARG, pr.message);
+  for (const ModelConfig& m : cfg.models) {
+    if (find_model(ps, m.model_name.c_str()) != nullptr) continue;
+    int rc = add_model_cfg(ps, m, 0.f);
+    if (rc == HPSX_OK && m.use_gpu_embedding_cache && m.init_ec)
+      rc = hpsx_ps_create_embedding_cache_per_model(ps, m.model_name.c_str());
+    if (rc != HPSX_OK) return rc;
+    if (num_added) ++*num_added;
+  }
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_copy_to_host(int device, void* h_dst, const void* d_src, size_t bytes) {
+  if (bytes == 0) return HPSX_OK;
+  if (!h_dst || !d_src) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
   return HPSX_OK;
 }
 
@@ -906,14 +996,18 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   HPSX_CU(cudaMalloc(&s->d_miss_keys, cap * sizeof(int64_t)));
   HPSX_CU(cudaMalloc(&s->d_counters, 2 * T * sizeof(uint32_t)));
   HPSX_CU(cudaMallocHost(&s->h_counters, 2 * T * sizeof(uint32_t)));
-  HPSX_CU(cudaMallocHost(&s->h_miss_keys, cap * sizeof(int64_t)));
-  const size_t chunk_rows = std::min<size_t>(kStageChunkRows, cap);
-  for (int b = 0; b < 2; ++b) {
-    HPSX_CU(cudaMallocHost(&s->h_stage[b], kStageChunkRows * s->max_dim * sizeof(float)));
-    HPSX_CU(cudaMalloc(&s->d_stage[b], kStageChunkRows * s->max_dim * sizeof(float)));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  // miss keys are written by the probe kernels straight into this mapped buffer (zero-copy)
+  HPSX_CU(cudaHostAlloc(&s->h_miss_keys, cap * sizeof(int64_t),
+                        cudaHostAllocMapped | cudaHostAllocPortable));
+  HPSX_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&s->hd_miss_keys), s->h_miss_keys, 0));
+  const size_t stage_rows = std::min<size_t>(kStageChunkRows, std::max<size_t>(cap, kMinStageChunkRows));
+  for (int b = 0; b < kNumStages; ++b) {
+    HPSX_CU(cudaMallocHost(&s->h_stage[b], stage_rows * s->max_dim * sizeof(float)));
+    HPSX_CU(cudaMalloc(&s->d_stage[b], stage_rows * s->max_dim * sizeof(float)));
     HPSX_CU(cudaEventCreateWithFlags(&s->stage_free[b], cudaEventDisableTiming));
   }
-  (void)chunk_rows;
+  HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * T);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
   *out = s.release();
@@ -987,6 +1081,55 @@ int hpsx_session_lookup_device_keys(hpsx_session* s, const int64_t* const* d_key
   HPSX_GUARD_END
 }
 
+int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,
+                           float* const* vectors_per_table, int vector_memory,
+                           const size_t* num_keys_per_table, size_t num_tables) {
+  HPSX_GUARD_BEGIN
+  const bool keys_dev = key_memory == HPSX_MEM_DEVICE, vec_dev = vector_memory == HPSX_MEM_DEVICE;
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (!s->cache) {
+    if (keys_dev || vec_dev)
+      return fail(HPSX_ERR_UNSUPPORTED, "a CPU session (gpucache = false) takes host keys and host vectors");
+    return hpsx_session_lookup(s, keys_per_table, vectors_per_table, num_keys_per_table, num_tables);
+  }
+  if (vec_dev) {
+    return keys_dev ? hpsx_session_lookup_device_keys(s, reinterpret_cast<const int64_t* const*>(keys_per_table),
+                                                      vectors_per_table, num_keys_per_table, num_tables)
+                    : hpsx_session_lookup(s, keys_per_table, vectors_per_table, num_keys_per_table, num_tables);
+  }
+  // GPU session, host vectors: gather into the session's device result buffer, then D2H per table.
+  int rc = check_tables(s, num_keys_per_table, num_tables);
+  if (rc != HPSX_OK) return rc;
+  if (num_tables > 0 && (!keys_per_table || !vectors_per_table))
+    return fail(HPSX_ERR_INVALID_ARG, "null pointer arrays");
+  std::lock_guard<std::mutex> lk(s->mu);
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  if (!s->d_result) {
+    size_t floats = 0;
+    for (size_t t = 0; t < s->cap_per_table.size(); ++t) floats += s->cap_per_table[t] * s->model->tables[t]->dim();
+    HPSX_CU(cudaMalloc(&s->d_result, std::max<size_t>(floats, 1) * sizeof(float)));
+  }
+  std::vector<float*> d_out(num_tables, nullptr);
+  size_t off = 0;
+  for (size_t t = 0; t < num_tables; ++t) {
+    d_out[t] = s->d_result + off;
+    off += num_keys_per_table[t] * s->model->tables[t]->dim();
+  }
+  rc = gpu_lookup(s, keys_per_table, keys_dev, d_out.data(), num_keys_per_table, num_tables);
+  if (rc != HPSX_OK) return rc;
+  for (size_t t = 0; t < num_tables; ++t) {
+    const size_t bytes = num_keys_per_table[t] * s->model->tables[t]->dim() * sizeof(float);
+    if (bytes == 0) continue;
+    if (!vectors_per_table[t]) return fail(HPSX_ERR_INVALID_ARG, "null vector pointer for table " + std::to_string(t));
+    HPSX_CU(cudaMemcpyAsync(vectors_per_table[t], d_out[t], bytes, cudaMemcpyDeviceToHost, s->stream));
+    s->stats.d2h_bytes += bytes;
+  }
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
 static int pooled_common(hpsx_session* s, size_t table, const int64_t* keys, bool on_device,
                          size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
@@ -1017,16 +1160,38 @@ int hpsx_session_lookup_pooled_device_keys(hpsx_session* s, size_t table, const 
   HPSX_GUARD_END
 }
 
-int hpsx_session_get_stats(const hpsx_session* s, hpsx_session_stats* out) {
-  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  *out = s->stats;
+// rows inserted into the cache are counted on the device (cumulative since the last reset)
+static int read_inserted(hpsx_session* s, uint64_t* out) {
+  *out = 0;
+  if (!s->cache) return HPSX_OK;
+  DeviceGuard guard(s->device);
+  const size_t T = s->model->tables.size();
+  std::vector<uint32_t> h(T, 0);
+  HPSX_CU(cudaMemcpyAsync(h.data(), s->d_counters + T, T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  for (uint32_t v : h) *out += v;
   return HPSX_OK;
+}
+
+int hpsx_session_get_stats(const hpsx_session* cs, hpsx_session_stats* out) {
+  if (!cs || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  hpsx_session* s = const_cast<hpsx_session*>(cs);
+  std::lock_guard<std::mutex> lk(s->mu);
+  *out = s->stats;
+  return read_inserted(s, &out->inserted);
 }
 
 int hpsx_session_reset_stats(hpsx_session* s) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
   std::lock_guard<std::mutex> lk(s->mu);
   s->stats = hpsx_session_stats{};
+  if (s->cache) {
+    DeviceGuard guard(s->device);
+    const size_t T = s->model->tables.size();
+    HPSX_CU(cudaMemsetAsync(s->d_counters + T, 0, T * sizeof(uint32_t), s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+  }
   return HPSX_OK;
 }
 

@@ -118,6 +118,7 @@ struct ProbeArgs {
   uint32_t* miss_count;
   uint32_t* miss_pos;
   int64_t* miss_keys;
+  int64_t* miss_keys_host;  // optional mirror in mapped pinned host memory (zero-copy PCIe writes)
   uint32_t* src;  // probe_index only
 };
 
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
     a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
     a.miss_keys[r] = key;
+    if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
   }
 }
 
@@ -317,6 +319,7 @@ __global__ void __launch_bounds__(kWarps * 32) probe_gather_tma_kernel(const Pro
           const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
           a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
           a.miss_keys[r] = key;
+          if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
         }
         fence_proxy_async_smem();  // generic-proxy default rows -> visible to the later bulk store
       }
@@ -360,6 +363,7 @@ __global__ void __launch_bounds__(kBlock) probe_index_kernel(const ProbeArgs a) 
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
     a.miss_pos[r] = static_cast<uint32_t>(idx);
     a.miss_keys[r] = key;
+    if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
     slot = kSrcMissBit | r;
   }
   if (valid) a.src[idx] = slot;
@@ -783,8 +787,8 @@ cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
 
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
-                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int variant,
-                                cudaStream_t stream) {
+                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
+                                int variant, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.buckets = t.buckets;
@@ -800,6 +804,7 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
   a.miss_count = d_miss_count;
   a.miss_pos = d_miss_pos;
   a.miss_keys = d_miss_keys;
+  a.miss_keys_host = hd_miss_keys;
   a.src = nullptr;
   const int vb = vec_bytes(t.dim, d_out, t.values);
   if (variant == kProbeTma && vb == 16) {
@@ -813,7 +818,8 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
 
 cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size_t n, uint32_t epoch,
                                bool touch, uint32_t* d_src, uint32_t* d_miss_count,
-                               uint32_t* d_miss_pos, int64_t* d_miss_keys, cudaStream_t stream) {
+                               uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
+                               cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.buckets = t.buckets;
@@ -829,6 +835,7 @@ cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size
   a.miss_count = d_miss_count;
   a.miss_pos = d_miss_pos;
   a.miss_keys = d_miss_keys;
+  a.miss_keys_host = hd_miss_keys;
   a.src = d_src;
   probe_index_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
   return cudaGetLastError();

@@ -29,15 +29,18 @@ enum ProbeVariant : int {
 // write the default vector for misses, touch LRU stamps, and append (position,key) of every miss to
 // the miss list (warp ballot + prefix, one atomic per warp tile).
 // `miss_count` must be zeroed by the caller (stream-ordered).  `touch`=false for static caches.
+// `hd_miss_keys` (nullable) is the device-visible address of a mapped pinned host buffer that
+// receives a mirror of the miss keys, so the host needs no separate D2H copy of them.
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
-                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int variant,
-                                cudaStream_t stream);
+                                uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
+                                int variant, cudaStream_t stream);
 
 // Probe only (pooled path): d_src[i] = slot index on hit, kSrcMissBit | miss-list index on miss.
 cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size_t n, uint32_t epoch,
                                bool touch, uint32_t* d_src, uint32_t* d_miss_count,
-                               uint32_t* d_miss_pos, int64_t* d_miss_keys, cudaStream_t stream);
+                               uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
+                               cudaStream_t stream);
 
 // K4+K5 fused: for every miss i in [0,m): row = stage[i*dim..); if d_out: out[pos[i]*dim..) = row
 // (merge); if `insert`: put (key,row) into the cache — skip when present, else first empty way, else

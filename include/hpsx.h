@@ -138,6 +138,14 @@ int hpsx_ps_load_table(hpsx_ps* ps, const char* model, size_t table, const int64
 int hpsx_ps_load_table_procedural(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
                                   uint64_t seed);
 int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_t* out);
+/* ~ get_hps_model_configuration_map().at(model) -> InferenceParams      src/backend.cpp:70-71, hps.cc:221-223
+ * Fills `out` with pointers into the server's own storage; they stay valid until the server is
+ * destroyed.  cache_load_factor is the effective value. */
+int hpsx_ps_get_model_params(hpsx_ps* ps, const char* model, hpsx_model_params* out);
+/* ~ HPSBackend::ParseParameterServer(ps.json) for online deployment       src/hps.cc:207-219, src/backend.cpp:102-526
+ * Re-reads ps.json and registers (and loads the sparse files of) every model that the server does
+ * not know yet; known models are left untouched.  `num_added` may be NULL. */
+int hpsx_ps_sync_models_from_json(hpsx_ps* ps, const char* ps_json_path, size_t* num_added);
 
 /* ~ HierParameterServerBase::lookup(h_keys, n, h_vectors, model, table)   (CPU path, gpucache=false;
  * semantics docs/hierarchical_parameter_server.md:67-78,244-246): volatile-db fetch, absent keys get
@@ -190,6 +198,20 @@ int hpsx_session_lookup(hpsx_session* s, const void* const* h_keys_per_table,
 int hpsx_session_lookup_device_keys(hpsx_session* s, const int64_t* const* d_keys_per_table,
                                     float* const* d_vectors_per_table,
                                     const size_t* num_keys_per_table, size_t num_tables);
+/* Where a buffer handed to hpsx_session_lookup_ex lives. */
+typedef enum hpsx_memory { HPSX_MEM_HOST = 0, HPSX_MEM_DEVICE = 1 } hpsx_memory;
+/* General form used by the Triton shell, which must take whatever buffers Triton hands it
+ * (src/hps.cc:586-597 input buffer, :638-648 output buffer whose memory type Triton may override):
+ * keys and vectors each in host or device memory.  GPU session + host vectors: the rows are
+ * gathered into the session's device result buffer and copied D2H (reference: hps.cc:681-685).
+ * CPU session: both must be host memory. */
+int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,
+                           float* const* vectors_per_table, int vector_memory,
+                           const size_t* num_keys_per_table, size_t num_tables);
+/* Blocking device -> host copy on `device` (small control tensors such as NUMKEYS that Triton
+ * delivered in GPU memory). */
+int hpsx_copy_to_host(int device, void* h_dst, const void* d_src, size_t bytes);
+
 /* Fused slot-wise gather + reduce (north-star stage a8): keys of table `table` laid out
  * [num_bags, hotness]; d_pooled[b*d .. ) = sum_j row(key[b,j]) (MEAN: divided by hotness), fp32,
  * accumulated in ascending j.  Misses are resolved (sync insert) before pooling. */

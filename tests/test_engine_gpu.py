@@ -255,7 +255,7 @@ def test_route_and_scatter(cuda_device, shards):
     perm = d_perm.cpu().numpy().view(np.uint32)
     assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))                   # a permutation
     assert np.array_equal(routed, keys[perm])
-    bounds = np.concatenate([[0], np.cumsum(counts)])
+    bounds = np.concatenate([[0], np.cumsum(counts.astype(np.int64))]).astype(np.int64)
     for g in range(shards):
         assert np.all(O.owner(routed[bounds[g]:bounds[g + 1]], shards) == g)
     for i in range(64):
