@@ -45,8 +45,11 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=26)
     ap.add_argument("--hit", type=float, default=0.90, help="fraction of keys drawn from the cached hot set")
     ap.add_argument("--gpucacheper", type=float, default=0.2)
-    ap.add_argument("--load-factor", type=float, default=0.8,
-                    help="cache slots = gpucacheper*rows/load_factor (8-way buckets; little slack so that few cold keys stay resident)")
+    ap.add_argument("--load-factor", type=float, default=0.5,
+                    help="cache slots = gpucacheper*rows/load_factor (8-way buckets)")
+    ap.add_argument("--miss-path", default="direct", choices=["direct", "staged"],
+                    help="direct: enable_pagelock, kernels pull missing rows from pinned host tables over PCIe; "
+                         "staged: CPU gather + cudaMemcpyAsync")
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
     ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "ldg"), choices=["ldg", "tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -198,7 +201,7 @@ def run_ours(a):
     hps = hb.HPS(num_partitions=16)
     hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
                                  cache_size_percentage=a.gpucacheper, deployed_devices=[local],
-                                 cache_load_factor=a.load_factor))
+                                 cache_load_factor=a.load_factor, enable_pagelock=(a.miss_path == "direct")))
     hps.load_table_procedural("dcn", 0, a.rows, SEED)
     hps.create_embedding_cache("dcn")
     setup_s = time.perf_counter() - t0
@@ -312,7 +315,7 @@ def run_ours(a):
                    "gpucacheper": a.gpucacheper, "hit_rate_measured": st.hits / max(1, st.keys),
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches",
-                   "load_factor": a.load_factor,
+                   "load_factor": a.load_factor, "miss_path": a.miss_path,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "cache_hit": cache_hit,
         "gpu_launches": int(st.kernel_launches), "clocks": clocks,

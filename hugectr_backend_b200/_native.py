@@ -38,6 +38,7 @@ class ModelParamsC(ctypes.Structure):
         ("num_deployed_devices", ctypes.c_size_t),
         ("embedding_cache_type", ctypes.c_int),
         ("cache_load_factor", ctypes.c_float),
+        ("enable_pagelock", ctypes.c_int),
     ]
 
 

@@ -36,6 +36,8 @@ struct hpsx_cache {
   bool is_static = false;
   std::vector<hpsx::DeviceTable> tables;
   std::vector<size_t> slots;            // capacity of every table (ways * buckets)
+  bool direct_pull = false;             // enable_pagelock: misses are pulled by kernels from pinned host rows
+  std::vector<hpsx::IndexSlot*> indexes;  // HBM mirrors of the host tables' key -> row-address index
   std::atomic<uint32_t> epoch{1};       // one tick per lookup call; LRU stamps are epochs
   // Probes (readers) run concurrently; a kernel that rewrites slots (insert) excludes them, so a
   // row is never copied while it is being replaced.
@@ -60,6 +62,7 @@ namespace hpsx {
 struct Model {
   ModelConfig cfg;
   float load_factor = 0.5f;
+  bool direct_pull = false;  // cfg.enable_pagelock (or HPSX_DIRECT_PULL=0/1)
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
   std::vector<std::string> table_names;
@@ -92,7 +95,7 @@ struct hpsx_session {
   int64_t* d_keys = nullptr;           // [cap_keys]
   uint32_t* d_miss_pos = nullptr;      // [cap_keys]
   int64_t* d_miss_keys = nullptr;      // [cap_keys]
-  uint32_t* d_counters = nullptr;      // [T] miss counts, [T..2T) inserted counts
+  uint32_t* d_counters = nullptr;      // [0,T) miss counts, [T,2T) inserted (cumulative), [2T,3T) absent keys
   uint32_t* h_counters = nullptr;      // pinned mirror
   int64_t* h_miss_keys = nullptr;      // mapped pinned [cap_keys]: the probe kernels mirror miss keys here
   int64_t* hd_miss_keys = nullptr;     // device-visible address of h_miss_keys
@@ -105,6 +108,7 @@ struct hpsx_session {
   size_t pool_stage_rows = 0;
   size_t max_dim = 0;
   std::vector<cudaEvent_t> ev;         // 2 per table: probe start / stop
+  std::vector<cudaEvent_t> ev_pull;    // 1 per table: end of the direct-pull kernel
   hpsx_session_stats stats{};
   std::mutex mu;  // one lookup at a time per session (Triton guarantees it; tests may not)
 

@@ -1,5 +1,7 @@
 #include "host_ps.hpp"
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -127,8 +129,75 @@ HostTable::HostTable(size_t dim, float default_value, size_t num_partitions, siz
 }
 
 HostTable::~HostTable() {
-  for (auto& p : parts_)
-    for (float* s : p->slabs) std::free(s);
+  for (auto& p : parts_) {
+    for (size_t i = 0; i < p->slabs.size(); ++i) {
+      if (i < p->locked_bytes.size() && p->locked_bytes[i] != 0) cudaHostUnregister(p->slabs[i]);
+      std::free(p->slabs[i]);
+    }
+  }
+}
+
+bool HostTable::pagelock(std::string* err) {
+  std::unique_lock<std::shared_mutex> lk(rw_);
+  const size_t row_bytes = dim_ * sizeof(float);
+  const size_t rows_per_slab = static_cast<size_t>(1) << slab_shift_;
+  for (auto& pp : parts_) {
+    Partition& p = *pp;
+    p.locked_bytes.resize(p.slabs.size(), 0);
+    p.slab_device.resize(p.slabs.size(), nullptr);
+    for (size_t i = 0; i < p.slabs.size(); ++i) {
+      const size_t used_rows = std::min(rows_per_slab, p.rows_used - std::min(p.rows_used, i * rows_per_slab));
+      const size_t want = (used_rows * row_bytes + 4095) & ~static_cast<size_t>(4095);
+      if (want == 0 || want <= p.locked_bytes[i]) continue;
+      if (p.locked_bytes[i] != 0) {
+        cudaHostUnregister(p.slabs[i]);
+        p.locked_bytes[i] = 0;
+      }
+      cudaError_t e = cudaHostRegister(p.slabs[i], want, cudaHostRegisterMapped | cudaHostRegisterPortable);
+      void* dev = nullptr;
+      if (e == cudaSuccess) e = cudaHostGetDevicePointer(&dev, p.slabs[i], 0);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (err) *err = std::string("page-locking a host table slab failed: ") + cudaGetErrorString(e);
+        return false;
+      }
+      p.locked_bytes[i] = want;
+      p.slab_device[i] = static_cast<char*>(dev);
+    }
+  }
+  pagelocked_ = true;
+  return true;
+}
+
+void HostTable::export_rows(size_t chunk,
+                            const std::function<void(const int64_t*, const uint64_t*, size_t)>& fn) const {
+  std::shared_lock<std::shared_mutex> lk(rw_);
+  std::vector<int64_t> keys;
+  std::vector<uint64_t> addrs;
+  keys.reserve(chunk);
+  addrs.reserve(chunk);
+  for (const auto& pp : parts_) {
+    const Partition& p = *pp;
+    for (const Slot& s : p.slots) {
+      if (s.key == kEmpty) continue;
+      keys.push_back(s.key);
+      addrs.push_back(row_device_addr(p, s.row));
+      if (keys.size() == chunk) {
+        fn(keys.data(), addrs.data(), keys.size());
+        keys.clear();
+        addrs.clear();
+      }
+    }
+  }
+  if (!keys.empty()) fn(keys.data(), addrs.data(), keys.size());
+}
+
+const float* HostTable::sentinel_row_device() const {
+  std::shared_lock<std::shared_mutex> lk(rw_);
+  for (const auto& pp : parts_)
+    if (pp->has_sentinel && !pp->slab_device.empty())
+      return reinterpret_cast<const float*>(row_device_addr(*pp, pp->sentinel_row));
+  return nullptr;
 }
 
 uint64_t HostTable::alloc_row(Partition& p) {

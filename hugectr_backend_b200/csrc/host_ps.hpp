@@ -81,6 +81,17 @@ class HostTable {
   // Pre-size the partition maps for `rows` more rows (avoids rehashing during bulk loads).
   void reserve(size_t rows);
 
+  // enable_pagelock (reference key: src/backend.cpp:506-511): page-lock the used part of every value
+  // slab and map it into the CUDA address space, so kernels can read rows straight from host DRAM
+  // ("direct pull").  Idempotent; call again after the table grew.  False + *err on failure.
+  bool pagelock(std::string* err);
+  bool pagelocked() const { return pagelocked_; }
+  // Visits every (key, device-visible row address) pair of a page-locked table in chunks of at most
+  // `chunk` rows (the key that doubles as the empty marker is reported by sentinel_row_device()).
+  void export_rows(size_t chunk,
+                   const std::function<void(const int64_t*, const uint64_t*, size_t)>& fn) const;
+  const float* sentinel_row_device() const;
+
  private:
   struct Slot {
     int64_t key;
@@ -90,6 +101,8 @@ class HostTable {
     std::vector<Slot> slots;  // open addressing, power-of-two capacity
     size_t count = 0;
     std::vector<float*> slabs;
+    std::vector<size_t> locked_bytes;   // page-locked prefix of every slab (0: not registered)
+    std::vector<char*> slab_device;     // device-visible base address of every registered slab
     size_t rows_used = 0;
     bool has_sentinel = false;  // row of the key that doubles as the empty marker
     uint64_t sentinel_row = 0;
@@ -100,6 +113,10 @@ class HostTable {
   size_t partition_of(uint64_t h) const { return ((h >> 32) * parts_.size()) >> 32; }
   float* row_ptr(const Partition& p, uint64_t row) const {
     return p.slabs[row >> slab_shift_] + (row & slab_mask_) * dim_;
+  }
+  uint64_t row_device_addr(const Partition& p, uint64_t row) const {
+    return reinterpret_cast<uint64_t>(p.slab_device[row >> slab_shift_]) +
+           (row & slab_mask_) * dim_ * sizeof(float);
   }
   // returns the row pointer of `key` in partition `p`, inserting a fresh row if absent
   float* upsert(Partition& p, int64_t key, uint64_t h);
@@ -117,6 +134,7 @@ class HostTable {
   mutable std::shared_mutex rw_;  // fetch: shared; insert/fill: exclusive
   std::vector<int64_t> load_order_;   // keys in the order insert() first saw them
   size_t procedural_rows_ = 0;        // fill_procedural(n): keys [0,n) precede load_order_
+  bool pagelocked_ = false;
 };
 
 }  // namespace hpsx

@@ -240,6 +240,44 @@ int build_cache(hpsx_ps* ps, Model* model, int device, std::unique_ptr<hpsx_cach
                                  d_stage, chunk, nullptr);
     }
   }
+  // enable_pagelock: page-lock the host tables and mirror their key -> row-address index in HBM, so
+  // that misses are pulled by kernels straight from host DRAM (no CPU gather, no staging copy)
+  if (rc == HPSX_OK && model->direct_pull) {
+    int64_t* d_ikeys = nullptr;
+    uint64_t* d_iaddrs = nullptr;
+    constexpr size_t kIndexChunk = 1 << 20;
+    HPSX_CU(cudaMalloc(&d_ikeys, kIndexChunk * sizeof(int64_t)));
+    HPSX_CU(cudaMalloc(&d_iaddrs, kIndexChunk * sizeof(uint64_t)));
+    for (size_t t = 0; t < T && rc == HPSX_OK; ++t) {
+      HostTable& ht = *model->tables[t];
+      std::string err;
+      if (!ht.pagelock(&err)) {
+        rc = fail(HPSX_ERR_CUDA, err);
+        break;
+      }
+      uint64_t cap = 1024;
+      while (cap < 2 * ht.rows()) cap <<= 1;
+      IndexSlot* slots = nullptr;
+      HPSX_CU(cudaMalloc(&slots, cap * sizeof(IndexSlot)));
+      c->indexes.push_back(slots);
+      HPSX_CU(launch_index_clear(slots, cap, stream));
+      cudaError_t ce = cudaSuccess;
+      ht.export_rows(kIndexChunk, [&](const int64_t* k, const uint64_t* a, size_t n) {
+        if (ce != cudaSuccess) return;
+        ce = cudaMemcpyAsync(d_ikeys, k, n * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_iaddrs, a, n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream);
+        if (ce == cudaSuccess) ce = launch_index_build(slots, cap - 1, d_ikeys, d_iaddrs, n, stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);  // the pageable vectors are reused
+      });
+      HPSX_CU(ce);
+      c->tables[t].index = slots;
+      c->tables[t].index_mask = cap - 1;
+      c->tables[t].sentinel_row = ht.sentinel_row_device();
+    }
+    cudaFree(d_ikeys);
+    cudaFree(d_iaddrs);
+    c->direct_pull = rc == HPSX_OK;
+  }
   cudaFree(d_inserted);
   cudaStreamDestroy(stream);
   if (rc != HPSX_OK) return rc;
@@ -377,11 +415,84 @@ void account_probe_time(hpsx_session* s, size_t t, size_t n) {
   }
 }
 
+// Direct-pull lookup (enable_pagelock): probe+gather, then one kernel that resolves the misses by
+// reading their rows straight from the page-locked host table over PCIe and inserting them.  The miss
+// list never leaves the device and the host waits exactly once, at the end.
+int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
+                      float* const* out_per_table, const size_t* n_per_table, size_t num_tables) {
+  hpsx_cache* c = s->cache;
+  const size_t T = s->model->tables.size();
+  const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  size_t total = 0;
+  for (size_t t = 0; t < num_tables; ++t) total += n_per_table[t];
+  ++s->stats.lookups;
+  s->stats.keys += total;
+  if (total == 0) return HPSX_OK;
+  for (size_t t = 0; t < num_tables; ++t)
+    if (n_per_table[t] != 0 && (!keys_per_table[t] || !out_per_table[t]))
+      return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
+
+  // the pull kernel rewrites cache slots: exclusive unless the cache is static (never inserts)
+  std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
+  std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
+  if (c->is_static) rlock.lock(); else wlock.lock();
+
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
+  size_t off = 0;
+  for (size_t t = 0; t < num_tables; ++t) {
+    const size_t n = n_per_table[t];
+    if (n == 0) continue;
+    const int64_t* d_keys;
+    if (keys_on_device) {
+      d_keys = static_cast<const int64_t*>(keys_per_table[t]);
+    } else {
+      HPSX_CU(cudaMemcpyAsync(s->d_keys + off, keys_per_table[t], n * sizeof(int64_t),
+                              cudaMemcpyHostToDevice, s->stream));
+      s->stats.h2d_bytes += n * sizeof(int64_t);
+      d_keys = s->d_keys + off;
+    }
+    HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
+    HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
+                                s->d_counters + t, s->d_miss_pos + off, s->d_miss_keys + off, nullptr,
+                                s->probe_variant, s->stream));
+    HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
+    HPSX_CU(launch_pull_misses(c->tables[t], s->d_miss_keys + off, s->d_miss_pos + off, s->d_counters + t, n,
+                               out_per_table[t], nullptr, !c->is_static, s->insert_mode,
+                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + T + t,
+                               s->d_counters + 2 * T + t, s->stream));
+    HPSX_CU(cudaEventRecord(s->ev_pull[t], s->stream));
+    s->stats.kernel_launches += 2;
+    off += n;
+  }
+  HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, 3 * T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  s->stats.d2h_bytes += 3 * T * sizeof(uint32_t);
+  for (size_t t = 0; t < num_tables; ++t) {
+    const size_t n = n_per_table[t];
+    if (n == 0) continue;
+    account_probe_time(s, t, n);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[2 * t + 1], s->ev_pull[t]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    const uint32_t m = s->h_counters[t];
+    s->stats.hits += n - m;
+    s->stats.misses += m;
+    const size_t row_bytes = s->model->tables[t]->dim() * sizeof(float);
+    const uint32_t absent = s->h_counters[2 * T + t];
+    s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * row_bytes;  // rows pulled over PCIe by the kernel
+    s->stats.default_filled += (m != 0 && !decide_sync(s, n, m)) ? m : absent;
+  }
+  return HPSX_OK;
+}
+
 int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
                float* const* out_per_table, const size_t* n_per_table, size_t num_tables) {
   hpsx_cache* c = s->cache;
   DeviceGuard guard(s->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  if (c->direct_pull)
+    return gpu_lookup_direct(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables);
   const size_t T = s->model->tables.size();
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
   size_t total = 0;
@@ -510,8 +621,19 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
         HPSX_CU(cudaMalloc(&s->d_pool_stage, static_cast<size_t>(m) * s->max_dim * sizeof(float)));
         s->pool_stage_rows = m;
       }
-      const int rc = stream_miss_rows(s, table, 0, m, nullptr, false, epoch, s->d_pool_stage, nullptr);
-      if (rc != HPSX_OK) return rc;
+      if (c->direct_pull) {
+        // rows pulled by the GPU straight from the page-locked host table into the stage
+        HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
+        HPSX_CU(launch_pull_misses(c->tables[table], s->d_miss_keys, s->d_miss_pos, s->d_counters + table, n,
+                                   nullptr, s->d_pool_stage, false, 1, 0.f, epoch, nullptr,
+                                   s->d_counters + 2 * T + table, s->stream));
+        ++s->stats.kernel_launches;
+        s->stats.misses += m;
+        s->stats.h2d_bytes += static_cast<uint64_t>(m) * s->model->tables[table]->dim() * sizeof(float);
+      } else {
+        const int rc = stream_miss_rows(s, table, 0, m, nullptr, false, epoch, s->d_pool_stage, nullptr);
+        if (rc != HPSX_OK) return rc;
+      }
     }
     HPSX_CU(cudaEventRecord(s->ev[2 * table], s->stream));
     HPSX_CU(launch_pooled_gather(c->tables[table], s->d_src, s->d_pool_stage, num_bags, hotness,
@@ -544,6 +666,7 @@ hpsx_cache::~hpsx_cache() {
       if (t.buckets) cudaFree(t.buckets);
       if (t.values) cudaFree(t.values);
     }
+    for (hpsx::IndexSlot* ix : indexes) cudaFree(ix);
     if (async_d_keys) cudaFree(async_d_keys);
     if (async_d_stage) cudaFree(async_d_stage);
     if (async_h_stage) cudaFreeHost(async_h_stage);
@@ -570,6 +693,7 @@ hpsx_session::~hpsx_session() {
       if (stage_free[b]) cudaEventDestroy(stage_free[b]);
     }
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_pull) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 }
@@ -648,6 +772,8 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
   std::unique_ptr<Model> m(new Model());
   m->cfg = cfg;
   m->load_factor = load_factor > 0.f ? load_factor : 0.5f;
+  m->direct_pull = cfg.enable_pagelock;
+  if (const char* env = std::getenv("HPSX_DIRECT_PULL")) m->direct_pull = env[0] == '1';
   for (size_t t = 0; t < T; ++t) {
     if (cfg.embedding_vecsize_per_table[t] == 0)
       return fail(HPSX_ERR_INVALID_ARG, "embedding_vecsize_per_table must be > 0");
@@ -705,6 +831,7 @@ int hpsx_ps_add_model(hpsx_ps* ps, const hpsx_model_params* p) {
   cfg.device_id = cfg.deployed_devices.back();
   cfg.embedding_cache_type = p->embedding_cache_type == HPSX_CACHE_STATIC ? CacheType::Static
                                                                           : CacheType::Dynamic;
+  cfg.enable_pagelock = p->enable_pagelock != 0;
   return add_model_cfg(ps, cfg, p->cache_load_factor);
   HPSX_GUARD_END
 }
@@ -803,6 +930,7 @@ int hpsx_ps_get_model_params(hpsx_ps* ps, const char* model, hpsx_model_params* 
   out->num_deployed_devices = c.deployed_devices.size();
   out->embedding_cache_type = c.embedding_cache_type == CacheType::Static ? HPSX_CACHE_STATIC : HPSX_CACHE_DYNAMIC;
   out->cache_load_factor = m->load_factor;
+  out->enable_pagelock = c.enable_pagelock ? 1 : 0;
   return HPSX_OK;
 }
 
@@ -994,9 +1122,9 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   HPSX_CU(cudaMalloc(&s->d_keys, cap * sizeof(int64_t)));
   HPSX_CU(cudaMalloc(&s->d_miss_pos, cap * sizeof(uint32_t)));
   HPSX_CU(cudaMalloc(&s->d_miss_keys, cap * sizeof(int64_t)));
-  HPSX_CU(cudaMalloc(&s->d_counters, 2 * T * sizeof(uint32_t)));
-  HPSX_CU(cudaMallocHost(&s->h_counters, 2 * T * sizeof(uint32_t)));
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 2 * T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMalloc(&s->d_counters, 3 * T * sizeof(uint32_t)));
+  HPSX_CU(cudaMallocHost(&s->h_counters, 3 * T * sizeof(uint32_t)));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * T * sizeof(uint32_t), s->stream));
   // miss keys are written by the probe kernels straight into this mapped buffer (zero-copy)
   HPSX_CU(cudaHostAlloc(&s->h_miss_keys, cap * sizeof(int64_t),
                         cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1010,6 +1138,8 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * T);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
+  s->ev_pull.resize(T);
+  for (auto& e : s->ev_pull) HPSX_CU(cudaEventCreate(&e));
   *out = s.release();
   return HPSX_OK;
   HPSX_GUARD_END

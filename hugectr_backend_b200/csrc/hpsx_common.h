@@ -27,6 +27,14 @@ struct alignas(128) Bucket {
 };
 static_assert(sizeof(Bucket) == 128, "bucket must be one 128-B line");
 
+// One slot of the HBM-resident index of a page-locked host table ("direct pull" mode): key -> address
+// of the row in mapped pinned host memory.  Open addressing, linear probing, power-of-two capacity.
+struct alignas(16) IndexSlot {
+  int64_t key;           // kEmptyKey = free
+  const float* row;      // device-visible address of the row in host memory
+};
+static_assert(sizeof(IndexSlot) == 16, "index slot must be 16 B");
+
 // murmur3 64-bit finalizer.
 HPSX_HD uint64_t mix64(uint64_t h) {
   h ^= h >> 33;

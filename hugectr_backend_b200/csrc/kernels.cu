@@ -387,6 +387,55 @@ struct InsertArgs {
   uint32_t* inserted;
 };
 
+// Claims the cache slot for `key` in its bucket.  Called by a whole warp; returns with the bucket lock
+// HELD (release_bucket() must follow) and the way to write, or -1 when the key is already resident
+// (LRU refreshed) or no way may be evicted (every way was touched in this very epoch).
+__device__ __forceinline__ int claim_way(Bucket* B, int64_t key, uint32_t epoch, uint32_t lane) {
+  if (lane == 0) {
+    while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
+    __threadfence();
+  }
+  __syncwarp();
+  int64_t k = kEmptyKey;
+  uint32_t st = epoch;
+  if (lane < kWays) {
+    k = __ldcg(reinterpret_cast<const long long*>(&B->keys[lane]));
+    st = __ldcg(&B->stamp[lane]);
+  }
+  const unsigned present = __ballot_sync(kFull, lane < kWays && k == key);
+  if (present != 0u) {
+    if (lane == 0) B->stamp[__ffs(present) - 1] = epoch;  // already cached: refresh LRU only
+    return -1;
+  }
+  int way = -1;
+  const unsigned empties = __ballot_sync(kFull, lane < kWays && k == kEmptyKey);
+  if (empties != 0u) {
+    way = __ffs(empties) - 1;
+  } else {
+    // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted
+    const uint32_t age = lane < kWays ? epoch - st : 0u;
+    unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
+      packed = o > packed ? o : packed;
+    }
+    packed = __shfl_sync(kFull, packed, 0);
+    if ((packed >> 8) != 0ull) way = 255 - static_cast<int>(packed & 255ull);
+  }
+  if (way >= 0 && lane == 0) {
+    B->keys[way] = key;
+    B->stamp[way] = epoch;
+  }
+  return way;
+}
+
+__device__ __forceinline__ void release_bucket(Bucket* B, uint32_t lane) {
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(&B->lock, 0u);
+}
+
 template <typename VecT>
 __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -403,45 +452,9 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
     if (a.insert && key != kEmptyKey) {
       const uint32_t b = bucket_of(key, a.num_buckets);
       B = &a.buckets[b];
-      if (lane == 0) {
-        while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
-        __threadfence();
-      }
-      __syncwarp();
-      int64_t k = kEmptyKey;
-      uint32_t st = a.epoch;
-      if (lane < kWays) {
-        k = __ldcg(reinterpret_cast<const long long*>(&B->keys[lane]));
-        st = __ldcg(&B->stamp[lane]);
-      }
-      const unsigned present = __ballot_sync(kFull, lane < kWays && k == key);
-      int way = -1;
-      if (present != 0u) {
-        if (lane == 0) B->stamp[__ffs(present) - 1] = a.epoch;  // already cached: refresh LRU only
-      } else {
-        const unsigned empties = __ballot_sync(kFull, lane < kWays && k == kEmptyKey);
-        if (empties != 0u) {
-          way = __ffs(empties) - 1;
-        } else {
-          // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted
-          const uint32_t age = lane < kWays ? a.epoch - st : 0u;
-          unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
-#pragma unroll
-          for (int off = 4; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
-            packed = o > packed ? o : packed;
-          }
-          packed = __shfl_sync(kFull, packed, 0);
-          if ((packed >> 8) != 0ull) way = 255 - static_cast<int>(packed & 255ull);
-        }
-        if (way >= 0) {
-          dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
-          if (lane == 0) {
-            B->keys[way] = key;
-            B->stamp[way] = a.epoch;
-          }
-        }
-      }
+      const int way = claim_way(B, key, a.epoch, lane);
+      if (way >= 0)
+        dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
     }
     for (uint32_t v = lane; v < V; v += 32u) {
       const VecT x = src[v];
@@ -449,13 +462,144 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
       if (dst_slab) dst_slab[v] = x;
     }
     if (B != nullptr) {
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        atomicExch(&B->lock, 0u);
-        if (dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
-      }
+      release_bucket(B, lane);
+      if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// direct pull: index of the page-locked host table in HBM, rows read zero-copy over PCIe
+// ------------------------------------------------------------------------------------------------
+__global__ void index_clear_kernel(IndexSlot* slots, uint64_t capacity) {
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < capacity) {
+    // one 16-B store per slot
+    const unsigned long long e = static_cast<unsigned long long>(kEmptyKey);
+    *reinterpret_cast<uint4*>(&slots[i]) =
+        make_uint4(static_cast<uint32_t>(e), static_cast<uint32_t>(e >> 32), 0u, 0u);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) index_build_kernel(IndexSlot* slots, uint64_t mask,
+                                                             const int64_t* __restrict__ keys,
+                                                             const uint64_t* __restrict__ rows, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int64_t key = keys[i];
+  if (key == kEmptyKey) return;  // carried separately (DeviceTable::sentinel_row)
+  uint64_t slot = mix64(static_cast<uint64_t>(key)) & mask;
+  while (true) {
+    const unsigned long long prev =
+        atomicCAS(reinterpret_cast<unsigned long long*>(&slots[slot].key),
+                  static_cast<unsigned long long>(kEmptyKey), static_cast<unsigned long long>(key));
+    if (prev == static_cast<unsigned long long>(kEmptyKey) || prev == static_cast<unsigned long long>(key)) {
+      slots[slot].row = reinterpret_cast<const float*>(rows[i]);
+      return;
+    }
+    slot = (slot + 1) & mask;
+  }
+}
+
+// Warp-cooperative index lookup: 8 lanes read 8 consecutive slots (one 128-B line), the first match
+// before the first empty slot wins.  Returns the host row address or nullptr (key not in the table).
+__device__ __forceinline__ const float* index_find(const IndexSlot* __restrict__ index, uint64_t mask,
+                                                   int64_t key, uint32_t lane) {
+  uint64_t base = mix64(static_cast<uint64_t>(key)) & mask;
+  while (true) {
+    int64_t k = kEmptyKey;
+    unsigned long long row = 0;
+    if (lane < 8) {
+      const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(&index[(base + lane) & mask]));
+      k = static_cast<int64_t>((static_cast<unsigned long long>(raw.y) << 32) | raw.x);
+      row = (static_cast<unsigned long long>(raw.w) << 32) | raw.z;
+    }
+    const unsigned hit = __ballot_sync(kFull, lane < 8 && k == key);
+    const unsigned empty = __ballot_sync(kFull, lane < 8 && k == kEmptyKey);
+    if (hit != 0u && (empty == 0u || __ffs(hit) < __ffs(empty)))
+      return reinterpret_cast<const float*>(__shfl_sync(kFull, row, __ffs(hit) - 1));
+    if (empty != 0u) return nullptr;
+    base = (base + 8) & mask;
+  }
+}
+
+struct PullArgs {
+  Bucket* buckets;
+  float* values;
+  uint32_t num_buckets;
+  uint32_t dim;
+  float default_value;
+  const IndexSlot* index;
+  uint64_t index_mask;
+  const float* sentinel_row;
+  const int64_t* miss_keys;
+  const uint32_t* miss_pos;
+  const uint32_t* miss_count;
+  uint32_t n_keys;
+  float* out;
+  float* stage;
+  int insert;
+  int insert_mode;
+  float hit_rate_threshold;
+  uint32_t epoch;
+  uint32_t* inserted;
+  uint32_t* absent;
+};
+
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  const uint32_t m = *a.miss_count;
+  bool sync_mode = a.insert_mode != 0;
+  if (a.insert_mode < 0) {
+    // [UPSTREAM] hit_rate < hit_rate_threshold -> synchronous insertion; decided here, on the device
+    const double hit_rate = 1.0 - static_cast<double>(m) / static_cast<double>(a.n_keys);
+    sync_mode = hit_rate < static_cast<double>(a.hit_rate_threshold);
+  }
+  const bool write_out = a.out != nullptr && sync_mode;
+  const VecT defv = splat<VecT>(a.default_value);
+  for (size_t i = warp; i < m; i += nwarps) {
+    const int64_t key = a.miss_keys[i];
+    const float* row = key == kEmptyKey ? a.sentinel_row : index_find(a.index, a.index_mask, key, lane);
+    const VecT* src = reinterpret_cast<const VecT*>(row);
+    // issue the PCIe reads first: they are the long pole (~2 us), the bucket claim overlaps them
+    VecT x0 = defv, x1 = defv;
+    if (src != nullptr) {
+      if (lane < V) x0 = ld_stream(src + lane);
+      if (lane + 32u < V) x1 = ld_stream(src + lane + 32u);
+    }
+    VecT* dst_out =
+        write_out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
+    VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
+    VecT* dst_slab = nullptr;
+    Bucket* B = nullptr;
+    if (a.insert && src != nullptr && key != kEmptyKey) {
+      const uint32_t b = bucket_of(key, a.num_buckets);
+      B = &a.buckets[b];
+      const int way = claim_way(B, key, a.epoch, lane);
+      if (way >= 0)
+        dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+    }
+    for (uint32_t v = lane; v < V; v += 32u) {
+      VecT x;
+      if (v == lane)
+        x = x0;
+      else if (v == lane + 32u)
+        x = x1;
+      else
+        x = src != nullptr ? ld_stream(src + v) : defv;
+      if (dst_out) st_stream(dst_out + v, x);
+      if (dst_stage) dst_stage[v] = x;
+      if (dst_slab) dst_slab[v] = x;
+    }
+    if (B != nullptr) {
+      release_bucket(B, lane);
+      if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+    }
+    if (lane == 0 && src == nullptr && a.absent != nullptr) atomicAdd(a.absent, 1u);
   }
 }
 
@@ -869,6 +1013,62 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
     insert_merge_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
   else
     insert_merge_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys, const uint32_t* d_miss_pos,
+                               const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
+                               bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
+                               uint32_t* d_inserted, uint32_t* d_absent, cudaStream_t stream) {
+  if (n_keys == 0) return cudaSuccess;
+  if (t.index == nullptr) return cudaErrorInvalidValue;
+  PullArgs a{};
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.dim = t.dim;
+  a.default_value = t.default_value;
+  a.index = t.index;
+  a.index_mask = t.index_mask;
+  a.sentinel_row = t.sentinel_row;
+  a.miss_keys = d_miss_keys;
+  a.miss_pos = d_miss_pos;
+  a.miss_count = d_miss_count;
+  a.n_keys = static_cast<uint32_t>(n_keys);
+  a.out = d_out;
+  a.stage = d_stage;
+  a.insert = insert ? 1 : 0;
+  a.insert_mode = insert_mode;
+  a.hit_rate_threshold = hit_rate_threshold;
+  a.epoch = epoch;
+  a.inserted = d_inserted;
+  a.absent = d_absent;
+  // The miss count is only known on the device: a fixed grid of 4 CTAs per SM loops over the list.
+  // PCIe needs ~100 KB in flight (51 GB/s x ~2 us); 4736 warps x 512 B is far more than enough.
+  const size_t warps_needed = n_keys;
+  const unsigned grid = static_cast<unsigned>(
+      min(static_cast<size_t>(148 * 4), (warps_needed * 32 + kBlock - 1) / kBlock));
+  // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
+  const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
+  if (vb == 16)
+    pull_misses_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 8)
+    pull_misses_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+  else
+    pull_misses_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t stream) {
+  if (capacity == 0) return cudaSuccess;
+  index_clear_kernel<<<grid_for(capacity), kBlock, 0, stream>>>(slots, capacity);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_build(IndexSlot* slots, uint64_t mask, const int64_t* d_keys,
+                               const uint64_t* d_row_addrs, size_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  index_build_kernel<<<grid_for(n), kBlock, 0, stream>>>(slots, mask, d_keys, d_row_addrs, n);
   return cudaGetLastError();
 }
 

@@ -15,6 +15,10 @@ struct DeviceTable {
   uint32_t num_buckets = 0;
   uint32_t dim = 0;            // floats per row
   float default_value = 0.f;
+  // direct-pull mode (enable_pagelock): index of the whole host table, rows read over PCIe by kernels
+  const IndexSlot* index = nullptr;  // [index_mask + 1]
+  uint64_t index_mask = 0;
+  const float* sentinel_row = nullptr;  // row of the key that doubles as the empty marker, if loaded
 };
 
 constexpr uint32_t kMissSlot = 0xFFFFFFFFu;
@@ -49,6 +53,25 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
                                 const uint32_t* d_miss_pos, const float* d_stage, size_t m,
                                 float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
                                 cudaStream_t stream);
+
+// Direct pull (K4+K5 without the CPU): for every miss i in [0, *d_miss_count): find the key in the
+// HBM-resident index of the page-locked host table, read the row straight from mapped pinned host
+// memory (zero-copy over PCIe), then merge it into out[pos[i]] (when `d_out` and the lookup runs in
+// synchronous-insertion mode), keep it in stage[i] (when `d_stage`), and insert it into the cache
+// (when `insert`).  Keys absent from the host table get the default vector and are counted in
+// *d_absent.  The miss count stays on the device: no host round trip between probe and pull.
+// insert_mode: 1 synchronous, 0 asynchronous semantics (misses keep the default vector in `out`),
+// -1 decide on the device: synchronous iff 1 - m/n < hit_rate_threshold.
+cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys, const uint32_t* d_miss_pos,
+                               const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
+                               bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
+                               uint32_t* d_inserted, uint32_t* d_absent, cudaStream_t stream);
+
+// Adds (key -> host row address) pairs to a direct-pull index.  Slots must have been cleared with
+// launch_index_clear.  Duplicated keys keep the last address written.
+cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t stream);
+cudaError_t launch_index_build(IndexSlot* slots, uint64_t mask, const int64_t* d_keys,
+                               const uint64_t* d_row_addrs, size_t n, cudaStream_t stream);
 
 // a8: pooled[b*dim..) = sum_{j<hotness} row(src[b*hotness+j]) (mean: / hotness), ascending j, fp32.
 // Rows come from the cache slab or (kSrcMissBit) from the staged miss rows.

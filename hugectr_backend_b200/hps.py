@@ -50,6 +50,7 @@ class ModelParams:
     deployed_devices: Sequence[int] = field(default_factory=lambda: [0])
     embedding_cache_type: str = "dynamic"
     cache_load_factor: float = 0.0
+    enable_pagelock: bool = False
 
 
 @dataclass
@@ -140,6 +141,7 @@ class HPS:
         c.num_deployed_devices = len(p.deployed_devices)
         c.embedding_cache_type = 1 if p.embedding_cache_type.lower() == "static" else 0
         c.cache_load_factor = p.cache_load_factor
+        c.enable_pagelock = 1 if p.enable_pagelock else 0
         N.check(self._L.hpsx_ps_add_model(self._h, ctypes.byref(c)))
         self._dims[p.model_name] = [int(v) for v in p.embedding_vecsize_per_table]
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HPSX_ABI_VERSION 1
+#define HPSX_ABI_VERSION 2
 
 typedef enum hpsx_status {
   HPSX_OK = 0,
@@ -72,6 +72,11 @@ typedef struct hpsx_model_params {
   int embedding_cache_type;                /* hpsx_cache_type               :479-492 */
   /* engine extensions (not in the reference config; 0 selects the default) */
   float cache_load_factor;                 /* slots = gpucacheper*rows/load_factor, default 0.5 */
+  int enable_pagelock;                     /* "enable_pagelock"             :506-511.  Page-locks the host
+                                              tables; this engine then resolves cache misses on the GPU:
+                                              kernels read the missing rows straight from host DRAM over
+                                              PCIe through an HBM-resident key index ("direct pull"),
+                                              instead of CPU gather + cudaMemcpyAsync */
 } hpsx_model_params;
 
 /* ~ HugeCTR::VolatileDatabaseParams, hash_map / parallel_hash_map only (src/backend.cpp:129-216). */

@@ -88,6 +88,7 @@ struct TRITONBACKEND_Output {
   TRITONSERVER_MemoryType mt = TRITONSERVER_MEMORY_CPU;
   int64_t mt_id = 0;
   bool owned = false;
+  TRITONBACKEND_Request* request = nullptr;
 };
 struct TRITONBACKEND_Response {
   TRITONBACKEND_Request* request = nullptr;
@@ -420,17 +421,15 @@ TRITONSERVER_Error* TRITONBACKEND_ResponseOutput(TRITONBACKEND_Response* respons
   o->name = name ? name : "";
   o->dtype = datatype;
   o->shape.assign(shape, shape + dims_count);
+  o->request = response->request;
   *output = o;
   return nullptr;
 }
 TRITONSERVER_Error* TRITONBACKEND_OutputBuffer(TRITONBACKEND_Output* o, void** buffer,
                                                const uint64_t buffer_byte_size, TRITONSERVER_MemoryType* memory_type,
                                                int64_t* memory_type_id) {
-  TRITONBACKEND_Request* req = nullptr;
-  // find the owning request through the response list is not possible from the output alone; the
-  // harness keeps one in-flight map instead
-  extern thread_local TRITONBACKEND_Request* ft_current_request;
-  req = ft_current_request;
+  // the output's owning request: the one whose ResponseOutput call created it
+  TRITONBACKEND_Request* req = o->request;
   if (req != nullptr && req->fail_output_buffer)
     return new_error(TRITONSERVER_ERROR_INTERNAL, "fake_triton: output buffer allocation failed (injected)");
   TRITONSERVER_MemoryType want = *memory_type;
@@ -458,8 +457,6 @@ TRITONSERVER_Error* TRITONBACKEND_OutputBuffer(TRITONBACKEND_Output* o, void** b
   *memory_type_id = o->mt_id;
   return nullptr;
 }
-thread_local TRITONBACKEND_Request* ft_current_request = nullptr;
-
 TRITONSERVER_Error* TRITONBACKEND_ResponseSetIntParameter(TRITONBACKEND_Response* response, const char* name,
                                                           const int64_t value) {
   if (response == nullptr) return new_error(TRITONSERVER_ERROR_INVALID_ARG, "null response");
@@ -622,16 +619,9 @@ void ft_request_set_gpu_output(TRITONBACKEND_Request* r, void* d_ptr, uint64_t c
 void ft_request_force_output_memory(TRITONBACKEND_Request* r, int memory_type) { r->force_output_memory = memory_type; }
 void ft_request_fail_output_buffer(TRITONBACKEND_Request* r, int fail) { r->fail_output_buffer = fail != 0; }
 
-// Runs TRITONBACKEND_ModelInstanceExecute.  The harness serves OutputBuffer calls from the request
-// whose turn it is: like the reference backend, ours handles requests one after another, and asks for
-// the output buffer of request r before touching request r+1, so the "current request" is tracked by
-// counting ResponseOutput/OutputBuffer pairs — simpler: requests are executed one call at a time when a
-// per-request output policy is needed.
+// Runs TRITONBACKEND_ModelInstanceExecute on `n` requests (one call, like Triton's scheduler).
 int ft_execute(TRITONBACKEND_ModelInstance* i, TRITONBACKEND_Request** reqs, uint32_t n) {
-  ft_current_request = (n == 1) ? reqs[0] : nullptr;
-  TRITONSERVER_Error* e = i->model->backend->execute(i, reqs, n);
-  ft_current_request = nullptr;
-  return consume(e);
+  return consume(i->model->backend->execute(i, reqs, n));
 }
 
 int ft_request_released(TRITONBACKEND_Request* r) { return r->released; }

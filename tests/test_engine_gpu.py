@@ -22,6 +22,14 @@ def _torch():
     return torch
 
 
+@pytest.fixture(autouse=True, params=["staged", "direct"])
+def miss_path(request, monkeypatch):
+    """Every test runs with both miss paths: CPU gather + cudaMemcpyAsync staging (default) and the
+    GPU direct pull from page-locked host tables (enable_pagelock).  HPSX_DIRECT_PULL overrides ps.json."""
+    monkeypatch.setenv("HPSX_DIRECT_PULL", "1" if request.param == "direct" else "0")
+    return request.param
+
+
 def make_server(rows, dim, *, cache_pct=1.0, thr=1.0, default=0.5, max_batch=4096, maxq=1, static=False,
                 load_factor=0.0, name="m"):
     hps = hb.HPS(num_partitions=8)

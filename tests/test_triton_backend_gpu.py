@@ -1,0 +1,140 @@
+"""libtriton_hps.so end to end on the GPU, driven through the fake-Triton harness:
+TRITONBACKEND_ModelInstanceExecute -> hpsx C ABI -> sm_100a kernels writing straight into the "Triton"
+output buffer.  Parity against the CPU oracle is bit-exact (the path only copies fp32 rows).
+Reference flow: hps_backend/src/hps.cc:348-788, src/model_instance_state.cpp:176-197.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fake_triton as FT  # tests/fake_triton
+from oracle import hps_oracle as O
+from test_triton_backend_cpu import model_entry, ps_json, wdl_request, write_tables
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["staged", "direct"])
+def wdl_gpu(request, tmp_path, cuda_device):
+    dirs, tables = write_tables(str(tmp_path), [(500, 1), (20000, 16)])
+    entry = model_entry("wdl", dirs, [1, 16], [2, 26], gpucache=True, defaults=[0.0, 1.5], max_batch=1024,
+                        hit_rate_threshold=1.0, gpucacheper=0.3, enable_pagelock=(request.param == "direct"))
+    ps = ps_json(str(tmp_path / "ps.json"), [entry])
+    ref = []
+    for (keys, vecs), default in zip(tables, [0.0, 1.5]):
+        t = O.NumpyTable(vecs.shape[1], default)
+        t.insert(keys, vecs)
+        ref.append(t)
+    return ps, ref, tables
+
+
+def test_gpu_output_buffer_is_written_in_place(wdl_gpu):
+    import torch
+    ps, ref, tables = wdl_gpu
+    errors0 = FT.live_errors()
+    with FT.Backend(ps) as be:
+        model = be.model("wdl", FT.model_config("wdl", gpus=[0], max_batch_size=1024))
+        inst = model.instance(kind=FT.KIND_GPU, device=0)
+        rng = np.random.default_rng(0)
+        for samples in (10, 1, 1024, 333):
+            keys, numkeys = wdl_request(tables, samples, rng)
+            keys[::7] = 10**15 + np.arange(len(keys[::7]))  # keys in no table -> default vector
+            n_out = samples * 2 * 1 + samples * 26 * 16
+            out = torch.full((n_out + 64,), float("nan"), device="cuda")
+            r = inst.infer(keys, numkeys, gpu_out=out)
+            assert r.error_code is None, r.error_message
+            assert r.memory_type == FT.MEM_GPU and r.device_ptr == out.data_ptr() and r.shape == [n_out]
+            got = out.cpu().numpy()
+            assert np.array_equal(got[:n_out], O.request(ref, keys, numkeys.ravel()))
+            assert np.isnan(got[n_out:]).all()  # nothing written past the tensor
+            assert r.params == {"NumSample": samples, "DeviceID": 0} and r.sent == 1 and r.released == 1
+        inst.close()
+        model.close()
+    assert FT.live_errors() == errors0 and FT.live_messages() == 0
+
+
+def test_triton_may_hand_back_cpu_memory_for_the_output(wdl_gpu):
+    """OutputBuffer's memory type is only a preference (hps.cc:638-648): with a CPU buffer the rows are gathered on
+    the GPU and copied D2H (hps.cc:681-685)."""
+    ps, ref, tables = wdl_gpu
+    with FT.Backend(ps) as be:
+        model = be.model("wdl", FT.model_config("wdl", gpus=[0]))
+        inst = model.instance(kind=FT.KIND_GPU, device=0)
+        keys, numkeys = wdl_request(tables, 77, np.random.default_rng(4))
+        r = inst.infer(keys, numkeys)  # no GPU buffer offered -> harness answers with CPU memory
+        assert r.error_code is None, r.error_message
+        assert r.memory_type == FT.MEM_CPU
+        assert np.array_equal(r.data, O.request(ref, keys, numkeys.ravel()))
+        inst.close()
+        model.close()
+
+
+def test_inputs_already_in_gpu_memory_and_split_buffers(wdl_gpu):
+    import torch
+    ps, ref, tables = wdl_gpu
+    with FT.Backend(ps) as be:
+        model = be.model("wdl", FT.model_config("wdl", gpus=[0]))
+        inst = model.instance(kind=FT.KIND_GPU, device=0)
+        keys, numkeys = wdl_request(tables, 50, np.random.default_rng(8))
+        expect = O.request(ref, keys, numkeys.ravel())
+        out = torch.empty(len(expect), device="cuda")
+        d_keys = torch.from_numpy(keys).cuda()
+        d_nk = torch.from_numpy(numkeys).cuda()
+        r = inst.infer(keys, numkeys, gpu_out=out, keys_device_ptr=d_keys.data_ptr(), numkeys_device_ptr=d_nk.data_ptr())
+        assert r.error_code is None, r.error_message
+        assert np.array_equal(out.cpu().numpy(), expect)
+        out.zero_()
+        r = inst.infer(keys, numkeys, gpu_out=out, key_buffers=5)
+        assert r.error_code is None and np.array_equal(out.cpu().numpy(), expect)
+        inst.close()
+        model.close()
+
+
+def test_two_instances_share_one_cache_and_errors_stay_per_request(wdl_gpu):
+    import threading
+    import torch
+    ps, ref, tables = wdl_gpu
+    with FT.Backend(ps) as be:
+        cfg = FT.model_config("wdl", gpus=[0], count=2)
+        model = be.model("wdl", cfg)
+        insts = [model.instance(name=f"wdl_0_{i}", kind=FT.KIND_GPU, device=0) for i in range(2)]
+        results = {}
+
+        def work(i):
+            rng = np.random.default_rng(100 + i)
+            ok = True
+            for _ in range(20):
+                keys, numkeys = wdl_request(tables, 64, rng)
+                out = torch.empty(64 * 2 + 64 * 26 * 16, device="cuda")
+                r = insts[i].infer(keys, numkeys, gpu_out=out)
+                ok &= r.error_code is None and np.array_equal(out.cpu().numpy(), O.request(ref, keys, numkeys.ravel()))
+            results[i] = ok
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        assert results == {0: True, 1: True}
+        # an oversize request fails alone; the instance keeps serving
+        big_keys, big_nk = wdl_request(tables, 1025, np.random.default_rng(1))
+        r = insts[0].infer(big_keys, big_nk)
+        assert r.error_code == FT.ERR["UNSUPPORTED"]
+        keys, numkeys = wdl_request(tables, 3, np.random.default_rng(2))
+        r = insts[0].infer(keys, numkeys)
+        assert r.error_code is None and np.array_equal(r.data, O.request(ref, keys, numkeys.ravel()))
+        for i in insts:
+            i.close()
+        model.close()
+
+
+def test_instance_on_undeployed_device_is_rejected(wdl_gpu):
+    ps, _, _ = wdl_gpu
+    with FT.Backend(ps) as be:
+        model = be.model("wdl", FT.model_config("wdl", gpus=[0]))
+        with pytest.raises(FT.TritonError) as e:
+            model.instance(kind=FT.KIND_GPU, device=5)
+        assert e.value.code == FT.ERR["INVALID_ARG"]
+        with pytest.raises(FT.TritonError):
+            model.instance(kind=FT.KIND_CPU, device=0)
+        model.close()

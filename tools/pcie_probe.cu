@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstdint>
 #include <vector>
+#include <sys/mman.h>
+#include <cstring>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
 
 __global__ void gather_rows(const float4* __restrict__ table, const uint32_t* __restrict__ idx, size_t n, int V,
@@ -51,6 +53,30 @@ int main(int argc, char** argv) {
       CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
     }
     printf("zero-copy gather %zu x 512 B, %d blocks: %.3f ms  %.1f GB/s\n", n, blocks, ms, bytes / ms / 1e6);
+  }
+  // registered (not cudaHostAlloc'd) tables, 4 GiB, with and without transparent huge pages
+  {
+    FILE* f = fopen("/sys/kernel/mm/transparent_hugepage/enabled", "r");
+    char buf[128] = {0};
+    if (f) { fgets(buf, 127, f); fclose(f); }
+    printf("THP: %s", buf[0] ? buf : "unknown\n");
+  }
+  for (int mode = 0; mode < 2; ++mode) {
+    const size_t big_rows = 1 << 23;  // 8 Mi rows x 512 B = 4 GiB
+    void* mem = nullptr;
+    if (posix_memalign(&mem, mode ? (2u << 20) : 4096, big_rows * V * 16) != 0) { printf("alloc failed\n"); break; }
+    if (mode) madvise(mem, big_rows * V * 16, MADV_HUGEPAGE);
+    memset(mem, 1, big_rows * V * 16);
+    CK(cudaHostRegister(mem, big_rows * V * 16, cudaHostRegisterMapped | cudaHostRegisterPortable));
+    float4* dev; CK(cudaHostGetDevicePointer((void**)&dev, mem, 0));
+    for (auto& x : idx) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (uint32_t)(s % big_rows); }
+    CK(cudaMemcpy(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice));
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0)); gather_rows<<<592, 256>>>(dev, d_idx, n, V, d_out); CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    printf("zero-copy gather from cudaHostRegister'd 4 GiB (%s): %.3f ms  %.1f GB/s\n", mode ? "2M-aligned + MADV_HUGEPAGE" : "4K pages", ms, bytes / ms / 1e6);
+    CK(cudaHostUnregister(mem)); free(mem);
   }
   // small transfers: latency of a 16 KiB and a 1 MiB H2D
   for (size_t b : {16384ul, 1048576ul, 16777216ul}) {
