@@ -86,6 +86,7 @@ SYMBOLS = {
     "hpsx_ps_add_model": (_int, [_vp, ctypes.POINTER(ModelParamsC)]),
     "hpsx_ps_load_table": (_int, [_vp, _cp, _sz, _vp, _vp, _sz]),
     "hpsx_ps_load_table_procedural": (_int, [_vp, _cp, _sz, _sz, ctypes.c_uint64]),
+    "hpsx_ps_load_table_procedural_shard": (_int, [_vp, _cp, _sz, _sz, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]),
     "hpsx_ps_table_rows": (_int, [_vp, _cp, _sz, c_size_p]),
     "hpsx_ps_get_model_params": (_int, [_vp, _cp, ctypes.POINTER(ModelParamsC)]),
     "hpsx_ps_sync_models_from_json": (_int, [_vp, _cp, c_size_p]),
@@ -115,6 +116,7 @@ SYMBOLS = {
     "hpsx_cache_drain_async": (_int, [_vp]),
     "hpsx_unique": (_int, [_int, _vp, _sz, _vp, _vp, c_size_p, _vp]),
     "hpsx_owner": (ctypes.c_uint32, [ctypes.c_int64, ctypes.c_uint32]),
+    "hpsx_owner_batch": (_int, [_vp, _sz, ctypes.c_uint32, _vp]),
     "hpsx_route_keys": (_int, [_int, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]),
     "hpsx_scatter_rows": (_int, [_int, _vp, _vp, _sz, _sz, _vp, _vp]),
 }

@@ -300,33 +300,44 @@ void HostTable::insert(const int64_t* keys, const float* vectors, size_t n, Thre
   });
 }
 
-void HostTable::fill_procedural(size_t n, uint64_t seed, ThreadPool& pool) {
+void HostTable::fill_procedural(size_t n, uint64_t seed, ThreadPool& pool, uint32_t shard,
+                                uint32_t num_shards) {
   std::unique_lock<std::shared_mutex> lk(rw_);
-  procedural_rows_ = std::max(procedural_rows_, n);
+  const bool sharded = num_shards > 1;
+  if (!sharded) procedural_rows_ = std::max(procedural_rows_, n);
   const size_t P = parts_.size();
   {
-    const size_t per_part = n / P + n / (P * 8) + 64;
+    const size_t mine = sharded ? n / num_shards + n / (8 * num_shards) : n;
+    const size_t per_part = mine / P + mine / (P * 8) + 64;
     for (auto& pp : parts_)
       while ((pp->count + per_part) * 2 > pp->slots.size()) grow(*pp);
   }
   // pass 1 (one task per partition: the maps are not concurrent): claim a row for every key
-  std::vector<float*> dst(n);
+  std::vector<float*> dst(n, nullptr);
   pool.parallel_for(P, [&](size_t p) {
     Partition& part = *parts_[p];
     for (size_t k = 0; k < n; ++k) {
       const int64_t key = static_cast<int64_t>(k);
       const uint64_t h = mix64(static_cast<uint64_t>(key));
       if (partition_of(h) != p) continue;
+      if (sharded && owner_of(key, num_shards) != shard) continue;
       dst[k] = upsert(part, key, h);
     }
   });
+  if (sharded) {
+    // model-parallel shard: only the keys this shard owns exist here; they are also the warm-up order
+    for (size_t k = 0; k < n; ++k)
+      if (dst[k] != nullptr) load_order_.push_back(static_cast<int64_t>(k));
+  }
   // pass 2 (all threads): generate the rows
   constexpr size_t kRowsPerTask = 4096;
   pool.parallel_for((n + kRowsPerTask - 1) / kRowsPerTask, [&](size_t task) {
     const size_t e = std::min(n, (task + 1) * kRowsPerTask);
-    for (size_t k = task * kRowsPerTask; k < e; ++k)
+    for (size_t k = task * kRowsPerTask; k < e; ++k) {
+      if (dst[k] == nullptr) continue;
       for (size_t j = 0; j < dim_; ++j)
         dst[k][j] = synth_value(static_cast<int64_t>(k), static_cast<uint32_t>(j), seed);
+    }
   });
 }
 

@@ -68,7 +68,9 @@ class HostTable {
   // Insert or overwrite `n` rows (key file + vector file contents).
   void insert(const int64_t* keys, const float* vectors, size_t n, ThreadPool& pool);
   // keys [0,n) with synthetic rows, see hpsx_common.h synth_value().
-  void fill_procedural(size_t n, uint64_t seed, ThreadPool& pool);
+  // With num_shards > 1 only the keys whose owner_of(key, num_shards) == shard are loaded
+  // (model-parallel row sharding).
+  void fill_procedural(size_t n, uint64_t seed, ThreadPool& pool, uint32_t shard = 0, uint32_t num_shards = 1);
 
   // out[i*stride .. +dim) = row(keys[i]) or default.  Returns the number of absent keys.
   // Multi-threaded over key ranges; software-prefetched probe + row gather.

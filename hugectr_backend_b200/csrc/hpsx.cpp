@@ -93,6 +93,15 @@ bool trace_on() {
 // (docs/architecture.md:185-218; writer samples/hps-triton-ensemble/01_model_training.ipynb:498-505)
 // ------------------------------------------------------------------------------------------------
 int load_sparse_dir(hpsx_ps* ps, HostTable* table, const std::string& dir) {
+  // engine extension for benchmarks: "synthetic:rows=<N>,seed=<S>" names a procedural table
+  // (keys [0,N), rows from synth_value()) instead of a directory, so that a 10 M-row table needs no 5 GB file
+  if (dir.rfind("synthetic:", 0) == 0) {
+    unsigned long long rows = 0, seed = 0;
+    if (std::sscanf(dir.c_str(), "synthetic:rows=%llu,seed=%llu", &rows, &seed) != 2)
+      return fail(HPSX_ERR_INVALID_ARG, "malformed synthetic table spec '" + dir + "' (want synthetic:rows=<N>,seed=<S>)");
+    table->fill_procedural(static_cast<size_t>(rows), static_cast<uint64_t>(seed), *ps->pool);
+    return HPSX_OK;
+  }
   const std::string key_path = dir + "/key";
   const std::string vec_path = dir + "/emb_vector";
   struct stat ks {}, vs {};
@@ -901,6 +910,18 @@ int hpsx_ps_load_table_procedural(hpsx_ps* ps, const char* model, size_t table, 
   HPSX_GUARD_END
 }
 
+int hpsx_ps_load_table_procedural_shard(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
+                                        uint64_t seed, uint32_t shard, uint32_t num_shards) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (num_shards == 0 || shard >= num_shards) return fail(HPSX_ERR_INVALID_ARG, "shard must be < num_shards");
+  m->tables[table]->fill_procedural(num_rows, seed, *ps->pool, shard, num_shards);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
 int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_t* out) {
   Model* m = find_model(const_cast<hpsx_ps*>(ps), model);
   if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, "unknown model");
@@ -1376,6 +1397,13 @@ int hpsx_unique(int device, const int64_t* d_keys, size_t n, int64_t* d_unique, 
 }
 
 uint32_t hpsx_owner(int64_t key, uint32_t num_shards) { return owner_of(key, num_shards); }
+
+int hpsx_owner_batch(const int64_t* h_keys, size_t n, uint32_t num_shards, uint32_t* h_owners) {
+  if (n > 0 && (!h_keys || !h_owners)) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (num_shards == 0) return fail(HPSX_ERR_INVALID_ARG, "num_shards must be > 0");
+  for (size_t i = 0; i < n; ++i) h_owners[i] = owner_of(h_keys[i], num_shards);
+  return HPSX_OK;
+}
 
 int hpsx_route_keys(int device, const int64_t* d_keys, size_t n, uint32_t num_shards,
                     int64_t* d_routed_keys, uint32_t* d_perm, uint32_t* d_counts, uint32_t* h_counts,

@@ -153,6 +153,10 @@ class HPS:
     def load_table_procedural(self, model: str, table: int, rows: int, seed: int) -> None:
         N.check(self._L.hpsx_ps_load_table_procedural(self._h, model.encode(), table, rows, seed & ((1 << 64) - 1)))
 
+    def load_table_procedural_shard(self, model: str, table: int, rows: int, seed: int, shard: int, num_shards: int) -> None:
+        N.check(self._L.hpsx_ps_load_table_procedural_shard(self._h, model.encode(), table, rows,
+                                                            seed & ((1 << 64) - 1), shard, num_shards))
+
     def table_rows(self, model: str, table: int) -> int:
         n = ctypes.c_size_t()
         N.check(self._L.hpsx_ps_table_rows(self._h, model.encode(), table, ctypes.byref(n)))
@@ -276,6 +280,13 @@ def unique(device: int, d_keys, n: int, d_unique, d_inverse, stream: int = 0) ->
 
 def owner(key: int, num_shards: int) -> int:
     return int(N.lib().hpsx_owner(int(key), int(num_shards)))
+
+
+def owner_batch(keys: np.ndarray, num_shards: int) -> np.ndarray:
+    keys = np.ascontiguousarray(keys, dtype=np.int64).ravel()
+    out = np.empty(len(keys), dtype=np.uint32)
+    N.check(N.lib().hpsx_owner_batch(_addr(keys), len(keys), num_shards, _addr(out)))
+    return out
 
 
 def route_keys(device: int, d_keys, n: int, num_shards: int, d_routed, d_perm, d_counts, stream: int = 0) -> np.ndarray:

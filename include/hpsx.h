@@ -142,6 +142,10 @@ int hpsx_ps_load_table(hpsx_ps* ps, const char* model, size_t table, const int64
  *  — the synthetic table of the benchmark configs; no files needed. */
 int hpsx_ps_load_table_procedural(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
                                   uint64_t seed);
+/* Model-parallel variant: of the keys [0,num_rows) load only those with
+ * hpsx_owner(key, num_shards) == shard — one shard of a table too large for one GPU / one host. */
+int hpsx_ps_load_table_procedural_shard(hpsx_ps* ps, const char* model, size_t table, size_t num_rows,
+                                        uint64_t seed, uint32_t shard, uint32_t num_shards);
 int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_t* out);
 /* ~ get_hps_model_configuration_map().at(model) -> InferenceParams      src/backend.cpp:70-71, hps.cc:221-223
  * Fills `out` with pointers into the server's own storage; they stay valid until the server is
@@ -247,6 +251,8 @@ int hpsx_unique(int device, const int64_t* d_keys, size_t n, int64_t* d_unique, 
                 size_t* h_num_unique, void* stream);
 /* Shard routing of the model-parallel mode: owner(key) in [0, num_shards). */
 uint32_t hpsx_owner(int64_t key, uint32_t num_shards);
+/* Host-side batch form: h_owners[i] = hpsx_owner(h_keys[i], num_shards). */
+int hpsx_owner_batch(const int64_t* h_keys, size_t n, uint32_t num_shards, uint32_t* h_owners);
 /* Bucket `n` device keys by owner: d_counts[num_shards] (u32), d_perm[n] = original positions grouped
  * by owner (stable within a CTA-tile, unspecified across), d_routed_keys[n] = keys in that order.
  * h_counts receives the counts.  Synchronises `stream`. */
