@@ -1135,7 +1135,7 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   s->cache = c;
   s->device = device;
   if (const char* env = std::getenv("HPSX_PROBE"))
-    s->probe_variant = std::strcmp(env, "tma") == 0 ? kProbeTma : kProbeLdg;
+    s->probe_variant = std::strcmp(env, "tma") == 0 ? kProbeTma : (std::strcmp(env, "pipe") == 0 ? kProbePipe : kProbeLdg);
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -1354,7 +1354,7 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
 
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
-  if (variant != kProbeLdg && variant != kProbeTma)
+  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe)
     return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
   s->probe_variant = variant;
   return HPSX_OK;

@@ -190,6 +190,116 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2 pipelined variant.  Persistent grid (a multiple of the SM count); a warp strides over tiles and
+// software-pipelines the dependent chain key -> bucket -> rows across tiles: while it copies the rows
+// of tile t, the bucket lines of tile t+1 and the keys of tile t+2 are already in flight, so the two
+// latency hops at the head of a tile no longer idle the warp.
+// ------------------------------------------------------------------------------------------------
+struct BucketKeys {
+  longlong2 k01, k23, k45, k67;
+};
+
+__device__ __forceinline__ BucketKeys load_bucket_keys(const Bucket* __restrict__ buckets, uint32_t b) {
+  const longlong2* kp = reinterpret_cast<const longlong2*>(buckets[b].keys);
+  BucketKeys r;
+  r.k01 = __ldcg(kp + 0);
+  r.k23 = __ldcg(kp + 1);
+  r.k45 = __ldcg(kp + 2);
+  r.k67 = __ldcg(kp + 3);
+  return r;
+}
+
+__device__ __forceinline__ int match_way(const BucketKeys& k, int64_t key) {
+  int way = -1;
+  way = (k.k01.x == key) ? 0 : way;
+  way = (k.k01.y == key) ? 1 : way;
+  way = (k.k23.x == key) ? 2 : way;
+  way = (k.k23.y == key) ? 3 : way;
+  way = (k.k45.x == key) ? 4 : way;
+  way = (k.k45.y == key) ? 5 : way;
+  way = (k.k67.x == key) ? 6 : way;
+  way = (k.k67.y == key) ? 7 : way;
+  return way;
+}
+
+template <typename VecT, int kV, int kUnroll>
+__global__ void __launch_bounds__(kBlock) probe_gather_pipe_kernel(const ProbeArgs a) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp_global = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t total_warps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
+  const size_t num_tiles = (a.n + 31) / 32;
+  if (warp_global >= num_tiles) return;
+  constexpr uint32_t V = static_cast<uint32_t>(kV);
+  const VecT* __restrict__ vals = reinterpret_cast<const VecT*>(a.values);
+  const VecT defv = splat<VecT>(a.default_value);
+
+  auto load_key = [&](size_t tile) -> int64_t {
+    const size_t i = tile * 32 + lane;
+    return (tile < num_tiles && i < a.n) ? __ldcs(reinterpret_cast<const long long*>(a.keys) + i) : kEmptyKey;
+  };
+
+  size_t tile = warp_global;
+  int64_t key_cur = load_key(tile);
+  int64_t key_nxt = load_key(tile + total_warps);
+  uint32_t b_cur = bucket_of(key_cur, a.num_buckets);
+  BucketKeys bk_cur = load_bucket_keys(a.buckets, b_cur);
+  for (; tile < num_tiles; tile += total_warps) {
+    // stage A (tile t+1): bucket lines, (tile t+2): keys — in flight during the copy below
+    const uint32_t b_nxt = bucket_of(key_nxt, a.num_buckets);
+    const BucketKeys bk_nxt = load_bucket_keys(a.buckets, b_nxt);
+    const int64_t key_nn = load_key(tile + 2 * total_warps);
+
+    // stage B (tile t): resolve slots, claim miss-list space
+    const size_t tile_base = tile * 32;
+    const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), a.n - tile_base));
+    const bool valid = lane < nk;
+    uint32_t slot = kMissSlot;
+    if (valid && key_cur != kEmptyKey) {
+      const int way = match_way(bk_cur, key_cur);
+      if (way >= 0) {
+        slot = b_cur * kWays + static_cast<uint32_t>(way);
+        if (a.touch) a.buckets[b_cur].stamp[way] = a.epoch;
+      }
+    }
+    const bool is_miss = valid && slot == kMissSlot;
+    unsigned miss_mask;
+    const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+
+    // stage C (tile t): cooperative row copy, kUnroll independent 16-B loads per lane in flight
+    VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + tile_base * V;
+    const uint32_t total = nk * V;
+#pragma unroll 1
+    for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
+      VecT buf[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t i = i0 + u * 32u + lane;
+        const uint32_t kk = min(i / V, 31u);
+        const uint32_t s = __shfl_sync(kFull, slot, kk);
+        const uint32_t v = i - kk * V;
+        buf[u] = defv;
+        if (i < total && s != kMissSlot) buf[u] = ld_stream(vals + static_cast<size_t>(s) * V + v);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t i = i0 + u * 32u + lane;
+        if (i < total) st_stream(outv + i, buf[u]);
+      }
+    }
+    if (is_miss) {
+      const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
+      a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+      a.miss_keys[r] = key_cur;
+      if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key_cur;
+    }
+    key_cur = key_nxt;
+    key_nxt = key_nn;
+    b_cur = b_nxt;
+    bk_cur = bk_nxt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2 TMA variant: rows are staged global -> shared with cp.async.bulk (UBLKCP, the TMA engine's
 // 1-D path) and leave with ONE bulk store per tile, because the 32 output rows of a tile are
 // contiguous.  No row data passes through registers.  Ring of kStages tiles per warp-group-free
@@ -873,6 +983,43 @@ cudaError_t launch_probe_ldg_vec(const ProbeArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+// HPSX_PIPE_CFG="<unroll>x<ctas_per_sm>" tunes the pipelined variant (defaults 8x4).
+template <typename VecT>
+cudaError_t launch_probe_pipe(const ProbeArgs& a, cudaStream_t stream) {
+  static int cfg_u = 0, cfg_c = 0;
+  if (cfg_u == 0) {
+    cfg_u = 8;
+    cfg_c = 4;
+    if (const char* env = getenv("HPSX_PIPE_CFG")) {
+      int u = 0, c = 0;
+      if (sscanf(env, "%dx%d", &u, &c) == 2 && (u == 4 || u == 8) && c > 0 && c <= 8) {
+        cfg_u = u;
+        cfg_c = c;
+      }
+    }
+  }
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  const size_t num_tiles = (a.n + 31) / 32;
+  const unsigned grid = static_cast<unsigned>(
+      min(static_cast<size_t>(148 * cfg_c), (num_tiles * 32 + kBlock - 1) / kBlock));
+#define HPSX_PIPE(VV)                                                                   \
+  do {                                                                                  \
+    if (cfg_u == 4)                                                                     \
+      probe_gather_pipe_kernel<VecT, VV, 4><<<grid, kBlock, 0, stream>>>(a);            \
+    else                                                                                \
+      probe_gather_pipe_kernel<VecT, VV, 8><<<grid, kBlock, 0, stream>>>(a);            \
+    return cudaGetLastError();                                                          \
+  } while (0)
+  switch (V) {
+    case 32: HPSX_PIPE(32);
+    case 16: HPSX_PIPE(16);
+    case 8: HPSX_PIPE(8);
+    case 4: HPSX_PIPE(4);
+    default: return cudaErrorNotSupported;
+  }
+#undef HPSX_PIPE
+}
+
 template <int kWarps, int kStages>
 cudaError_t launch_probe_tma_cfg(const ProbeArgs& a, uint32_t tiles_per_warp, cudaStream_t stream) {
   const uint32_t row_bytes = a.dim * 4u;
@@ -953,6 +1100,10 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
   const int vb = vec_bytes(t.dim, d_out, t.values);
   if (variant == kProbeTma && vb == 16) {
     const cudaError_t e = launch_probe_tma(a, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  if (variant == kProbePipe && vb == 16) {
+    const cudaError_t e = launch_probe_pipe<float4>(a, stream);
     if (e != cudaErrorNotSupported) return e;
   }
   if (vb == 16) return launch_probe_ldg_vec<float4>(a, stream);

@@ -27,6 +27,7 @@ constexpr uint32_t kSrcMissBit = 0x80000000u;  // pooled path: src index refers 
 enum ProbeVariant : int {
   kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers
   kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
+  kProbePipe = 2, // persistent grid, key -> bucket -> rows chain software-pipelined across tiles
 };
 
 // K2+K3+K6 fused: probe the cache for keys[0..n), copy hit rows to out[i*dim..),

@@ -268,7 +268,7 @@ class LookupSession:
         N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
 
     def set_probe_variant(self, variant: str) -> None:
-        N.check(self._L.hpsx_session_set_probe_variant(self._h, 1 if variant == "tma" else 0))
+        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2}[variant]))
 
 
 # -- stand-alone device primitives ---------------------------------------------------------------

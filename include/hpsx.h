@@ -236,7 +236,8 @@ int hpsx_session_reset_stats(hpsx_session* s);
  * asynchronous (misses answered with the default vector), 1 always synchronous. */
 int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
 /* Select the probe+gather kernel: 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
- * staging through shared memory.  The environment variable HPSX_PROBE=ldg|tma sets the default. */
+ * staging through shared memory, 2 = persistent grid with the key->bucket->row chain software-pipelined
+ * across tiles.  The environment variable HPSX_PROBE=ldg|tma|pipe sets the default. */
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);

@@ -78,6 +78,23 @@ int main(int argc, char** argv) {
     printf("zero-copy gather from cudaHostRegister'd 4 GiB (%s): %.3f ms  %.1f GB/s\n", mode ? "2M-aligned + MADV_HUGEPAGE" : "4K pages", ms, bytes / ms / 1e6);
     CK(cudaHostUnregister(mem)); free(mem);
   }
+  {  // cudaHostAlloc'd 4 GiB: does the allocation method or the table size set the zero-copy rate?
+    const size_t big_rows = 1 << 23;
+    float4 *hb, *hbd;
+    CK(cudaHostAlloc(&hb, big_rows * V * 16, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&hbd, hb, 0));
+    memset(hb, 1, big_rows * V * 16);
+    for (auto& x : idx) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (uint32_t)(s % big_rows); }
+    CK(cudaMemcpy(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice));
+    for (int blocks : {592, 2368}) {
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0)); gather_rows<<<blocks, 256>>>(hbd, d_idx, n, V, d_out); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+      }
+      printf("zero-copy gather from cudaHostAlloc'd 4 GiB, %d blocks: %.3f ms  %.1f GB/s\n", blocks, ms, bytes / ms / 1e6);
+    }
+    CK(cudaFreeHost(hb));
+  }
   // small transfers: latency of a 16 KiB and a 1 MiB H2D
   for (size_t b : {16384ul, 1048576ul, 16777216ul}) {
     CK(cudaEventRecord(e0)); CK(cudaMemcpyAsync(d_out, h_stage, b, cudaMemcpyHostToDevice)); CK(cudaEventRecord(e1));
