@@ -192,6 +192,29 @@ def measure_host_link_gbs(torch) -> float:
     return best
 
 
+def measure_random_gather_gbs(torch, hb, local, n, dim, rows=4_000_000) -> float:
+    """Plain random gather of 512-B rows (no hashing, same launch shape): the practical HBM random-gather ceiling."""
+    from hugectr_backend_b200 import hps as H
+
+    if dim != 128:
+        return 0.0
+    table = torch.empty((rows, dim), device="cuda", dtype=torch.float32).normal_()
+    out = torch.empty((n, dim), device="cuda", dtype=torch.float32)
+    idx = [torch.randint(0, rows, (n,), device="cuda", dtype=torch.int32) for _ in range(4)]
+    for i in range(3):
+        H.gather_rows(local, table, idx[i], n, dim, out)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    reps = 10
+    for i in range(reps):
+        H.gather_rows(local, table, idx[i % 4], n, dim, out)  # launched on the legacy default stream = torch's current
+    e1.record()
+    e1.synchronize()
+    del table
+    return reps * n * (4 + 8 * dim) / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
 def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
     """Times a.steps requests through TRITONBACKEND_ModelInstanceExecute (tests/fake_triton plays the server)."""
     import tempfile
@@ -350,6 +373,11 @@ def run_ours(a):
                 "traffic_source": traffic_src, "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": probe_ms / (ms / a.steps),
                 "note": "the HBM-bound kernel of the path; the rest of the step is the PCIe-bound miss kernel, see roofline_host_link"}
+    ceiling = measure_random_gather_gbs(torch, hb, local, n, a.dim)
+    roofline["random_gather_ceiling_gbs"] = ceiling
+    roofline["frac_of_random_gather_ceiling"] = achieved / ceiling if ceiling > 0 else None
+    roofline["ceiling_note"] = ("plain out[i]=table[idx[i]] gather of 512-B rows from a 2 GB table with the same tile/unroll shape, "
+                                "measured in this run: what HBM3e delivers for random 512-B rows, vs `peak` = streaming copy")
     # the miss kernel is bound by the host link, not HBM: judge it against a pinned cudaMemcpyAsync measured here
     link_gbs = measure_host_link_gbs(torch)
     pull_ms = st.insert_kernel_ms / a.steps

@@ -109,6 +109,7 @@ SYMBOLS = {
     "hpsx_session_lookup_device_keys": (_int, [_vp, _vpp, _vpp, c_size_p, _sz]),
     "hpsx_session_lookup_pooled": (_int, [_vp, _sz, _vp, _sz, _sz, _int, _vp]),
     "hpsx_session_lookup_pooled_device_keys": (_int, [_vp, _sz, _vp, _sz, _sz, _int, _vp]),
+    "hpsx_session_lookup_pooled_ex": (_int, [_vp, _sz, _vp, _int, _sz, _sz, _int, _vp, _int]),
     "hpsx_session_get_stats": (_int, [_vp, ctypes.POINTER(SessionStatsC)]),
     "hpsx_session_reset_stats": (_int, [_vp]),
     "hpsx_session_set_insert_mode": (_int, [_vp, _int]),
@@ -118,6 +119,7 @@ SYMBOLS = {
     "hpsx_owner": (ctypes.c_uint32, [ctypes.c_int64, ctypes.c_uint32]),
     "hpsx_owner_batch": (_int, [_vp, _sz, ctypes.c_uint32, _vp]),
     "hpsx_route_keys": (_int, [_int, _vp, _sz, ctypes.c_uint32, _vp, _vp, _vp, _vp, _vp]),
+    "hpsx_gather_rows": (_int, [_int, _vp, _vp, _sz, _sz, _vp, _vp]),
     "hpsx_scatter_rows": (_int, [_int, _vp, _vp, _sz, _sz, _vp, _vp]),
 }
 

@@ -1311,6 +1311,73 @@ int hpsx_session_lookup_pooled_device_keys(hpsx_session* s, size_t table, const 
   HPSX_GUARD_END
 }
 
+// CPU session: rows fetched from the host table chunk by chunk and reduced in ascending slot order in
+// fp32 — the same order as the oracle and the pooled kernel.
+static int cpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, size_t num_bags, size_t hotness,
+                             int combiner, float* pooled) {
+  const HostTable& ht = *s->model->tables[table];
+  const size_t dim = ht.dim();
+  constexpr size_t kChunkBags = 4096;
+  std::vector<float> rows(std::min(num_bags, kChunkBags) * hotness * dim);
+  ++s->stats.lookups;
+  s->stats.keys += num_bags * hotness;
+  s->stats.misses += num_bags * hotness;
+  for (size_t b0 = 0; b0 < num_bags; b0 += kChunkBags) {
+    const size_t nb = std::min(kChunkBags, num_bags - b0);
+    s->stats.default_filled += ht.fetch(keys + b0 * hotness, nb * hotness, rows.data(), dim, *s->ps->pool);
+    s->ps->pool->parallel_for(nb, [&](size_t b) {
+      float* acc = pooled + (b0 + b) * dim;
+      const float* r = rows.data() + b * hotness * dim;
+      for (size_t d = 0; d < dim; ++d) acc[d] = 0.f;
+      for (size_t j = 0; j < hotness; ++j)
+        for (size_t d = 0; d < dim; ++d) acc[d] += r[j * dim + d];
+      if (combiner == HPSX_COMBINER_MEAN)
+        for (size_t d = 0; d < dim; ++d) acc[d] /= static_cast<float>(hotness);
+    });
+  }
+  return HPSX_OK;
+}
+
+int hpsx_session_lookup_pooled_ex(hpsx_session* s, size_t table, const int64_t* keys, int key_memory,
+                                  size_t num_bags, size_t hotness, int combiner, float* pooled,
+                                  int pooled_memory) {
+  HPSX_GUARD_BEGIN
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  const bool keys_dev = key_memory == HPSX_MEM_DEVICE, out_dev = pooled_memory == HPSX_MEM_DEVICE;
+  if (table >= s->model->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (combiner != HPSX_COMBINER_SUM && combiner != HPSX_COMBINER_MEAN)
+    return fail(HPSX_ERR_INVALID_ARG, "unknown combiner");
+  if (hotness == 0 && num_bags > 0) return fail(HPSX_ERR_INVALID_ARG, "hotness must be > 0");
+  if (num_bags * hotness > s->cap_per_table[table])
+    return fail(HPSX_ERR_INVALID_ARG, "pooled lookup exceeds the table's key capacity");
+  if (num_bags == 0) return HPSX_OK;
+  if (!keys || !pooled) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
+  if (!s->cache) {
+    if (keys_dev || out_dev)
+      return fail(HPSX_ERR_UNSUPPORTED, "a CPU session (gpucache = false) takes host keys and host vectors");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return cpu_lookup_pooled(s, table, keys, num_bags, hotness, combiner, pooled);
+  }
+  if (out_dev) return pooled_common(s, table, keys, keys_dev, num_bags, hotness, combiner, pooled);
+  // GPU session, host output: pool into the device result buffer, then D2H
+  std::lock_guard<std::mutex> lk(s->mu);
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  if (!s->d_result) {
+    size_t floats = 0;
+    for (size_t t = 0; t < s->cap_per_table.size(); ++t) floats += s->cap_per_table[t] * s->model->tables[t]->dim();
+    HPSX_CU(cudaMalloc(&s->d_result, std::max<size_t>(floats, 1) * sizeof(float)));
+  }
+  const int rc = gpu_lookup_pooled(s, table, keys, keys_dev, num_bags, hotness, combiner, s->d_result);
+  if (rc != HPSX_OK) return rc;
+  const size_t bytes = num_bags * s->model->tables[table]->dim() * sizeof(float);
+  HPSX_CU(cudaMemcpyAsync(pooled, s->d_result, bytes, cudaMemcpyDeviceToHost, s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  s->stats.d2h_bytes += bytes;
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
 // rows inserted into the cache are counted on the device (cumulative since the last reset)
 static int read_inserted(hpsx_session* s, uint64_t* out) {
   *out = 0;
@@ -1436,6 +1503,18 @@ int hpsx_scatter_rows(int device, const float* d_rows, const uint32_t* d_perm, s
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(launch_scatter_rows(d_rows, d_perm, n, d, d_out, static_cast<cudaStream_t>(stream)));
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_gather_rows(int device, const float* d_table, const uint32_t* d_idx, size_t n, size_t dim,
+                     float* d_out, void* stream) {
+  HPSX_GUARD_BEGIN
+  if (n == 0) return HPSX_OK;
+  if (!d_table || !d_idx || !d_out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(launch_gather_rows(d_table, d_idx, n, dim, d_out, static_cast<cudaStream_t>(stream)));
   return HPSX_OK;
   HPSX_GUARD_END
 }

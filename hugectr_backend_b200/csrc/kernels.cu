@@ -937,6 +937,37 @@ __global__ void __launch_bounds__(kBlock) scatter_rows_kernel(const float* __res
   st_stream(reinterpret_cast<VecT*>(out) + static_cast<size_t>(perm[row]) * V + v, x);
 }
 
+// Plain random row gather out[i] = table[idx[i]] with the same tile/unroll shape as the probe+gather
+// kernel but no hashing and no bucket reads: the measured ceiling of "HBM random-gather" on this part.
+template <int kV, int kUnroll>
+__global__ void __launch_bounds__(kBlock) gather_rows_kernel(const float4* __restrict__ table,
+                                                             const uint32_t* __restrict__ idx, size_t n,
+                                                             float4* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t tile_base = ((static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5) * 32;
+  if (tile_base >= n) return;
+  const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), n - tile_base));
+  const uint32_t slot = lane < nk ? idx[tile_base + lane] : 0u;
+  constexpr uint32_t V = kV;
+  float4* __restrict__ outv = out + tile_base * V;
+  const uint32_t total = nk * V;
+  for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
+    float4 buf[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      const uint32_t kk = min(i / V, 31u);
+      const uint32_t s = __shfl_sync(kFull, slot, kk);
+      if (i < total) buf[u] = ld_stream(table + static_cast<size_t>(s) * V + (i - kk * V));
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      if (i < total) st_stream(outv + i, buf[u]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) synth_rows_kernel(const int64_t* __restrict__ keys, size_t n,
                                                             uint32_t dim, uint64_t seed, float* rows) {
   const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
@@ -1196,9 +1227,17 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
   a.absent = d_absent;
   // The miss count is only known on the device: a fixed grid of 4 CTAs per SM loops over the list.
   // PCIe needs ~100 KB in flight (51 GB/s x ~2 us); 4736 warps x 512 B is far more than enough.
+  static int ctas_per_sm = 0;  // HPSX_PULL_CTAS tunes it (1..8 resident CTAs of 256 threads per SM)
+  if (ctas_per_sm == 0) {
+    ctas_per_sm = 4;
+    if (const char* env = getenv("HPSX_PULL_CTAS")) {
+      const int v = atoi(env);
+      if (v >= 1 && v <= 32) ctas_per_sm = v;
+    }
+  }
   const size_t warps_needed = n_keys;
   const unsigned grid = static_cast<unsigned>(
-      min(static_cast<size_t>(148 * 4), (warps_needed * 32 + kBlock - 1) / kBlock));
+      min(static_cast<size_t>(148 * ctas_per_sm), (warps_needed * 32 + kBlock - 1) / kBlock));
   // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
   const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
   if (vb == 16)
@@ -1334,6 +1373,16 @@ cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, siz
     const uint32_t V = static_cast<uint32_t>(dim);
     scatter_rows_kernel<float><<<grid_for(n * V), kBlock, 0, stream>>>(d_rows, d_perm, n, V, d_out);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* d_table, const uint32_t* d_idx, size_t n, size_t dim,
+                               float* d_out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (dim != 128 || ((reinterpret_cast<uintptr_t>(d_table) | reinterpret_cast<uintptr_t>(d_out)) & 15u) != 0)
+    return cudaErrorNotSupported;  // measurement primitive: the benchmark's row shape only
+  gather_rows_kernel<32, 8><<<grid_for(n), kBlock, 0, stream>>>(reinterpret_cast<const float4*>(d_table), d_idx, n,
+                                                                 reinterpret_cast<float4*>(d_out));
   return cudaGetLastError();
 }
 

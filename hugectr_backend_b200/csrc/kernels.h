@@ -100,6 +100,11 @@ cudaError_t launch_route_keys(const int64_t* d_keys, size_t n, uint32_t num_shar
 cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, size_t n, size_t dim,
                                 float* d_out, cudaStream_t stream);
 
+// Measurement primitive: out[i] = table[idx[i]] for 128-float rows (the random-gather ceiling the
+// probe+gather kernel is compared with in bench.py).
+cudaError_t launch_gather_rows(const float* d_table, const uint32_t* d_idx, size_t n, size_t dim,
+                               float* d_out, cudaStream_t stream);
+
 // Synthetic rows generated on the device (model-parallel shards too large for host memory).
 cudaError_t launch_synth_rows(const int64_t* d_keys, size_t n, size_t dim, uint64_t seed,
                               float* d_rows, cudaStream_t stream);

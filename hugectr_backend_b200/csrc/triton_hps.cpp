@@ -167,6 +167,12 @@ struct ModelState {
   float refresh_interval = 0.f, refresh_delay = 0.f;
   bool freeze_sparse = false;
   std::string output_name;
+  // Opt-in extension (north-star stage a8): config.pbtxt parameters `hps_pooling` = "sum" | "mean" and
+  // `hps_pooling_hotness` = "h0,h1,..." (keys per slot of every table, default 1).  OUTPUT0 then holds the
+  // slot-wise reduced vectors: sum_t (n_t / h_t) * d_t floats.  Without them the reference's un-pooled
+  // contract applies.
+  int pooling = -1;  // -1 off, else hpsx_combiner
+  std::vector<size_t> pooling_hotness;
 
   bool gpucache() const { return params.use_gpu_embedding_cache != 0; }
   size_t num_tables() const { return params.num_tables; }
@@ -269,6 +275,28 @@ TRITONSERVER_Error* ModelState::parse() {
         hpsx::json_get(*v, "string_value", &refresh_delay);
       if (const Value* v = p->find("freeze_sparse"); v && v->is_object())
         hpsx::json_get(*v, "string_value", &freeze_sparse);
+      std::string pool_mode, pool_hot;
+      if (const Value* v = p->find("hps_pooling"); v && v->is_object()) hpsx::json_get(*v, "string_value", &pool_mode);
+      if (const Value* v = p->find("hps_pooling_hotness"); v && v->is_object())
+        hpsx::json_get(*v, "string_value", &pool_hot);
+      if (!pool_mode.empty() && pool_mode != "none") {
+        if (pool_mode == "sum")
+          pooling = HPSX_COMBINER_SUM;
+        else if (pool_mode == "mean")
+          pooling = HPSX_COMBINER_MEAN;
+        else
+          return HPS_ERROR(INVALID_ARG, "model '", name, "': hps_pooling must be sum, mean or none, got ", pool_mode);
+        pooling_hotness.assign(params.num_tables, 1);
+        size_t t = 0;
+        std::stringstream ss(pool_hot);
+        for (std::string tok; std::getline(ss, tok, ',');) {
+          if (t >= params.num_tables)
+            return HPS_ERROR(INVALID_ARG, "model '", name, "': hps_pooling_hotness lists more entries than tables");
+          const long long h = std::stoll(tok);
+          if (h <= 0) return HPS_ERROR(INVALID_ARG, "model '", name, "': hps_pooling_hotness entries must be > 0");
+          pooling_hotness[t++] = static_cast<size_t>(h);
+        }
+      }
     } catch (const std::exception& e) {
       return HPS_ERROR(INVALID_ARG, "model '", name, "' parameters: ", e.what());
     }
@@ -469,7 +497,14 @@ TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* re
     if (numkeys[t] < 0) return HPS_ERROR(INVALID_ARG, "NUMKEYS[", t, "] is negative (", numkeys[t], ")");
     n_per_table[t] = static_cast<size_t>(numkeys[t]);
     key_sum += n_per_table[t];
-    out_floats += static_cast<int64_t>(n_per_table[t]) * static_cast<int64_t>(ms->params.embedding_vecsize_per_table[t]);
+    size_t out_rows = n_per_table[t];
+    if (ms->pooling >= 0) {
+      if (n_per_table[t] % ms->pooling_hotness[t] != 0)
+        return HPS_ERROR(INVALID_ARG, "NUMKEYS[", t, "] = ", numkeys[t], " is not a multiple of the table's pooling hotness ",
+                         ms->pooling_hotness[t]);
+      out_rows = n_per_table[t] / ms->pooling_hotness[t];
+    }
+    out_floats += static_cast<int64_t>(out_rows) * static_cast<int64_t>(ms->params.embedding_vecsize_per_table[t]);
     if (n_per_table[t] > ms->max_batch_size * ms->params.maxnum_catfeature_query_per_table_per_sample[t])
       return HPS_ERROR(UNSUPPORTED, "NUMKEYS[", t, "] = ", numkeys[t], " exceeds max_batch_size * "
                        "maxnum_catfeature_query_per_table_per_sample = ",
@@ -511,9 +546,26 @@ TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* re
     keys_pt[t] = kbase + koff;
     out_pt[t] = obase + ooff;
     koff += n_per_table[t];
-    ooff += n_per_table[t] * ms->params.embedding_vecsize_per_table[t];
+    ooff += (ms->pooling >= 0 ? n_per_table[t] / ms->pooling_hotness[t] : n_per_table[t]) *
+            ms->params.embedding_vecsize_per_table[t];
   }
   *compute_start_ns = now_ns();
+  if (ms->pooling >= 0) {
+    // fused slot-wise gather + reduce, one table at a time
+    for (size_t t = 0; t < T; ++t) {
+      if (n_per_table[t] == 0) continue;
+      const size_t h = ms->pooling_hotness[t];
+      const int prc = hpsx_session_lookup_pooled_ex(
+          inst->session, t, static_cast<const int64_t*>(keys_pt[t]), key_view.on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
+          n_per_table[t] / h, h, ms->pooling, out_pt[t], out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST);
+      if (prc != HPSX_OK) {
+        *compute_end_ns = now_ns();
+        return engine_error(prc, "pooled embedding lookup of model " + ms->name);
+      }
+    }
+    *compute_end_ns = now_ns();
+    return nullptr;
+  }
   const int rc = hpsx_session_lookup_ex(inst->session, keys_pt.data(), key_view.on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
                                         out_pt.data(), out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
                                         n_per_table.data(), T);

@@ -298,3 +298,8 @@ def route_keys(device: int, d_keys, n: int, num_shards: int, d_routed, d_perm, d
 
 def scatter_rows(device: int, d_rows, d_perm, n: int, dim: int, d_out, stream: int = 0) -> None:
     N.check(N.lib().hpsx_scatter_rows(device, _addr(d_rows), _addr(d_perm), n, dim, _addr(d_out), stream))
+
+
+def gather_rows(device: int, d_table, d_idx, n: int, dim: int, d_out, stream: int = 0) -> None:
+    """Measurement primitive: d_out[i] = d_table[d_idx[i]] (rows of 128 floats)."""
+    N.check(N.lib().hpsx_gather_rows(device, _addr(d_table), _addr(d_idx), n, dim, _addr(d_out), stream))

@@ -230,6 +230,12 @@ int hpsx_session_lookup_pooled_device_keys(hpsx_session* s, size_t table, const 
                                            size_t num_bags, size_t hotness, int combiner,
                                            float* d_pooled);
 
+/* General form (keys and pooled vectors each in host or device memory; CPU sessions pool on the host
+ * in the same ascending-slot fp32 order) — what the Triton shell calls when a model opts into pooling. */
+int hpsx_session_lookup_pooled_ex(hpsx_session* s, size_t table, const int64_t* keys, int key_memory,
+                                  size_t num_bags, size_t hotness, int combiner, float* pooled,
+                                  int pooled_memory);
+
 int hpsx_session_get_stats(const hpsx_session* s, hpsx_session_stats* out);
 int hpsx_session_reset_stats(hpsx_session* s);
 /* Force the insertion mode of subsequent lookups: <0 use hit_rate_threshold (default), 0 always
@@ -263,6 +269,11 @@ int hpsx_route_keys(int device, const int64_t* d_keys, size_t n, uint32_t num_sh
 /* out[perm[i]*d .. ) = rows[i*d .. ) — return path of routed lookups (inverse permutation). */
 int hpsx_scatter_rows(int device, const float* d_rows, const uint32_t* d_perm, size_t n, size_t d,
                       float* d_out, void* stream);
+
+/* Measurement primitive (bench.py): d_out[i] = d_table[d_idx[i]] for rows of 128 floats, same launch
+ * shape as the probe+gather kernel without hashing — the practical "HBM random-gather" ceiling. */
+int hpsx_gather_rows(int device, const float* d_table, const uint32_t* d_idx, size_t n, size_t dim,
+                     float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,14 +1,8 @@
 #!/bin/bash
-# experiment pass: kernel variants + host-link probe
 mkdir -p gpurun_out
-{
-python scripts/probe_variants.py ldg 1.0
-python scripts/probe_variants.py ldg 0.9
-for cfg in 4x4 4x3 8x2 4x2 8x1; do
-  HPSX_PIPE_CFG=$cfg python scripts/probe_variants.py pipe 1.0
+for c in 4 8 16; do
+  HPSX_PULL_CTAS=$c timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_pull$c.json 2> gpurun_out/bench_pull$c.err
+  python -c "
+import json; d=json.load(open('gpurun_out/bench_pull$c.json'))
+print('pull ctas $c: value %.1fM ms %.3f hit %.4f' % (d['value']/1e6, d['ms_per_step'], d['config']['hit_rate_measured']), 'probe', round(d['roofline']['frac'],3), 'ceiling', round(d['roofline']['random_gather_ceiling_gbs'],1), 'link', d['roofline_host_link'], 'e2e %.1fM' % (d['e2e']['value']/1e6))"
 done
-HPSX_PIPE_CFG=4x4 python scripts/probe_variants.py pipe 0.9
-HPSX_PIPE_CFG=8x2 python scripts/probe_variants.py pipe 0.9
-} > gpurun_out/variants.txt 2>&1
-./tools/pcie_probe > gpurun_out/pcie_probe3.txt 2>&1
-cat gpurun_out/variants.txt; grep "4 GiB" gpurun_out/pcie_probe3.txt

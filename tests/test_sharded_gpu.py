@@ -1,0 +1,70 @@
+"""Model-parallel rows over 2+ GPUs of one box with NCCL all-to-all key routing (config C4 shape, scaled down).
+Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_sharded_gpu.py -m gpu`."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, rows, dim, seed, pagelock, ret):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import hugectr_backend_b200 as hb
+    from hugectr_backend_b200.sharded import ShardedLookup
+    from oracle import hps_oracle as O
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        hps = hb.HPS(num_partitions=8, num_threads=4)
+        hps.add_model(hb.ModelParams("dlrm", 1 << 17, [dim], [1], [0.25], cache_size_percentage=0.6,
+                                     hit_rate_threshold=1.0, deployed_devices=[rank], enable_pagelock=pagelock))
+        hps.load_table_procedural_shard("dlrm", 0, rows, seed, rank, world)
+        hps.create_embedding_cache("dlrm")
+        ref = O.NumpyTable(dim, 0.25)
+        ref.fill_procedural(rows, seed)
+        sl = ShardedLookup(hps, "dlrm", 0, dim, device=rank)
+        ok = True
+        rng = np.random.default_rng(100 + rank)
+        for n in (1, 4097, 60000, 0, 60000):
+            keys = rng.integers(-5, rows + 5, size=n)
+            out = sl.lookup(torch.from_numpy(keys).cuda())
+            ok &= bool(np.array_equal(out.cpu().numpy(), ref.lookup(keys)))
+            if n:
+                ok &= bool(np.array_equal(sl.last["send_counts"], np.bincount(O.owner(keys, world), minlength=world)))
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("pagelock", [False, True])
+def test_sharded_lookup_nccl(cuda_device, pagelock):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rows, dim, seed = 200_000, 128, 21
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, dim, seed, pagelock, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert all(ret[r] for r in range(world))

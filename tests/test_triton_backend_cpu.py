@@ -311,3 +311,38 @@ def test_gpucache_model_needs_gpu_instances_and_deployed_devices(tmp_path):
             with pytest.raises(FT.TritonError) as e:
                 be.model("g", FT.model_config("g", gpus=[0]))
             assert "CUDA" in e.value.message  # no silent CPU fallback for a gpucache model
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_opt_in_slot_pooling_matches_golden(tmp_path, mode):
+    """North-star stage a8 behind the Triton boundary: config.pbtxt parameters hps_pooling / hps_pooling_hotness turn
+    OUTPUT0 into the slot-wise reduced tensor.  Golden: the ensemble sample's request (64 samples x 3 keys, dim 16,
+    default 1.0 for absent keys), reduced longhand in tests/golden/make_golden.py."""
+    kat = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hps_kat.npz"))
+    d = str(tmp_path / "ens")
+    O.write_sparse_dir(d, kat["ens_keys"], kat["ens_vecs"])
+    ps = ps_json(str(tmp_path / "ps.json"), [model_entry("ens", [d], [16], [3], defaults=[1.0], max_batch=64)])
+    with FT.Backend(ps) as be:
+        cfg = FT.model_config("ens", kind="KIND_CPU", parameters={"hps_pooling": mode, "hps_pooling_hotness": "3"})
+        model = be.model("ens", cfg)
+        inst = model.instance(kind=FT.KIND_CPU)
+        r = inst.infer(kat["ens_KEYS"], kat["ens_NUMKEYS"])
+        assert r.error_code is None, r.error_message
+        assert r.shape == [64 * 16] and r.params["NumSample"] == 64
+        assert np.array_equal(r.data.reshape(64, 16), kat[f"ens_pooled_{mode}"])
+        # a key count that is not a multiple of the hotness is a request error
+        r = inst.infer(kat["ens_KEYS"].ravel()[:10], np.array([[10]], dtype=np.int32))
+        assert r.error_code == FT.ERR["INVALID_ARG"] and "pooling hotness" in r.error_message
+        inst.close()
+        model.close()
+    with FT.Backend(ps) as be:
+        with pytest.raises(FT.TritonError) as e:
+            be.model("ens", FT.model_config("ens", kind="KIND_CPU", parameters={"hps_pooling": "max"}))
+        assert e.value.code == FT.ERR["INVALID_ARG"]
+        # without the parameters the reference's un-pooled contract applies
+        model = be.model("ens", FT.model_config("ens", kind="KIND_CPU"))
+        inst = model.instance(kind=FT.KIND_CPU)
+        r = inst.infer(kat["ens_KEYS"], kat["ens_NUMKEYS"])
+        assert r.shape == [3072] and np.array_equal(r.data, kat["ens_OUTPUT0"])
+        inst.close()
+        model.close()

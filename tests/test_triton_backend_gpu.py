@@ -138,3 +138,27 @@ def test_instance_on_undeployed_device_is_rejected(wdl_gpu):
         with pytest.raises(FT.TritonError):
             model.instance(kind=FT.KIND_CPU, device=0)
         model.close()
+
+
+@pytest.mark.parametrize("mode", ["sum", "mean"])
+def test_opt_in_slot_pooling_on_gpu(wdl_gpu, mode):
+    import torch
+    ps, ref, tables = wdl_gpu
+    with FT.Backend(ps) as be:
+        cfg = FT.model_config("wdl", gpus=[0], parameters={"hps_pooling": mode, "hps_pooling_hotness": "2,13"})
+        model = be.model("wdl", cfg)
+        inst = model.instance(kind=FT.KIND_GPU, device=0)
+        samples = 200
+        keys, numkeys = wdl_request(tables, samples, np.random.default_rng(6))
+        n0, n1 = int(numkeys[0, 0]), int(numkeys[0, 1])
+        expect = np.concatenate([O.pooled(ref[0], keys[:n0], n0 // 2, 2, mode).ravel(),
+                                 O.pooled(ref[1], keys[n0:], n1 // 13, 13, mode).ravel()])
+        out = torch.full((len(expect),), float("nan"), device="cuda")
+        r = inst.infer(keys, numkeys, gpu_out=out)
+        assert r.error_code is None, r.error_message
+        assert r.shape == [len(expect)]
+        np.testing.assert_allclose(out.cpu().numpy(), expect, rtol=0, atol=1e-5)  # north-star tolerance on fp32 slot sums
+        r = inst.infer(keys, numkeys)  # CPU output buffer
+        np.testing.assert_allclose(r.data, expect, rtol=0, atol=1e-5)
+        inst.close()
+        model.close()
