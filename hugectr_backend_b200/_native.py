@@ -90,6 +90,12 @@ SYMBOLS = {
     "hpsx_ps_table_rows": (_int, [_vp, _cp, _sz, c_size_p]),
     "hpsx_ps_get_model_params": (_int, [_vp, _cp, ctypes.POINTER(ModelParamsC)]),
     "hpsx_ps_sync_models_from_json": (_int, [_vp, _cp, c_size_p]),
+    "hpsx_session_lookup_scatter": (_int, [_vp, _sz, _vp, _vp, _sz, _vp]),
+    "hpsx_device_malloc": (_int, [_int, _sz, _vpp]),
+    "hpsx_device_free": (_int, [_int, _vp]),
+    "hpsx_ipc_export": (_int, [_int, _vp, _vp]),
+    "hpsx_ipc_open": (_int, [_int, _vp, _vpp]),
+    "hpsx_ipc_close": (_int, [_int, _vp]),
     "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),
     "hpsx_session_lookup_ex": (_int, [_vp, _vpp, _int, _vpp, _int, c_size_p, _sz]),
     "hpsx_ps_lookup": (_int, [_vp, _cp, _sz, _vp, _sz, _vp]),

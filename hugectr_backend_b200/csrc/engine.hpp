@@ -108,7 +108,12 @@ struct hpsx_session {
   size_t pool_stage_rows = 0;
   size_t max_dim = 0;
   std::vector<cudaEvent_t> ev;         // 2 per table: probe start / stop
-  std::vector<cudaEvent_t> ev_pull;    // 1 per table: end of the direct-pull kernel
+  std::vector<cudaEvent_t> ev_pull;    // 2 per table: start / end of the direct-pull phase
+  // address-sorted pull: [0] unsorted, [1] sorted host addresses / miss-list indices; CUB temp storage
+  unsigned long long* d_addr[2] = {nullptr, nullptr};
+  uint32_t* d_sidx[2] = {nullptr, nullptr};
+  void* d_sort_temp = nullptr;
+  size_t sort_temp_bytes = 0;
   hpsx_session_stats stats{};
   std::mutex mu;  // one lookup at a time per session (Triton guarantees it; tests may not)
 

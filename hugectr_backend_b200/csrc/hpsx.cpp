@@ -424,11 +424,35 @@ void account_probe_time(hpsx_session* s, size_t t, size_t n) {
   }
 }
 
-// Direct-pull lookup (enable_pagelock): probe+gather, then one kernel that resolves the misses by
-// reading their rows straight from the page-locked host table over PCIe and inserting them.  The miss
-// list never leaves the device and the host waits exactly once, at the end.
+bool pull_sort_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HPSX_PULL_SORT");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+// Workspace of the address-sorted pull, allocated on first use.
+int ensure_sort_workspace(hpsx_session* s) {
+  if (s->d_sort_temp != nullptr) return HPSX_OK;
+  const size_t cap = std::max<size_t>(s->cap_keys, 1);
+  for (int i = 0; i < 2; ++i) {
+    HPSX_CU(cudaMalloc(&s->d_addr[i], cap * sizeof(unsigned long long)));
+    HPSX_CU(cudaMalloc(&s->d_sidx[i], cap * sizeof(uint32_t)));
+  }
+  s->sort_temp_bytes = sort_misses_temp_bytes(cap);
+  HPSX_CU(cudaMalloc(&s->d_sort_temp, std::max<size_t>(s->sort_temp_bytes, 16)));
+  return HPSX_OK;
+}
+
+// Direct-pull lookup (enable_pagelock): probe+gather, then the misses are resolved ON THE GPU: their
+// rows are read straight from the page-locked host table over PCIe and inserted.  No CPU gather, no
+// staging copy.  With HPSX_PULL_SORT (default) the host reads the miss counts once, and the misses
+// are walked in ascending host-address order, which the host link rewards with ~1.5x the bandwidth;
+// with HPSX_PULL_SORT=0 the miss list never leaves the device and the host waits exactly once.
 int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
-                      float* const* out_per_table, const size_t* n_per_table, size_t num_tables) {
+                      float* const* out_per_table, const size_t* n_per_table, size_t num_tables,
+                      const uint32_t* const* pos_per_table) {
   hpsx_cache* c = s->cache;
   const size_t T = s->model->tables.size();
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
@@ -440,6 +464,11 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   for (size_t t = 0; t < num_tables; ++t)
     if (n_per_table[t] != 0 && (!keys_per_table[t] || !out_per_table[t]))
       return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
+  const bool sorted = pull_sort_enabled();
+  if (sorted) {
+    const int rc = ensure_sort_workspace(s);
+    if (rc != HPSX_OK) return rc;
+  }
 
   // the pull kernel rewrites cache slots: exclusive unless the cache is static (never inserts)
   std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
@@ -448,43 +477,76 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
 
   HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
   HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
-  size_t off = 0;
+  std::vector<size_t> off(num_tables + 1, 0);
+  auto pull = [&](size_t t, size_t m_hint) -> cudaError_t {
+    const bool use_sorted = sorted && m_hint > 0;
+    return launch_pull_misses(c->tables[t], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
+                              n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
+                              s->model->cfg.hit_rate_threshold, epoch, s->d_counters + T + t,
+                              s->d_counters + 2 * T + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
+                              use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream);
+  };
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t n = n_per_table[t];
+    off[t + 1] = off[t] + n;
     if (n == 0) continue;
     const int64_t* d_keys;
     if (keys_on_device) {
       d_keys = static_cast<const int64_t*>(keys_per_table[t]);
     } else {
-      HPSX_CU(cudaMemcpyAsync(s->d_keys + off, keys_per_table[t], n * sizeof(int64_t),
+      HPSX_CU(cudaMemcpyAsync(s->d_keys + off[t], keys_per_table[t], n * sizeof(int64_t),
                               cudaMemcpyHostToDevice, s->stream));
       s->stats.h2d_bytes += n * sizeof(int64_t);
-      d_keys = s->d_keys + off;
+      d_keys = s->d_keys + off[t];
     }
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
     HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
-                                s->d_counters + t, s->d_miss_pos + off, s->d_miss_keys + off, nullptr,
-                                s->probe_variant, s->stream));
+                                s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t], nullptr,
+                                s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr));
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
-    HPSX_CU(launch_pull_misses(c->tables[t], s->d_miss_keys + off, s->d_miss_pos + off, s->d_counters + t, n,
-                               out_per_table[t], nullptr, !c->is_static, s->insert_mode,
-                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + T + t,
-                               s->d_counters + 2 * T + t, s->stream));
-    HPSX_CU(cudaEventRecord(s->ev_pull[t], s->stream));
-    s->stats.kernel_launches += 2;
-    off += n;
+    ++s->stats.kernel_launches;
+    if (!sorted) {
+      HPSX_CU(pull(t, 0));
+      HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
+      ++s->stats.kernel_launches;
+    }
   }
-  HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, 3 * T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+  if (sorted) {
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes += T * sizeof(uint32_t);
+    for (size_t t = 0; t < num_tables; ++t)
+      if (n_per_table[t] != 0) account_probe_time(s, t, n_per_table[t]);
+    for (size_t t = 0; t < num_tables; ++t) {
+      const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
+      if (m == 0) continue;
+      HPSX_CU(cudaEventRecord(s->ev_pull[2 * t], s->stream));
+      HPSX_CU(launch_resolve_and_sort_misses(c->tables[t], s->d_miss_keys + off[t], m, s->d_addr[0] + off[t],
+                                             s->d_sidx[0] + off[t], s->d_addr[1] + off[t], s->d_sidx[1] + off[t],
+                                             s->d_sort_temp, s->sort_temp_bytes, s->stream));
+      HPSX_CU(pull(t, m));
+      HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
+      s->stats.kernel_launches += 2;  // resolve + pull (the CUB radix-sort passes are library kernels, not counted)
+    }
+  }
+  HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, 2 * T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           s->stream));
+  if (!sorted)
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->stats.d2h_bytes += 3 * T * sizeof(uint32_t);
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t n = n_per_table[t];
     if (n == 0) continue;
-    account_probe_time(s, t, n);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev[2 * t + 1], s->ev_pull[t]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
     const uint32_t m = s->h_counters[t];
+    float ms = 0.f;
+    if (sorted) {
+      if (m != 0 && cudaEventElapsedTime(&ms, s->ev_pull[2 * t], s->ev_pull[2 * t + 1]) == cudaSuccess)
+        s->stats.insert_kernel_ms += ms;  // resolve + sort + pull
+    } else {
+      account_probe_time(s, t, n);
+      if (cudaEventElapsedTime(&ms, s->ev[2 * t + 1], s->ev_pull[2 * t + 1]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    }
     s->stats.hits += n - m;
     s->stats.misses += m;
     const size_t row_bytes = s->model->tables[t]->dim() * sizeof(float);
@@ -495,13 +557,17 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   return HPSX_OK;
 }
 
+// `pos_per_table` (nullable, device memory): key i of table t is delivered to row pos[t][i] of out[t]
+// instead of row i (model-parallel return leg; out[t] may be a peer GPU's buffer).
 int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
-               float* const* out_per_table, const size_t* n_per_table, size_t num_tables) {
+               float* const* out_per_table, const size_t* n_per_table, size_t num_tables,
+               const uint32_t* const* pos_per_table = nullptr) {
   hpsx_cache* c = s->cache;
   DeviceGuard guard(s->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   if (c->direct_pull)
-    return gpu_lookup_direct(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables);
+    return gpu_lookup_direct(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables,
+                             pos_per_table);
   const size_t T = s->model->tables.size();
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
   size_t total = 0;
@@ -533,7 +599,8 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
       HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
       HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
-                                  s->hd_miss_keys + off[t], s->probe_variant, s->stream));
+                                  s->hd_miss_keys + off[t], s->probe_variant, s->stream,
+                                  pos_per_table ? pos_per_table[t] : nullptr));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
     }
@@ -633,9 +700,19 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
       if (c->direct_pull) {
         // rows pulled by the GPU straight from the page-locked host table into the stage
         HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
+        const bool use_sorted = pull_sort_enabled();
+        if (use_sorted) {
+          const int wrc = ensure_sort_workspace(s);
+          if (wrc != HPSX_OK) return wrc;
+          HPSX_CU(launch_resolve_and_sort_misses(c->tables[table], s->d_miss_keys, m, s->d_addr[0], s->d_sidx[0],
+                                                 s->d_addr[1], s->d_sidx[1], s->d_sort_temp, s->sort_temp_bytes,
+                                                 s->stream));
+          ++s->stats.kernel_launches;
+        }
         HPSX_CU(launch_pull_misses(c->tables[table], s->d_miss_keys, s->d_miss_pos, s->d_counters + table, n,
                                    nullptr, s->d_pool_stage, false, 1, 0.f, epoch, nullptr,
-                                   s->d_counters + 2 * T + table, s->stream));
+                                   s->d_counters + 2 * T + table, use_sorted ? s->d_addr[1] : nullptr,
+                                   use_sorted ? s->d_sidx[1] : nullptr, m, s->stream));
         ++s->stats.kernel_launches;
         s->stats.misses += m;
         s->stats.h2d_bytes += static_cast<uint64_t>(m) * s->model->tables[table]->dim() * sizeof(float);
@@ -692,6 +769,11 @@ hpsx_session::~hpsx_session() {
     cudaFree(d_miss_keys);
     cudaFree(d_counters);
     cudaFree(d_src);
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(d_addr[i]);
+      cudaFree(d_sidx[i]);
+    }
+    cudaFree(d_sort_temp);
     cudaFree(d_result);
     cudaFree(d_pool_stage);
     if (h_counters) cudaFreeHost(h_counters);
@@ -1159,7 +1241,7 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * T);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
-  s->ev_pull.resize(T);
+  s->ev_pull.resize(2 * T);
   for (auto& e : s->ev_pull) HPSX_CU(cudaEventCreate(&e));
   *out = s.release();
   return HPSX_OK;
@@ -1230,6 +1312,76 @@ int hpsx_session_lookup_device_keys(hpsx_session* s, const int64_t* const* d_key
   return gpu_lookup(s, reinterpret_cast<const void* const*>(d_keys_per_table), true,
                     d_vectors_per_table, num_keys_per_table, num_tables);
   HPSX_GUARD_END
+}
+
+int hpsx_session_lookup_scatter(hpsx_session* s, size_t table, const int64_t* d_keys, const uint32_t* d_pos,
+                                size_t n, float* d_out_base) {
+  HPSX_GUARD_BEGIN
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (!s->cache) return fail(HPSX_ERR_UNSUPPORTED, "scatter lookup needs a GPU session (gpucache = true)");
+  const size_t T = s->model->tables.size();
+  if (table >= T) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (n > s->cap_per_table[table])
+    return fail(HPSX_ERR_INVALID_ARG, "scatter lookup exceeds the table's key capacity (max_batch_size * maxnum_catfeature)");
+  if (n == 0) return HPSX_OK;
+  if (!d_keys || !d_pos || !d_out_base) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  std::vector<const void*> keys(T, nullptr);
+  std::vector<float*> out(T, nullptr);
+  std::vector<size_t> cnt(T, 0);
+  std::vector<const uint32_t*> pos(T, nullptr);
+  keys[table] = d_keys;
+  out[table] = d_out_base;
+  cnt[table] = n;
+  pos[table] = d_pos;
+  std::lock_guard<std::mutex> lk(s->mu);
+  return gpu_lookup(s, keys.data(), true, out.data(), cnt.data(), T, pos.data());
+  HPSX_GUARD_END
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffers shareable between the processes of one box (one process per GPU): CUDA IPC
+// ------------------------------------------------------------------------------------------------
+int hpsx_device_malloc(int device, size_t bytes, void** d_ptr) {
+  if (!d_ptr) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(cudaMalloc(d_ptr, std::max<size_t>(bytes, 16)));
+  return HPSX_OK;
+}
+
+int hpsx_device_free(int device, void* d_ptr) {
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(cudaFree(d_ptr));
+  return HPSX_OK;
+}
+
+int hpsx_ipc_export(int device, void* d_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!d_ptr || !handle64) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t h;
+  HPSX_CU(cudaIpcGetMemHandle(&h, d_ptr));
+  std::memcpy(handle64, &h, sizeof(h));
+  return HPSX_OK;
+}
+
+int hpsx_ipc_open(int device, const void* handle64, void** d_ptr) {
+  if (!handle64 || !d_ptr) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle64, sizeof(h));
+  HPSX_CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return HPSX_OK;
+}
+
+int hpsx_ipc_close(int device, void* d_ptr) {
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  HPSX_CU(cudaIpcCloseMemHandle(d_ptr));
+  return HPSX_OK;
 }
 
 int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,

@@ -8,6 +8,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "kernels.h"
 
 namespace hpsx {
@@ -120,6 +122,7 @@ struct ProbeArgs {
   int64_t* miss_keys;
   int64_t* miss_keys_host;  // optional mirror in mapped pinned host memory (zero-copy PCIe writes)
   uint32_t* src;  // probe_index only
+  const uint32_t* pos;  // optional: key i is delivered to row pos[i] of `out` (which may be peer memory)
 };
 
 // Append the misses of one warp tile to the global miss list: ballot -> popc prefix -> one atomic.
@@ -141,7 +144,10 @@ __device__ __forceinline__ uint32_t warp_claim_misses(bool is_miss, uint32_t lan
 // addresses contiguous across the whole tile (rows of consecutive keys are adjacent in `out`).
 // kV = vectors per row when known at compile time (0: runtime).
 // ------------------------------------------------------------------------------------------------
-template <typename VecT, int kV, int kUnroll>
+// kScatter: every key carries its destination row (`pos`), and `out` may be another GPU's buffer mapped
+// through NVLink peer access — the owner's gather kernel then IS the return leg of the model-parallel
+// exchange (rows leave as 512-B peer stores; no all-to-all of vectors, no scatter pass).
+template <typename VecT, int kV, int kUnroll, bool kScatter = false>
 __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const size_t tile = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
@@ -160,7 +166,8 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
   const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
 
   const VecT* __restrict__ vals = reinterpret_cast<const VecT*>(a.values);
-  VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + tile_base * V;
+  VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + (kScatter ? 0 : tile_base * V);
+  const uint32_t dst = (kScatter && valid) ? a.pos[tile_base + lane] : static_cast<uint32_t>(tile_base + lane);
   const VecT defv = splat<VecT>(a.default_value);
   const uint32_t total = nk * V;
   for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
@@ -177,13 +184,19 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
-      if (i < total) st_stream(outv + i, buf[u]);
+      if (kScatter) {
+        const uint32_t kk = min(i / V, 31u);
+        const uint32_t d = __shfl_sync(kFull, dst, kk);
+        if (i < total) st_stream(outv + static_cast<size_t>(d) * V + (i - kk * V), buf[u]);
+      } else {
+        if (i < total) st_stream(outv + i, buf[u]);
+      }
     }
   }
 
   if (is_miss) {
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+    a.miss_pos[r] = dst;
     a.miss_keys[r] = key;
     if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
   }
@@ -654,9 +667,61 @@ struct PullArgs {
   uint32_t epoch;
   uint32_t* inserted;
   uint32_t* absent;
+  int load_mode;
+  // optional: the misses in ascending host-address order (resolve_rows_kernel + radix sort); then entry i
+  // is miss sorted_idx[i] and its row lives at sorted_addr[i] (0: key absent from the host table)
+  const unsigned long long* sorted_addr;
+  const uint32_t* sorted_idx;
 };
 
+// Step 1 of the sorted pull: host address of every missed key (8 lanes per key, one 128-B index line each)
+// plus the identity permutation the radix sort carries along.
+__global__ void __launch_bounds__(kBlock) resolve_rows_kernel(const IndexSlot* __restrict__ index, uint64_t mask,
+                                                              const float* sentinel_row,
+                                                              const int64_t* __restrict__ miss_keys, uint32_t m,
+                                                              unsigned long long* addr, uint32_t* idx) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t sub = lane & 7u;           // lane within the 8-lane group
+  const uint32_t group_shift = lane & ~7u;  // first lane of the group
+  const unsigned group_mask = 0xffu << group_shift;
+  const size_t g = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 3;
+  if (g >= m) return;  // whole 8-lane groups retire together
+  const int64_t key = miss_keys[g];
+  unsigned long long row = 0;
+  if (key == kEmptyKey) {
+    row = reinterpret_cast<unsigned long long>(sentinel_row);
+  } else {
+    uint64_t base = mix64(static_cast<uint64_t>(key)) & mask;
+    while (true) {
+      const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(&index[(base + sub) & mask]));
+      const int64_t k = static_cast<int64_t>((static_cast<unsigned long long>(raw.y) << 32) | raw.x);
+      const unsigned long long r = (static_cast<unsigned long long>(raw.w) << 32) | raw.z;
+      const unsigned hit = (__ballot_sync(group_mask, k == key) & group_mask) >> group_shift;
+      const unsigned empty = (__ballot_sync(group_mask, k == kEmptyKey) & group_mask) >> group_shift;
+      if (hit != 0u && (empty == 0u || __ffs(hit) < __ffs(empty))) {
+        row = __shfl_sync(group_mask, r, group_shift + __ffs(hit) - 1);
+        break;
+      }
+      if (empty != 0u) break;
+      base = (base + 8) & mask;
+    }
+  }
+  if (sub == 0) {
+    addr[g] = row;
+    idx[g] = static_cast<uint32_t>(g);
+  }
+}
+
+// Host-row loads.  mode 0: default-cached ld.global (full 128-B line requests to the host link),
+// 1: ld.global.nc.L1::no_allocate, 2: ld.global.cg.
 template <typename VecT>
+__device__ __forceinline__ VecT ld_host(const VecT* p, int mode) {
+  if (mode == 1) return ld_stream(p);
+  if (mode == 2) return __ldcg(p);
+  return *p;
+}
+
+template <typename VecT, int kRows>
 __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
@@ -671,45 +736,74 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
   }
   const bool write_out = a.out != nullptr && sync_mode;
   const VecT defv = splat<VecT>(a.default_value);
-  for (size_t i = warp; i < m; i += nwarps) {
-    const int64_t key = a.miss_keys[i];
-    const float* row = key == kEmptyKey ? a.sentinel_row : index_find(a.index, a.index_mask, key, lane);
-    const VecT* src = reinterpret_cast<const VecT*>(row);
-    // issue the PCIe reads first: they are the long pole (~2 us), the bucket claim overlaps them
-    VecT x0 = defv, x1 = defv;
-    if (src != nullptr) {
-      if (lane < V) x0 = ld_stream(src + lane);
-      if (lane + 32u < V) x1 = ld_stream(src + lane + 32u);
+  for (size_t i0 = warp * kRows; i0 < m; i0 += nwarps * kRows) {
+    int64_t key[kRows];
+    const VecT* src[kRows];
+    VecT x0[kRows], x1[kRows];
+    // index probes of all rows first, then every PCIe read of the group: kRows x 512 B in flight per warp.
+    // The PCIe reads are the long pole (~2-3 us); the bucket claims below overlap them.
+    size_t idx[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const size_t i = i0 + r;
+      idx[r] = i;
+      key[r] = kEmptyKey;
+      const float* row = nullptr;
+      if (i < m) {
+        if (a.sorted_addr != nullptr) {
+          idx[r] = a.sorted_idx[i];
+          key[r] = a.miss_keys[idx[r]];
+          row = reinterpret_cast<const float*>(a.sorted_addr[i]);
+        } else {
+          key[r] = a.miss_keys[i];
+          row = key[r] == kEmptyKey ? a.sentinel_row : index_find(a.index, a.index_mask, key[r], lane);
+        }
+      }
+      src[r] = reinterpret_cast<const VecT*>(row);
     }
-    VecT* dst_out =
-        write_out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
-    VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
-    VecT* dst_slab = nullptr;
-    Bucket* B = nullptr;
-    if (a.insert && src != nullptr && key != kEmptyKey) {
-      const uint32_t b = bucket_of(key, a.num_buckets);
-      B = &a.buckets[b];
-      const int way = claim_way(B, key, a.epoch, lane);
-      if (way >= 0)
-        dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      x0[r] = defv;
+      x1[r] = defv;
+      if (src[r] != nullptr) {
+        if (lane < V) x0[r] = ld_host(src[r] + lane, a.load_mode);
+        if (lane + 32u < V) x1[r] = ld_host(src[r] + lane + 32u, a.load_mode);
+      }
     }
-    for (uint32_t v = lane; v < V; v += 32u) {
-      VecT x;
-      if (v == lane)
-        x = x0;
-      else if (v == lane + 32u)
-        x = x1;
-      else
-        x = src != nullptr ? ld_stream(src + v) : defv;
-      if (dst_out) st_stream(dst_out + v, x);
-      if (dst_stage) dst_stage[v] = x;
-      if (dst_slab) dst_slab[v] = x;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      if (i0 + r >= m) break;
+      const size_t i = idx[r];  // position in the miss list (stage row, miss_pos entry)
+      VecT* dst_out =
+          write_out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
+      VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
+      VecT* dst_slab = nullptr;
+      Bucket* B = nullptr;
+      if (a.insert && src[r] != nullptr && key[r] != kEmptyKey) {
+        const uint32_t b = bucket_of(key[r], a.num_buckets);
+        B = &a.buckets[b];
+        const int way = claim_way(B, key[r], a.epoch, lane);
+        if (way >= 0)
+          dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+      }
+      for (uint32_t v = lane; v < V; v += 32u) {
+        VecT x;
+        if (v == lane)
+          x = x0[r];
+        else if (v == lane + 32u)
+          x = x1[r];
+        else
+          x = src[r] != nullptr ? ld_host(src[r] + v, a.load_mode) : defv;
+        if (dst_out) st_stream(dst_out + v, x);
+        if (dst_stage) dst_stage[v] = x;
+        if (dst_slab) dst_slab[v] = x;
+      }
+      if (B != nullptr) {
+        release_bucket(B, lane);
+        if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+      }
+      if (lane == 0 && src[r] == nullptr && a.absent != nullptr) atomicAdd(a.absent, 1u);
     }
-    if (B != nullptr) {
-      release_bucket(B, lane);
-      if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
-    }
-    if (lane == 0 && src == nullptr && a.absent != nullptr) atomicAdd(a.absent, 1u);
   }
 }
 
@@ -991,6 +1085,17 @@ inline unsigned grid_for(size_t threads) {
 }
 
 template <typename VecT>
+cudaError_t launch_probe_ldg_scatter(const ProbeArgs& a, cudaStream_t stream) {
+  const unsigned grid = grid_for(a.n);
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  if (V == 32)
+    probe_gather_ldg_kernel<VecT, 32, 8, true><<<grid, kBlock, 0, stream>>>(a);
+  else
+    probe_gather_ldg_kernel<VecT, 0, 4, true><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <typename VecT>
 cudaError_t launch_probe_ldg_vec(const ProbeArgs& a, cudaStream_t stream) {
   const unsigned grid = grid_for(a.n);
   const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
@@ -1110,7 +1215,7 @@ cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream) {
+                                int variant, cudaStream_t stream, const uint32_t* d_pos) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.buckets = t.buckets;
@@ -1128,7 +1233,13 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
   a.miss_keys = d_miss_keys;
   a.miss_keys_host = hd_miss_keys;
   a.src = nullptr;
+  a.pos = d_pos;
   const int vb = vec_bytes(t.dim, d_out, t.values);
+  if (d_pos != nullptr) {
+    if (vb == 16) return launch_probe_ldg_scatter<float4>(a, stream);
+    if (vb == 8) return launch_probe_ldg_scatter<float2>(a, stream);
+    return launch_probe_ldg_scatter<float>(a, stream);
+  }
   if (variant == kProbeTma && vb == 16) {
     const cudaError_t e = launch_probe_tma(a, stream);
     if (e != cudaErrorNotSupported) return e;
@@ -1201,10 +1312,13 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
 cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys, const uint32_t* d_miss_pos,
                                const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
-                               uint32_t* d_inserted, uint32_t* d_absent, cudaStream_t stream) {
+                               uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
+                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream) {
   if (n_keys == 0) return cudaSuccess;
   if (t.index == nullptr) return cudaErrorInvalidValue;
   PullArgs a{};
+  a.sorted_addr = d_sorted_addr;
+  a.sorted_idx = d_sorted_idx;
   a.buckets = t.buckets;
   a.values = t.values;
   a.num_buckets = t.num_buckets;
@@ -1227,26 +1341,56 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
   a.absent = d_absent;
   // The miss count is only known on the device: a fixed grid of 4 CTAs per SM loops over the list.
   // PCIe needs ~100 KB in flight (51 GB/s x ~2 us); 4736 warps x 512 B is far more than enough.
-  static int ctas_per_sm = 0;  // HPSX_PULL_CTAS tunes it (1..8 resident CTAs of 256 threads per SM)
+  // tuning knobs: HPSX_PULL_CTAS (CTAs of 256 threads per SM), HPSX_PULL_LD (0 ld.global, 1 .nc.L1::no_allocate,
+  // 2 .cg), HPSX_PULL_ROWS (host rows in flight per warp: 1 or 2)
+  static int ctas_per_sm = 0, load_mode = 0, rows_per_warp = 1;
   if (ctas_per_sm == 0) {
-    ctas_per_sm = 4;
+    ctas_per_sm = 8;
     if (const char* env = getenv("HPSX_PULL_CTAS")) {
       const int v = atoi(env);
       if (v >= 1 && v <= 32) ctas_per_sm = v;
     }
+    if (const char* env = getenv("HPSX_PULL_LD")) load_mode = atoi(env);
+    if (const char* env = getenv("HPSX_PULL_ROWS")) rows_per_warp = atoi(env) == 2 ? 2 : 1;
   }
-  const size_t warps_needed = n_keys;
+  a.load_mode = load_mode;
+  const size_t warps_needed = m_hint > 0 ? m_hint : n_keys;
   const unsigned grid = static_cast<unsigned>(
       min(static_cast<size_t>(148 * ctas_per_sm), (warps_needed * 32 + kBlock - 1) / kBlock));
   // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
   const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
-  if (vb == 16)
-    pull_misses_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  if (vb == 16 && rows_per_warp == 2)
+    pull_misses_kernel<float4, 2><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 16)
+    pull_misses_kernel<float4, 1><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 8)
-    pull_misses_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+    pull_misses_kernel<float2, 1><<<grid, kBlock, 0, stream>>>(a);
   else
-    pull_misses_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+    pull_misses_kernel<float, 1><<<grid, kBlock, 0, stream>>>(a);
   return cudaGetLastError();
+}
+
+size_t sort_misses_temp_bytes(size_t max_items) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, static_cast<const unsigned long long*>(nullptr),
+                                  static_cast<unsigned long long*>(nullptr), static_cast<const uint32_t*>(nullptr),
+                                  static_cast<uint32_t*>(nullptr), static_cast<int>(max_items), 12, 48);
+  return bytes;
+}
+
+cudaError_t launch_resolve_and_sort_misses(const DeviceTable& t, const int64_t* d_miss_keys, size_t m,
+                                           unsigned long long* d_addr_tmp, uint32_t* d_idx_tmp,
+                                           unsigned long long* d_addr_sorted, uint32_t* d_idx_sorted, void* d_temp,
+                                           size_t temp_bytes, cudaStream_t stream) {
+  if (m == 0) return cudaSuccess;
+  if (t.index == nullptr) return cudaErrorInvalidValue;
+  resolve_rows_kernel<<<grid_for(m * 8), kBlock, 0, stream>>>(t.index, t.index_mask, t.sentinel_row, d_miss_keys,
+                                                              static_cast<uint32_t>(m), d_addr_tmp, d_idx_tmp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // 4-KiB page number and above: bits [12, 48) of the host virtual address
+  return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_addr_tmp, d_addr_sorted, d_idx_tmp, d_idx_sorted,
+                                         static_cast<int>(m), 12, 48, stream);
 }
 
 cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t stream) {

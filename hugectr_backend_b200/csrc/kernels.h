@@ -39,7 +39,9 @@ enum ProbeVariant : int {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream);
+                                int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr);
+// With `d_pos`, key i is delivered to row d_pos[i] of d_out instead of row i, and d_out may be another
+// GPU's buffer (NVLink peer mapping): the model-parallel return leg fused into the gather.
 
 // Probe only (pooled path): d_src[i] = slot index on hit, kSrcMissBit | miss-list index on miss.
 cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size_t n, uint32_t epoch,
@@ -66,7 +68,18 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
 cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys, const uint32_t* d_miss_pos,
                                const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
-                               uint32_t* d_inserted, uint32_t* d_absent, cudaStream_t stream);
+                               uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
+                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream);
+
+// Locality for the host link: random 512-B reads over a multi-GB pinned table run at ~32-42 GB/s, the same
+// reads in ascending address order at ~51 GB/s (tools/pcie_probe.cu: page-table / IOTLB reach).  So when the
+// host knows the miss count `m`, the misses are first resolved to host addresses and radix-sorted by page
+// number; launch_pull_misses then walks them in that order (d_sorted_addr / d_sorted_idx, m_hint = m).
+size_t sort_misses_temp_bytes(size_t max_items);
+cudaError_t launch_resolve_and_sort_misses(const DeviceTable& t, const int64_t* d_miss_keys, size_t m,
+                                           unsigned long long* d_addr_tmp, uint32_t* d_idx_tmp,
+                                           unsigned long long* d_addr_sorted, uint32_t* d_idx_sorted, void* d_temp,
+                                           size_t temp_bytes, cudaStream_t stream);
 
 // Adds (key -> host row address) pairs to a direct-pull index.  Slots must have been cleared with
 // launch_index_clear.  Duplicated keys keep the last address written.

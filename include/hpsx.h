@@ -217,6 +217,21 @@ typedef enum hpsx_memory { HPSX_MEM_HOST = 0, HPSX_MEM_DEVICE = 1 } hpsx_memory;
 int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,
                            float* const* vectors_per_table, int vector_memory,
                            const size_t* num_keys_per_table, size_t num_tables);
+/* Model-parallel return leg fused into the gather: key i of `table` is delivered to row
+ * d_pos[i] of d_out_base, which may be ANOTHER GPU's buffer opened with hpsx_ipc_open — the rows then leave
+ * the owner's gather kernel as NVLink peer stores, no all-to-all of vectors and no scatter pass.  Misses are
+ * resolved as usual and land in the same rows.  Blocks until this GPU's stores have been issued and the
+ * kernels have completed. */
+int hpsx_session_lookup_scatter(hpsx_session* s, size_t table, const int64_t* d_keys, const uint32_t* d_pos,
+                                size_t n, float* d_out_base);
+/* Device buffers that other processes of the box (one per GPU) can map: cudaMalloc + CUDA IPC handles
+ * (64 opaque bytes, exchanged by the caller, e.g. over torch.distributed). */
+int hpsx_device_malloc(int device, size_t bytes, void** d_ptr);
+int hpsx_device_free(int device, void* d_ptr);
+int hpsx_ipc_export(int device, void* d_ptr, void* handle64);
+int hpsx_ipc_open(int device, const void* handle64, void** d_ptr);
+int hpsx_ipc_close(int device, void* d_ptr);
+
 /* Blocking device -> host copy on `device` (small control tensors such as NUMKEYS that Triton
  * delivered in GPU memory). */
 int hpsx_copy_to_host(int device, void* h_dst, const void* d_src, size_t bytes);

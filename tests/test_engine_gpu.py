@@ -326,3 +326,29 @@ def test_full_size_criteo_request_properties(cuda_device):
     ref = O.NumpyTable(dim, 0.0)
     ref.fill_procedural(rows, SEED)
     assert np.array_equal(out[torch.from_numpy(idx).cuda()].cpu().numpy(), ref.lookup(d_keys.cpu().numpy()[idx]))
+
+
+def test_int64_min_key_is_a_real_key_when_loaded(cuda_device):
+    """INT64_MIN doubles as the HBM cache's empty marker, so it is never cached — but if the table holds it, it must
+    still be answered with its row (from the host table), in both miss paths and in the pooled path."""
+    torch = _torch()
+    dim = 16
+    hps = hb.HPS(num_partitions=4)
+    hps.add_model(hb.ModelParams("m", 64, [dim], [4], [9.0], cache_size_percentage=1.0))
+    kmin = np.iinfo(np.int64).min
+    keys = np.array([kmin, 5, 6, 7], dtype=np.int64)
+    vecs = np.arange(4 * dim, dtype=np.float32).reshape(4, dim)
+    hps.load_table("m", 0, keys, vecs)
+    hps.create_embedding_cache("m")
+    ref = O.NumpyTable(dim, 9.0)
+    ref.insert(keys, vecs)
+    s = hps.session("m", 0)
+    q = np.array([5, kmin, kmin, 8, 7, kmin], dtype=np.int64)
+    for _ in range(2):  # the second pass must not have cached (or lost) it either
+        out = torch.full((len(q), dim), float("nan"), device="cuda")
+        s.lookup([q], [out], [len(q)])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(q))
+    pooled = torch.empty((3, dim), device="cuda")
+    s.lookup_pooled(0, q, 3, 2, pooled, "sum")
+    assert np.array_equal(pooled.cpu().numpy(), O.pooled(ref, q, 3, 2))
+    assert kmin not in set(hps.cache_keys("m", 0, 0).tolist())

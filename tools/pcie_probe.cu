@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstdint>
 #include <vector>
+#include <algorithm>
 #include <sys/mman.h>
 #include <cstring>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
@@ -77,6 +78,27 @@ int main(int argc, char** argv) {
     }
     printf("zero-copy gather from cudaHostRegister'd 4 GiB (%s): %.3f ms  %.1f GB/s\n", mode ? "2M-aligned + MADV_HUGEPAGE" : "4K pages", ms, bytes / ms / 1e6);
     CK(cudaHostUnregister(mem)); free(mem);
+  }
+  {  // locality: sorted row order over a cudaHostAlloc'd 8 GiB table (TLB / IOTLB reach?)
+    const size_t big_rows = 1 << 24;
+    float4 *hb, *hbd;
+    CK(cudaHostAlloc(&hb, big_rows * V * 16, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&hbd, hb, 0));
+    memset(hb, 1, big_rows * V * 16);
+    for (auto& x : idx) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x = (uint32_t)(s % big_rows); }
+    for (int sorted = 0; sorted < 2; ++sorted) {
+      if (sorted) std::sort(idx.begin(), idx.end());
+      CK(cudaMemcpy(d_idx, idx.data(), n * 4, cudaMemcpyHostToDevice));
+      for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0)); gather_rows<<<1184, 256>>>(hbd, d_idx, n, V, d_out); CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1));
+      }
+      printf("zero-copy gather from cudaHostAlloc'd 8 GiB, %s rows: %.3f ms  %.1f GB/s\n", sorted ? "SORTED" : "random", ms, bytes / ms / 1e6);
+    }
+    CK(cudaFreeHost(hb));
+    FILE* f = fopen("/proc/meminfo", "r"); char line[256];
+    while (f && fgets(line, 255, f)) if (strstr(line, "Huge")) printf("%s", line);
+    if (f) fclose(f);
   }
   {  // cudaHostAlloc'd 4 GiB: does the allocation method or the table size set the zero-copy rate?
     const size_t big_rows = 1 << 23;
