@@ -363,7 +363,8 @@ def run_ours(a):
     achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")))
+        import glob
+        tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))[-1]))
         k = tr[f"probe_gather_{a.variant}"]
         traffic, traffic_src = k["dram_bytes_read"] + k["dram_bytes_write"], tr["source"]
     except (OSError, KeyError, ValueError):
