@@ -70,6 +70,18 @@ class SessionStatsC(ctypes.Structure):
     ]
 
 
+class ShardStatsC(ctypes.Structure):
+    _fields_ = [
+        ("keys_sent_remote", ctypes.c_uint64),
+        ("keys_received", ctypes.c_uint64),
+        ("keys_received_remote", ctypes.c_uint64),
+        ("misses", ctypes.c_uint64),
+        ("status", ctypes.c_uint32),
+        ("sent", ctypes.c_uint32 * 16),
+        ("received", ctypes.c_uint32 * 16),
+    ]
+
+
 # every symbol include/hpsx.h declares: name -> (restype, argtypes)
 _vp, _sz, _int, _cp = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_char_p
 _vpp = ctypes.POINTER(ctypes.c_void_p)
@@ -96,6 +108,13 @@ SYMBOLS = {
     "hpsx_ipc_export": (_int, [_int, _vp, _vp]),
     "hpsx_ipc_open": (_int, [_int, _vp, _vpp]),
     "hpsx_ipc_close": (_int, [_int, _vp]),
+    "hpsx_shard_group_create": (_int, [_vp, _sz, ctypes.c_uint32, ctypes.c_uint32, _vpp, _vp]),
+    "hpsx_shard_group_connect_ipc": (_int, [_vp, _vp]),
+    "hpsx_shard_group_connect_local": (_int, [_vp, _vpp]),
+    "hpsx_shard_group_lookup": (_int, [_vp, _vp, _sz, _vpp]),
+    "hpsx_shard_group_get_stats": (_int, [_vp, ctypes.POINTER(ShardStatsC)]),
+    "hpsx_shard_group_set_timeout_ms": (_int, [_vp, ctypes.c_uint64]),
+    "hpsx_shard_group_destroy": (_int, [_vp]),
     "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),
     "hpsx_session_lookup_ex": (_int, [_vp, _vpp, _int, _vpp, _int, c_size_p, _sz]),
     "hpsx_ps_lookup": (_int, [_vp, _cp, _sz, _vp, _sz, _vp]),

@@ -119,3 +119,35 @@ struct hpsx_session {
 
   ~hpsx_session();
 };
+
+// Rank-local half of a model-parallel group (include/hpsx.h: hpsx_shard_group_*): one table of one model,
+// rows sharded by owner_of(key, world) over the GPUs of one box.  The exchange arena is one cudaMalloc
+// (so one CUDA IPC handle): [control words | inbox keys | inbox positions | output rows].
+struct hpsx_shard_group {
+  hpsx_session* s = nullptr;
+  size_t table = 0;
+  uint32_t rank = 0, world = 1;
+  uint32_t slot_cap = 0;  // keys one rank may send to one owner = keys per request of this table
+  size_t dim = 0;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0, off_keys = 0, off_pos = 0, off_out = 0;
+  std::vector<unsigned char*> peer_arena;  // [world]; [rank] == arena
+  std::vector<bool> peer_ipc;              // opened with cudaIpcOpenMemHandle (must be closed)
+  hpsx::ShardPeers peers{};
+  bool connected = false;
+  uint32_t seq = 0;
+  // miss list of the keys received from all peers (a rank can receive up to world * slot_cap keys)
+  size_t miss_cap = 0;
+  uint32_t* d_miss_pos = nullptr;
+  int64_t* d_miss_keys = nullptr;
+  int64_t* h_miss_keys = nullptr;   // mapped pinned mirror (staged miss path only)
+  int64_t* hd_miss_keys = nullptr;
+  uint32_t* h_ctrl = nullptr;       // pinned copy of the control words
+  unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+  hpsx_shard_stats last{};
+
+  // control words (uint32 index into the arena)
+  static constexpr uint32_t kCnt = 0, kFlagDispatch = 16, kFlagReturn = 32, kCursor = 48, kStatus = 64, kWords = 80;
+  uint32_t* ctrl() const { return reinterpret_cast<uint32_t*>(arena); }
+  ~hpsx_shard_group();
+};

@@ -356,12 +356,22 @@ void run_async_insert(AsyncJob job) {
 // reuse a stage.  With `d_all_stage` the rows land at d_all_stage + i*dim and stay there for the
 // caller (pooled path).  The first kernel that rewrites cache slots takes `wlock` (exclusive) and
 // keeps it; the caller synchronises the stream before releasing it.
+// `mb` (nullable) replaces the session's own miss list (model-parallel groups keep a larger one).
+struct MissBufs {
+  const int64_t* h_keys;
+  const int64_t* d_keys;
+  const uint32_t* d_pos;
+};
+
 int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, float* d_out, bool insert,
-                     uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock) {
+                     uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock,
+                     const MissBufs* mb = nullptr) {
   hpsx_cache* c = s->cache;
   const HostTable& ht = *s->model->tables[t];
   const size_t dim = ht.dim();
-  const int64_t* h_keys = s->h_miss_keys + key_off;
+  const int64_t* h_keys = mb ? mb->h_keys : s->h_miss_keys + key_off;
+  const int64_t* d_mkeys = mb ? mb->d_keys : s->d_miss_keys + key_off;
+  const uint32_t* d_mpos = mb ? mb->d_pos : s->d_miss_pos + key_off;
   uint32_t* d_inserted = s->d_counters + s->model->tables.size() + t;
   s->stats.misses += m;
   size_t chunk = (static_cast<size_t>(m) + 3) / 4;
@@ -382,8 +392,7 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
     s->stats.h2d_bytes += mc * dim * sizeof(float);
     if (d_out != nullptr || insert) {
       if (insert && wlock != nullptr && !wlock->owns_lock()) wlock->lock();
-      HPSX_CU(launch_insert_merge(c->tables[t], s->d_miss_keys + key_off + off,
-                                  s->d_miss_pos + key_off + off, d_rows, mc, d_out, insert, epoch,
+      HPSX_CU(launch_insert_merge(c->tables[t], d_mkeys + off, d_mpos + off, d_rows, mc, d_out, insert, epoch,
                                   d_inserted, s->stream));
       ++s->stats.kernel_launches;
     }
@@ -651,6 +660,20 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
   return HPSX_OK;
 }
 
+// The per-call stage that keeps all miss rows of one request (pooled path, model-parallel groups).
+// Stream-ordered (cudaMallocAsync/cudaFreeAsync): growing it never synchronises the device, which matters when
+// another rank's flag-wait kernel is resident on the same GPU.
+int ensure_pool_stage(hpsx_session* s, size_t m) {
+  if (s->pool_stage_rows >= m) return HPSX_OK;
+  if (s->d_pool_stage) HPSX_CU(cudaFreeAsync(s->d_pool_stage, s->stream));
+  s->d_pool_stage = nullptr;
+  s->pool_stage_rows = 0;
+  const size_t rows = std::max(m, std::min<size_t>(2 * m, std::max<size_t>(s->cap_keys, m)));
+  HPSX_CU(cudaMallocAsync(reinterpret_cast<void**>(&s->d_pool_stage), rows * s->max_dim * sizeof(float), s->stream));
+  s->pool_stage_rows = rows;
+  return HPSX_OK;
+}
+
 int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool keys_on_device,
                       size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
   hpsx_cache* c = s->cache;
@@ -690,12 +713,9 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
     if (m > 0) {
       // the pooled sum needs every row: misses are always fetched before pooling
       s->stats.d2h_bytes += static_cast<uint64_t>(m) * sizeof(int64_t);
-      if (s->pool_stage_rows < m) {
-        if (s->d_pool_stage) cudaFree(s->d_pool_stage);
-        s->d_pool_stage = nullptr;
-        s->pool_stage_rows = 0;
-        HPSX_CU(cudaMalloc(&s->d_pool_stage, static_cast<size_t>(m) * s->max_dim * sizeof(float)));
-        s->pool_stage_rows = m;
+      {
+        const int prc = ensure_pool_stage(s, m);
+        if (prc != HPSX_OK) return prc;
       }
       if (c->direct_pull) {
         // rows pulled by the GPU straight from the page-locked host table into the stage
@@ -736,6 +756,157 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
     ++s->stats.kernel_launches;
     HPSX_CU(cudaStreamSynchronize(s->stream));
   }
+  return HPSX_OK;
+}
+
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void shard_fill_peers(hpsx_shard_group* g) {
+  using G = hpsx_shard_group;
+  for (uint32_t p = 0; p < g->world; ++p) {
+    unsigned char* base = g->peer_arena[p];
+    uint32_t* ctrl = reinterpret_cast<uint32_t*>(base);
+    // the slot / cells of rank p that belong to THIS rank
+    g->peers.inbox_keys[p] = reinterpret_cast<int64_t*>(base + g->off_keys) + static_cast<size_t>(g->rank) * g->slot_cap;
+    g->peers.inbox_pos[p] = reinterpret_cast<uint32_t*>(base + g->off_pos) + static_cast<size_t>(g->rank) * g->slot_cap;
+    g->peers.inbox_cnt[p] = ctrl + G::kCnt + g->rank;
+    g->peers.flag_dispatch[p] = ctrl + G::kFlagDispatch + g->rank;
+    g->peers.flag_return[p] = ctrl + G::kFlagReturn + g->rank;
+    g->peers.out[p] = reinterpret_cast<float*>(base + g->off_out);
+  }
+  g->connected = true;
+}
+
+int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out) {
+  using G = hpsx_shard_group;
+  hpsx_session* s = g->s;
+  hpsx_cache* c = s->cache;
+  const size_t t = g->table;
+  const size_t T = s->model->tables.size();
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  const uint32_t seq = ++g->seq;
+  const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  uint32_t* ctrl = g->ctrl();
+  uint32_t* d_status = ctrl + G::kStatus;
+  uint32_t* d_miss_count = s->d_counters + t;
+  const DeviceTable& dt = c->tables[t];
+  ++s->stats.lookups;
+  s->stats.keys += n;
+
+  HPSX_CU(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(d_miss_count, 0, sizeof(uint32_t), s->stream));
+  uint32_t m = 0, status = 0;
+  {
+    std::shared_lock<std::shared_mutex> rlock(c->rw);
+    HPSX_CU(launch_shard_dispatch(d_keys, n, g->world, g->peers, ctrl + G::kCursor, s->stream));
+    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 0, ctrl + G::kCursor, ctrl + G::kCnt,
+                                     ctrl + G::kFlagDispatch, static_cast<uint32_t>(std::min<size_t>(g->miss_cap, 0xFFFFFFFFu)),
+                                     d_status, g->timeout_ns, s->stream));
+    HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
+    HPSX_CU(launch_probe_gather_inbox(dt, g->peers, g->world, g->slot_cap,
+                                      reinterpret_cast<const int64_t*>(g->arena + g->off_keys),
+                                      reinterpret_cast<const uint32_t*>(g->arena + g->off_pos), ctrl + G::kCnt, d_status,
+                                      epoch, !c->is_static, d_miss_count, g->d_miss_pos, g->d_miss_keys, g->hd_miss_keys,
+                                      n, s->stream));
+    HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
+    s->stats.kernel_launches += 3;
+    HPSX_CU(cudaMemcpyAsync(g->h_ctrl, ctrl, G::kWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kWords, d_miss_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    status = g->h_ctrl[G::kStatus];
+    m = status ? 0u : g->h_ctrl[G::kWords];
+  }
+  s->stats.d2h_bytes += (G::kWords + 1) * sizeof(uint32_t);
+  hpsx_shard_stats& st = g->last;
+  st = hpsx_shard_stats{};
+  for (uint32_t p = 0; p < g->world; ++p) {
+    st.sent[p] = g->h_ctrl[G::kCursor + p];
+    st.received[p] = status ? 0u : g->h_ctrl[G::kCnt + p];
+    st.keys_received += st.received[p];
+    if (p != g->rank) {
+      st.keys_sent_remote += st.sent[p];
+      st.keys_received_remote += st.received[p];
+    }
+  }
+  st.misses = m;
+  if (status == 0) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]) == cudaSuccess) {
+      s->stats.probe_kernel_ms += ms;
+      ++s->stats.probe_kernel_launches;
+      s->stats.probe_kernel_keys += st.keys_received;
+    }
+    s->stats.hits += st.keys_received - m;
+  }
+
+  int rc = HPSX_OK;
+  if (m > 0) {
+    // resolve the misses into a local stage, forward the rows to their requesters, insert them here
+    rc = ensure_pool_stage(s, m);
+    std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
+    if (rc == HPSX_OK && c->direct_pull) {
+      if (!c->is_static) wlock.lock();
+      const bool use_sorted = pull_sort_enabled() && m <= s->cap_keys;
+      cudaError_t e = cudaMemsetAsync(s->d_counters + 2 * T + t, 0, sizeof(uint32_t), s->stream);
+      if (e == cudaSuccess && use_sorted) {
+        rc = ensure_sort_workspace(s);
+        if (rc == HPSX_OK)
+          e = launch_resolve_and_sort_misses(dt, g->d_miss_keys, m, s->d_addr[0], s->d_sidx[0], s->d_addr[1],
+                                             s->d_sidx[1], s->d_sort_temp, s->sort_temp_bytes, s->stream);
+      }
+      if (rc == HPSX_OK && e == cudaSuccess)
+        e = launch_pull_misses(dt, g->d_miss_keys, g->d_miss_pos, d_miss_count, st.keys_received, nullptr,
+                               s->d_pool_stage, !c->is_static, 1, 0.f, epoch, s->d_counters + T + t,
+                               s->d_counters + 2 * T + t, use_sorted ? s->d_addr[1] : nullptr,
+                               use_sorted ? s->d_sidx[1] : nullptr, m, s->stream);
+      if (rc == HPSX_OK && e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("direct pull: ") + cudaGetErrorString(e));
+      s->stats.kernel_launches += use_sorted ? 2 : 1;
+      s->stats.misses += m;
+      s->stats.h2d_bytes += static_cast<uint64_t>(m) * g->dim * sizeof(float);
+    } else if (rc == HPSX_OK) {
+      const MissBufs mb{g->h_miss_keys, g->d_miss_keys, g->d_miss_pos};
+      s->stats.d2h_bytes += static_cast<uint64_t>(m) * sizeof(int64_t);
+      rc = stream_miss_rows(s, t, 0, m, nullptr, false, epoch, s->d_pool_stage, nullptr, &mb);
+      if (rc == HPSX_OK && !c->is_static) {
+        wlock.lock();
+        const cudaError_t e = launch_insert_merge(dt, g->d_miss_keys, nullptr, s->d_pool_stage, m, nullptr, true, epoch,
+                                                  s->d_counters + T + t, s->stream);
+        if (e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("insert: ") + cudaGetErrorString(e));
+        ++s->stats.kernel_launches;
+      }
+    }
+    if (rc == HPSX_OK) {
+      const cudaError_t e = launch_shard_scatter_stage(s->d_pool_stage, g->d_miss_pos, m, g->dim, g->peers, g->world, s->stream);
+      if (e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("scatter: ") + cudaGetErrorString(e));
+      ++s->stats.kernel_launches;
+    }
+    if (rc != HPSX_OK) {
+      // the peers still wait for this rank's return flag: raise the error bit and fall through
+      const uint32_t one = 1;
+      cudaMemcpyAsync(d_status, &one, sizeof(one), cudaMemcpyHostToDevice, s->stream);
+    }
+    if (wlock.owns_lock()) cudaStreamSynchronize(s->stream);  // slots are rewritten under the exclusive lock only
+  }
+  // after a timeout nobody is listening any more: publish, do not wait again
+  const unsigned long long wait_ns = (status & 2u) ? 0ull : g->timeout_ns;
+  const std::string keep = g_err;
+  HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
+                                   d_status, wait_ns, s->stream));
+  ++s->stats.kernel_launches;
+  HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  status |= g->h_ctrl[G::kStatus];
+  st.status = status;
+  if (rc != HPSX_OK) return fail(rc, keep);
+  if (status != 0) {
+    std::string why = (status & 2u) ? "a rank did not arrive before the timeout"
+                      : (status & 4u) ? "this rank received more keys than its miss list can hold"
+                                      : "another rank of the group reported a failure";
+    return fail(HPSX_ERR_INTERNAL, "model-parallel lookup failed: " + why);
+  }
+  if (d_out) *d_out = reinterpret_cast<float*>(g->arena + g->off_out);
   return HPSX_OK;
 }
 
@@ -787,6 +958,20 @@ hpsx_session::~hpsx_session() {
     for (cudaEvent_t e : ev_pull) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
+}
+
+
+hpsx_shard_group::~hpsx_shard_group() {
+  if (!s || s->device < 0) return;
+  DeviceGuard guard(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (uint32_t p = 0; p < peer_arena.size(); ++p)
+    if (p != rank && peer_arena[p] != nullptr && peer_ipc[p]) cudaIpcCloseMemHandle(peer_arena[p]);
+  cudaFree(arena);
+  cudaFree(d_miss_pos);
+  cudaFree(d_miss_keys);
+  if (h_miss_keys) cudaFreeHost(h_miss_keys);
+  if (h_ctrl) cudaFreeHost(h_ctrl);
 }
 
 // ================================================================================================
@@ -1382,6 +1567,138 @@ int hpsx_ipc_close(int device, void* d_ptr) {
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(cudaIpcCloseMemHandle(d_ptr));
   return HPSX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model-parallel group
+// ------------------------------------------------------------------------------------------------
+int hpsx_shard_group_create(hpsx_session* s, size_t table, uint32_t rank, uint32_t world, hpsx_shard_group** out,
+                            void* handle64) {
+  HPSX_GUARD_BEGIN
+  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (!s->cache) return fail(HPSX_ERR_UNSUPPORTED, "a model-parallel group needs a GPU session (gpucache = true)");
+  if (table >= s->model->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (world == 0 || world > static_cast<uint32_t>(kMaxPeers) || rank >= world)
+    return fail(HPSX_ERR_INVALID_ARG, "need rank < world <= " + std::to_string(kMaxPeers));
+  const size_t cap = s->cap_per_table[table];
+  if (cap == 0 || cap >= (1ull << kShardPosBits))
+    return fail(HPSX_ERR_UNSUPPORTED, "keys per request of the sharded table must be in [1, 2^26)");
+  DeviceGuard guard(s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  std::unique_ptr<hpsx_shard_group> g(new hpsx_shard_group());
+  g->s = s;
+  g->table = table;
+  g->rank = rank;
+  g->world = world;
+  g->slot_cap = static_cast<uint32_t>(cap);
+  g->dim = s->model->tables[table]->dim();
+  g->off_keys = 4096;
+  g->off_pos = align_up(g->off_keys + static_cast<size_t>(world) * cap * sizeof(int64_t), 512);
+  g->off_out = align_up(g->off_pos + static_cast<size_t>(world) * cap * sizeof(uint32_t), 512);
+  g->arena_bytes = g->off_out + cap * g->dim * sizeof(float);
+  HPSX_CU(cudaMalloc(&g->arena, g->arena_bytes));
+  HPSX_CU(cudaMemset(g->arena, 0, 4096));
+  g->miss_cap = static_cast<size_t>(world) * cap;
+  HPSX_CU(cudaMalloc(&g->d_miss_pos, g->miss_cap * sizeof(uint32_t)));
+  HPSX_CU(cudaMalloc(&g->d_miss_keys, g->miss_cap * sizeof(int64_t)));
+  if (!s->cache->direct_pull) {
+    HPSX_CU(cudaHostAlloc(&g->h_miss_keys, g->miss_cap * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable));
+    HPSX_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->hd_miss_keys), g->h_miss_keys, 0));
+  }
+  HPSX_CU(cudaMallocHost(&g->h_ctrl, (hpsx_shard_group::kWords + 1) * sizeof(uint32_t)));
+  if (const char* env = std::getenv("HPSX_SHARD_TIMEOUT_MS")) {
+    const long long v = std::atoll(env);
+    if (v > 0) g->timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
+  }
+  g->peer_arena.assign(world, nullptr);
+  g->peer_ipc.assign(world, false);
+  g->peer_arena[rank] = g->arena;
+  if (handle64) {
+    cudaIpcMemHandle_t h;
+    HPSX_CU(cudaIpcGetMemHandle(&h, g->arena));
+    std::memcpy(handle64, &h, sizeof(h));
+  }
+  if (world == 1) shard_fill_peers(g.get());
+  *out = g.release();
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_shard_group_connect_ipc(hpsx_shard_group* g, const void* all_handles) {
+  HPSX_GUARD_BEGIN
+  if (!g || !all_handles) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(g->s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  const unsigned char* hs = static_cast<const unsigned char*>(all_handles);
+  for (uint32_t p = 0; p < g->world; ++p) {
+    if (p == g->rank || g->peer_arena[p] != nullptr) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hs + static_cast<size_t>(p) * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    HPSX_CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    g->peer_arena[p] = static_cast<unsigned char*>(ptr);
+    g->peer_ipc[p] = true;
+  }
+  shard_fill_peers(g);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_shard_group_connect_local(hpsx_shard_group* g, hpsx_shard_group* const* groups) {
+  HPSX_GUARD_BEGIN
+  if (!g || !groups) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  DeviceGuard guard(g->s->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  for (uint32_t p = 0; p < g->world; ++p) {
+    if (p == g->rank) continue;
+    const hpsx_shard_group* o = groups[p];
+    if (!o || o->world != g->world || o->rank != p || o->slot_cap != g->slot_cap || o->dim != g->dim)
+      return fail(HPSX_ERR_INVALID_ARG, "group " + std::to_string(p) + " does not match (world, rank, capacity, dim)");
+    if (o->s->device != g->s->device) {
+      int can = 0;
+      HPSX_CU(cudaDeviceCanAccessPeer(&can, g->s->device, o->s->device));
+      if (!can) return fail(HPSX_ERR_UNSUPPORTED, "no peer access between the devices of the group");
+      const cudaError_t e = cudaDeviceEnablePeerAccess(o->s->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) HPSX_CU(e);
+      cudaGetLastError();
+    }
+    g->peer_arena[p] = o->arena;
+  }
+  shard_fill_peers(g);
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_shard_group_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out) {
+  HPSX_GUARD_BEGIN
+  if (!g) return fail(HPSX_ERR_INVALID_ARG, "null group");
+  if (!g->connected) return fail(HPSX_ERR_INVALID_ARG, "the group is not connected to its peers yet");
+  if (n > g->slot_cap)
+    return fail(HPSX_ERR_INVALID_ARG, std::to_string(n) + " keys exceed max_batch_size * maxnum_catfeature_query_per_table_per_sample = " +
+                                          std::to_string(g->slot_cap));
+  if (n > 0 && !d_keys) return fail(HPSX_ERR_INVALID_ARG, "null keys");
+  std::lock_guard<std::mutex> lk(g->s->mu);
+  return shard_lookup(g, d_keys, n, d_out);
+  HPSX_GUARD_END
+}
+
+int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out) {
+  if (!g || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *out = g->last;
+  return HPSX_OK;
+}
+
+int hpsx_shard_group_set_timeout_ms(hpsx_shard_group* g, uint64_t ms) {
+  if (!g || ms == 0) return fail(HPSX_ERR_INVALID_ARG, "null group / zero timeout");
+  g->timeout_ns = ms * 1000000ull;
+  return HPSX_OK;
+}
+
+int hpsx_shard_group_destroy(hpsx_shard_group* g) {
+  HPSX_GUARD_BEGIN
+  delete g;
+  return HPSX_OK;
+  HPSX_GUARD_END
 }
 
 int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,

@@ -113,6 +113,45 @@ cudaError_t launch_route_keys(const int64_t* d_keys, size_t n, uint32_t num_shar
 cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, size_t n, size_t dim,
                                 float* d_out, cudaStream_t stream);
 
+// ------------------------------------------------------------------------------------------------
+// Fused model-parallel exchange over NVLink peer memory (hpsx_shard_group in hpsx.h).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;            // GPUs of one box
+constexpr uint32_t kShardPosBits = 26;   // miss destination = (requester << 26) | row in its output
+
+// What rank r knows about every rank p of the group (entry r = its own arena).  Passed to kernels by value.
+struct ShardPeers {
+  int64_t* inbox_keys[kMaxPeers];   // p's inbox slot for keys sent by r: [slot_cap]
+  uint32_t* inbox_pos[kMaxPeers];   // matching request positions
+  uint32_t* inbox_cnt[kMaxPeers];   // cell of p's count array that r writes
+  uint32_t* flag_dispatch[kMaxPeers];  // cell of p's dispatch-flag array that r writes
+  uint32_t* flag_return[kMaxPeers];    // cell of p's return-flag array that r writes
+  float* out[kMaxPeers];            // p's output buffer [slot_cap, dim]
+};
+
+// Step 1: bucket keys by owner_of(key, world) and store (key, position) into the owners' inboxes.
+// d_cursor[kMaxPeers] (local) receives the per-owner counts.
+cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t world, const ShardPeers& peers,
+                                  uint32_t* d_cursor, cudaStream_t stream);
+// Steps 2 and 4: publish (phase 0: counts + dispatch flag, phase 1: return flag with this rank's error bit)
+// to every peer, then spin until every peer's flag for sequence `seq` has arrived in our own control block.
+// *d_status: bit 0 error (ours or a peer's), bit 1 timeout, bit 2 more keys received than `capacity`.
+cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, uint32_t seq, int phase,
+                                     const uint32_t* d_cursor, const uint32_t* d_my_cnt, const uint32_t* d_my_flags,
+                                     uint32_t capacity, uint32_t* d_status, unsigned long long timeout_ns,
+                                     cudaStream_t stream);
+// Step 3: probe the cache for every key in the local inbox and store the rows (or the default vector) into
+// row pos of the SENDER's output buffer; misses are appended to the miss list with kShardPosBits-encoded
+// destinations.  Does nothing when *d_status != 0.
+cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& peers, uint32_t world, uint32_t slot_cap,
+                                      const int64_t* d_inbox_keys, const uint32_t* d_inbox_pos,
+                                      const uint32_t* d_inbox_cnt, const uint32_t* d_status, uint32_t epoch, bool touch,
+                                      uint32_t* d_miss_count, uint32_t* d_miss_pos, int64_t* d_miss_keys,
+                                      int64_t* hd_miss_keys, size_t expected_keys, cudaStream_t stream);
+// Rows of resolved misses (d_stage[i]) to their requesters' outputs.
+cudaError_t launch_shard_scatter_stage(const float* d_stage, const uint32_t* d_miss_pos, size_t m, size_t dim,
+                                       const ShardPeers& peers, uint32_t world, cudaStream_t stream);
+
 // Measurement primitive: out[i] = table[idx[i]] for 128-float rows (the random-gather ceiling the
 // probe+gather kernel is compared with in bench.py).
 cudaError_t launch_gather_rows(const float* d_table, const uint32_t* d_idx, size_t n, size_t dim,

@@ -271,6 +271,69 @@ class LookupSession:
         N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2}[variant]))
 
 
+class _DeviceRows:
+    """Zero-copy view of a device buffer owned by the engine (``__cuda_array_interface__``):
+    ``torch.as_tensor(view, device="cuda")`` aliases it."""
+
+    def __init__(self, ptr: int, rows: int, dim: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (rows, dim), "typestr": "<f4", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class ShardGroup:
+    """~ ``hpsx_shard_group`` (include/hpsx.h): rank-local half of a model-parallel table.  The reference has no
+    counterpart (replicas only, hps_backend/src/model_state.cpp:395-419)."""
+
+    def __init__(self, session: LookupSession, table: int, rank: int, world: int, dim: int):
+        self._L = N.lib()
+        self._session = session
+        self.rank, self.world, self.dim = int(rank), int(world), int(dim)
+        h = ctypes.c_void_p()
+        self.handle = np.zeros(64, dtype=np.uint8)
+        N.check(self._L.hpsx_shard_group_create(session._h, table, rank, world, ctypes.byref(h), _addr(self.handle)))
+        self._h = h
+
+    def connect_ipc(self, all_handles: np.ndarray) -> None:
+        """``all_handles``: uint8 [world, 64], row r = rank r's ``handle`` (other processes of the box)."""
+        hs = np.ascontiguousarray(all_handles, dtype=np.uint8).reshape(self.world, 64)
+        N.check(self._L.hpsx_shard_group_connect_ipc(self._h, _addr(hs)))
+
+    def connect_local(self, groups: Sequence["ShardGroup"]) -> None:
+        """All ranks live in this process (threads, one per GPU)."""
+        arr = (ctypes.c_void_p * self.world)(*[g._h for g in groups])
+        N.check(self._L.hpsx_shard_group_connect_local(self._h, arr))
+
+    def lookup(self, d_keys, n: int):
+        """Collective.  Returns a zero-copy [n, dim] view of this rank's output buffer (valid until the next lookup)."""
+        out = ctypes.c_void_p()
+        N.check(self._L.hpsx_shard_group_lookup(self._h, _addr(d_keys), n, ctypes.byref(out)))
+        return _DeviceRows(out.value or 0, n, self.dim, self)
+
+    def lookup_ptr(self, d_keys, n: int) -> int:
+        out = ctypes.c_void_p()
+        N.check(self._L.hpsx_shard_group_lookup(self._h, _addr(d_keys), n, ctypes.byref(out)))
+        return out.value or 0
+
+    def stats(self) -> dict:
+        s = N.ShardStatsC()
+        N.check(self._L.hpsx_shard_group_get_stats(self._h, ctypes.byref(s)))
+        return {"keys_sent_remote": s.keys_sent_remote, "keys_received": s.keys_received,
+                "keys_received_remote": s.keys_received_remote, "misses": s.misses, "status": s.status,
+                "sent": np.array(s.sent[:self.world], dtype=np.int64), "received": np.array(s.received[:self.world], dtype=np.int64)}
+
+    def set_timeout_ms(self, ms: int) -> None:
+        N.check(self._L.hpsx_shard_group_set_timeout_ms(self._h, int(ms)))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.hpsx_shard_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 # -- stand-alone device primitives ---------------------------------------------------------------
 def unique(device: int, d_keys, n: int, d_unique, d_inverse, stream: int = 0) -> int:
     u = ctypes.c_size_t()

@@ -10,6 +10,11 @@ partitioned here by ``owner(key) = mix64(key).lo * G >> 32`` and a request is se
   4. all-to-all-v of the rows back                         (4·D B/key)
   5. scatter rows to their original request positions      (scatter_rows kernel, hpsx_scatter_rows)
 
+``mode="p2p"`` replaces steps 1-5 by ONE fused exchange over NVLink peer memory (``hpsx_shard_group_*`` in
+include/hpsx.h): keys and request positions are stored straight into the owners' inboxes, each owner's probe+gather
+kernel stores the rows straight into the requesters' output buffers, and device-side flags order the steps — no NCCL
+call and no host round trip on the data path (torch.distributed only exchanges the CUDA IPC handles once).
+
 Python only sequences the calls: every computation is a kernel or a C-ABI function of libhpsx.so, every
 exchange a torch.distributed collective (``nccl`` on GPUs; point-to-point ``gloo`` ops on the CPU path, where the
 lookup is the host parameter server and the routing is ``hpsx_owner_batch``).
@@ -56,7 +61,7 @@ class ShardedLookup:
     """One table of one model, rows sharded over the ranks of ``group``.  Every rank must have loaded the shard
     ``owner(key) == rank`` into its own ``HPS`` (e.g. ``load_table_procedural_shard``)."""
 
-    def __init__(self, hps: H.HPS, model: str, table: int, dim: int, device: int, group=None):
+    def __init__(self, hps: H.HPS, model: str, table: int, dim: int, device: int, group=None, mode: str = "nccl"):
         import torch
         import torch.distributed as dist
 
@@ -66,6 +71,45 @@ class ShardedLookup:
         self.session = hps.session(model, device)
         self.on_gpu = device >= 0
         self.last = {}
+        self.mode = mode
+        self.p2p = None
+        if mode == "p2p":
+            if not self.on_gpu:
+                raise ValueError("mode='p2p' needs GPU sessions")
+            self.p2p = H.ShardGroup(self.session, table, self.rank, self.world, self.dim)
+            mine = torch.from_numpy(self.p2p.handle.copy())
+            if dist.get_backend(group) == "nccl":
+                mine = mine.cuda(device)
+            handles = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(handles, mine, group=group)
+            self.p2p.connect_ipc(np.stack([h.cpu().numpy() for h in handles]))
+            dist.barrier(group=group)
+        elif mode != "nccl":
+            raise ValueError(f"unknown mode {mode!r}")
+
+    def close(self):
+        """Collective: no rank may free its arena while a peer can still store into it."""
+        if self.p2p is not None:
+            self.dist.barrier(group=self.group)
+            self.p2p.close()
+            self.p2p = None
+
+    def _lookup_p2p(self, keys, out):
+        torch = self.torch
+        n = keys.numel()
+        torch.cuda.current_stream().synchronize()  # the session launches on its own stream
+        view = self.p2p.lookup(keys, n)
+        st = self.p2p.stats()
+        self.last = {"sent_keys": int(st["keys_sent_remote"]), "received_keys": int(st["keys_received_remote"]),
+                     "send_counts": st["sent"], "recv_counts": st["received"], "misses": int(st["misses"])}
+        if n == 0:
+            rows = torch.empty((0, self.dim), dtype=torch.float32, device=keys.device)
+        else:
+            rows = torch.as_tensor(view, device=keys.device)
+        if out is not None:
+            out.copy_(rows)
+            return out
+        return rows
 
     # -- step 1: bucket keys by owner ---------------------------------------------------------------------
     def _route(self, keys):
@@ -106,6 +150,8 @@ class ShardedLookup:
         torch, dist = self.torch, self.dist
         keys = keys.contiguous().view(-1)
         n = keys.numel()
+        if self.p2p is not None:
+            return self._lookup_p2p(keys, out)
         routed, perm, send_counts = self._route(keys)
         # step 2a: counts
         sc = torch.from_numpy(send_counts.copy())

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HPSX_ABI_VERSION 2
+#define HPSX_ABI_VERSION 3
 
 typedef enum hpsx_status {
   HPSX_OK = 0,
@@ -231,6 +231,42 @@ int hpsx_device_free(int device, void* d_ptr);
 int hpsx_ipc_export(int device, void* d_ptr, void* handle64);
 int hpsx_ipc_open(int device, const void* handle64, void** d_ptr);
 int hpsx_ipc_close(int device, void* d_ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * model-parallel group: rows of one table sharded over the GPUs of one box by
+ * hpsx_owner(key, world); the reference has no such mode (one full cache per device,
+ * hps_backend/src/model_state.cpp:395-419).  One hpsx_shard_group per rank, built on that rank's session
+ * (whose parameter server holds the shard owner == rank).  A lookup is ONE fused exchange over NVLink peer
+ * memory: keys + request positions are stored straight into the owners' inboxes, each owner's probe+gather
+ * kernel stores the rows straight into the requesters' output buffers, and two flag waves (device-side, no
+ * NCCL call, no host round trip) order the steps.  Every rank of the group must call lookup the same number of
+ * times (it is a collective); misses are always resolved synchronously.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hpsx_shard_group hpsx_shard_group;
+#define HPSX_SHARD_HANDLE_BYTES 64 /* one CUDA IPC memory handle */
+typedef struct hpsx_shard_stats {
+  uint64_t keys_sent_remote;     /* keys of the last request owned by other ranks */
+  uint64_t keys_received;        /* keys this rank looked up for the group in the last request (own included) */
+  uint64_t keys_received_remote;
+  uint64_t misses;               /* of keys_received */
+  uint32_t status;               /* 0 ok; bit 0 a rank failed, bit 1 timeout, bit 2 capacity */
+  uint32_t sent[16];             /* per owner */
+  uint32_t received[16];         /* per requester */
+} hpsx_shard_stats;
+/* Allocates the rank's exchange arena (inbox for world x cap keys, output for cap rows; cap = the session's
+ * key capacity for `table`) and writes its IPC handle to handle64 (may be NULL for same-process groups). */
+int hpsx_shard_group_create(hpsx_session* s, size_t table, uint32_t rank, uint32_t world, hpsx_shard_group** out,
+                            void* handle64);
+/* One process per GPU: all_handles = world x 64 bytes, rank-major (exchanged by the caller, e.g. all_gather). */
+int hpsx_shard_group_connect_ipc(hpsx_shard_group* g, const void* all_handles);
+/* All ranks in this process (e.g. one Triton server driving 8 GPUs): groups[world], entry `rank` == g. */
+int hpsx_shard_group_connect_local(hpsx_shard_group* g, hpsx_shard_group* const* groups);
+/* Collective.  d_keys: this rank's request (device memory, n <= cap).  On return *d_out is this rank's output
+ * buffer [n, dim] (owned by the group, valid until the next lookup), rows in request order. */
+int hpsx_shard_group_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out);
+int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out);
+int hpsx_shard_group_set_timeout_ms(hpsx_shard_group* g, uint64_t ms);
+int hpsx_shard_group_destroy(hpsx_shard_group* g);
 
 /* Blocking device -> host copy on `device` (small control tensors such as NUMKEYS that Triton
  * delivered in GPU memory). */

@@ -1,0 +1,126 @@
+"""Fused model-parallel exchange (hpsx_shard_group_*, include/hpsx.h) on ONE GPU.
+
+The reference has no model-parallel mode (one full cache per device, hps_backend/src/model_state.cpp:395-419);
+parity is against the CPU oracle of the lookup contract, bit-exact, plus the integer artefacts of the routing
+(owner(key) and per-peer counts).  Two cases run on a single device: the degenerate world = 1 group, and a
+world = 2 group whose ranks are two parameter servers + sessions of this process on the same GPU (threads,
+`connect_local`), which exercises inboxes, flags and cross-rank stores without a second device.  The
+multi-process CUDA-IPC form runs in tests/test_sharded_gpu.py on a box with >= 2 GPUs.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+import hugectr_backend_b200 as hb
+from oracle import hps_oracle as O
+
+pytestmark = pytest.mark.gpu
+SEED = 0xB2000004
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _rank_server(rows, dim, rank, world, pagelock, cache_pct, default=0.25, max_batch=1 << 16):
+    hps = hb.HPS(num_partitions=4, num_threads=2)
+    hps.add_model(hb.ModelParams("dlrm", max_batch, [dim], [1], [default], cache_size_percentage=cache_pct,
+                                 hit_rate_threshold=1.0, deployed_devices=[0], enable_pagelock=pagelock))
+    hps.load_table_procedural_shard("dlrm", 0, rows, SEED, rank, world)
+    hps.create_embedding_cache("dlrm")
+    return hps
+
+
+@pytest.mark.parametrize("pagelock", [False, True])
+@pytest.mark.parametrize("dim", [128, 24])
+def test_world1_group_matches_oracle(cuda_device, pagelock, dim):
+    torch = _torch()
+    rows = 60_000
+    hps = _rank_server(rows, dim, 0, 1, pagelock, 0.5)
+    ref = O.NumpyTable(dim, 0.25)
+    ref.fill_procedural(rows, SEED)
+    s = hps.session("dlrm", 0)
+    g = hb.ShardGroup(s, 0, 0, 1, dim)
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 4097, 0, 50_000, 65_536):
+        keys = rng.integers(-3, rows + 3, size=n)
+        dk = torch.from_numpy(keys).cuda()
+        torch.cuda.current_stream().synchronize()
+        view = g.lookup(dk, n)
+        if n == 0:
+            continue
+        out = torch.as_tensor(view, device="cuda").cpu().numpy()
+        assert np.array_equal(out, ref.lookup(keys)), (n, pagelock, dim)
+        st = g.stats()
+        assert st["status"] == 0 and st["keys_received"] == n and st["keys_sent_remote"] == 0
+    with pytest.raises(hb.HpsxError):
+        g.lookup(dk, (1 << 16) + 1)  # more keys than max_batch_size * maxnum_catfeature
+    g.close()
+
+
+@pytest.mark.parametrize("pagelock", [False, True])
+def test_world2_same_device_threads(cuda_device, pagelock):
+    """Two ranks of one process on one GPU: every cross-rank key/row moves through the peer pointers."""
+    torch = _torch()
+    rows, dim, world = 80_000, 128, 2
+    ref = O.NumpyTable(dim, 0.25)
+    ref.fill_procedural(rows, SEED)
+    servers = [_rank_server(rows, dim, r, world, pagelock, 0.6) for r in range(world)]
+    sessions = [servers[r].session("dlrm", 0) for r in range(world)]
+    groups = [hb.ShardGroup(sessions[r], 0, r, world, dim) for r in range(world)]
+    for g in groups:
+        g.set_timeout_ms(20_000)
+        g.connect_local(groups)
+    sizes = [(1, 0), (4097, 333), (60_000, 60_000), (0, 0), (65_536, 12_345)]
+    results = {}
+
+    def run(rank):
+        torch.cuda.set_device(0)
+        rng = np.random.default_rng(10 + rank)
+        ok = True
+        for it, pair in enumerate(sizes):
+            n = pair[rank]
+            keys = rng.integers(-5, rows + 5, size=n)
+            dk = torch.from_numpy(keys).cuda()
+            torch.cuda.current_stream().synchronize()
+            view = groups[rank].lookup(dk, n)
+            st = groups[rank].stats()
+            ok &= st["status"] == 0
+            ok &= bool(np.array_equal(st["sent"], np.bincount(O.owner(keys, world), minlength=world)))
+            if n:
+                out = torch.as_tensor(view, device="cuda").cpu().numpy()
+                ok &= bool(np.array_equal(out, ref.lookup(keys)))
+        results[rank] = ok
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in threads]
+    [t.join(180) for t in threads]
+    assert not any(t.is_alive() for t in threads), "a rank hung"
+    assert results == {0: True, 1: True}
+    # what one rank received is what the other sent
+    a, b = groups[0].stats(), groups[1].stats()
+    assert a["received"][1] == b["sent"][0] and b["received"][0] == a["sent"][1]
+    for g in groups:
+        g.close()
+
+
+def test_absent_peer_times_out(cuda_device):
+    """A rank whose peer never calls lookup gets an error after the timeout instead of hanging the GPU."""
+    torch = _torch()
+    rows, dim, world = 5_000, 32, 2
+    servers = [_rank_server(rows, dim, r, world, False, 1.0, max_batch=1024) for r in range(world)]
+    sessions = [servers[r].session("dlrm", 0) for r in range(world)]
+    groups = [hb.ShardGroup(sessions[r], 0, r, world, dim) for r in range(world)]
+    for g in groups:
+        g.set_timeout_ms(300)
+        g.connect_local(groups)
+    dk = torch.arange(100, dtype=torch.int64, device="cuda")
+    torch.cuda.current_stream().synchronize()
+    with pytest.raises(hb.HpsxError, match="timeout"):
+        groups[0].lookup(dk, 100)
+    assert groups[0].stats()["status"] & 2
+    for g in groups:
+        g.close()

@@ -1,4 +1,5 @@
-"""Model-parallel rows over 2+ GPUs of one box with NCCL all-to-all key routing (config C4 shape, scaled down).
+"""Model-parallel rows over 2+ GPUs of one box (config C4 shape, scaled down): NCCL all-to-all key routing
+(mode "nccl") and the fused exchange over NVLink peer memory through CUDA IPC (mode "p2p", hpsx_shard_group_*).
 Skipped on a single-GPU box; run with `gpurun --gpus 2 -- python -m pytest tests/test_sharded_gpu.py -m gpu`."""
 import os
 import socket
@@ -17,7 +18,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, rows, dim, seed, pagelock, ret):
+def _worker(rank, world, port, rows, dim, seed, pagelock, mode, ret):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -37,7 +38,7 @@ def _worker(rank, world, port, rows, dim, seed, pagelock, ret):
         hps.create_embedding_cache("dlrm")
         ref = O.NumpyTable(dim, 0.25)
         ref.fill_procedural(rows, seed)
-        sl = ShardedLookup(hps, "dlrm", 0, dim, device=rank)
+        sl = ShardedLookup(hps, "dlrm", 0, dim, device=rank, mode=mode)
         ok = True
         rng = np.random.default_rng(100 + rank)
         for n in (1, 4097, 60000, 0, 60000):
@@ -46,13 +47,15 @@ def _worker(rank, world, port, rows, dim, seed, pagelock, ret):
             ok &= bool(np.array_equal(out.cpu().numpy(), ref.lookup(keys)))
             if n:
                 ok &= bool(np.array_equal(sl.last["send_counts"], np.bincount(O.owner(keys, world), minlength=world)))
+        sl.close()
         ret[rank] = ok
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
 @pytest.mark.parametrize("pagelock", [False, True])
-def test_sharded_lookup_nccl(cuda_device, pagelock):
+def test_sharded_lookup_nccl(cuda_device, pagelock, mode):
     import torch
     import torch.multiprocessing as mp
 
@@ -63,7 +66,7 @@ def test_sharded_lookup_nccl(cuda_device, pagelock):
     port = _free_port()
     ctx = mp.get_context("spawn")
     ret = ctx.Manager().dict()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, dim, seed, pagelock, ret)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, rows, dim, seed, pagelock, mode, ret)) for r in range(world)]
     [p.start() for p in procs]
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
