@@ -57,6 +57,14 @@ def parse_args():
                          "staged: CPU gather + cudaMemcpyAsync")
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
     ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "ldg"), choices=["ldg", "tma"])
+    ap.add_argument("--workload", default="dcn", choices=["dcn", "c4"],
+                    help="dcn: BASELINE.json configs[1] (default, replicas over --gpus); c4: DLRM-shaped model-parallel table "
+                         "(configs[3]): rows sharded over the GPUs by owner(key), global batch split over the ranks, 100 %% HBM-resident")
+    ap.add_argument("--rows-per-gpu", type=int, default=16_000_000,
+                    help="c4 only: rows of the sharded table per GPU (configs[3] is 1B rows / 8 GPUs = 125M per GPU = 64 GB of HBM "
+                         "and as much host memory per rank; the default keeps set-up time and host memory small)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -79,6 +87,20 @@ def make_requests(a, hot_keys: np.ndarray, cold_lo: int, count: int, seed: int):
         k[is_hot] = hot_keys[rng.integers(0, len(hot_keys), size=int(is_hot.sum()))]
         reqs.append(k)
     return reqs
+
+
+class stdout_to_stderr:
+    """NCCL prints its version banner on stdout while a communicator is created: keep stdout for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 class ClockSampler:
@@ -281,7 +303,9 @@ def run_ours(a):
         raise SystemExit("bench.py needs a CUDA device: the lookup path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
 
     n = a.batch * a.slots
     peaks = {}
@@ -462,10 +486,142 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_sharded(a):
+    """configs[3]-shaped: one table sharded by owner(key) over the ranks, every rank serves its slice of the global
+    batch, every key is HBM-resident at its owner.  value = keys of ALL ranks / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+
+    import hugectr_backend_b200 as hb
+    from hugectr_backend_b200.sharded import ShardedLookup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the lookup path has no CPU fallback")
+    torch.cuda.set_device(local)
+    with stdout_to_stderr():
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    batch = a.batch if a.batch != 65536 else 131072  # configs[3]: batch 131072
+    n = batch * a.slots // world
+    rows = a.rows_per_gpu * world
+    t0 = time.perf_counter()
+    hps = hb.HPS(num_partitions=16)
+    # a rank receives ~n keys from the group, not exactly n: leave the owner-side workspaces 2 % + 4096 keys of headroom
+    hps.add_model(hb.ModelParams("dlrm", n + n // 50 + 4096, [a.dim], [1], [0.0], hit_rate_threshold=1.0, cache_size_percentage=1.0,
+                                 deployed_devices=[local], cache_load_factor=a.load_factor, enable_pagelock=False))
+    hps.load_table_procedural_shard("dlrm", 0, rows, SEED + 2, rank, world)
+    hps.create_embedding_cache("dlrm")
+    setup_s = time.perf_counter() - t0
+    sl = ShardedLookup(hps, "dlrm", 0, a.dim, device=local, mode=a.exchange)
+    sess = sl.session
+    ext = torch.cuda.ExternalStream(sess.stream) if a.exchange == "p2p" else torch.cuda.current_stream()
+    R = a.distinct if a.distinct > 0 else min(16, a.steps + a.warmup)
+    rng = np.random.default_rng(SEED + 100 + rank)
+    h_reqs = [torch.from_numpy(rng.integers(0, rows, size=n, dtype=np.int64)).pin_memory() for _ in range(R)]
+    d_reqs = [k.cuda() for k in h_reqs]
+    d_stage = torch.empty(n, dtype=torch.int64, device="cuda")
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for i in range(steps):
+            fn(i)
+        e1.record(ext)
+        torch.cuda.synchronize()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    dev_step = lambda i: sl.lookup(d_reqs[i % R])
+
+    def e2e_step(i):
+        d_stage.copy_(h_reqs[i % R], non_blocking=True)  # 8 B/key H2D from pinned memory
+        return sl.lookup(d_stage)
+
+    for i in range(a.warmup):
+        dev_step(a.steps + i)
+    sess.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(dev_step, a.steps)
+    clocks = sampler.stop()
+    st = sess.stats()
+    last = dict(sl.last)
+    for i in range(a.warmup):
+        e2e_step(a.steps + i)
+    # the H2D copy runs on torch's stream, the exchange on the session stream: bracket both with wall clock + syncs
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(a.steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - w0
+    barrier()
+    t = torch.tensor([wall], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall = float(t[0])
+    sl.close()
+
+    probe_ms = st.probe_kernel_ms / max(1, st.probe_kernel_launches)
+    recv = st.probe_kernel_keys / max(1, st.probe_kernel_launches)
+    remote_frac = (world - 1) / world
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    alg = recv * (8 + 4 + 8 * a.dim)
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": world * a.steps * n / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"DLRM-shape (configs[3]) model-parallel: {a.slots} slots, {rows // 1_000_000}M-row table sharded over "
+                                   f"{world} GPU(s) ({a.rows_per_gpu // 1_000_000}M rows per GPU), dim {a.dim}, global batch {batch}, 100% HBM-resident",
+                       "keys_per_step_per_gpu": n, "keys_per_step": n * world, "rows": rows, "exchange": a.exchange,
+                       "l2": f"{R} distinct key batches; rows >> L2", "setup_s": setup_s,
+                       "note": "configs[3] is 1B rows over 8 GPUs (125M rows = 64 GB per GPU); rows per GPU are scaled by --rows-per-gpu"},
+            "roofline": {"bound": "hbm", "kernel": "probe_gather_inbox" if a.exchange == "p2p" else "probe_gather_ldg",
+                         "achieved": alg / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0, "peak": peak_gbs, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": (alg / (probe_ms / 1e3) / 1e9 / peak_gbs) if probe_ms > 0 else 0.0, "traffic": None,
+                         "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg,
+                         "share_of_step": probe_ms / (ms / a.steps),
+                         "nvlink_out_gbs_per_gpu": recv * remote_frac * 4 * a.dim / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0,
+                         "note": "owner-side gather: 8 B key + 4 B position + 4D row read from local HBM, 4D row written into the "
+                                 "requester's buffer ((N-1)/N of them over NVLink); rank 0's kernel"},
+            "cpu_baseline": None,
+            "e2e": {"value": world * a.steps * n / wall, "unit": UNIT, "ms_per_step": wall / a.steps * 1e3,
+                    "h2d_bytes_per_step": n * 8, "d2h_bytes_per_step": 0 if a.exchange == "p2p" else 8 * world,
+                    "call": "ShardedLookup.lookup (hpsx_shard_group_lookup): pinned host keys -> rows in this rank's device buffer",
+                    "timer": "host wall clock + synchronize, max over ranks"},
+            "gpu_launches": int(st.kernel_launches), "clocks": clocks,
+            "exchange_stats_rank0": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in last.items()},
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "c4":
+        run_sharded(a)
     else:
         run_ours(a)
 

@@ -51,6 +51,14 @@ HPSX_HD uint32_t bucket_of(int64_t key, uint32_t num_buckets) {
   return static_cast<uint32_t>(((h >> 32) * static_cast<uint64_t>(num_buckets)) >> 32);
 }
 
+// Second-choice bucket (two-choice hashing): an independent hash of the key.  A key lives in bucket_of() unless
+// that bucket was full when it was inserted; ways are never emptied, so a probe that misses in a primary
+// bucket with a free way knows the key is not cached and reads nothing else.
+HPSX_HD uint32_t bucket2_of(int64_t key, uint32_t num_buckets) {
+  const uint64_t h = mix64(static_cast<uint64_t>(key) ^ 0x9E3779B97F4A7C15ULL);
+  return static_cast<uint32_t>(((h >> 32) * static_cast<uint64_t>(num_buckets)) >> 32);
+}
+
 // Owning shard of a key in the model-parallel mode: low 32 hash bits, so that the bucket index
 // (high bits) stays uniform inside one shard.
 HPSX_HD uint32_t owner_of(int64_t key, uint32_t num_shards) {

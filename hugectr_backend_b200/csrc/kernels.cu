@@ -83,29 +83,60 @@ __device__ __forceinline__ void vdiv(float2& a, float d) {
 __device__ __forceinline__ void vdiv(float& a, float d) { a = __fdiv_rn(a, d); }
 
 // ------------------------------------------------------------------------------------------------
-// probe: one thread, one key, one 64-B bucket (two DRAM sectors, four LDG.128 through L2 only)
+// probe: one thread, one key, one 64-B bucket (two DRAM sectors, four LDG.128 through L2 only); the
+// second-choice bucket is read only when the key is not in a FULL primary bucket
 // ------------------------------------------------------------------------------------------------
+struct BucketKeys {
+  longlong2 k01, k23, k45, k67;
+};
+
+__device__ __forceinline__ BucketKeys load_bucket_keys(const Bucket* __restrict__ buckets, uint32_t b) {
+  const longlong2* kp = reinterpret_cast<const longlong2*>(buckets[b].keys);
+  BucketKeys r;
+  r.k01 = __ldcg(kp + 0);
+  r.k23 = __ldcg(kp + 1);
+  r.k45 = __ldcg(kp + 2);
+  r.k67 = __ldcg(kp + 3);
+  return r;
+}
+
+__device__ __forceinline__ int match_way(const BucketKeys& k, int64_t key) {
+  int way = -1;
+  way = (k.k01.x == key) ? 0 : way;
+  way = (k.k01.y == key) ? 1 : way;
+  way = (k.k23.x == key) ? 2 : way;
+  way = (k.k23.y == key) ? 3 : way;
+  way = (k.k45.x == key) ? 4 : way;
+  way = (k.k45.y == key) ? 5 : way;
+  way = (k.k67.x == key) ? 6 : way;
+  way = (k.k67.y == key) ? 7 : way;
+  return way;
+}
+
+__device__ __forceinline__ bool bucket_full(const BucketKeys& k) {
+  return k.k01.x != kEmptyKey && k.k01.y != kEmptyKey && k.k23.x != kEmptyKey && k.k23.y != kEmptyKey &&
+         k.k45.x != kEmptyKey && k.k45.y != kEmptyKey && k.k67.x != kEmptyKey && k.k67.y != kEmptyKey;
+}
+
+// Second half of a probe whose primary bucket `bk` (index b) is already in registers.
+__device__ __forceinline__ uint32_t resolve_slot(Bucket* __restrict__ buckets, uint32_t num_buckets, int64_t key,
+                                                 uint32_t b, const BucketKeys& bk, uint32_t epoch, bool touch) {
+  int way = match_way(bk, key);
+  if (way < 0) {
+    if (!bucket_full(bk)) return kMissSlot;
+    b = bucket2_of(key, num_buckets);
+    way = match_way(load_bucket_keys(buckets, b), key);
+    if (way < 0) return kMissSlot;
+  }
+  if (touch) buckets[b].stamp[way] = epoch;  // LRU touch: 4-B store into the line's third sector
+  return b * kWays + static_cast<uint32_t>(way);
+}
+
 __device__ __forceinline__ uint32_t probe_bucket(Bucket* __restrict__ buckets, uint32_t num_buckets,
                                                  int64_t key, uint32_t epoch, bool touch) {
   if (key == kEmptyKey) return kMissSlot;
   const uint32_t b = bucket_of(key, num_buckets);
-  const longlong2* kp = reinterpret_cast<const longlong2*>(buckets[b].keys);
-  const longlong2 k01 = __ldcg(kp + 0);
-  const longlong2 k23 = __ldcg(kp + 1);
-  const longlong2 k45 = __ldcg(kp + 2);
-  const longlong2 k67 = __ldcg(kp + 3);
-  int way = -1;
-  way = (k01.x == key) ? 0 : way;
-  way = (k01.y == key) ? 1 : way;
-  way = (k23.x == key) ? 2 : way;
-  way = (k23.y == key) ? 3 : way;
-  way = (k45.x == key) ? 4 : way;
-  way = (k45.y == key) ? 5 : way;
-  way = (k67.x == key) ? 6 : way;
-  way = (k67.y == key) ? 7 : way;
-  if (way < 0) return kMissSlot;
-  if (touch) buckets[b].stamp[way] = epoch;  // LRU touch: 4-B store into the line's third sector
-  return b * kWays + static_cast<uint32_t>(way);
+  return resolve_slot(buckets, num_buckets, key, b, load_bucket_keys(buckets, b), epoch, touch);
 }
 
 struct ProbeArgs {
@@ -210,33 +241,6 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
 // of tile t, the bucket lines of tile t+1 and the keys of tile t+2 are already in flight, so the two
 // latency hops at the head of a tile no longer idle the warp.
 // ------------------------------------------------------------------------------------------------
-struct BucketKeys {
-  longlong2 k01, k23, k45, k67;
-};
-
-__device__ __forceinline__ BucketKeys load_bucket_keys(const Bucket* __restrict__ buckets, uint32_t b) {
-  const longlong2* kp = reinterpret_cast<const longlong2*>(buckets[b].keys);
-  BucketKeys r;
-  r.k01 = __ldcg(kp + 0);
-  r.k23 = __ldcg(kp + 1);
-  r.k45 = __ldcg(kp + 2);
-  r.k67 = __ldcg(kp + 3);
-  return r;
-}
-
-__device__ __forceinline__ int match_way(const BucketKeys& k, int64_t key) {
-  int way = -1;
-  way = (k.k01.x == key) ? 0 : way;
-  way = (k.k01.y == key) ? 1 : way;
-  way = (k.k23.x == key) ? 2 : way;
-  way = (k.k23.y == key) ? 3 : way;
-  way = (k.k45.x == key) ? 4 : way;
-  way = (k.k45.y == key) ? 5 : way;
-  way = (k.k67.x == key) ? 6 : way;
-  way = (k.k67.y == key) ? 7 : way;
-  return way;
-}
-
 template <typename VecT, int kV, int kUnroll>
 __global__ void __launch_bounds__(kBlock) probe_gather_pipe_kernel(const ProbeArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -269,13 +273,8 @@ __global__ void __launch_bounds__(kBlock) probe_gather_pipe_kernel(const ProbeAr
     const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), a.n - tile_base));
     const bool valid = lane < nk;
     uint32_t slot = kMissSlot;
-    if (valid && key_cur != kEmptyKey) {
-      const int way = match_way(bk_cur, key_cur);
-      if (way >= 0) {
-        slot = b_cur * kWays + static_cast<uint32_t>(way);
-        if (a.touch) a.buckets[b_cur].stamp[way] = a.epoch;
-      }
-    }
+    if (valid && key_cur != kEmptyKey)
+      slot = resolve_slot(a.buckets, a.num_buckets, key_cur, b_cur, bk_cur, a.epoch, a.touch != 0);
     const bool is_miss = valid && slot == kMissSlot;
     unsigned miss_mask;
     const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
@@ -512,53 +511,81 @@ struct InsertArgs {
   uint32_t* inserted;
 };
 
-// Claims the cache slot for `key` in its bucket.  Called by a whole warp; returns with the bucket lock
-// HELD (release_bucket() must follow) and the way to write, or -1 when the key is already resident
-// (LRU refreshed) or no way may be evicted (every way was touched in this very epoch).
-__device__ __forceinline__ int claim_way(Bucket* B, int64_t key, uint32_t epoch, uint32_t lane) {
+// Claims the cache slot for `key`.  Called by a whole warp.  Both candidate buckets (primary and second
+// choice) are locked in ascending index order, so concurrent inserts can neither deadlock nor place one key
+// twice; returns with the locks HELD (release_claim() must follow).  Result: slot index to write, or
+// kMissSlot when the key is already resident (LRU refreshed) or nothing may be evicted (all 16 ways were
+// touched in this very epoch).  Placement: a free way of the primary bucket, else a free way of the second
+// choice, else the way with the oldest stamp of the 16 (primary wins ties).
+struct Claim {
+  Bucket* lo;
+  Bucket* hi;  // nullptr when both choices are the same bucket
+};
+
+__device__ __forceinline__ void lock_bucket(Bucket* B) {
+  while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
+}
+
+__device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buckets, int64_t key, uint32_t epoch,
+                                               uint32_t lane, Claim* claim) {
+  const uint32_t b1 = bucket_of(key, num_buckets);
+  const uint32_t b2 = bucket2_of(key, num_buckets);
+  claim->lo = &buckets[min(b1, b2)];
+  claim->hi = b1 == b2 ? nullptr : &buckets[max(b1, b2)];
   if (lane == 0) {
-    while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
+    lock_bucket(claim->lo);
+    if (claim->hi != nullptr) lock_bucket(claim->hi);
     __threadfence();
   }
   __syncwarp();
+  // lanes 0-7: ways of the primary bucket, lanes 8-15: ways of the second choice
+  const uint32_t nways = b1 == b2 ? kWays : 2 * kWays;
+  const uint32_t my_b = lane < kWays ? b1 : b2;
+  const uint32_t my_w = lane & (kWays - 1);
   int64_t k = kEmptyKey;
   uint32_t st = epoch;
-  if (lane < kWays) {
-    k = __ldcg(reinterpret_cast<const long long*>(&B->keys[lane]));
-    st = __ldcg(&B->stamp[lane]);
+  if (lane < nways) {
+    k = __ldcg(reinterpret_cast<const long long*>(&buckets[my_b].keys[my_w]));
+    st = __ldcg(&buckets[my_b].stamp[my_w]);
   }
-  const unsigned present = __ballot_sync(kFull, lane < kWays && k == key);
+  const unsigned present = __ballot_sync(kFull, lane < nways && k == key);
+  int pick = -1;  // lane index of the chosen way
   if (present != 0u) {
-    if (lane == 0) B->stamp[__ffs(present) - 1] = epoch;  // already cached: refresh LRU only
-    return -1;
+    if (lane == __ffs(present) - 1) buckets[my_b].stamp[my_w] = epoch;  // already cached: refresh LRU only
+    return kMissSlot;
   }
-  int way = -1;
-  const unsigned empties = __ballot_sync(kFull, lane < kWays && k == kEmptyKey);
+  const unsigned empties = __ballot_sync(kFull, lane < nways && k == kEmptyKey);
   if (empties != 0u) {
-    way = __ffs(empties) - 1;
+    pick = __ffs(empties) - 1;  // primary ways come first
   } else {
     // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted
-    const uint32_t age = lane < kWays ? epoch - st : 0u;
+    const uint32_t age = lane < nways ? epoch - st : 0u;
     unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
 #pragma unroll
-    for (int off = 4; off > 0; off >>= 1) {
+    for (int off = 8; off > 0; off >>= 1) {
       const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
       packed = o > packed ? o : packed;
     }
     packed = __shfl_sync(kFull, packed, 0);
-    if ((packed >> 8) != 0ull) way = 255 - static_cast<int>(packed & 255ull);
+    if ((packed >> 8) != 0ull) pick = 255 - static_cast<int>(packed & 255ull);
   }
-  if (way >= 0 && lane == 0) {
-    B->keys[way] = key;
-    B->stamp[way] = epoch;
+  if (pick < 0) return kMissSlot;
+  const uint32_t pb = pick < kWays ? b1 : b2;
+  const uint32_t pw = static_cast<uint32_t>(pick) & (kWays - 1);
+  if (lane == 0) {
+    buckets[pb].keys[pw] = key;
+    buckets[pb].stamp[pw] = epoch;
   }
-  return way;
+  return pb * kWays + pw;
 }
 
-__device__ __forceinline__ void release_bucket(Bucket* B, uint32_t lane) {
+__device__ __forceinline__ void release_claim(const Claim& c, uint32_t lane) {
   __threadfence();
   __syncwarp();
-  if (lane == 0) atomicExch(&B->lock, 0u);
+  if (lane == 0) {
+    if (c.hi != nullptr) atomicExch(&c.hi->lock, 0u);
+    atomicExch(&c.lo->lock, 0u);
+  }
 }
 
 template <typename VecT>
@@ -573,21 +600,18 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
     VecT* dst_out =
         a.out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
     VecT* dst_slab = nullptr;
-    Bucket* B = nullptr;
+    Claim claim{nullptr, nullptr};
     if (a.insert && key != kEmptyKey) {
-      const uint32_t b = bucket_of(key, a.num_buckets);
-      B = &a.buckets[b];
-      const int way = claim_way(B, key, a.epoch, lane);
-      if (way >= 0)
-        dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+      const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+      if (slot != kMissSlot) dst_slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
     }
     for (uint32_t v = lane; v < V; v += 32u) {
       const VecT x = src[v];
       if (dst_out) dst_out[v] = x;
       if (dst_slab) dst_slab[v] = x;
     }
-    if (B != nullptr) {
-      release_bucket(B, lane);
+    if (claim.lo != nullptr) {
+      release_claim(claim, lane);
       if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
     }
   }
@@ -780,13 +804,10 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
           write_out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
       VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
       VecT* dst_slab = nullptr;
-      Bucket* B = nullptr;
+      Claim claim{nullptr, nullptr};
       if (a.insert && src[r] != nullptr && key[r] != kEmptyKey) {
-        const uint32_t b = bucket_of(key[r], a.num_buckets);
-        B = &a.buckets[b];
-        const int way = claim_way(B, key[r], a.epoch, lane);
-        if (way >= 0)
-          dst_slab = reinterpret_cast<VecT*>(a.values) + (static_cast<size_t>(b) * kWays + way) * V;
+        const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key[r], a.epoch, lane, &claim);
+        if (slot != kMissSlot) dst_slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
       }
       for (uint32_t v = lane; v < V; v += 32u) {
         VecT x;
@@ -800,8 +821,8 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
         if (dst_stage) dst_stage[v] = x;
         if (dst_slab) dst_slab[v] = x;
       }
-      if (B != nullptr) {
-        release_bucket(B, lane);
+      if (claim.lo != nullptr) {
+        release_claim(claim, lane);
         if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
       }
       if (lane == 0 && src[r] == nullptr && a.absent != nullptr) atomicAdd(a.absent, 1u);
@@ -1680,7 +1701,7 @@ struct InboxArgs {
 // The owner's gather: persistent grid, warps stride over 32-key tiles of the inbox; tiles never straddle two
 // sources.  Hit rows leave as 512-B peer stores into the requester's output (`peers.out[src]`), misses get
 // the default vector there and are appended to the miss list with their (src, position) destination.
-template <typename VecT, int kV, int kUnroll>
+template <typename VecT, int kV, int kUnroll, bool kStreamStores = false>
 __global__ void __launch_bounds__(kBlock, 4) probe_gather_inbox_kernel(const InboxArgs a, const ShardPeers peers) {
   __shared__ uint32_t tile_end[kMaxPeers];  // inclusive prefix of per-source tile counts
   if (*a.status != 0u) return;
@@ -1731,7 +1752,12 @@ __global__ void __launch_bounds__(kBlock, 4) probe_gather_inbox_kernel(const Inb
         const uint32_t i = i0 + u * 32u + lane;
         const uint32_t kk = min(i / V, 31u);
         const uint32_t d = __shfl_sync(kFull, dst, kk);
-        if (i < total) outv[static_cast<size_t>(d) * V + (i - kk * V)] = buf[u];
+        if (i < total) {
+          if (kStreamStores)
+            st_stream(outv + static_cast<size_t>(d) * V + (i - kk * V), buf[u]);
+          else
+            outv[static_cast<size_t>(d) * V + (i - kk * V)] = buf[u];
+        }
       }
     }
     if (is_miss) {
@@ -1803,13 +1829,27 @@ cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& pe
   a.miss_pos = d_miss_pos;
   a.miss_keys = d_miss_keys;
   a.miss_keys_host = hd_miss_keys;
-  // the received count is only known on the device: persistent grid of at most 4 CTAs per SM (what the
-  // register budget keeps resident), never more warps than an even split of the request would need
+  // the received count is only known on the device: the grid is sized for an even split of the request
   const size_t tiles = (std::max<size_t>(expected_keys, 32) + 31) / 32 + world;
-  const unsigned grid = static_cast<unsigned>(std::min<size_t>(148 * 4, (tiles * 32 + kBlock - 1) / kBlock));
+  static int ctas_per_sm = -1;
+  if (ctas_per_sm < 0) {
+    // measured (profiles/): one tile per warp + 3 % slack beats a persistent grid of 4-8 CTAs/SM by ~10 %; under
+    // heavier skew the surplus tiles are picked up by the stride loop.  HPSX_INBOX_CTAS=<n> forces n CTAs per SM.
+    ctas_per_sm = 0;
+    if (const char* env = getenv("HPSX_INBOX_CTAS")) ctas_per_sm = atoi(env);
+  }
+  const size_t want = ((tiles + tiles / 32) * 32 + kBlock - 1) / kBlock;
+  const unsigned grid = static_cast<unsigned>(ctas_per_sm > 0 ? std::min<size_t>(148 * ctas_per_sm, want) : want);
   bool aligned = ((reinterpret_cast<uintptr_t>(t.values) | (static_cast<uintptr_t>(t.dim) * 4u)) & 15u) == 0;
   for (uint32_t p = 0; p < world; ++p) aligned = aligned && (reinterpret_cast<uintptr_t>(peers.out[p]) & 15u) == 0;
-  if (aligned && t.dim == 128)
+  static int stream_stores = -1;
+  if (stream_stores < 0) {
+    stream_stores = 1;  // st.global.cs: output rows are written once and not re-read by this kernel
+    if (const char* env = getenv("HPSX_INBOX_ST")) stream_stores = atoi(env);
+  }
+  if (aligned && t.dim == 128 && stream_stores)
+    probe_gather_inbox_kernel<float4, 32, 8, true><<<grid, kBlock, 0, stream>>>(a, peers);
+  else if (aligned && t.dim == 128)
     probe_gather_inbox_kernel<float4, 32, 8><<<grid, kBlock, 0, stream>>>(a, peers);
   else if (aligned)
     probe_gather_inbox_kernel<float4, 0, 4><<<grid, kBlock, 0, stream>>>(a, peers);
