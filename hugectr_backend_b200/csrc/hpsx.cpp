@@ -788,6 +788,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   const uint32_t seq = ++g->seq;
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  const double tr0 = now_ms();
   uint32_t* ctrl = g->ctrl();
   uint32_t* d_status = ctrl + G::kStatus;
   uint32_t* d_miss_count = s->d_counters + t;
@@ -805,7 +806,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
                                      ctrl + G::kFlagDispatch, static_cast<uint32_t>(std::min<size_t>(g->miss_cap, 0xFFFFFFFFu)),
                                      d_status, g->timeout_ns, s->stream));
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
-    HPSX_CU(launch_probe_gather_inbox(dt, g->peers, g->world, g->slot_cap,
+    HPSX_CU(launch_probe_gather_inbox(dt, g->peers, g->world, g->rank, g->slot_cap,
                                       reinterpret_cast<const int64_t*>(g->arena + g->off_keys),
                                       reinterpret_cast<const uint32_t*>(g->arena + g->off_pos), ctrl + G::kCnt, d_status,
                                       epoch, !c->is_static, d_miss_count, g->d_miss_pos, g->d_miss_keys, g->hd_miss_keys,
@@ -818,6 +819,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     status = g->h_ctrl[G::kStatus];
     m = status ? 0u : g->h_ctrl[G::kWords];
   }
+  const double tr1 = now_ms();
   s->stats.d2h_bytes += (G::kWords + 1) * sizeof(uint32_t);
   hpsx_shard_stats& st = g->last;
   st = hpsx_shard_stats{};
@@ -889,6 +891,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     }
     if (wlock.owns_lock()) cudaStreamSynchronize(s->stream);  // slots are rewritten under the exclusive lock only
   }
+  const double tr2 = now_ms();
   // after a timeout nobody is listening any more: publish, do not wait again
   const unsigned long long wait_ns = (status & 2u) ? 0ull : g->timeout_ns;
   const std::string keep = g_err;
@@ -899,6 +902,9 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
   HPSX_CU(cudaStreamSynchronize(s->stream));
   status |= g->h_ctrl[G::kStatus];
   st.status = status;
+  if (trace_on())
+    std::fprintf(stderr, "[hpsx] shard lookup rank %u n=%zu: dispatch+wait+gather+sync %.3f ms | misses %u: %.3f ms | return wave %.3f ms\n",
+                 g->rank, n, tr1 - tr0, m, tr2 - tr1, now_ms() - tr2);
   if (rc != HPSX_OK) return fail(rc, keep);
   if (status != 0) {
     std::string why = (status & 2u) ? "a rank did not arrive before the timeout"

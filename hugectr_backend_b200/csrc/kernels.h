@@ -143,7 +143,8 @@ cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, ui
 // Step 3: probe the cache for every key in the local inbox and store the rows (or the default vector) into
 // row pos of the SENDER's output buffer; misses are appended to the miss list with kShardPosBits-encoded
 // destinations.  Does nothing when *d_status != 0.
-cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& peers, uint32_t world, uint32_t slot_cap,
+cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& peers, uint32_t world, uint32_t rank,
+                                      uint32_t slot_cap,
                                       const int64_t* d_inbox_keys, const uint32_t* d_inbox_pos,
                                       const uint32_t* d_inbox_cnt, const uint32_t* d_status, uint32_t epoch, bool touch,
                                       uint32_t* d_miss_count, uint32_t* d_miss_pos, int64_t* d_miss_keys,
