@@ -121,6 +121,8 @@ SYMBOLS = {
     "hpsx_ps_create_embedding_cache_per_model": (_int, [_vp, _cp]),
     "hpsx_ps_get_embedding_cache": (_int, [_vp, _cp, _int, _vpp]),
     "hpsx_ps_destroy_embedding_cache_per_model": (_int, [_vp, _cp]),
+    "hpsx_ps_update_database_per_model": (_int, [_vp, _cp]),
+    "hpsx_ps_refresh_embedding_cache": (_int, [_vp, _cp, _int, c_size_p]),
     "hpsx_cache_num_tables": (_int, [_vp, c_size_p]),
     "hpsx_cache_device": (_int, [_vp, ctypes.POINTER(_int)]),
     "hpsx_cache_capacity": (_int, [_vp, _sz, c_size_p]),

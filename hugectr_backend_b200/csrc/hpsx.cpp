@@ -184,6 +184,64 @@ int insert_rows_from_host(hpsx_ps* ps, hpsx_cache* c, size_t t, const int64_t* k
   return HPSX_OK;
 }
 
+// enable_pagelock: page-lock the host tables and mirror their key -> row-address index in HBM, so that misses
+// are pulled by kernels straight from host DRAM (no CPU gather, no staging copy).  Called at cache creation
+// and again after the host tables changed (update_database): registers the new slab ranges, re-allocates an
+// index that became too small and rebuilds it.  The caller excludes lookups (c->rw exclusive, or the cache is
+// not published yet) and has the device selected.
+int sync_direct_pull_index(hpsx_cache* c, cudaStream_t stream) {
+  Model* model = c->model;
+  const size_t T = model->tables.size();
+  int64_t* d_ikeys = nullptr;
+  uint64_t* d_iaddrs = nullptr;
+  constexpr size_t kIndexChunk = 1 << 20;
+  HPSX_CU(cudaMalloc(&d_ikeys, kIndexChunk * sizeof(int64_t)));
+  HPSX_CU(cudaMalloc(&d_iaddrs, kIndexChunk * sizeof(uint64_t)));
+  int rc = HPSX_OK;
+  if (c->indexes.size() < T) c->indexes.resize(T, nullptr);
+  for (size_t t = 0; t < T && rc == HPSX_OK; ++t) {
+    HostTable& ht = *model->tables[t];
+    std::string err;
+    if (!ht.pagelock(&err)) {
+      rc = fail(HPSX_ERR_CUDA, err);
+      break;
+    }
+    uint64_t cap = 1024;
+    while (cap < 2 * ht.rows()) cap <<= 1;
+    IndexSlot* slots = c->indexes[t];
+    cudaError_t ce = cudaSuccess;
+    if (slots == nullptr || c->tables[t].index_mask + 1 < cap) {
+      if (slots != nullptr) cudaFree(slots);
+      c->indexes[t] = slots = nullptr;
+      c->tables[t].index = nullptr;
+      ce = cudaMalloc(&slots, cap * sizeof(IndexSlot));
+      if (ce == cudaSuccess) c->indexes[t] = slots;
+    } else {
+      cap = c->tables[t].index_mask + 1;
+    }
+    if (ce == cudaSuccess) ce = launch_index_clear(slots, cap, stream);
+    if (ce == cudaSuccess) {
+      ht.export_rows(kIndexChunk, [&](const int64_t* k, const uint64_t* a, size_t n) {
+        if (ce != cudaSuccess) return;
+        ce = cudaMemcpyAsync(d_ikeys, k, n * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_iaddrs, a, n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream);
+        if (ce == cudaSuccess) ce = launch_index_build(slots, cap - 1, d_ikeys, d_iaddrs, n, stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);  // the pageable vectors are reused
+      });
+    }
+    if (ce != cudaSuccess) {
+      rc = fail(HPSX_ERR_CUDA, std::string("building the direct-pull index: ") + cudaGetErrorString(ce));
+      break;
+    }
+    c->tables[t].index = slots;
+    c->tables[t].index_mask = cap - 1;
+    c->tables[t].sentinel_row = ht.sentinel_row_device();
+  }
+  cudaFree(d_ikeys);
+  cudaFree(d_iaddrs);
+  return rc;
+}
+
 int build_cache(hpsx_ps* ps, Model* model, int device, std::unique_ptr<hpsx_cache>* out) {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
@@ -249,42 +307,8 @@ int build_cache(hpsx_ps* ps, Model* model, int device, std::unique_ptr<hpsx_cach
                                  d_stage, chunk, nullptr);
     }
   }
-  // enable_pagelock: page-lock the host tables and mirror their key -> row-address index in HBM, so
-  // that misses are pulled by kernels straight from host DRAM (no CPU gather, no staging copy)
   if (rc == HPSX_OK && model->direct_pull) {
-    int64_t* d_ikeys = nullptr;
-    uint64_t* d_iaddrs = nullptr;
-    constexpr size_t kIndexChunk = 1 << 20;
-    HPSX_CU(cudaMalloc(&d_ikeys, kIndexChunk * sizeof(int64_t)));
-    HPSX_CU(cudaMalloc(&d_iaddrs, kIndexChunk * sizeof(uint64_t)));
-    for (size_t t = 0; t < T && rc == HPSX_OK; ++t) {
-      HostTable& ht = *model->tables[t];
-      std::string err;
-      if (!ht.pagelock(&err)) {
-        rc = fail(HPSX_ERR_CUDA, err);
-        break;
-      }
-      uint64_t cap = 1024;
-      while (cap < 2 * ht.rows()) cap <<= 1;
-      IndexSlot* slots = nullptr;
-      HPSX_CU(cudaMalloc(&slots, cap * sizeof(IndexSlot)));
-      c->indexes.push_back(slots);
-      HPSX_CU(launch_index_clear(slots, cap, stream));
-      cudaError_t ce = cudaSuccess;
-      ht.export_rows(kIndexChunk, [&](const int64_t* k, const uint64_t* a, size_t n) {
-        if (ce != cudaSuccess) return;
-        ce = cudaMemcpyAsync(d_ikeys, k, n * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_iaddrs, a, n * sizeof(uint64_t), cudaMemcpyHostToDevice, stream);
-        if (ce == cudaSuccess) ce = launch_index_build(slots, cap - 1, d_ikeys, d_iaddrs, n, stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);  // the pageable vectors are reused
-      });
-      HPSX_CU(ce);
-      c->tables[t].index = slots;
-      c->tables[t].index_mask = cap - 1;
-      c->tables[t].sentinel_row = ht.sentinel_row_device();
-    }
-    cudaFree(d_ikeys);
-    cudaFree(d_iaddrs);
+    rc = sync_direct_pull_index(c.get(), stream);
     c->direct_pull = rc == HPSX_OK;
   }
   cudaFree(d_inserted);
@@ -511,7 +535,8 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
     HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                 s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t], nullptr,
-                                s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr));
+                                s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr,
+                                s->d_src ? s->d_src + off[t] : nullptr));
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
     ++s->stats.kernel_launches;
     if (!sorted) {
@@ -609,7 +634,7 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
       HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
                                   s->hd_miss_keys + off[t], s->probe_variant, s->stream,
-                                  pos_per_table ? pos_per_table[t] : nullptr));
+                                  pos_per_table ? pos_per_table[t] : nullptr, s->d_src ? s->d_src + off[t] : nullptr));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
     }
@@ -1304,6 +1329,91 @@ int hpsx_ps_get_embedding_cache(hpsx_ps* ps, const char* model, int device, hpsx
   return HPSX_OK;
 }
 
+int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model) {
+  HPSX_GUARD_BEGIN
+  Model* m = find_model(ps, model);
+  if (!m) return fail(HPSX_ERR_NOT_FOUND, std::string("unknown model '") + (model ? model : "") + "'");
+  // Page-locked tables are read in place by the pull kernels: keep lookups out while rows are rewritten.
+  std::vector<hpsx_cache*> caches;
+  {
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (auto& kv : m->caches) caches.push_back(kv.second.get());
+  }
+  // lock order everywhere: async_mu (workspace owner) before rw
+  std::vector<std::unique_lock<std::mutex>> held_ws;
+  std::vector<std::unique_lock<std::shared_mutex>> held;
+  for (hpsx_cache* c : caches)
+    if (c->direct_pull) held_ws.emplace_back(c->async_mu);
+  for (hpsx_cache* c : caches)
+    if (c->direct_pull) held.emplace_back(c->rw);
+  for (size_t t = 0; t < m->tables.size() && t < m->cfg.sparse_files.size(); ++t) {
+    if (m->cfg.sparse_files[t].empty()) continue;
+    const int rc = load_sparse_dir(ps, m->tables[t].get(), m->cfg.sparse_files[t]);
+    if (rc != HPSX_OK) return rc;
+  }
+  for (hpsx_cache* c : caches) {
+    if (!c->direct_pull) continue;
+    DeviceGuard guard(c->device);
+    if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+    const int rc = sync_direct_pull_index(c, c->async_stream);
+    if (rc != HPSX_OK) return rc;
+  }
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_ps_refresh_embedding_cache(hpsx_ps* ps, const char* model, int device, size_t* refreshed_rows) {
+  HPSX_GUARD_BEGIN
+  if (refreshed_rows) *refreshed_rows = 0;
+  hpsx_cache* c = nullptr;
+  int rc = hpsx_ps_get_embedding_cache(ps, model, device, &c);
+  if (rc != HPSX_OK) return rc;
+  Model* m = c->model;
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  std::lock_guard<std::mutex> ws(c->async_mu);  // one owner of the refresh / async-insert workspace
+  uint32_t* d_updated = nullptr;
+  HPSX_CU(cudaMalloc(&d_updated, sizeof(uint32_t)));
+  HPSX_CU(cudaMemsetAsync(d_updated, 0, sizeof(uint32_t), c->async_stream));
+  std::vector<int64_t> keys;
+  for (size_t t = 0; t < c->tables.size() && rc == HPSX_OK; ++t) {
+    keys.resize(c->slots[t]);
+    size_t n = 0;
+    rc = hpsx_cache_dump_keys(c, t, keys.data(), keys.size(), &n);
+    if (rc != HPSX_OK) break;
+    // cache_refresh_percentage_per_iteration (src/backend.cpp:411-416): share of the cache rewritten per
+    // exclusive section, so that lookups interleave with a long refresh
+    const double pct = m->cfg.cache_refresh_percentage_per_iteration;
+    size_t chunk = pct > 0.0 ? static_cast<size_t>(pct * static_cast<double>(c->slots[t])) : c->async_rows;
+    chunk = std::min(c->async_rows, std::max<size_t>(chunk, 1024));
+    const HostTable& ht = *m->tables[t];
+    const size_t dim = ht.dim();
+    for (size_t off = 0; off < n; off += chunk) {
+      const size_t mc = std::min(chunk, n - off);
+      ht.fetch(keys.data() + off, mc, c->async_h_stage, dim, *ps->pool);
+      std::unique_lock<std::shared_mutex> wl(c->rw);
+      cudaError_t e = cudaMemcpyAsync(c->async_d_keys, keys.data() + off, mc * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                      c->async_stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->async_d_stage, c->async_h_stage, mc * dim * sizeof(float), cudaMemcpyHostToDevice,
+                            c->async_stream);
+      if (e == cudaSuccess) e = launch_update_values(c->tables[t], c->async_d_keys, c->async_d_stage, mc, d_updated, c->async_stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->async_stream);
+      if (e != cudaSuccess) {
+        rc = fail(HPSX_ERR_CUDA, std::string("cache refresh: ") + cudaGetErrorString(e));
+        break;
+      }
+    }
+  }
+  uint32_t h = 0;
+  if (rc == HPSX_OK && cudaMemcpy(&h, d_updated, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess)
+    rc = fail(HPSX_ERR_CUDA, "cache refresh: reading the counter failed");
+  cudaFree(d_updated);
+  if (rc == HPSX_OK && refreshed_rows) *refreshed_rows = h;
+  return rc;
+  HPSX_GUARD_END
+}
+
 int hpsx_ps_destroy_embedding_cache_per_model(hpsx_ps* ps, const char* model) {
   HPSX_GUARD_BEGIN
   Model* m = find_model(ps, model);
@@ -1408,7 +1518,10 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   s->cache = c;
   s->device = device;
   if (const char* env = std::getenv("HPSX_PROBE"))
-    s->probe_variant = std::strcmp(env, "tma") == 0 ? kProbeTma : (std::strcmp(env, "pipe") == 0 ? kProbePipe : kProbeLdg);
+    s->probe_variant = std::strcmp(env, "tma") == 0     ? kProbeTma
+                       : std::strcmp(env, "pipe") == 0  ? kProbePipe
+                       : std::strcmp(env, "split") == 0 ? kProbeSplit
+                                                        : kProbeLdg;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -1429,6 +1542,7 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
     HPSX_CU(cudaMalloc(&s->d_stage[b], stage_rows * s->max_dim * sizeof(float)));
     HPSX_CU(cudaEventCreateWithFlags(&s->stage_free[b], cudaEventDisableTiming));
   }
+  if (s->probe_variant == kProbeSplit) HPSX_CU(cudaMalloc(&s->d_src, cap * sizeof(uint32_t)));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * T);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
@@ -1896,8 +2010,15 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
 
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
-  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe)
+  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe && variant != kProbeSplit)
     return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
+  if (variant == kProbeSplit && s->cache && !s->d_src) {
+    // the split variant keeps one slot index per key between its two launches
+    DeviceGuard guard(s->device);
+    if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+    std::lock_guard<std::mutex> lk(s->mu);
+    HPSX_CU(cudaMalloc(&s->d_src, std::max<size_t>(s->cap_keys, 1) * sizeof(uint32_t)));
+  }
   s->probe_variant = variant;
   return HPSX_OK;
 }

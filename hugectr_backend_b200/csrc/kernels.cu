@@ -617,6 +617,39 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
   }
 }
 
+// K9 value update (cache refresh): overwrite the cached row of every key that is still
+// resident; keys that left the cache meanwhile are skipped.  One warp per key; lanes 0-15 compare the 16
+// candidate ways (primary + second-choice bucket).  Runs with the cache's host lock held exclusively, so no
+// probe copies a row while it is rewritten.
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) update_values_kernel(const Bucket* __restrict__ buckets, float* values,
+                                                               uint32_t num_buckets, uint32_t dim,
+                                                               const int64_t* __restrict__ keys,
+                                                               const float* __restrict__ stage, size_t n,
+                                                               uint32_t* updated) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
+  const uint32_t V = dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  for (size_t i = warp; i < n; i += nwarps) {
+    const int64_t key = keys[i];
+    if (key == kEmptyKey) continue;
+    const uint32_t b1 = bucket_of(key, num_buckets), b2 = bucket2_of(key, num_buckets);
+    const uint32_t my_b = lane < kWays ? b1 : b2;
+    const uint32_t my_w = lane & (kWays - 1);
+    int64_t k = kEmptyKey;
+    if (lane < 2 * kWays) k = __ldcg(reinterpret_cast<const long long*>(&buckets[my_b].keys[my_w]));
+    const unsigned hit = __ballot_sync(kFull, lane < 2 * kWays && k == key);
+    if (hit == 0u) continue;
+    const uint32_t src_lane = __ffs(hit) - 1;
+    const uint32_t slot = __shfl_sync(kFull, my_b * kWays + my_w, src_lane);
+    const VecT* src = reinterpret_cast<const VecT*>(stage) + i * V;
+    VecT* dst = reinterpret_cast<VecT*>(values) + static_cast<size_t>(slot) * V;
+    for (uint32_t v = lane; v < V; v += 32u) dst[v] = src[v];
+    if (lane == 0 && updated != nullptr) atomicAdd(updated, 1u);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // direct pull: index of the page-locked host table in HBM, rows read zero-copy over PCIe
 // ------------------------------------------------------------------------------------------------
@@ -1085,6 +1118,40 @@ __global__ void __launch_bounds__(kBlock) gather_rows_kernel(const float4* __res
   }
 }
 
+// Second half of the split probe/gather variant: out[i] = slab[src[i]], or the default vector when src[i]
+// carries kSrcMissBit.  No hashing and no dependent bucket hop in this kernel: it runs at the random-gather
+// ceiling, and the probe that feeds it (probe_index_kernel) only moves 76 B per key.
+template <int kV, int kUnroll>
+__global__ void __launch_bounds__(kBlock) gather_src_kernel(const float4* __restrict__ table,
+                                                            const uint32_t* __restrict__ src, size_t n,
+                                                            float default_value, float4* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t tile_base = ((static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5) * 32;
+  if (tile_base >= n) return;
+  const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), n - tile_base));
+  const uint32_t slot = lane < nk ? __ldcs(src + tile_base + lane) : kSrcMissBit;
+  constexpr uint32_t V = kV;
+  const float4 defv = make_float4(default_value, default_value, default_value, default_value);
+  float4* __restrict__ outv = out + tile_base * V;
+  const uint32_t total = nk * V;
+  for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
+    float4 buf[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      const uint32_t kk = min(i / V, 31u);
+      const uint32_t s = __shfl_sync(kFull, slot, kk);
+      buf[u] = defv;
+      if (i < total && (s & kSrcMissBit) == 0u) buf[u] = ld_stream(table + static_cast<size_t>(s) * V + (i - kk * V));
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const uint32_t i = i0 + u * 32u + lane;
+      if (i < total) st_stream(outv + i, buf[u]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) synth_rows_kernel(const int64_t* __restrict__ keys, size_t n,
                                                             uint32_t dim, uint64_t seed, float* rows) {
   const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
@@ -1238,7 +1305,7 @@ cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream, const uint32_t* d_pos) {
+                                int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t* d_slot_scratch) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.buckets = t.buckets;
@@ -1262,6 +1329,13 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
     if (vb == 16) return launch_probe_ldg_scatter<float4>(a, stream);
     if (vb == 8) return launch_probe_ldg_scatter<float2>(a, stream);
     return launch_probe_ldg_scatter<float>(a, stream);
+  }
+  if (variant == kProbeSplit && vb == 16 && t.dim == 128 && d_slot_scratch != nullptr) {
+    a.src = d_slot_scratch;
+    probe_index_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
+    gather_src_kernel<32, 8><<<grid_for(n), kBlock, 0, stream>>>(reinterpret_cast<const float4*>(t.values), d_slot_scratch,
+                                                                  n, t.default_value, reinterpret_cast<float4*>(d_out));
+    return cudaGetLastError();
   }
   if (variant == kProbeTma && vb == 16) {
     const cudaError_t e = launch_probe_tma(a, stream);
@@ -1329,6 +1403,20 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
     insert_merge_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
   else
     insert_merge_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_update_values(const DeviceTable& t, const int64_t* d_keys, const float* d_stage, size_t n,
+                                 uint32_t* d_updated, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>(148 * 32, (n * 32 + kBlock - 1) / kBlock));
+  const int vb = vec_bytes(t.dim, d_stage, t.values);
+  if (vb == 16)
+    update_values_kernel<float4><<<grid, kBlock, 0, stream>>>(t.buckets, t.values, t.num_buckets, t.dim, d_keys, d_stage, n, d_updated);
+  else if (vb == 8)
+    update_values_kernel<float2><<<grid, kBlock, 0, stream>>>(t.buckets, t.values, t.num_buckets, t.dim, d_keys, d_stage, n, d_updated);
+  else
+    update_values_kernel<float><<<grid, kBlock, 0, stream>>>(t.buckets, t.values, t.num_buckets, t.dim, d_keys, d_stage, n, d_updated);
   return cudaGetLastError();
 }
 

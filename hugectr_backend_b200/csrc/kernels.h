@@ -28,6 +28,7 @@ enum ProbeVariant : int {
   kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers
   kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
   kProbePipe = 2, // persistent grid, key -> bucket -> rows chain software-pipelined across tiles
+  kProbeSplit = 3, // two launches: probe (slot per key, 76 B/key) then a hash-free gather at the random-gather ceiling
 };
 
 // K2+K3+K6 fused: probe the cache for keys[0..n), copy hit rows to out[i*dim..),
@@ -39,7 +40,8 @@ enum ProbeVariant : int {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr);
+                                int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr,
+                                uint32_t* d_slot_scratch = nullptr);
 // With `d_pos`, key i is delivered to row d_pos[i] of d_out instead of row i, and d_out may be another
 // GPU's buffer (NVLink peer mapping): the model-parallel return leg fused into the gather.
 
@@ -56,6 +58,11 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
                                 const uint32_t* d_miss_pos, const float* d_stage, size_t m,
                                 float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
                                 cudaStream_t stream);
+
+// K9 (cache refresh): for every key that is still resident overwrite its cached row with d_stage[i*dim..);
+// *d_updated (nullable) counts the rows rewritten.  Caller holds the cache's host lock exclusively.
+cudaError_t launch_update_values(const DeviceTable& t, const int64_t* d_keys, const float* d_stage, size_t n,
+                                 uint32_t* d_updated, cudaStream_t stream);
 
 // Direct pull (K4+K5 without the CPU): for every miss i in [0, *d_miss_count): find the key in the
 // HBM-resident index of the page-locked host table, read the row straight from mapped pinned host

@@ -17,7 +17,9 @@
 #include <mutex>
 #include <numeric>
 #include <sstream>
+#include <condition_variable>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/hpsx.h"
@@ -180,6 +182,20 @@ struct ModelState {
   TRITONSERVER_Error* validate();         // ~ ValidateModelConfig   model_state.cpp:180-261
   TRITONSERVER_Error* parse();            // ~ ParseModelConfig      model_state.cpp:263-371
   TRITONSERVER_Error* ensure_caches();    // ~ Create_EmbeddingCache model_state.cpp:373-432
+
+  // Cache refresh (model_state.cpp:124-178, 413-427; include/timer.hpp): a periodic thread when
+  // refresh_interval > 0, and one asynchronous database reload + refresh when a new version of an already
+  // served model is initialised.  Both run beside lookups and are joined before the state is destroyed.
+  uint64_t previous_version = 0;  // version the parameter server last initialised for this model (0: none)
+  std::mutex refresh_mu;
+  std::condition_variable refresh_cv;
+  bool stopping = false;
+  std::thread periodic;
+  std::vector<std::thread> one_shot;
+  void refresh_all_devices();           // ~ Refresh_Embedding_Cache
+  void reload_and_refresh(int device);  // ~ EmbeddingCacheRefresh
+  void start_refresh_threads();
+  ~ModelState();
 };
 
 TRITONSERVER_Error* ModelState::validate() {
@@ -325,7 +341,10 @@ TRITONSERVER_Error* ModelState::parse() {
 }
 
 TRITONSERVER_Error* ModelState::ensure_caches() {
-  if (!gpucache()) return nullptr;
+  if (!gpucache()) {
+    start_refresh_threads();  // CPU models still reload their database when a new version arrives
+    return nullptr;
+  }
   for (int dev : gpus) {
     const int* b = params.deployed_devices;
     const int* e = b + params.num_deployed_devices;
@@ -342,10 +361,69 @@ TRITONSERVER_Error* ModelState::ensure_caches() {
                                "fetching the embedding cache of model " + name);
     HPS_LOG(INFO, "******Embedding cache of model ", name, " ready on device ", dev);
   }
-  if (refresh_interval > 1e-6f)
-    HPS_LOG(WARN, "model ", name, ": refresh_interval = ", refresh_interval,
-            " requested, but periodic cache refresh (online update) is not part of this backend; ignored");
+  start_refresh_threads();
   return nullptr;
+}
+
+void ModelState::refresh_all_devices() {
+  const uint64_t t0 = now_ns();
+  for (int dev : gpus) {
+    if (!gpucache()) continue;
+    HPS_LOG(INFO, "The model ", name, " is periodically refreshing the embedding cache asynchronously on device ", dev);
+    size_t rows = 0;
+    const int rc = hpsx_ps_refresh_embedding_cache(server->ps, name.c_str(), dev, &rows);
+    if (rc != HPSX_OK)
+      HPS_LOG(ERROR, "refreshing the embedding cache of model ", name, " on device ", dev, " failed: ", hpsx_last_error());
+    else
+      HPS_LOG(INFO, "The model ", name, " has refreshed the embedding cache asynchronously on device ", dev, " (", rows,
+              " rows)");
+  }
+  HPS_LOG(INFO, "Refresh embedding table execution time is ", (now_ns() - t0) / 1000000, " ms");
+}
+
+void ModelState::reload_and_refresh(int device) {
+  HPS_LOG(INFO, "The model ", name, " is refreshing the embedding cache asynchronously on device ", device, ".");
+  if (!freeze_sparse) {
+    const int rc = hpsx_ps_update_database_per_model(server->ps, name.c_str());
+    if (rc != HPSX_OK) HPS_LOG(ERROR, "updating the database of model ", name, " failed: ", hpsx_last_error());
+  }
+  if (gpucache()) {
+    const int rc = hpsx_ps_refresh_embedding_cache(server->ps, name.c_str(), device, nullptr);
+    if (rc != HPSX_OK)
+      HPS_LOG(ERROR, "refreshing the embedding cache of model ", name, " on device ", device, " failed: ", hpsx_last_error());
+  }
+  HPS_LOG(INFO, "The model ", name, " has completed the asynchronous refresh of the embedding cache on device ", device, ".");
+}
+
+void ModelState::start_refresh_threads() {
+  // a new version of a model the parameter server already serves: reload its sparse files (unless
+  // freeze_sparse) and refresh the caches, once, in the background (model_state.cpp:413-420)
+  if (previous_version > 0 && previous_version != version)
+    for (int dev : gpus) one_shot.emplace_back([this, dev] { reload_and_refresh(dev); });
+  if (refresh_interval > 1e-6f) {
+    HPS_LOG(INFO, "model ", name, ": refreshing the embedding cache every ", refresh_interval, " s");
+    periodic = std::thread([this] {
+      const auto period = std::chrono::duration<double>(std::max(0.01, static_cast<double>(refresh_interval)));
+      std::unique_lock<std::mutex> lk(refresh_mu);
+      while (!stopping) {
+        if (refresh_cv.wait_for(lk, period, [this] { return stopping; })) break;
+        lk.unlock();
+        refresh_all_devices();
+        lk.lock();
+      }
+    });
+  }
+}
+
+ModelState::~ModelState() {
+  {
+    std::lock_guard<std::mutex> lk(refresh_mu);
+    stopping = true;
+  }
+  refresh_cv.notify_all();
+  if (periodic.joinable()) periodic.join();
+  for (std::thread& t : one_shot)
+    if (t.joinable()) t.join();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,6 +746,7 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInitialize(TRITONBACKEND_Model* model) {
   ms->server = server;
   ms->name = name;
   ms->version = version;
+  ms->previous_version = server->version_of(name);
   HPS_RETURN_IF_ENGINE_ERROR(hpsx_ps_get_model_params(server->ps, name, &ms->params),
                              std::string("reading the parameters of model ") + name);
   TRITONSERVER_Message* cfg_msg = nullptr;

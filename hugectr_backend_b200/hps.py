@@ -175,6 +175,16 @@ class HPS:
     def create_embedding_cache(self, model: str) -> None:
         N.check(self._L.hpsx_ps_create_embedding_cache_per_model(self._h, model.encode()))
 
+    def update_database(self, model: str) -> None:
+        """~ ``update_database_per_model``: re-read the model's sparse files into the host database."""
+        N.check(self._L.hpsx_ps_update_database_per_model(self._h, model.encode()))
+
+    def refresh_embedding_cache(self, model: str, device: int = 0) -> int:
+        """~ ``refresh_embedding_cache(model, device)``: rewrite every cached row from the host database."""
+        n = ctypes.c_size_t()
+        N.check(self._L.hpsx_ps_refresh_embedding_cache(self._h, model.encode(), device, ctypes.byref(n)))
+        return n.value
+
     def destroy_embedding_cache(self, model: str) -> None:
         N.check(self._L.hpsx_ps_destroy_embedding_cache_per_model(self._h, model.encode()))
 
@@ -268,7 +278,7 @@ class LookupSession:
         N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
 
     def set_probe_variant(self, variant: str) -> None:
-        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2}[variant]))
+        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2, "split": 3}[variant]))
 
 
 class _DeviceRows:

@@ -171,6 +171,16 @@ int hpsx_ps_lookup(hpsx_ps* ps, const char* model, size_t table, const int64_t* 
 int hpsx_ps_create_embedding_cache_per_model(hpsx_ps* ps, const char* model);
 /* ~ get_embedding_cache(model, device) — NULL/NOT_FOUND when absent        src/model_state.cpp:379,411 */
 int hpsx_ps_get_embedding_cache(hpsx_ps* ps, const char* model, int device, hpsx_cache** out);
+/* ~ update_database_per_model(InferenceParams)                             src/model_state.cpp:132,389
+ * Re-reads the model's sparse_files into the host database: rows are inserted or overwritten in place.  Tables
+ * that are page-locked (enable_pagelock) get their new rows registered and their HBM row index rebuilt, with
+ * lookups excluded meanwhile.  HBM caches keep the vectors they hold until hpsx_ps_refresh_embedding_cache. */
+int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model);
+/* ~ refresh_embedding_cache(model, device)                                  src/model_state.cpp:135,161
+ * Re-reads the vector of every key resident in the (model, device) cache from the host database and rewrites
+ * the cached row (value-update kernel), cache_refresh_percentage_per_iteration of the cache per exclusive
+ * section.  Residency does not change.  `refreshed_rows` (nullable) receives the number of rows rewritten. */
+int hpsx_ps_refresh_embedding_cache(hpsx_ps* ps, const char* model, int device, size_t* refreshed_rows);
 /* ~ destory_embedding_cache_per_model(model)                              src/model_state.cpp:111 */
 int hpsx_ps_destroy_embedding_cache_per_model(hpsx_ps* ps, const char* model);
 /* ~ get_cache_config().num_emb_table_                                     src/model_instance_state.cpp:107-109 */
@@ -294,7 +304,8 @@ int hpsx_session_reset_stats(hpsx_session* s);
 int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
 /* Select the probe+gather kernel: 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
  * staging through shared memory, 2 = persistent grid with the key->bucket->row chain software-pipelined
- * across tiles.  The environment variable HPSX_PROBE=ldg|tma|pipe sets the default. */
+ * across tiles, 3 = two launches (probe to slot indices, then a hash-free row gather).  The environment variable
+ * HPSX_PROBE=ldg|tma|pipe|split sets the default. */
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);

@@ -1,8 +1,19 @@
 #!/bin/bash
-# 2-GPU experiment: NVLink peer-store methods + phase trace of the fused exchange
 mkdir -p gpurun_out
-timeout 120 ./tools/nvlink_probe > gpurun_out/nvlink_probe.txt 2>&1
-cat gpurun_out/nvlink_probe.txt
-HPSX_TRACE=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --workload c4 --gpus 2 --exchange p2p --steps 6 --warmup 2 > gpurun_out/trace_c4.json 2> gpurun_out/trace_c4.err
-grep "shard lookup rank 0" gpurun_out/trace_c4.err | tail -8
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
+run() {
+  tag=$1; shift
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.err
+  python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('gpurun_out/exp_$tag.json').read().splitlines() if l.startswith('{')][-1]); r=d['roofline']; c=d['cache_hit']
+    print('$tag: step %.3f ms, probe %.3f ms %.0f GB/s (%.3f) | all-hit %.3f ms %.0f GB/s (%.3f) | e2e %.3f ms' % (d['ms_per_step'], r['avg_launch_ms'], r['achieved'], r['frac'], c['kernel_ms'], c['hbm_gbs'], c['frac_of_peak'], d['e2e']['ms_per_step']))
+except Exception as e:
+    print('$tag failed', e); print(open('gpurun_out/exp_$tag.err').read()[-600:])
+PY
+}
+run ldg HPSX_PROBE=ldg
+run split HPSX_PROBE=split

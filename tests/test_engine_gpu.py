@@ -61,7 +61,7 @@ def test_lookup_all_resident_bit_exact(cuda_device, variant, dim, n):
     assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
 
 
-@pytest.mark.parametrize("variant", ["ldg", "tma"])
+@pytest.mark.parametrize("variant", ["ldg", "tma", "split"])
 def test_sync_insert_miss_path_bit_exact(cuda_device, variant):
     torch = _torch()
     rows, dim, n = 50000, 128, 4096
@@ -352,3 +352,80 @@ def test_int64_min_key_is_a_real_key_when_loaded(cuda_device):
     s.lookup_pooled(0, q, 3, 2, pooled, "sum")
     assert np.array_equal(pooled.cpu().numpy(), O.pooled(ref, q, 3, 2))
     assert kmin not in set(hps.cache_keys("m", 0, 0).tolist())
+
+
+@pytest.mark.parametrize("variant", ["ldg", "tma", "pipe", "split"])
+def test_two_choice_cache_under_eviction_pressure(cuda_device, variant):
+    """A cache far smaller than the working set (every bucket full, constant eviction, keys living in their
+    second-choice bucket): lookups stay bit-exact, no key is ever resident twice (SURVEY.md §8c iii), and a key
+    that was just served is found again by the probe (primary-full -> second-choice rule)."""
+    torch = _torch()
+    rows, dim, n = 40_000, 64, 8192
+    hps, ref = make_server(rows, dim, cache_pct=0.02, thr=1.0, max_batch=n, load_factor=1.0)  # 800 slots = 100 buckets
+    cap = hps.cache_capacity("m", 0, 0)
+    assert cap <= 1024
+    s = hps.session("m", 0)
+    s.set_probe_variant(variant)
+    rng = np.random.default_rng(99)
+    out = torch.empty((n, dim), device="cuda")
+    for it in range(6):
+        keys = rng.integers(0, rows, size=n)
+        keys[::3] = keys[0]  # heavy duplication of one missing key inside a request
+        out.fill_(float("nan"))
+        s.lookup([keys], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys)), it
+        res = hps.cache_keys("m", 0, 0)
+        assert len(res) == len(set(res.tolist())) == hps.cache_resident("m", 0, 0) <= cap
+    # a small hot set that fits: after one pass everything hits, including keys placed in second-choice buckets
+    hot = rng.choice(rows, size=cap // 4, replace=False)
+    s.lookup([hot], [out[:len(hot)]], [len(hot)])
+    s.reset_stats()
+    out.fill_(float("nan"))
+    s.lookup([hot], [out[:len(hot)]], [len(hot)])
+    assert s.stats().misses == 0
+    assert np.array_equal(out[:len(hot)].cpu().numpy(), ref.lookup(hot))
+
+
+def test_refresh_rewrites_cached_rows_from_the_database(cuda_device, miss_path):
+    """Online update: the host database is rewritten (update_database_per_model ~
+    hps_backend/src/model_state.cpp:132), cached rows stay as they were until refresh_embedding_cache
+    (~ model_state.cpp:135,161) rewrites every resident row; residency itself does not change."""
+    import tempfile
+
+    torch = _torch()
+    rows, dim, n = 6000, 32, 4096
+    rng = np.random.default_rng(5)
+    keys = np.arange(rows, dtype=np.int64) * 7 + 3
+    v1 = rng.standard_normal((rows, dim)).astype(np.float32)
+    with tempfile.TemporaryDirectory() as tmp:
+        O.write_sparse_dir(tmp, keys, v1)
+        hps = hb.HPS(num_partitions=4)
+        hps.add_model(hb.ModelParams("m", n, [dim], [1], [0.5], sparse_files=[tmp], hit_rate_threshold=1.0,
+                                     cache_size_percentage=0.5))
+        hps.create_embedding_cache("m")
+        s = hps.session("m", 0)
+        q = rng.choice(keys, size=n)
+        out = torch.empty((n, dim), device="cuda")
+        ref1 = O.NumpyTable(dim, 0.5)
+        ref1.insert(keys, v1)
+        s.lookup([q], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref1.lookup(q))
+        resident = np.sort(hps.cache_keys("m", 0, 0))
+        # new dump: all vectors change, 100 new keys appear
+        keys2 = np.concatenate([keys, np.arange(100, dtype=np.int64) * 7 + 4])
+        v2 = rng.standard_normal((len(keys2), dim)).astype(np.float32)
+        O.write_sparse_dir(tmp, keys2, v2)
+        ref2 = O.NumpyTable(dim, 0.5)
+        ref2.insert(keys2, v2)
+        hps.update_database("m")
+        assert hps.table_rows("m", 0) == len(keys2)
+        # cached rows are stale by design; rows that come from the database are new
+        qc = rng.choice(resident, size=512)
+        s.lookup([qc], [out[:512]], [512])
+        assert np.array_equal(out[:512].cpu().numpy(), ref1.lookup(qc))
+        refreshed = hps.refresh_embedding_cache("m", 0)
+        assert refreshed == len(resident)
+        assert np.array_equal(np.sort(hps.cache_keys("m", 0, 0)), resident)
+        q2 = rng.choice(keys2, size=n)
+        s.lookup([q2], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref2.lookup(q2))

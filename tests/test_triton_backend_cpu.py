@@ -346,3 +346,36 @@ def test_opt_in_slot_pooling_matches_golden(tmp_path, mode):
         assert r.shape == [3072] and np.array_equal(r.data, kat["ens_OUTPUT0"])
         inst.close()
         model.close()
+
+
+@pytest.mark.parametrize("freeze", [False, True])
+def test_new_version_reloads_the_database_unless_frozen(tmp_path, freeze):
+    """Loading version 2 of a model that is already served re-reads its sparse files in the background
+    (update_database_per_model, hps_backend/src/model_state.cpp:124-143,413-420) unless `freeze_sparse`."""
+    root = str(tmp_path)
+    dirs, tabs = write_tables(root, [(200, 8)], seed=1)
+    keys_v1, vecs_v1 = tabs[0]
+    ps = ps_json(str(tmp_path / "ps.json"), [model_entry("m", dirs, [8], [4], defaults=[-2.0])])
+    params = {"freeze_sparse": "true"} if freeze else None
+    with FT.Backend(ps) as be:
+        m1 = be.model("m", FT.model_config("m", kind="KIND_CPU", parameters=params), version=1)
+        i1 = m1.instance(kind=FT.KIND_CPU)
+        q = np.array([1, 4, 598, 601, 1000], dtype=np.int64)  # 601 and 1000 are not in version 1
+        nk = np.array([[len(q)]], dtype=np.int32)
+        t1 = O.NumpyTable(8, -2.0)
+        t1.insert(keys_v1, vecs_v1)
+        assert np.array_equal(i1.infer(q, nk).data, O.request([t1], q, [len(q)]))
+        # the trainer dumps a new model: every vector changes and key 601 appears
+        keys_v2 = np.concatenate([keys_v1, np.array([601], dtype=np.int64)])
+        vecs_v2 = np.random.default_rng(2).standard_normal((len(keys_v2), 8)).astype(np.float32)
+        O.write_sparse_dir(dirs[0], keys_v2, vecs_v2)
+        t2 = O.NumpyTable(8, -2.0)
+        t2.insert(keys_v2, vecs_v2)
+        m2 = be.model("m", FT.model_config("m", kind="KIND_CPU", parameters=params), version=2)
+        i2 = m2.instance(kind=FT.KIND_CPU)
+        i2.close()
+        m2.close()  # ModelFinalize joins the background reload
+        want = t1 if freeze else t2
+        assert np.array_equal(i1.infer(q, nk).data, O.request([want], q, [len(q)]))
+        i1.close()
+        m1.close()

@@ -162,3 +162,45 @@ def test_opt_in_slot_pooling_on_gpu(wdl_gpu, mode):
         np.testing.assert_allclose(r.data, expect, rtol=0, atol=1e-5)
         inst.close()
         model.close()
+
+
+def test_version_reload_and_periodic_refresh_on_gpu(tmp_path, cuda_device):
+    """f3 through the Triton boundary: version 2 of a served model reloads the sparse files and refreshes the HBM
+    cache in the background (model_state.cpp:124-143,413-420); `refresh_interval` keeps a periodic refresh thread
+    alive beside lookups (model_state.cpp:145-178,422-427) and ModelFinalize stops it."""
+    import time
+
+    import torch
+    dirs, tabs = write_tables(str(tmp_path), [(3000, 16)], seed=4)
+    keys1, vecs1 = tabs[0]
+    entry = model_entry("m", dirs, [16], [8], gpucache=True, defaults=[0.25], max_batch=256, hit_rate_threshold=1.0,
+                        gpucacheper=1.0, enable_pagelock=True)
+    ps = ps_json(str(tmp_path / "ps.json"), [entry])
+    with FT.Backend(ps) as be:
+        cfg = FT.model_config("m", gpus=[0], max_batch_size=256, parameters={"refresh_interval": "0.05"})
+        m1 = be.model("m", cfg, version=1)
+        i1 = m1.instance(kind=FT.KIND_GPU, device=0)
+        rng = np.random.default_rng(1)
+        q = rng.choice(keys1, size=2048)
+        nk = np.array([[len(q)]], dtype=np.int32)
+        out = torch.empty(len(q) * 16, device="cuda")
+        t1 = O.NumpyTable(16, 0.25)
+        t1.insert(keys1, vecs1)
+        for _ in range(20):  # lookups race the periodic refresh; values never change because the database did not
+            r = i1.infer(q, nk, gpu_out=out)
+            assert r.error_code is None, r.error_message
+            assert np.array_equal(out.cpu().numpy(), O.request([t1], q, [len(q)]))
+            time.sleep(0.01)
+        vecs2 = np.random.default_rng(9).standard_normal(vecs1.shape).astype(np.float32)
+        O.write_sparse_dir(dirs[0], keys1, vecs2)
+        t2 = O.NumpyTable(16, 0.25)
+        t2.insert(keys1, vecs2)
+        m2 = be.model("m", cfg, version=2)
+        i2 = m2.instance(kind=FT.KIND_GPU, device=0)
+        i2.close()
+        m2.close()  # joins the background reload + refresh
+        r = i1.infer(q, nk, gpu_out=out)
+        assert r.error_code is None, r.error_message
+        assert np.array_equal(out.cpu().numpy(), O.request([t2], q, [len(q)]))
+        i1.close()
+        m1.close()
