@@ -56,7 +56,7 @@ def parse_args():
                     help="direct: enable_pagelock, kernels pull missing rows from pinned host tables over PCIe; "
                          "staged: CPU gather + cudaMemcpyAsync")
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
-    ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "ldg"), choices=["ldg", "tma", "pipe", "split"])
+    ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "v8"), choices=["ldg", "tma", "pipe", "split", "v8"])
     ap.add_argument("--workload", default="dcn", choices=["dcn", "c4"],
                     help="dcn: BASELINE.json configs[1] (default, replicas over --gpus); c4: DLRM-shaped model-parallel table "
                          "(configs[3]): rows sharded over the GPUs by owner(key), global batch split over the ranks, 100 %% HBM-resident")

@@ -87,7 +87,7 @@ struct hpsx_session {
   hpsx_cache* cache = nullptr;  // nullptr: CPU session
   int device = -1;
   cudaStream_t stream = nullptr;
-  int probe_variant = hpsx::kProbeLdg;
+  int probe_variant = hpsx::kProbeV8;  // falls back to the LDG.128 variant for rows that are not 32-B multiples
   int insert_mode = -1;
 
   size_t cap_keys = 0;                 // sum over tables of max_batch * maxnum_catfeature

@@ -1521,7 +1521,8 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
     s->probe_variant = std::strcmp(env, "tma") == 0     ? kProbeTma
                        : std::strcmp(env, "pipe") == 0  ? kProbePipe
                        : std::strcmp(env, "split") == 0 ? kProbeSplit
-                                                        : kProbeLdg;
+                       : std::strcmp(env, "ldg") == 0   ? kProbeLdg
+                                                        : kProbeV8;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -2010,7 +2011,7 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
 
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
-  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe && variant != kProbeSplit)
+  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe && variant != kProbeSplit && variant != kProbeV8)
     return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
   if (variant == kProbeSplit && s->cache && !s->d_src) {
     // the split variant keeps one slot index per key between its two launches

@@ -28,6 +28,7 @@ enum ProbeVariant : int {
   kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers
   kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
   kProbePipe = 2, // persistent grid, key -> bucket -> rows chain software-pipelined across tiles
+  kProbeV8 = 4,   // 256-bit row vectors with L2 evict_first, bucket keys kept in L2 (evict_last)
   kProbeSplit = 3, // two launches: probe (slot per key, 76 B/key) then a hash-free gather at the random-gather ceiling
 };
 

@@ -278,7 +278,7 @@ class LookupSession:
         N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
 
     def set_probe_variant(self, variant: str) -> None:
-        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2, "split": 3}[variant]))
+        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2, "split": 3, "v8": 4}[variant]))
 
 
 class _DeviceRows:

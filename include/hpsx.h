@@ -302,10 +302,11 @@ int hpsx_session_reset_stats(hpsx_session* s);
 /* Force the insertion mode of subsequent lookups: <0 use hit_rate_threshold (default), 0 always
  * asynchronous (misses answered with the default vector), 1 always synchronous. */
 int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
-/* Select the probe+gather kernel: 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
+/* Select the probe+gather kernel (default 4): 4 = 256-bit row vectors with L2 evict_first and bucket keys kept in
+ * L2 (rows must be multiples of 32 B, else 0 is used), 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
  * staging through shared memory, 2 = persistent grid with the key->bucket->row chain software-pipelined
  * across tiles, 3 = two launches (probe to slot indices, then a hash-free row gather).  The environment variable
- * HPSX_PROBE=ldg|tma|pipe|split sets the default. */
+ * HPSX_PROBE=v8|ldg|tma|pipe|split sets the default. */
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+timeout 900 python -m pytest tests/test_engine_gpu.py -m gpu -q -x -k "v8 or resident" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -25 gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
 run() {
   tag=$1; shift
   env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.err
@@ -16,4 +16,6 @@ except Exception as e:
 PY
 }
 run ldg HPSX_PROBE=ldg
-run split HPSX_PROBE=split
+run v8u4 HPSX_PROBE=v8 HPSX_V8_UNROLL=4
+run v8u2 HPSX_PROBE=v8 HPSX_V8_UNROLL=2
+run v8u8 HPSX_PROBE=v8 HPSX_V8_UNROLL=8

@@ -131,7 +131,7 @@ def main():
                 if m in c:
                     lines.append(f"| `{m}` | {c[m][0]} | {c[m][1]} |")
             lines.append("")
-            key = "probe_gather_ldg" if "probe_gather_ldg" in c["kernel"] else ("pull_misses" if "pull_misses" in c["kernel"] else c["kernel"])
+            key = c["kernel"].split("<")[0].replace("_kernel", "")
             if key not in traffic and "dram__bytes_read.sum" in c:
                 traffic[key] = {"dram_bytes_read": int(to_bytes(*c["dram__bytes_read.sum"])),
                                 "dram_bytes_write": int(to_bytes(*c["dram__bytes_write.sum"])),

@@ -43,7 +43,7 @@ def make_server(rows, dim, *, cache_pct=1.0, thr=1.0, default=0.5, max_batch=409
     return hps, ref
 
 
-@pytest.mark.parametrize("variant", ["ldg", "tma"])
+@pytest.mark.parametrize("variant", ["ldg", "tma", "v8"])
 @pytest.mark.parametrize("dim,n", [(128, 4096), (128, 4001), (32, 1024), (16, 777), (64, 33), (128, 1)])
 def test_lookup_all_resident_bit_exact(cuda_device, variant, dim, n):
     torch = _torch()
@@ -61,7 +61,7 @@ def test_lookup_all_resident_bit_exact(cuda_device, variant, dim, n):
     assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
 
 
-@pytest.mark.parametrize("variant", ["ldg", "tma", "split"])
+@pytest.mark.parametrize("variant", ["ldg", "tma", "split", "v8"])
 def test_sync_insert_miss_path_bit_exact(cuda_device, variant):
     torch = _torch()
     rows, dim, n = 50000, 128, 4096
@@ -354,7 +354,7 @@ def test_int64_min_key_is_a_real_key_when_loaded(cuda_device):
     assert kmin not in set(hps.cache_keys("m", 0, 0).tolist())
 
 
-@pytest.mark.parametrize("variant", ["ldg", "tma", "pipe", "split"])
+@pytest.mark.parametrize("variant", ["ldg", "tma", "pipe", "split", "v8"])
 def test_two_choice_cache_under_eviction_pressure(cuda_device, variant):
     """A cache far smaller than the working set (every bucket full, constant eviction, keys living in their
     second-choice bucket): lookups stay bit-exact, no key is ever resident twice (SURVEY.md §8c iii), and a key
