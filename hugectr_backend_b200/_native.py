@@ -117,6 +117,7 @@ SYMBOLS = {
     "hpsx_shard_group_destroy": (_int, [_vp]),
     "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),
     "hpsx_session_lookup_ex": (_int, [_vp, _vpp, _int, _vpp, _int, c_size_p, _sz]),
+    "hpsx_session_lookup_batch": (_int, [_vp, _sz, _vpp, _int, _vpp, _int, c_size_p]),
     "hpsx_ps_lookup": (_int, [_vp, _cp, _sz, _vp, _sz, _vp]),
     "hpsx_ps_create_embedding_cache_per_model": (_int, [_vp, _cp]),
     "hpsx_ps_get_embedding_cache": (_int, [_vp, _cp, _int, _vpp]),

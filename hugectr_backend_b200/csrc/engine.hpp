@@ -24,6 +24,7 @@ namespace hpsx {
 constexpr size_t kStageChunkRows = 32768;    // most rows per host->device miss chunk (16 MiB at dim 128)
 constexpr size_t kMinStageChunkRows = 2048;  // smaller chunks cost more in launch + pool wake-ups than they hide
 constexpr int kNumStages = 3;                // pinned/device stage pairs rotating through the miss pipeline
+constexpr size_t kMaxBatchRequests = 16;     // requests one hpsx_session_lookup_batch call may serve
 
 struct Model;
 
@@ -90,6 +91,7 @@ struct hpsx_session {
   int probe_variant = hpsx::kProbeV8;  // falls back to the LDG.128 variant for rows that are not 32-B multiples
   int insert_mode = -1;
 
+  size_t vt = 0;                       // virtual tables (request x table) the counters / events are sized for
   size_t cap_keys = 0;                 // sum over tables of max_batch * maxnum_catfeature
   std::vector<size_t> cap_per_table;
   int64_t* d_keys = nullptr;           // [cap_keys]

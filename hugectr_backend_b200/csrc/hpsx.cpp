@@ -391,12 +391,13 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
                      uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock,
                      const MissBufs* mb = nullptr) {
   hpsx_cache* c = s->cache;
-  const HostTable& ht = *s->model->tables[t];
+  const size_t rt = t % s->model->tables.size();  // t may be a virtual table (request * T + table)
+  const HostTable& ht = *s->model->tables[rt];
   const size_t dim = ht.dim();
   const int64_t* h_keys = mb ? mb->h_keys : s->h_miss_keys + key_off;
   const int64_t* d_mkeys = mb ? mb->d_keys : s->d_miss_keys + key_off;
   const uint32_t* d_mpos = mb ? mb->d_pos : s->d_miss_pos + key_off;
-  uint32_t* d_inserted = s->d_counters + s->model->tables.size() + t;
+  uint32_t* d_inserted = s->d_counters + s->vt + t;
   s->stats.misses += m;
   size_t chunk = (static_cast<size_t>(m) + 3) / 4;
   chunk = std::min<size_t>(kStageChunkRows, std::max<size_t>(kMinStageChunkRows, chunk));
@@ -416,7 +417,7 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
     s->stats.h2d_bytes += mc * dim * sizeof(float);
     if (d_out != nullptr || insert) {
       if (insert && wlock != nullptr && !wlock->owns_lock()) wlock->lock();
-      HPSX_CU(launch_insert_merge(c->tables[t], d_mkeys + off, d_mpos + off, d_rows, mc, d_out, insert, epoch,
+      HPSX_CU(launch_insert_merge(c->tables[rt], d_mkeys + off, d_mpos + off, d_rows, mc, d_out, insert, epoch,
                                   d_inserted, s->stream));
       ++s->stats.kernel_launches;
     }
@@ -432,7 +433,7 @@ void post_async_insert(hpsx_session* s, size_t t, size_t key_off, uint32_t m) {
   s->stats.misses += m;
   s->stats.default_filled += m;
   const int64_t* h_keys = s->h_miss_keys + key_off;
-  AsyncJob job{s->ps, c, t, std::vector<int64_t>(h_keys, h_keys + m)};
+  AsyncJob job{s->ps, c, t % s->model->tables.size(), std::vector<int64_t>(h_keys, h_keys + m)};
   {
     std::lock_guard<std::mutex> lk(c->async_mu);
     ++c->async_pending;
@@ -508,15 +509,15 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
   if (c->is_static) rlock.lock(); else wlock.lock();
 
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
-  HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
   std::vector<size_t> off(num_tables + 1, 0);
   auto pull = [&](size_t t, size_t m_hint) -> cudaError_t {
     const bool use_sorted = sorted && m_hint > 0;
-    return launch_pull_misses(c->tables[t], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
+    return launch_pull_misses(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
                               n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
-                              s->model->cfg.hit_rate_threshold, epoch, s->d_counters + T + t,
-                              s->d_counters + 2 * T + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
+                              s->model->cfg.hit_rate_threshold, epoch, s->d_counters + s->vt + t,
+                              s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
                               use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream);
   };
   for (size_t t = 0; t < num_tables; ++t) {
@@ -533,7 +534,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       d_keys = s->d_keys + off[t];
     }
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
-    HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
+    HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                 s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t], nullptr,
                                 s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr,
                                 s->d_src ? s->d_src + off[t] : nullptr));
@@ -546,7 +547,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     }
   }
   if (sorted) {
-    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
     s->stats.d2h_bytes += T * sizeof(uint32_t);
     for (size_t t = 0; t < num_tables; ++t)
@@ -555,7 +556,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
       if (m == 0) continue;
       HPSX_CU(cudaEventRecord(s->ev_pull[2 * t], s->stream));
-      HPSX_CU(launch_resolve_and_sort_misses(c->tables[t], s->d_miss_keys + off[t], m, s->d_addr[0] + off[t],
+      HPSX_CU(launch_resolve_and_sort_misses(c->tables[t % T], s->d_miss_keys + off[t], m, s->d_addr[0] + off[t],
                                              s->d_sidx[0] + off[t], s->d_addr[1] + off[t], s->d_sidx[1] + off[t],
                                              s->d_sort_temp, s->sort_temp_bytes, s->stream));
       HPSX_CU(pull(t, m));
@@ -563,10 +564,10 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       s->stats.kernel_launches += 2;  // resolve + pull (the CUB radix-sort passes are library kernels, not counted)
     }
   }
-  HPSX_CU(cudaMemcpyAsync(s->h_counters + T, s->d_counters + T, 2 * T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+  HPSX_CU(cudaMemcpyAsync(s->h_counters + s->vt, s->d_counters + s->vt, 2 * s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           s->stream));
   if (!sorted)
-    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->stats.d2h_bytes += 3 * T * sizeof(uint32_t);
   for (size_t t = 0; t < num_tables; ++t) {
@@ -583,8 +584,8 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     }
     s->stats.hits += n - m;
     s->stats.misses += m;
-    const size_t row_bytes = s->model->tables[t]->dim() * sizeof(float);
-    const uint32_t absent = s->h_counters[2 * T + t];
+    const size_t row_bytes = s->model->tables[t % T]->dim() * sizeof(float);
+    const uint32_t absent = s->h_counters[2 * s->vt + t];
     s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * row_bytes;  // rows pulled over PCIe by the kernel
     s->stats.default_filled += (m != 0 && !decide_sync(s, n, m)) ? m : absent;
   }
@@ -611,7 +612,7 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
   if (total == 0) return HPSX_OK;
   const double tr0 = now_ms();
 
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
   std::vector<size_t> off(num_tables + 1, 0);
   {
     std::shared_lock<std::shared_mutex> lk(c->rw);
@@ -631,14 +632,14 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
         d_keys = s->d_keys + off[t];
       }
       HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
-      HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_per_table[t], epoch, !c->is_static,
+      HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
                                   s->hd_miss_keys + off[t], s->probe_variant, s->stream,
                                   pos_per_table ? pos_per_table[t] : nullptr, s->d_src ? s->d_src + off[t] : nullptr));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
     }
-    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, s->vt * sizeof(uint32_t),
                             cudaMemcpyDeviceToHost, s->stream));
     // one synchronisation: miss counts (copied) and miss keys (written by the kernel straight into
     // mapped pinned memory) are both on the host after it
@@ -712,7 +713,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
   if (!keys || !d_pooled) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
   if (!s->d_src) HPSX_CU(cudaMalloc(&s->d_src, s->cap_keys * sizeof(uint32_t)));
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, T * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
   const int64_t* d_keys = keys;
   uint32_t m = 0;
   {
@@ -729,7 +730,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
                                s->d_counters + table, s->d_miss_pos, s->d_miss_keys, s->hd_miss_keys,
                                s->stream));
     ++s->stats.kernel_launches;
-    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t),
+    HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, s->vt * sizeof(uint32_t),
                             cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
     s->stats.d2h_bytes += T * sizeof(uint32_t);
@@ -744,7 +745,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
       }
       if (c->direct_pull) {
         // rows pulled by the GPU straight from the page-locked host table into the stage
-        HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * T, 0, T * sizeof(uint32_t), s->stream));
+        HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
         const bool use_sorted = pull_sort_enabled();
         if (use_sorted) {
           const int wrc = ensure_sort_workspace(s);
@@ -756,7 +757,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
         }
         HPSX_CU(launch_pull_misses(c->tables[table], s->d_miss_keys, s->d_miss_pos, s->d_counters + table, n,
                                    nullptr, s->d_pool_stage, false, 1, 0.f, epoch, nullptr,
-                                   s->d_counters + 2 * T + table, use_sorted ? s->d_addr[1] : nullptr,
+                                   s->d_counters + 2 * s->vt + table, use_sorted ? s->d_addr[1] : nullptr,
                                    use_sorted ? s->d_sidx[1] : nullptr, m, s->stream));
         ++s->stats.kernel_launches;
         s->stats.misses += m;
@@ -777,7 +778,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
   if (m > 0 && !c->is_static) {
     std::unique_lock<std::shared_mutex> wlock(c->rw);
     HPSX_CU(launch_insert_merge(c->tables[table], s->d_miss_keys, s->d_miss_pos, s->d_pool_stage, m,
-                                nullptr, true, epoch, s->d_counters + T + table, s->stream));
+                                nullptr, true, epoch, s->d_counters + s->vt + table, s->stream));
     ++s->stats.kernel_launches;
     HPSX_CU(cudaStreamSynchronize(s->stream));
   }
@@ -808,7 +809,6 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
   hpsx_session* s = g->s;
   hpsx_cache* c = s->cache;
   const size_t t = g->table;
-  const size_t T = s->model->tables.size();
   DeviceGuard guard(s->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   const uint32_t seq = ++g->seq;
@@ -876,7 +876,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     if (rc == HPSX_OK && c->direct_pull) {
       if (!c->is_static) wlock.lock();
       const bool use_sorted = pull_sort_enabled() && m <= s->cap_keys;
-      cudaError_t e = cudaMemsetAsync(s->d_counters + 2 * T + t, 0, sizeof(uint32_t), s->stream);
+      cudaError_t e = cudaMemsetAsync(s->d_counters + 2 * s->vt + t, 0, sizeof(uint32_t), s->stream);
       if (e == cudaSuccess && use_sorted) {
         rc = ensure_sort_workspace(s);
         if (rc == HPSX_OK)
@@ -885,8 +885,8 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
       }
       if (rc == HPSX_OK && e == cudaSuccess)
         e = launch_pull_misses(dt, g->d_miss_keys, g->d_miss_pos, d_miss_count, st.keys_received, nullptr,
-                               s->d_pool_stage, !c->is_static, 1, 0.f, epoch, s->d_counters + T + t,
-                               s->d_counters + 2 * T + t, use_sorted ? s->d_addr[1] : nullptr,
+                               s->d_pool_stage, !c->is_static, 1, 0.f, epoch, s->d_counters + s->vt + t,
+                               s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] : nullptr,
                                use_sorted ? s->d_sidx[1] : nullptr, m, s->stream);
       if (rc == HPSX_OK && e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("direct pull: ") + cudaGetErrorString(e));
       s->stats.kernel_launches += use_sorted ? 2 : 1;
@@ -899,7 +899,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
       if (rc == HPSX_OK && !c->is_static) {
         wlock.lock();
         const cudaError_t e = launch_insert_merge(dt, g->d_miss_keys, nullptr, s->d_pool_stage, m, nullptr, true, epoch,
-                                                  s->d_counters + T + t, s->stream);
+                                                  s->d_counters + s->vt + t, s->stream);
         if (e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("insert: ") + cudaGetErrorString(e));
         ++s->stats.kernel_launches;
       }
@@ -1530,9 +1530,12 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   HPSX_CU(cudaMalloc(&s->d_keys, cap * sizeof(int64_t)));
   HPSX_CU(cudaMalloc(&s->d_miss_pos, cap * sizeof(uint32_t)));
   HPSX_CU(cudaMalloc(&s->d_miss_keys, cap * sizeof(int64_t)));
-  HPSX_CU(cudaMalloc(&s->d_counters, 3 * T * sizeof(uint32_t)));
-  HPSX_CU(cudaMallocHost(&s->h_counters, 3 * T * sizeof(uint32_t)));
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * T * sizeof(uint32_t), s->stream));
+  // counters and events are indexed by "virtual table" v = request * T + table, so that one call can serve a
+  // batch of up to kMaxBatchRequests requests (hpsx_session_lookup_batch); a plain lookup uses v = table
+  s->vt = T * kMaxBatchRequests;
+  HPSX_CU(cudaMalloc(&s->d_counters, 3 * s->vt * sizeof(uint32_t)));
+  HPSX_CU(cudaMallocHost(&s->h_counters, 3 * s->vt * sizeof(uint32_t)));
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * s->vt * sizeof(uint32_t), s->stream));
   // miss keys are written by the probe kernels straight into this mapped buffer (zero-copy)
   HPSX_CU(cudaHostAlloc(&s->h_miss_keys, cap * sizeof(int64_t),
                         cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1545,9 +1548,9 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   }
   if (s->probe_variant == kProbeSplit) HPSX_CU(cudaMalloc(&s->d_src, cap * sizeof(uint32_t)));
   HPSX_CU(cudaStreamSynchronize(s->stream));
-  s->ev.resize(2 * T);
+  s->ev.resize(2 * s->vt);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
-  s->ev_pull.resize(2 * T);
+  s->ev_pull.resize(2 * s->vt);
   for (auto& e : s->ev_pull) HPSX_CU(cudaEventCreate(&e));
   *out = s.release();
   return HPSX_OK;
@@ -1871,6 +1874,37 @@ int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, i
   HPSX_GUARD_END
 }
 
+static_assert(kMaxBatchRequests == HPSX_MAX_BATCH_REQUESTS, "header and engine disagree on the batch limit");
+
+int hpsx_session_lookup_batch(hpsx_session* s, size_t num_requests, const void* const* keys, int key_memory,
+                              float* const* vectors, int vector_memory, const size_t* num_keys) {
+  HPSX_GUARD_BEGIN
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (num_requests == 0) return HPSX_OK;
+  if (!keys || !vectors || !num_keys) return fail(HPSX_ERR_INVALID_ARG, "null pointer arrays");
+  const size_t T = s->model->tables.size();
+  if (num_requests > kMaxBatchRequests)
+    return fail(HPSX_ERR_INVALID_ARG, "a batch holds at most " + std::to_string(kMaxBatchRequests) + " requests");
+  size_t total = 0;
+  for (size_t r = 0; r < num_requests; ++r) {
+    const int rc = check_tables(s, num_keys + r * T, T);
+    if (rc != HPSX_OK) return rc;
+    for (size_t t = 0; t < T; ++t) total += num_keys[r * T + t];
+  }
+  const bool fused = s->cache != nullptr && vector_memory == HPSX_MEM_DEVICE && total <= s->cap_keys;
+  if (!fused) {
+    // CPU sessions, host output buffers and batches larger than the workspace: one request at a time
+    for (size_t r = 0; r < num_requests; ++r) {
+      const int rc = hpsx_session_lookup_ex(s, keys + r * T, key_memory, vectors + r * T, vector_memory, num_keys + r * T, T);
+      if (rc != HPSX_OK) return rc;
+    }
+    return HPSX_OK;
+  }
+  std::lock_guard<std::mutex> lk(s->mu);
+  return gpu_lookup(s, keys, key_memory == HPSX_MEM_DEVICE, vectors, num_keys, num_requests * T);
+  HPSX_GUARD_END
+}
+
 static int pooled_common(hpsx_session* s, size_t table, const int64_t* keys, bool on_device,
                          size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
@@ -1973,9 +2007,8 @@ static int read_inserted(hpsx_session* s, uint64_t* out) {
   *out = 0;
   if (!s->cache) return HPSX_OK;
   DeviceGuard guard(s->device);
-  const size_t T = s->model->tables.size();
-  std::vector<uint32_t> h(T, 0);
-  HPSX_CU(cudaMemcpyAsync(h.data(), s->d_counters + T, T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+  std::vector<uint32_t> h(s->vt, 0);
+  HPSX_CU(cudaMemcpyAsync(h.data(), s->d_counters + s->vt, s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                           s->stream));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   for (uint32_t v : h) *out += v;
@@ -1996,8 +2029,7 @@ int hpsx_session_reset_stats(hpsx_session* s) {
   s->stats = hpsx_session_stats{};
   if (s->cache) {
     DeviceGuard guard(s->device);
-    const size_t T = s->model->tables.size();
-    HPSX_CU(cudaMemsetAsync(s->d_counters + T, 0, T * sizeof(uint32_t), s->stream));
+    HPSX_CU(cudaMemsetAsync(s->d_counters + s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
   }
   return HPSX_OK;

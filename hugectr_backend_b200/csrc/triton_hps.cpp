@@ -506,12 +506,25 @@ TRITONSERVER_Error* gather_input(InstanceState* inst, TRITONBACKEND_Input* input
   return nullptr;
 }
 
-// One request.  Returns nullptr when a (success or error) response was produced; a non-null error is
-// turned into an error response by the caller.  *num_samples feeds NumSample and the batch statistics.
-TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* request,
-                                  TRITONBACKEND_Response* response, int64_t* num_samples,
-                                  uint64_t* compute_start_ns, uint64_t* compute_end_ns) {
+// Everything one request needs for its lookup, resolved up front so that the requests of one Execute call can be
+// served in one engine pass (the reference walks them one by one, src/hps.cc:392-406).
+struct RequestPlan {
+  bool has_output = false;  // false: nothing was requested (src/hps.cc:549-551), respond without a lookup
+  bool keys_on_device = false, out_on_device = false;
+  int64_t num_samples = 0;
+  uint64_t num_keys = 0;
+  std::vector<const void*> keys_pt;
+  std::vector<float*> out_pt;
+  std::vector<size_t> n_per_table;
+  std::vector<int64_t> key_staging;  // only for inputs Triton delivers in several buffers
+};
+
+// Validates one request, sizes and obtains its output buffer and splits keys/output per table.  A non-null
+// error is turned into an error response by the caller.
+TRITONSERVER_Error* prepare_request(InstanceState* inst, TRITONBACKEND_Request* request,
+                                    TRITONBACKEND_Response* response, RequestPlan* plan) {
   ModelState* ms = inst->model;
+  int64_t* num_samples = &plan->num_samples;
   uint32_t input_count = 0, requested_output_count = 0;
   HPS_RETURN_IF_ERROR(TRITONBACKEND_RequestInputCount(request, &input_count));
   HPS_RETURN_IF_ERROR(TRITONBACKEND_RequestOutputCount(request, &requested_output_count));
@@ -543,6 +556,7 @@ TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* re
                      TRITONSERVER_DataTypeString(numkeys_dt));
 
   const uint64_t num_keys = keys_bytes / sizeof(int64_t);
+  plan->num_keys = num_keys;
   *num_samples = static_cast<int64_t>(num_keys / ms->cat_num);
   if (requested_output_count == 0) return nullptr;  // nothing to produce (src/hps.cc:549-551)
   const char* out_name = nullptr;
@@ -592,7 +606,7 @@ TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* re
     return HPS_ERROR(INVALID_ARG, "NUMKEYS sums to ", key_sum, " but KEYS holds ", num_keys, " keys");
 
   InputView key_view;
-  HPS_RETURN_IF_ERROR(gather_input(inst, keys_in, keys_buffers, keys_bytes, &inst->key_staging, &key_view));
+  HPS_RETURN_IF_ERROR(gather_input(inst, keys_in, keys_buffers, keys_bytes, &plan->key_staging, &key_view));
   if (key_view.on_device && !ms->gpucache())
     return HPS_ERROR(UNSUPPORTED, "KEYS arrived in GPU memory but model ", ms->name, " runs without a GPU cache");
 
@@ -615,40 +629,65 @@ TRITONSERVER_Error* serve_request(InstanceState* inst, TRITONBACKEND_Request* re
 
   // per-table pointers by prefix sums (src/model_instance_state.cpp:180-193); the kernels write the
   // rows directly into Triton's buffer — no result buffer, no D2D hand-off (src/hps.cc:676-680)
-  std::vector<const void*> keys_pt(T, nullptr);
-  std::vector<float*> out_pt(T, nullptr);
+  plan->keys_pt.assign(T, nullptr);
+  plan->out_pt.assign(T, nullptr);
   const int64_t* kbase = static_cast<const int64_t*>(key_view.data);
   float* obase = static_cast<float*>(out_buf);
   size_t koff = 0, ooff = 0;
   for (size_t t = 0; t < T; ++t) {
-    keys_pt[t] = kbase + koff;
-    out_pt[t] = obase + ooff;
+    plan->keys_pt[t] = kbase + koff;
+    plan->out_pt[t] = obase + ooff;
     koff += n_per_table[t];
     ooff += (ms->pooling >= 0 ? n_per_table[t] / ms->pooling_hotness[t] : n_per_table[t]) *
             ms->params.embedding_vecsize_per_table[t];
   }
-  *compute_start_ns = now_ns();
+  plan->n_per_table = std::move(n_per_table);
+  plan->keys_on_device = key_view.on_device;
+  plan->out_on_device = out_on_device;
+  plan->has_output = true;
+  return nullptr;
+}
+
+// The lookup of one prepared request.
+TRITONSERVER_Error* run_single(InstanceState* inst, const RequestPlan& plan) {
+  ModelState* ms = inst->model;
+  const size_t T = ms->num_tables();
   if (ms->pooling >= 0) {
     // fused slot-wise gather + reduce, one table at a time
     for (size_t t = 0; t < T; ++t) {
-      if (n_per_table[t] == 0) continue;
+      if (plan.n_per_table[t] == 0) continue;
       const size_t h = ms->pooling_hotness[t];
       const int prc = hpsx_session_lookup_pooled_ex(
-          inst->session, t, static_cast<const int64_t*>(keys_pt[t]), key_view.on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
-          n_per_table[t] / h, h, ms->pooling, out_pt[t], out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST);
-      if (prc != HPSX_OK) {
-        *compute_end_ns = now_ns();
-        return engine_error(prc, "pooled embedding lookup of model " + ms->name);
-      }
+          inst->session, t, static_cast<const int64_t*>(plan.keys_pt[t]), plan.keys_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
+          plan.n_per_table[t] / h, h, ms->pooling, plan.out_pt[t], plan.out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST);
+      if (prc != HPSX_OK) return engine_error(prc, "pooled embedding lookup of model " + ms->name);
     }
-    *compute_end_ns = now_ns();
     return nullptr;
   }
-  const int rc = hpsx_session_lookup_ex(inst->session, keys_pt.data(), key_view.on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
-                                        out_pt.data(), out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
-                                        n_per_table.data(), T);
-  *compute_end_ns = now_ns();
+  const int rc = hpsx_session_lookup_ex(inst->session, plan.keys_pt.data(), plan.keys_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
+                                        plan.out_pt.data(), plan.out_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST,
+                                        plan.n_per_table.data(), T);
   if (rc != HPSX_OK) return engine_error(rc, "embedding lookup of model " + ms->name);
+  return nullptr;
+}
+
+// Requests [first, last) of `plans` in ONE engine pass (all are un-pooled GPU lookups into device buffers).
+TRITONSERVER_Error* run_batch(InstanceState* inst, const std::vector<RequestPlan>& plans, const std::vector<uint32_t>& group) {
+  ModelState* ms = inst->model;
+  const size_t T = ms->num_tables();
+  std::vector<const void*> keys;
+  std::vector<float*> out;
+  std::vector<size_t> n;
+  for (uint32_t r : group) {
+    keys.insert(keys.end(), plans[r].keys_pt.begin(), plans[r].keys_pt.end());
+    out.insert(out.end(), plans[r].out_pt.begin(), plans[r].out_pt.end());
+    n.insert(n.end(), plans[r].n_per_table.begin(), plans[r].n_per_table.end());
+  }
+  (void)T;
+  const int rc = hpsx_session_lookup_batch(inst->session, group.size(), keys.data(),
+                                           plans[group[0]].keys_on_device ? HPSX_MEM_DEVICE : HPSX_MEM_HOST, out.data(),
+                                           HPSX_MEM_DEVICE, n.data());
+  if (rc != HPSX_OK) return engine_error(rc, "batched embedding lookup of model " + ms->name);
   return nullptr;
 }
 
@@ -840,40 +879,96 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInstanceExecute(TRITONBACKEND_ModelInstan
   // From here on the requests are ours: exactly one FINAL response and one release each.
   uint64_t min_exec_start_ns = UINT64_MAX, max_exec_end_ns = 0, total_batch_size = 0;
   uint64_t batch_compute_start_ns = UINT64_MAX, batch_compute_end_ns = 0;
+  std::vector<bool> answered(request_count, false);  // a success response went out
   try {
+    // phase 1: validate every request and obtain its output buffer
+    std::vector<RequestPlan> plans(request_count);
+    std::vector<uint64_t> exec_start(request_count, 0), comp_start(request_count, 0), comp_end(request_count, 0);
+    std::vector<bool> ok(request_count, false);
     for (uint32_t r = 0; r < request_count; ++r) {
-      const uint64_t exec_start_ns = now_ns();
-      min_exec_start_ns = std::min(min_exec_start_ns, exec_start_ns);
-      int64_t num_samples = 0;
-      uint64_t compute_start_ns = exec_start_ns, compute_end_ns = exec_start_ns;
-      TRITONSERVER_Error* err =
-          serve_request(inst, requests[r], responses[r], &num_samples, &compute_start_ns, &compute_end_ns);
+      exec_start[r] = now_ns();
+      min_exec_start_ns = std::min(min_exec_start_ns, exec_start[r]);
+      TRITONSERVER_Error* err = prepare_request(inst, requests[r], responses[r], &plans[r]);
       if (err != nullptr) {
         HPS_LOG(ERROR, "request ", r, " of instance ", inst->name, ": ", TRITONSERVER_ErrorMessage(err),
                 ", error response sent");
         respond_error(responses, r, err);
         continue;
       }
-      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[r], "NumSample", num_samples),
+      ok[r] = true;
+    }
+    // phase 2: lookups.  Consecutive un-pooled GPU requests with device output buffers share one engine pass
+    // (cross-request batching) as long as they fit one request's key budget; everything else runs alone.
+    ModelState* ms = inst->model;
+    const uint64_t key_budget = static_cast<uint64_t>(ms->max_batch_size) * ms->cat_num;
+    auto batchable = [&](uint32_t r) {
+      return ok[r] && plans[r].has_output && ms->gpucache() && ms->pooling < 0 && plans[r].out_on_device;
+    };
+    uint32_t r = 0;
+    while (r < request_count) {
+      if (!ok[r]) {
+        ++r;
+        continue;
+      }
+      std::vector<uint32_t> group{r};
+      if (batchable(r)) {
+        uint64_t keys_in_group = plans[r].num_keys;
+        for (uint32_t q = r + 1; q < request_count && group.size() < HPSX_MAX_BATCH_REQUESTS; ++q) {
+          if (!ok[q]) continue;  // already answered with an error
+          if (!batchable(q) || plans[q].keys_on_device != plans[r].keys_on_device ||
+              keys_in_group + plans[q].num_keys > key_budget)
+            break;
+          keys_in_group += plans[q].num_keys;
+          group.push_back(q);
+        }
+      }
+      const uint64_t t0 = now_ns();
+      TRITONSERVER_Error* err = nullptr;
+      if (group.size() > 1)
+        err = run_batch(inst, plans, group);
+      else if (plans[r].has_output)
+        err = run_single(inst, plans[r]);
+      const uint64_t t1 = now_ns();
+      for (uint32_t q : group) {
+        comp_start[q] = t0;
+        comp_end[q] = t1;
+        if (err != nullptr) {
+          HPS_LOG(ERROR, "request ", q, " of instance ", inst->name, ": ", TRITONSERVER_ErrorMessage(err),
+                  ", error response sent");
+          respond_error(responses, q,
+                        TRITONSERVER_ErrorNew(TRITONSERVER_ErrorCode(err), TRITONSERVER_ErrorMessage(err)));
+          ok[q] = false;
+        }
+      }
+      if (err != nullptr) TRITONSERVER_ErrorDelete(err);
+      r = group.back() + 1;
+    }
+    // phase 3: responses and statistics
+    for (uint32_t q = 0; q < request_count; ++q) {
+      if (!ok[q]) continue;
+      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "NumSample", plans[q].num_samples),
                        "failed return Number of samples");
-      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[r], "DeviceID", inst->device),
+      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "DeviceID", inst->device),
                        "failed return device id");
-      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSend(responses[r], TRITONSERVER_RESPONSE_COMPLETE_FINAL, nullptr),
+      HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSend(responses[q], TRITONSERVER_RESPONSE_COMPLETE_FINAL, nullptr),
                        "failed sending response");
+      answered[q] = true;
       const uint64_t exec_end_ns = now_ns();
+      if (comp_start[q] == 0) comp_start[q] = comp_end[q] = exec_start[q];
       max_exec_end_ns = std::max(max_exec_end_ns, exec_end_ns);
-      batch_compute_start_ns = std::min(batch_compute_start_ns, compute_start_ns);
-      batch_compute_end_ns = std::max(batch_compute_end_ns, compute_end_ns);
-      total_batch_size += static_cast<uint64_t>(num_samples);
-      HPS_LOG_IF_ERROR(TRITONBACKEND_ModelInstanceReportStatistics(instance, requests[r], true /* success */,
-                                                                   exec_start_ns, compute_start_ns, compute_end_ns,
+      batch_compute_start_ns = std::min(batch_compute_start_ns, comp_start[q]);
+      batch_compute_end_ns = std::max(batch_compute_end_ns, comp_end[q]);
+      total_batch_size += static_cast<uint64_t>(plans[q].num_samples);
+      HPS_LOG_IF_ERROR(TRITONBACKEND_ModelInstanceReportStatistics(instance, requests[q], true /* success */,
+                                                                   exec_start[q], comp_start[q], comp_end[q],
                                                                    exec_end_ns),
                        "failed reporting request statistics");
     }
   } catch (const std::exception& e) {
     // nothing may unwind through the C ABI: fail whatever has not been answered yet
     for (uint32_t r = 0; r < request_count; ++r)
-      if (responses[r] != nullptr) respond_error(responses, r, HPS_ERROR(INTERNAL, "hps backend: ", e.what()));
+      if (responses[r] != nullptr && !answered[r])
+        respond_error(responses, r, HPS_ERROR(INTERNAL, "hps backend: ", e.what()));
   }
   if (max_exec_end_ns != 0) {
     HPS_LOG_IF_ERROR(TRITONBACKEND_ModelInstanceReportBatchStatistics(instance, total_batch_size, min_exec_start_ns,

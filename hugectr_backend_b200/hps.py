@@ -260,6 +260,19 @@ class LookupSession:
         k, o, n, T = self._arrays(d_keys_per_table, d_vectors_per_table, num_keys_per_table)
         N.check(self._L.hpsx_session_lookup_device_keys(self._h, k, o, n, T))
 
+    def lookup_batch(self, requests, device_keys: bool = False, device_vectors: bool = True) -> None:
+        """``requests``: list of (keys_per_table, vectors_per_table, num_keys_per_table), served in one pass."""
+        k, o, n = [], [], []
+        for kp, op, cp in requests:
+            k += [_addr(x) for x in kp]
+            o += [_addr(x) for x in op]
+            n += [int(c) for c in cp]
+        K = (ctypes.c_void_p * len(k))(*k)
+        O_ = (ctypes.c_void_p * len(o))(*o)
+        Nn = (ctypes.c_size_t * len(n))(*n)
+        N.check(self._L.hpsx_session_lookup_batch(self._h, len(requests), K, 1 if device_keys else 0, O_,
+                                                  1 if device_vectors else 0, Nn))
+
     def lookup_pooled(self, table: int, keys, num_bags: int, hotness: int, d_pooled, combiner: str = "sum",
                       device_keys: bool = False) -> None:
         comb = 1 if combiner == "mean" else 0

@@ -227,6 +227,15 @@ typedef enum hpsx_memory { HPSX_MEM_HOST = 0, HPSX_MEM_DEVICE = 1 } hpsx_memory;
 int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,
                            float* const* vectors_per_table, int vector_memory,
                            const size_t* num_keys_per_table, size_t num_tables);
+/* Cross-request batching (the reference serves the requests of one Execute call one by one,
+ * src/hps.cc:392-406): `num_requests` <= HPSX_MAX_BATCH_REQUESTS requests in ONE pass — all probes are launched
+ * back to back, the host waits once for all miss counts, every miss list is resolved, and the host waits once more.
+ * Arrays are request-major: entry [r * T + t] is table t of request r (T = tables of the model).  Falls back to one
+ * hpsx_session_lookup_ex per request for CPU sessions, host output buffers, or when the batch holds more keys than
+ * one request may (max_batch_size * sum of maxnum_catfeature). */
+#define HPSX_MAX_BATCH_REQUESTS 16
+int hpsx_session_lookup_batch(hpsx_session* s, size_t num_requests, const void* const* keys, int key_memory,
+                              float* const* vectors, int vector_memory, const size_t* num_keys);
 /* Model-parallel return leg fused into the gather: key i of `table` is delivered to row
  * d_pos[i] of d_out_base, which may be ANOTHER GPU's buffer opened with hpsx_ipc_open — the rows then leave
  * the owner's gather kernel as NVLink peer stores, no all-to-all of vectors and no scatter pass.  Misses are

@@ -429,3 +429,39 @@ def test_refresh_rewrites_cached_rows_from_the_database(cuda_device, miss_path):
         q2 = rng.choice(keys2, size=n)
         s.lookup([q2], [out], [n])
         assert np.array_equal(out.cpu().numpy(), ref2.lookup(q2))
+
+
+def test_batched_lookup_equals_separate_lookups(cuda_device):
+    """hpsx_session_lookup_batch (f4): R requests in one pass give exactly the rows of R separate lookups, for
+    host and device keys, including requests with empty tables and a batch that falls back (too many keys)."""
+    torch = _torch()
+    rows, dim = 30_000, 32
+    hps = hb.HPS(num_partitions=4)
+    hps.add_model(hb.ModelParams("m", 512, [dim, 8], [4, 2], [0.5, -1.0], hit_rate_threshold=1.0, cache_size_percentage=0.3))
+    hps.load_table_procedural("m", 0, rows, SEED)
+    hps.load_table_procedural("m", 1, 500, SEED + 1)
+    hps.create_embedding_cache("m")
+    ref0, ref1 = O.NumpyTable(dim, 0.5), O.NumpyTable(8, -1.0)
+    ref0.fill_procedural(rows, SEED)
+    ref1.fill_procedural(500, SEED + 1)
+    s = hps.session("m", 0)
+    rng = np.random.default_rng(12)
+    for device_keys in (False, True):
+        for counts in ([(100, 10), (0, 7), (2048, 0), (1, 1)], [(2048, 1024)] * 3, [(5, 5)] * 16):
+            reqs, want, keep = [], [], []
+            for n0, n1 in counts:
+                k0 = rng.integers(-2, rows + 2, size=n0)
+                k1 = rng.integers(-2, 502, size=n1)
+                o0 = torch.full((n0, dim), float("nan"), device="cuda")
+                o1 = torch.full((n1, 8), float("nan"), device="cuda")
+                want.append((ref0.lookup(k0), ref1.lookup(k1)))
+                if device_keys:
+                    k0, k1 = torch.from_numpy(k0).cuda(), torch.from_numpy(k1).cuda()
+                keep.append((k0, k1, o0, o1))
+                reqs.append(([k0, k1], [o0, o1], [n0, n1]))
+            torch.cuda.synchronize()
+            s.lookup_batch(reqs, device_keys=device_keys)
+            for (k0, k1, o0, o1), (w0, w1) in zip(keep, want):
+                assert np.array_equal(o0.cpu().numpy(), w0) and np.array_equal(o1.cpu().numpy(), w1)
+    with pytest.raises(hb.HpsxError):
+        s.lookup_batch([([None, None], [None, None], [0, 0])] * 17)

@@ -204,3 +204,47 @@ def test_version_reload_and_periodic_refresh_on_gpu(tmp_path, cuda_device):
         assert np.array_equal(out.cpu().numpy(), O.request([t2], q, [len(q)]))
         i1.close()
         m1.close()
+
+
+def test_many_requests_per_execute_are_served_in_one_pass(wdl_gpu):
+    """f4 cross-request batching: one Execute call with several requests (the reference serves them one by one,
+    hps.cc:392-406).  GPU-output requests share one engine pass; a bad request in the middle, a request whose
+    output lands in CPU memory and a batch that exceeds one request's key budget all still get exact answers."""
+    import torch
+    ps, ref, tables = wdl_gpu
+    with FT.Backend(ps) as be:
+        model = be.model("wdl", FT.model_config("wdl", gpus=[0], max_batch_size=1024))
+        inst = model.instance(kind=FT.KIND_GPU, device=0)
+        rng = np.random.default_rng(5)
+        for sizes in ([7, 1, 64, 33, 2], [600, 500, 400], [1] * 20):
+            reqs, outs, want = [], [], []
+            for i, samples in enumerate(sizes):
+                keys, numkeys = wdl_request(tables, samples, rng)
+                keys[::5] = 10**14 + np.arange(len(keys[::5]))
+                want.append(O.request(ref, keys, numkeys.ravel()))
+                if i == 1 and len(sizes) == 5:  # this one gets a CPU output buffer: it cannot join the fused pass
+                    reqs.append(dict(keys=keys, numkeys=numkeys))
+                    outs.append(None)
+                else:
+                    out = torch.full((len(want[-1]),), float("nan"), device="cuda")
+                    reqs.append(dict(keys=keys, numkeys=numkeys, gpu_out=out))
+                    outs.append(out)
+            if len(sizes) == 5:  # an invalid request in the middle fails alone
+                bad_keys, bad_nk = wdl_request(tables, 3, rng)
+                reqs.insert(3, dict(keys=bad_keys, numkeys=bad_nk + 1))
+                outs.insert(3, "bad")
+                want.insert(3, None)
+            rs = inst.infer_many(reqs)
+            assert len(rs) == len(reqs)
+            for r, out, w in zip(rs, outs, want):
+                if w is None:
+                    assert r.error_code == FT.ERR["INVALID_ARG"] and r.sent == 1 and r.released == 1
+                    continue
+                assert r.error_code is None, r.error_message
+                got = r.data if out is None else out.cpu().numpy()
+                assert np.array_equal(got, w)
+                assert r.sent == 1 and r.released == 1
+        st = inst.stats()
+        assert st["failed_requests"] == 1 and st["ok_requests"] == 5 + 3 + 20
+        inst.close()
+        model.close()
