@@ -116,6 +116,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -376,8 +378,11 @@ def run_ours(a):
     sampler.start()
     ms, wall = timed(dev_step, a.steps)
     clocks = sampler.stop()
-    st = sess.stats()
+    st_pipe = sess.stats()
     value = world * a.steps * n / (ms / 1e3)
+
+    st = st_pipe
+    ms_serial = ms
 
     probe_ms = st.probe_kernel_ms / max(1, st.probe_kernel_launches)
     hits_per, miss_per = st.hits / a.steps, st.misses / a.steps
@@ -396,7 +401,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "kernel": f"probe_gather_{a.variant}", "achieved": achieved, "peak": peak_gbs,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "traffic_source": traffic_src, "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "share_of_step": probe_ms / (ms / a.steps),
+                "share_of_step": probe_ms / (ms_serial / a.steps), "serial_ms_per_step": ms_serial / a.steps,
                 "note": "the HBM-bound kernel of the path; the rest of the step is the PCIe-bound miss kernel, see roofline_host_link"}
     ceiling = measure_random_gather_gbs(torch, hb, local, n, a.dim)
     roofline["random_gather_ceiling_gbs"] = ceiling
@@ -412,7 +417,7 @@ def run_ours(a):
                           "peak_source": "pinned 128 MiB cudaMemcpyAsync H2D measured in this run", "unit": "GB/s",
                           "frac": (miss_bytes / (pull_ms / 1e3) / 1e9 / link_gbs) if pull_ms > 0 and link_gbs > 0 else 0.0,
                           "avg_ms_per_step": pull_ms, "algorithmic_bytes_per_step": miss_bytes,
-                          "share_of_step": pull_ms / (ms / a.steps)}
+                          "share_of_step": pull_ms / (ms_serial / a.steps)}
 
     # ---- end-to-end arm 1: pinned host keys through the engine C-ABI call (exact byte counters) ---------
     for i in range(a.warmup):
@@ -451,6 +456,35 @@ def run_ours(a):
                  "hit_rate": st_h.hits / max(1, st_h.keys)}
     cache_hit["frac_of_peak"] = cache_hit["hbm_gbs"] / peak_gbs
 
+    # ---- small requests (configs[4] mixes batch 4096..65536): 16 requests of batch/16 samples per call, served in one
+    # engine pass (hpsx_session_lookup_batch, what the Triton shell does for the requests of one Execute call) vs one by one
+    small_n = n // 16
+    fresh = make_requests(a, hot, warm_rows, 2 * R, SEED + 1000 + rank)  # distinct keys again: ~8 % of them miss
+    fresh_pinned = [torch.from_numpy(k).pin_memory() for k in fresh]
+
+    def slices(j):
+        k = fresh_pinned[j].numpy()
+        return [([k[q * small_n:(q + 1) * small_n]], [out[q * small_n:(q + 1) * small_n]], [small_n]) for q in range(16)]
+
+    small_b, small_s = [slices(j) for j in range(R)], [slices(R + j) for j in range(R)]
+    batched_step = lambda i: sess.lookup_batch(small_b[i % R])
+
+    def single_step(i):
+        for kq, oq, nq in small_s[i % R]:
+            sess.lookup(kq, oq, nq)
+
+    for i in range(a.warmup):
+        batched_step(a.steps + i)
+    ms_b, _ = timed(batched_step, a.steps)
+    for i in range(a.warmup):
+        single_step(a.steps + i)
+    ms_s, _ = timed(single_step, a.steps)
+    small_batch = {"samples_per_request": a.batch // 16, "keys_per_request": small_n, "requests_per_call": 16,
+                   "batched_vectors_per_s": world * a.steps * 16 * small_n / (ms_b / 1e3),
+                   "one_by_one_vectors_per_s": world * a.steps * 16 * small_n / (ms_s / 1e3),
+                   "batched_ms_per_request": ms_b / a.steps / 16, "one_by_one_ms_per_request": ms_s / a.steps / 16,
+                   "call": "hpsx_session_lookup_batch vs 16 x hpsx_session_lookup, pinned host keys -> device vectors"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -467,15 +501,16 @@ def run_ours(a):
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
-                   "gpucacheper": a.gpucacheper, "hit_rate_measured": st.hits / max(1, st.keys),
+                   "gpucacheper": a.gpucacheper, "hit_rate_measured": st_pipe.hits / max(1, st_pipe.keys),
+                   "pipeline_chunks": int(os.environ.get("HPSX_PIPE_CHUNKS", "0")),
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches per arm",
                    "hot_draw_probability": a.hit, "prefill_requests": a.prefill,
                    "load_factor": a.load_factor, "miss_path": a.miss_path,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_session": e2e_session,
-        "cache_hit": cache_hit,
-        "gpu_launches": int(st.kernel_launches), "clocks": clocks,
+        "cache_hit": cache_hit, "small_batch": small_batch,
+        "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,
                       "insert_phase_ms_per_step": st.insert_kernel_ms / a.steps,

@@ -24,6 +24,7 @@ namespace hpsx {
 constexpr size_t kStageChunkRows = 32768;    // most rows per host->device miss chunk (16 MiB at dim 128)
 constexpr size_t kMinStageChunkRows = 2048;  // smaller chunks cost more in launch + pool wake-ups than they hide
 constexpr int kNumStages = 3;                // pinned/device stage pairs rotating through the miss pipeline
+constexpr size_t kPipelineMinKeys = 1u << 18; // smaller requests gain nothing from the chunked direct pull
 constexpr size_t kMaxBatchRequests = 16;     // requests one hpsx_session_lookup_batch call may serve
 
 struct Model;
@@ -88,6 +89,9 @@ struct hpsx_session {
   hpsx_cache* cache = nullptr;  // nullptr: CPU session
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_b = nullptr;     // pipelined direct pull: misses of chunk c are pulled while chunk c+1 is probed
+  std::vector<cudaEvent_t> ev_chunk;   // one per chunk: its probe (and miss count copy) has completed
+  int pipe_chunks = 0;                 // chunks of the opt-in pipelined direct pull (HPSX_PIPE_CHUNKS; < 2: off)
   int probe_variant = hpsx::kProbeV8;  // falls back to the LDG.128 variant for rows that are not 32-B multiples
   int insert_mode = -1;
 

@@ -691,9 +691,12 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
   const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
   for (size_t i = warp; i < a.m; i += nwarps) {
     const int64_t key = a.miss_keys[i];
-    const VecT* src = reinterpret_cast<const VecT*>(a.stage) + i * V;
-    VecT* dst_out =
-        a.out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
+    // stage == nullptr: the row already sits in out[pos[i]] (pipelined direct pull) and is only inserted
+    const VecT* src = a.stage ? reinterpret_cast<const VecT*>(a.stage) + i * V
+                              : reinterpret_cast<const VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V;
+    VecT* dst_out = (a.out && a.stage)
+                        ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V
+                        : nullptr;
     VecT* dst_slab = nullptr;
     Claim claim{nullptr, nullptr};
     if (a.insert && key != kEmptyKey) {
@@ -1537,7 +1540,7 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
-                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream) {
+                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream, int max_ctas_per_sm) {
   if (n_keys == 0) return cudaSuccess;
   if (t.index == nullptr) return cudaErrorInvalidValue;
   PullArgs a{};
@@ -1579,8 +1582,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
   }
   a.load_mode = load_mode;
   const size_t warps_needed = m_hint > 0 ? m_hint : n_keys;
+  const int ctas = max_ctas_per_sm > 0 ? std::min(max_ctas_per_sm, ctas_per_sm) : ctas_per_sm;
   const unsigned grid = static_cast<unsigned>(
-      min(static_cast<size_t>(148 * ctas_per_sm), (warps_needed * 32 + kBlock - 1) / kBlock));
+      min(static_cast<size_t>(148 * ctas), (warps_needed * 32 + kBlock - 1) / kBlock));
   // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
   const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
   if (vb == 16 && rows_per_warp == 2)

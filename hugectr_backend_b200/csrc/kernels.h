@@ -53,7 +53,7 @@ cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size
                                cudaStream_t stream);
 
 // K4+K5 fused: for every miss i in [0,m): row = stage[i*dim..); if d_out: out[pos[i]*dim..) = row
-// (merge); if `insert`: put (key,row) into the cache — skip when present, else first empty way, else
+// (merge); with d_stage == nullptr the row is read back from out[pos[i]*dim..) and only inserted; if `insert`: put (key,row) into the cache — skip when present, else first empty way, else
 // the way with the oldest stamp that was not touched in this epoch.  One warp per miss, per-bucket lock.
 cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys,
                                 const uint32_t* d_miss_pos, const float* d_stage, size_t m,
@@ -77,7 +77,10 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
-                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream);
+                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream,
+                               int max_ctas_per_sm = 0);
+// max_ctas_per_sm > 0 caps the persistent grid so that other kernels (the probes of later request chunks) keep
+// SM resources while the pull waits on PCIe.
 
 // Locality for the host link: random 512-B reads over a multi-GB pinned table run at ~32-42 GB/s, the same
 // reads in ascending address order at ~51 GB/s (tools/pcie_probe.cu: page-table / IOTLB reach).  So when the

@@ -11,6 +11,8 @@
 // The shell makes no CUDA call of its own: every device operation goes through include/hpsx.h.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -943,6 +945,7 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInstanceExecute(TRITONBACKEND_ModelInstan
       if (err != nullptr) TRITONSERVER_ErrorDelete(err);
       r = group.back() + 1;
     }
+    const uint64_t t_phase3 = now_ns();
     // phase 3: responses and statistics
     for (uint32_t q = 0; q < request_count; ++q) {
       if (!ok[q]) continue;
@@ -964,6 +967,11 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInstanceExecute(TRITONBACKEND_ModelInstan
                                                                    exec_end_ns),
                        "failed reporting request statistics");
     }
+    static const bool trace = std::getenv("HPS_TRACE") != nullptr;
+    if (trace && request_count > 0)
+      std::fprintf(stderr, "[hps] execute %u request(s): prepare %.3f ms | lookup %.3f ms | respond %.3f ms\n", request_count,
+                   (comp_start[0] ? comp_start[0] - exec_start[0] : 0) / 1e6,
+                   (comp_end[request_count - 1] - comp_start[0]) / 1e6, (now_ns() - t_phase3) / 1e6);
   } catch (const std::exception& e) {
     // nothing may unwind through the C ABI: fail whatever has not been answered yet
     for (uint32_t r = 0; r < request_count; ++r)

@@ -465,3 +465,39 @@ def test_batched_lookup_equals_separate_lookups(cuda_device):
                 assert np.array_equal(o0.cpu().numpy(), w0) and np.array_equal(o1.cpu().numpy(), w1)
     with pytest.raises(hb.HpsxError):
         s.lookup_batch([([None, None], [None, None], [0, 0])] * 17)
+
+
+@pytest.mark.parametrize("chunks", ["4", "7", "0"])
+def test_pipelined_direct_pull_large_request(cuda_device, miss_path, monkeypatch, chunks):
+    """Requests of >= 2^18 keys on the direct-pull path are cut into chunks whose PCIe pulls overlap the probes of
+    the following chunks, and the pulled rows are inserted from the output buffer afterwards: same rows, same
+    residency guarantees as the serial path (HPSX_PIPE_CHUNKS=0)."""
+    if miss_path != "direct":
+        pytest.skip("pipelining is a property of the direct-pull path")
+    torch = _torch()
+    monkeypatch.setenv("HPSX_PIPE_CHUNKS", chunks)
+    rows, dim, n = 400_000, 32, 300_001
+    hps, ref = make_server(rows, dim, cache_pct=0.6, thr=1.0, max_batch=n)
+    s = hps.session("m", 0)
+    rng = np.random.default_rng(31)
+    out = torch.empty((n, dim), device="cuda")
+    for it in range(3):
+        keys = rng.integers(-10, rows + 10, size=n)
+        out.fill_(float("nan"))
+        s.reset_stats()
+        if it == 1:
+            dk = torch.from_numpy(keys).cuda()
+            torch.cuda.synchronize()
+            s.lookup_device_keys([dk], [out], [n])
+        else:
+            s.lookup([keys], [out], [n])
+        st = s.stats()
+        assert st.hits + st.misses == n and st.misses > 0
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys)), (chunks, it)
+        res = hps.cache_keys("m", 0, 0)
+        assert len(res) == len(set(res.tolist())) == hps.cache_resident("m", 0, 0)
+    # the rows pulled in the last request are resident now: the same request again misses (almost) nothing new
+    s.reset_stats()
+    s.lookup([keys], [out], [n])
+    assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
+    assert s.stats().misses < 0.05 * n
