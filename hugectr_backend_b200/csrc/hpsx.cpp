@@ -654,6 +654,47 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     off[t + 1] = off[t] + n;
     if (n == 0) continue;
     const int64_t* d_keys;
+    const size_t dim = c->tables[t % T].dim;
+    if (!keys_on_device && n >= kPipelineMinKeys && s->copy_chunks >= 2 && pos_per_table == nullptr) {
+      // Large request with host keys: the copy engine moves the keys of chunk c+1 (second stream) while the SMs
+      // probe chunk c.  All chunks append to ONE miss list (request-relative positions), so the pull below is
+      // unchanged; the cache is only read here.
+      const size_t K = static_cast<size_t>(s->copy_chunks);
+      const size_t csz = ((n + K - 1) / K + 31) / 32 * 32;
+      if (!s->stream_b) HPSX_CU(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
+      while (s->ev_chunk.size() < K) {
+        cudaEvent_t e;
+        HPSX_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->ev_chunk.push_back(e);
+      }
+      const int64_t* h_keys = static_cast<const int64_t*>(keys_per_table[t]);
+      size_t nchunks = 0;
+      for (size_t o = 0; o < n; o += csz, ++nchunks) {
+        const size_t nc = std::min(csz, n - o);
+        HPSX_CU(cudaMemcpyAsync(s->d_keys + off[t] + o, h_keys + o, nc * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                s->stream_b));
+        HPSX_CU(cudaEventRecord(s->ev_chunk[nchunks], s->stream_b));
+      }
+      s->stats.h2d_bytes += n * sizeof(int64_t);
+      HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
+      size_t ci = 0;
+      for (size_t o = 0; o < n; o += csz, ++ci) {
+        const size_t nc = std::min(csz, n - o);
+        HPSX_CU(cudaStreamWaitEvent(s->stream, s->ev_chunk[ci], 0));
+        HPSX_CU(launch_probe_gather(c->tables[t % T], s->d_keys + off[t] + o, nc, out_per_table[t] + o * dim, epoch,
+                                    !c->is_static, s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
+                                    nullptr, s->probe_variant, s->stream, nullptr, s->d_src ? s->d_src + off[t] + o : nullptr,
+                                    static_cast<uint32_t>(o)));
+        ++s->stats.kernel_launches;
+      }
+      HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
+      if (!sorted) {
+        HPSX_CU(pull(t, 0));
+        HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
+        ++s->stats.kernel_launches;
+      }
+      continue;
+    }
     if (keys_on_device) {
       d_keys = static_cast<const int64_t*>(keys_per_table[t]);
     } else {
@@ -1686,6 +1727,7 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   }
   if (s->probe_variant == kProbeSplit) HPSX_CU(cudaMalloc(&s->d_src, cap * sizeof(uint32_t)));
   s->pipe_chunks = pipeline_chunks_from_env();
+  if (const char* e = std::getenv("HPSX_COPY_CHUNKS")) s->copy_chunks = std::max(0, std::min(std::atoi(e), 64));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * s->vt);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));

@@ -156,6 +156,7 @@ struct ProbeArgs {
   int64_t* miss_keys_host;  // optional mirror in mapped pinned host memory (zero-copy PCIe writes)
   uint32_t* src;  // probe_index only
   const uint32_t* pos;  // optional: key i is delivered to row pos[i] of `out` (which may be peer memory)
+  uint32_t pos_base;    // added to the positions recorded in the miss list (this launch covers keys [pos_base, pos_base + n))
 };
 
 // Append the misses of one warp tile to the global miss list: ballot -> popc prefix -> one atomic.
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
 
   if (is_miss) {
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = dst;
+    a.miss_pos[r] = kScatter ? dst : dst + a.pos_base;
     a.miss_keys[r] = key;
     if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
   }
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs
   }
   if (is_miss) {
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+    a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
     a.miss_keys[r] = key;
     if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
   }
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(kBlock) probe_gather_pipe_kernel(const ProbeAr
     }
     if (is_miss) {
       const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-      a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+      a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
       a.miss_keys[r] = key_cur;
       if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key_cur;
     }
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(kWarps * 32) probe_gather_tma_kernel(const Pro
         }
         if (is_miss) {
           const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-          a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane);
+          a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
           a.miss_keys[r] = key;
           if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
         }
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(kBlock) probe_index_kernel(const ProbeArgs a) 
   const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
   if (is_miss) {
     const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = static_cast<uint32_t>(idx);
+    a.miss_pos[r] = static_cast<uint32_t>(idx) + a.pos_base;
     a.miss_keys[r] = key;
     if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
     slot = kSrcMissBit | r;
@@ -1403,9 +1404,11 @@ cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t* d_slot_scratch) {
+                                int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t* d_slot_scratch,
+                                uint32_t pos_base) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
+  a.pos_base = pos_base;
   a.buckets = t.buckets;
   a.values = t.values;
   a.num_buckets = t.num_buckets;

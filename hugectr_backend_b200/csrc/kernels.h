@@ -42,7 +42,9 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
                                 int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr,
-                                uint32_t* d_slot_scratch = nullptr);
+                                uint32_t* d_slot_scratch = nullptr, uint32_t pos_base = 0);
+// `pos_base`: this launch covers keys [pos_base, pos_base + n) of a larger request whose chunks share one miss
+// list (d_out / d_keys already point at the chunk; recorded miss positions are request-relative).
 // With `d_pos`, key i is delivered to row d_pos[i] of d_out instead of row i, and d_out may be another
 // GPU's buffer (NVLink peer mapping): the model-parallel return leg fused into the gather.
 
