@@ -458,6 +458,16 @@ void account_probe_time(hpsx_session* s, size_t t, size_t n) {
   }
 }
 
+// Miss lists shorter than this are pulled in miss-list order: the resolve + radix sort costs ~70 us of launches,
+// more than the sorted order saves on a few thousand rows (HPSX_PULL_SORT_MIN overrides).
+size_t pull_sort_min() {
+  static const size_t v = [] {
+    const char* e = std::getenv("HPSX_PULL_SORT_MIN");
+    return e ? static_cast<size_t>(std::atoll(e)) : static_cast<size_t>(16384);
+  }();
+  return v;
+}
+
 bool pull_sort_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("HPSX_PULL_SORT");
@@ -642,7 +652,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
   std::vector<size_t> off(num_tables + 1, 0);
   auto pull = [&](size_t t, size_t m_hint) -> cudaError_t {
-    const bool use_sorted = sorted && m_hint > 0;
+    const bool use_sorted = sorted && m_hint >= std::max<size_t>(pull_sort_min(), 1);
     return launch_pull_misses(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
                               n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + s->vt + t,
@@ -726,12 +736,15 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
       if (m == 0) continue;
       HPSX_CU(cudaEventRecord(s->ev_pull[2 * t], s->stream));
-      HPSX_CU(launch_resolve_and_sort_misses(c->tables[t % T], s->d_miss_keys + off[t], m, s->d_addr[0] + off[t],
-                                             s->d_sidx[0] + off[t], s->d_addr[1] + off[t], s->d_sidx[1] + off[t],
-                                             s->d_sort_temp, s->sort_temp_bytes, s->stream));
+      if (m >= std::max<size_t>(pull_sort_min(), 1)) {
+        HPSX_CU(launch_resolve_and_sort_misses(c->tables[t % T], s->d_miss_keys + off[t], m, s->d_addr[0] + off[t],
+                                               s->d_sidx[0] + off[t], s->d_addr[1] + off[t], s->d_sidx[1] + off[t],
+                                               s->d_sort_temp, s->sort_temp_bytes, s->stream));
+        ++s->stats.kernel_launches;  // resolve (the CUB radix-sort passes are library kernels, not counted)
+      }
       HPSX_CU(pull(t, m));
       HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
-      s->stats.kernel_launches += 2;  // resolve + pull (the CUB radix-sort passes are library kernels, not counted)
+      ++s->stats.kernel_launches;
     }
   }
   HPSX_CU(cudaMemcpyAsync(s->h_counters + s->vt, s->d_counters + s->vt, 2 * s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
