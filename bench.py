@@ -66,6 +66,8 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--core-arms-only", action="store_true",
+                    help="skip the small-request and dense-head arms (used for the ncu launch list, so that it shows the step's kernels)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -458,32 +460,34 @@ def run_ours(a):
 
     # ---- small requests (configs[4] mixes batch 4096..65536): 16 requests of batch/16 samples per call, served in one
     # engine pass (hpsx_session_lookup_batch, what the Triton shell does for the requests of one Execute call) vs one by one
-    small_n = n // 16
-    fresh = make_requests(a, hot, warm_rows, 2 * R, SEED + 1000 + rank)  # distinct keys again: ~8 % of them miss
-    fresh_pinned = [torch.from_numpy(k).pin_memory() for k in fresh]
+    small_batch = None
+    if not a.core_arms_only:
+        small_n = n // 16
+        fresh = make_requests(a, hot, warm_rows, 2 * R, SEED + 1000 + rank)  # distinct keys again: ~8 % of them miss
+        fresh_pinned = [torch.from_numpy(k).pin_memory() for k in fresh]
 
-    def slices(j):
-        k = fresh_pinned[j].numpy()
-        return [([k[q * small_n:(q + 1) * small_n]], [out[q * small_n:(q + 1) * small_n]], [small_n]) for q in range(16)]
+        def slices(j):
+            k = fresh_pinned[j].numpy()
+            return [([k[q * small_n:(q + 1) * small_n]], [out[q * small_n:(q + 1) * small_n]], [small_n]) for q in range(16)]
 
-    small_b, small_s = [slices(j) for j in range(R)], [slices(R + j) for j in range(R)]
-    batched_step = lambda i: sess.lookup_batch(small_b[i % R])
+        small_b, small_s = [slices(j) for j in range(R)], [slices(R + j) for j in range(R)]
+        batched_step = lambda i: sess.lookup_batch(small_b[i % R])
 
-    def single_step(i):
-        for kq, oq, nq in small_s[i % R]:
-            sess.lookup(kq, oq, nq)
+        def single_step(i):
+            for kq, oq, nq in small_s[i % R]:
+                sess.lookup(kq, oq, nq)
 
-    for i in range(a.warmup):
-        batched_step(a.steps + i)
-    ms_b, _ = timed(batched_step, a.steps)
-    for i in range(a.warmup):
-        single_step(a.steps + i)
-    ms_s, _ = timed(single_step, a.steps)
-    small_batch = {"samples_per_request": a.batch // 16, "keys_per_request": small_n, "requests_per_call": 16,
-                   "batched_vectors_per_s": world * a.steps * 16 * small_n / (ms_b / 1e3),
-                   "one_by_one_vectors_per_s": world * a.steps * 16 * small_n / (ms_s / 1e3),
-                   "batched_ms_per_request": ms_b / a.steps / 16, "one_by_one_ms_per_request": ms_s / a.steps / 16,
-                   "call": "hpsx_session_lookup_batch vs 16 x hpsx_session_lookup, pinned host keys -> device vectors"}
+        for i in range(a.warmup):
+            batched_step(a.steps + i)
+        ms_b, _ = timed(batched_step, a.steps)
+        for i in range(a.warmup):
+            single_step(a.steps + i)
+        ms_s, _ = timed(single_step, a.steps)
+        small_batch = {"samples_per_request": a.batch // 16, "keys_per_request": small_n, "requests_per_call": 16,
+                       "batched_vectors_per_s": world * a.steps * 16 * small_n / (ms_b / 1e3),
+                       "one_by_one_vectors_per_s": world * a.steps * 16 * small_n / (ms_s / 1e3),
+                       "batched_ms_per_request": ms_b / a.steps / 16, "one_by_one_ms_per_request": ms_s / a.steps / 16,
+                       "call": "hpsx_session_lookup_batch vs 16 x hpsx_session_lookup, pinned host keys -> device vectors"}
 
     if rank != 0:
         if world > 1:
