@@ -489,6 +489,51 @@ def run_ours(a):
                        "batched_ms_per_request": ms_b / a.steps / 16, "one_by_one_ms_per_request": ms_s / a.steps / 16,
                        "call": "hpsx_session_lookup_batch vs 16 x hpsx_session_lookup, pinned host keys -> device vectors"}
 
+    # ---- dense head: the MLP that follows the lookup in the reference's ensembles, fed in place
+    # from the lookup's device output; Criteo-shape [26 x 128 -> 1024 -> 512 -> 256 -> 1], bf16 tensor cores
+    dense_head = None
+    if not a.core_arms_only and a.dim * a.slots % 8 == 0:
+        dims = [a.slots * a.dim, 1024, 512, 256, 1]
+        rng_w = np.random.default_rng(SEED + 5)
+        weights = [(rng_w.standard_normal((dims[l + 1], dims[l])) / np.sqrt(dims[l])).astype(np.float32) for l in range(4)]
+        mlp = hb.DenseMlp(local, weights, [np.zeros(d, np.float32) for d in dims[1:]], [1, 1, 1, 0])
+        logit = torch.empty((a.batch, 1), device="cuda")
+        cur = torch.cuda.current_stream()
+        for _ in range(3):
+            mlp.forward(out, a.batch, logit, stream=cur.cuda_stream)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(a.steps):
+            mlp.forward(out, a.batch, logit, stream=cur.cuda_stream)
+        ev1.record()
+        ev1.synchronize()
+        ms_d = ev0.elapsed_time(ev1) / a.steps
+        flops = 2.0 * a.batch * sum(dims[l] * dims[l + 1] for l in range(4))
+        # library baseline for the same GEMMs: torch (cuBLAS) bf16 matmuls on pre-converted operands
+        xb = out.view(a.batch, -1).to(torch.bfloat16)
+        wb = [torch.from_numpy(w).cuda().to(torch.bfloat16) for w in weights[:3]]
+        def lib_step():
+            h = xb
+            for w in wb:
+                h = torch.relu(h @ w.t())
+            return h
+        for _ in range(3):
+            lib_step()
+        ev0.record()
+        for _ in range(a.steps):
+            lib_step()
+        ev1.record()
+        ev1.synchronize()
+        ms_lib = ev0.elapsed_time(ev1) / a.steps
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0))
+        dense_head = {"dims": dims, "batch": a.batch, "ms_per_step": ms_d, "tflops": flops / (ms_d / 1e3) / 1e12,
+                      "peak_tflops": peak_tf, "frac_of_peak": flops / (ms_d / 1e3) / 1e12 / peak_tf,
+                      "includes": "fp32 -> bf16 conversion of the lookup output (0.87 GB read), 3 tcgen05 GEMM layers with fused bias+ReLU, final dot-product layer",
+                      "cublas_bf16_gemms_ms": ms_lib,
+                      "cublas_note": "torch bf16 matmul + relu of the three GEMM layers on pre-converted operands (no input conversion, no last layer)"}
+        mlp.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -513,7 +558,7 @@ def run_ours(a):
                    "load_factor": a.load_factor, "miss_path": a.miss_path,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_session": e2e_session,
-        "cache_hit": cache_hit, "small_batch": small_batch,
+        "cache_hit": cache_hit, "small_batch": small_batch, "dense_head": dense_head,
         "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,

@@ -6,6 +6,6 @@ thin ctypes binding used by the tests, ``bench.py`` and Python callers; it never
 itself and raises if the native library is missing.
 """
 from ._native import HpsxError, lib, lib_path  # noqa: F401
-from .hps import HPS, LookupSession, ModelParams, SessionStats, ShardGroup  # noqa: F401
+from .hps import HPS, LookupSession, ModelParams, SessionStats, ShardGroup, DenseMlp  # noqa: F401
 
-__all__ = ["HPS", "LookupSession", "ModelParams", "SessionStats", "ShardGroup", "HpsxError", "lib", "lib_path"]
+__all__ = ["HPS", "LookupSession", "ModelParams", "SessionStats", "ShardGroup", "DenseMlp", "HpsxError", "lib", "lib_path"]

@@ -357,6 +357,40 @@ class ShardGroup:
         self.close()
 
 
+class DenseMlp:
+    """~ the dense model of the reference's ensembles (hps-triton-ensemble/01_model_training.ipynb cells 7,11) on the
+    tcgen05 tensor cores.  ``weights[l]``: float32 [out, in]; ``biases[l]``: float32 [out] or None."""
+
+    def __init__(self, device: int, weights, biases=None, relu=None):
+        self._L = N.lib()
+        L = len(weights)
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
+        dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+        for l in range(L):
+            if ws[l].shape[1] != dims[l]:
+                raise ValueError(f"layer {l}: weight is {ws[l].shape}, expected [*, {dims[l]}]")
+        bs = [None if (biases is None or biases[l] is None) else np.ascontiguousarray(biases[l], dtype=np.float32) for l in range(L)]
+        self.dims = dims
+        D = (ctypes.c_size_t * (L + 1))(*dims)
+        W = (ctypes.c_void_p * L)(*[_addr(w) for w in ws])
+        B = (ctypes.c_void_p * L)(*[_addr(b) for b in bs])
+        R = (ctypes.c_int * L)(*[int(bool(r)) for r in (relu or [0] * L)])
+        h = ctypes.c_void_p()
+        N.check(self._L.hpsx_mlp_create(device, L, D, W, B, R, ctypes.byref(h)))
+        self._h = h
+
+    def forward(self, d_in, batch: int, d_out, stream: int = 0) -> None:
+        N.check(self._L.hpsx_mlp_forward(self._h, _addr(d_in), batch, _addr(d_out), stream))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.hpsx_mlp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 # -- stand-alone device primitives ---------------------------------------------------------------
 def unique(device: int, d_keys, n: int, d_unique, d_inverse, stream: int = 0) -> int:
     u = ctypes.c_size_t()

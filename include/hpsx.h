@@ -321,6 +321,24 @@ int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 int hpsx_cache_drain_async(hpsx_cache* cache);
 
 /* ---------------------------------------------------------------------------------------------
+ * dense MLP head: the dense model that follows the hps model in the reference's ensembles
+ * (samples/hps-triton-ensemble/01_model_training.ipynb cells 7,11: fc_1 -> fc_2 -> fc_3 over the reshaped lookup
+ * vectors; 02_model_inference_hps_tf_ensemble.ipynb:336-395 deploys it as a second Triton model).  Here it reads the
+ * lookup's device output in place.  Y = act(X W^T + b) per layer, bf16 operands with fp32 accumulation on the
+ * tcgen05 tensor cores; the result is fp32.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hpsx_mlp hpsx_mlp;
+/* dims[num_layers + 1]; weights[l]: host fp32 [dims[l+1], dims[l]] row-major; biases[l]: host fp32 [dims[l+1]] or
+ * NULL (biases may be NULL altogether); relu[l] != 0 applies max(x, 0) (relu may be NULL = linear layers, like the
+ * sample).  Every dims[l] (layer input width) must be a multiple of 8; a layer with one output unit must be last. */
+int hpsx_mlp_create(int device, size_t num_layers, const size_t* dims, const float* const* weights,
+                    const float* const* biases, const int* relu, hpsx_mlp** out);
+/* d_in: device fp32 [batch, dims[0]]; d_out: device fp32 [batch, dims[num_layers]].  Asynchronous on `stream`
+ * (a cudaStream_t, NULL = default stream). */
+int hpsx_mlp_forward(hpsx_mlp* m, const float* d_in, size_t batch, float* d_out, void* stream);
+int hpsx_mlp_destroy(hpsx_mlp* m);
+
+/* ---------------------------------------------------------------------------------------------
  * stand-alone device primitives (testable without a parameter server)
  * ------------------------------------------------------------------------------------------- */
 /* K1: dedup `n` device keys.  d_unique[0..*h_num_unique) holds each distinct key
