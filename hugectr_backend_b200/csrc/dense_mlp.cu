@@ -7,14 +7,15 @@
 //
 //   warp 0  (one elected lane)  TMA producer: cp.async.bulk.tensor 2-D tiles of X and W into a 128B-swizzled
 //                               shared-memory ring, completion on mbarriers
-//   warp 1  (one elected lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x 128 x 16 per instruction,
-//                               accumulator in 128 TMEM columns; tcgen05.commit releases ring slots / signals the epilogue
+//   warp 1  (one elected lane)  MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 per instruction,
+//                               accumulator in 256 TMEM columns; tcgen05.commit releases ring slots / signals the epilogue
 //   warps 2-5                   epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> bias + ReLU ->
 //                               bf16 (hidden layers) or fp32 (last GEMM layer) -> global
 //
-// Two CTAs are resident per SM (3-stage ring = 96 KB of shared memory and 128 of the 512 TMEM columns each), so the
-// epilogue of one tile overlaps the MMAs of the other.  A final layer with N == 1 (the samples' logit) is a dot
-// product per row and runs as a SIMT kernel.
+// Persistent kernel, one CTA per SM: a 4-stage ring of 48 KB stages (192 KB of shared memory) and two accumulators
+// (all 512 TMEM columns), so the epilogue of tile i overlaps the MMAs of tile i+1.  128 x 256 tiles halve the operand
+// bytes per flop of 128 x 128 ones (the first version: L2-bandwidth bound at 0.49 of the tensor peak).  A final layer
+// with N == 1 (the samples' logit) is a dot product per row and runs as a SIMT kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -29,15 +30,16 @@ namespace hpsx {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kBlockN = 128;
+constexpr int kBlockN = 256;  // one tcgen05.mma covers the whole 128 x 256 tile: half the operand bytes per flop of 128 x 128
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit operands
-constexpr int kStages = 3;
+constexpr int kStages = 4;
+constexpr int kAccStages = 2;  // accumulators in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int kThreads = 192;  // 6 warps
 constexpr uint32_t kTileABytes = kBlockM * kBlockK * 2;
 constexpr uint32_t kTileBBytes = kBlockN * kBlockK * 2;
 constexpr uint32_t kStageBytes = kTileABytes + kTileBBytes;
-constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kTmemCols = kAccStages * kBlockN;  // 512: all of an SM's tensor memory, one CTA per SM
 constexpr size_t kSmemBytes = 1024 /* alignment slack */ + kStages * kStageBytes + 256 /* barriers + tmem slot */;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -47,6 +49,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -120,21 +125,24 @@ struct GemmArgs {
   float* out_f32;           // [M, N] otherwise
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+// Persistent: CTA b works on tiles b, b + gridDim.x, ... (n fastest, so concurrently running CTAs share X rows in L2).
+__global__ void __launch_bounds__(kThreads, 1)
 mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* accum_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full_bar = empty_bar + kStages;
+  uint64_t* acc_empty_bar = acc_full_bar + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty_bar + kAccStages);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const int m0 = blockIdx.y * kBlockM;
-  const int n0 = blockIdx.x * kBlockN;
   const int num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  const int num_n = (g.N + kBlockN - 1) / kBlockN;
+  const int num_m = (g.M + kBlockM - 1) / kBlockM;
+  const int num_tiles = num_n * num_m;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -143,7 +151,10 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(&acc_full_bar[s], 1);
+      mbar_init(&acc_empty_bar[s], 4);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -160,93 +171,122 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer =====
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);  // passes immediately on the first round
-        unsigned char* a_tile = tiles + s * kStageBytes;
-        unsigned char* b_tile = a_tile + kTileABytes;
-        mbar_expect_tx(&full_bar[s], kStageBytes);
-        tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &full_bar[s]);
-        tma_load_2d(b_tile, &map_w, kb * kBlockK, n0, &full_bar[s]);
+      uint32_t it = 0;  // k-blocks issued so far, over all tiles of this CTA
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBlockM, n0 = (tile % num_n) * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const uint32_t s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);  // passes immediately on the first round
+          unsigned char* a_tile = tiles + s * kStageBytes;
+          unsigned char* b_tile = a_tile + kTileABytes;
+          mbar_expect_tx(&full_bar[s], kStageBytes);
+          tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &full_bar[s]);
+          tma_load_2d(b_tile, &map_w, kb * kBlockK, n0, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
       const uint32_t idesc = make_instr_desc(kBlockM, kBlockN);
-      for (int kb = 0; kb < num_k_blocks; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+        const uint32_t acc = t % kAccStages;
+        const uint32_t acc_ph = (t / kAccStages) & 1u;
+        mbar_wait(&acc_empty_bar[acc], acc_ph ^ 1u);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = smem_addr(tiles + s * kStageBytes);
-        const uint32_t b_addr = a_addr + kTileABytes;
+        const uint32_t tmem_d = tmem_base + acc * kBlockN;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const uint32_t s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = smem_addr(tiles + s * kStageBytes);
+          const uint32_t b_addr = a_addr + kTileABytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * kUmmaK * 2);
-          const uint64_t db = make_smem_desc(b_addr + k * kUmmaK * 2);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * kUmmaK * 2);
+            const uint64_t db = make_smem_desc(b_addr + k * kUmmaK * 2);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // the ring slot is free once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // the ring slot is free once these MMAs have read it
+        umma_commit(&acc_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(accum_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
     const uint32_t quad = warp & 3u;
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + static_cast<int>(quad * 32u + lane);
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / num_n) * kBlockM, n0 = (tile % num_n) * kBlockN;
+      const uint32_t acc = t % kAccStages;
+      const uint32_t acc_ph = (t / kAccStages) & 1u;
+      mbar_wait(&acc_full_bar[acc], acc_ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + static_cast<int>(quad * 32u + lane);
 #pragma unroll 1
-    for (int c = 0; c < kBlockN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + static_cast<uint32_t>(c), v);
-      if (m < g.M) {
-        const int n_base = n0 + c;
-        if (g.out_bf16 != nullptr) {
-          __nv_bfloat16* dst = g.out_bf16 + static_cast<size_t>(m) * g.N + n_base;
-          if (n_base + 32 <= g.N && (g.N & 7) == 0) {
+      for (int c = 0; c < kBlockN; c += 32) {
+        if (n0 + c >= g.N) break;  // warp-uniform: nothing of this column block is inside the matrix
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + acc * kBlockN + static_cast<uint32_t>(c), v);
+        if (m < g.M) {
+          const int n_base = n0 + c;
+          if (g.out_bf16 != nullptr) {
+            __nv_bfloat16* dst = g.out_bf16 + static_cast<size_t>(m) * g.N + n_base;
+            if (n_base + 32 <= g.N && (g.N & 7) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t packed[4];
+              for (int j = 0; j < 32; j += 8) {
+                uint32_t packed[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float x0 = __uint_as_float(v[j + 2 * q]), x1 = __uint_as_float(v[j + 2 * q + 1]);
-                if (g.bias != nullptr) {
-                  x0 += __ldg(g.bias + n_base + j + 2 * q);
-                  x1 += __ldg(g.bias + n_base + j + 2 * q + 1);
+                for (int q = 0; q < 4; ++q) {
+                  float x0 = __uint_as_float(v[j + 2 * q]), x1 = __uint_as_float(v[j + 2 * q + 1]);
+                  if (g.bias != nullptr) {
+                    x0 += __ldg(g.bias + n_base + j + 2 * q);
+                    x1 += __ldg(g.bias + n_base + j + 2 * q + 1);
+                  }
+                  if (g.relu) {
+                    x0 = fmaxf(x0, 0.f);
+                    x1 = fmaxf(x1, 0.f);
+                  }
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+                  packed[q] = *reinterpret_cast<const uint32_t*>(&h);
                 }
-                if (g.relu) {
-                  x0 = fmaxf(x0, 0.f);
-                  x1 = fmaxf(x1, 0.f);
-                }
-                const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
-                packed[q] = *reinterpret_cast<const uint32_t*>(&h);
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
               }
-              *reinterpret_cast<uint4*>(dst + j) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n_base + j < g.N) {
+                  float x = __uint_as_float(v[j]);
+                  if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
+                  if (g.relu) x = fmaxf(x, 0.f);
+                  dst[j] = __float2bfloat16_rn(x);
+                }
+              }
             }
           } else {
-            for (int j = 0; j < 32 && n_base + j < g.N; ++j) {
-              float x = __uint_as_float(v[j]);
-              if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
-              if (g.relu) x = fmaxf(x, 0.f);
-              dst[j] = __float2bfloat16_rn(x);
+            float* dst = g.out_f32 + static_cast<size_t>(m) * g.N + n_base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n_base + j < g.N) {
+                float x = __uint_as_float(v[j]);
+                if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
+                if (g.relu) x = fmaxf(x, 0.f);
+                dst[j] = x;
+              }
             }
-          }
-        } else {
-          float* dst = g.out_f32 + static_cast<size_t>(m) * g.N + n_base;
-          for (int j = 0; j < 32 && n_base + j < g.N; ++j) {
-            float x = __uint_as_float(v[j]);
-            if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
-            if (g.relu) x = fmaxf(x, 0.f);
-            dst[j] = x;
           }
         }
       }
+      // this warp has read its share of the accumulator: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty_bar[acc]);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -330,6 +370,7 @@ struct DenseMlp {
   __nv_bfloat16* act[2] = {nullptr, nullptr};
   size_t act_rows = 0;
   size_t max_dim = 0;
+  int num_sms = 148;
 };
 
 static thread_local std::string g_mlp_err;
@@ -361,6 +402,8 @@ cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const 
   }
   DenseMlp* m = new DenseMlp();
   m->device = device;
+  cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (m->num_sms <= 0) m->num_sms = 148;
   m->dims.assign(dims, dims + num_layers + 1);
   for (size_t d : m->dims) m->max_dim = d > m->max_dim ? d : m->max_dim;
   for (size_t l = 0; l < num_layers; ++l) {
@@ -457,7 +500,8 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
     g.relu = m->relu[l];
     g.out_bf16 = last ? nullptr : m->act[cur ^ 1];
     g.out_f32 = last ? d_out : nullptr;
-    const dim3 grid(static_cast<unsigned>((N + kBlockN - 1) / kBlockN), static_cast<unsigned>((batch + kBlockM - 1) / kBlockM));
+    const size_t tiles = ((N + kBlockN - 1) / kBlockN) * ((batch + kBlockM - 1) / kBlockM);
+    const unsigned grid = static_cast<unsigned>(tiles < static_cast<size_t>(m->num_sms) ? tiles : m->num_sms);
     mlp_gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, g);
     cur ^= 1;
   }
