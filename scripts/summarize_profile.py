@@ -20,7 +20,9 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
            "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
            "launch__waves_per_multiprocessor", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-           "pcie__read_bytes.sum.per_second"]
+           "pcie__read_bytes.sum.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+           "nvlrx__bytes.sum.per_second", "nvltx__bytes.sum.per_second"]
 
 
 def short(name):
@@ -30,8 +32,8 @@ def short(name):
     return name.split("(")[0]
 
 
-def launch_list(tag):
-    path = os.path.join(SRC, f"launches_{tag}.csv")
+def launch_list(tag, suffix=""):
+    path = os.path.join(SRC, f"launches_{tag}{suffix}.csv")
     rows = []
     with open(path) as f:
         text = f.read()
@@ -48,8 +50,8 @@ def launch_list(tag):
     return agg, total
 
 
-def full_capture(tag):
-    rep = os.path.join(SRC, f"hot_{tag}.ncu-rep")
+def full_capture(tag, suffix=""):
+    rep = os.path.join(SRC, f"hot_{tag}{suffix}.ncu-rep")
     if not os.path.exists(rep):
         return []
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -138,6 +140,28 @@ def main():
                                 "gpu_time_us": to_us(*c["gpu__time_duration.sum"])}
         with open(os.path.join(DST, f"ncu_traffic_{tag}.json"), "w") as f:
             json.dump(traffic, f, indent=1)
+    # extra passes: the single-GPU form of the model-parallel workload and the dense head
+    for suffix, title in (("_c4", "model-parallel workload on one GPU (`bench.py --workload c4 --gpus 1`)"),
+                          ("_mlp", "dense head, Criteo shape (`scripts/mlp_profile_driver.py`)")):
+        if not os.path.exists(os.path.join(SRC, f"launches_{tag}{suffix}.csv")):
+            continue
+        agg2, total2 = launch_list(tag, suffix)
+        shutil.copy(os.path.join(SRC, f"launches_{tag}{suffix}.csv"), os.path.join(DST, f"launches_{tag}{suffix}.csv"))
+        lines.append(f"## ncu launch list — {title}\n")
+        lines.append("| kernel | launches | total us | avg us | share of all kernel time | grid | block |")
+        lines.append("|---|---|---|---|---|---|---|")
+        for k, a in sorted(agg2.items(), key=lambda kv: -kv[1]["us"]):
+            lines.append("| `%s` | %d | %.1f | %.1f | %.1f %% | %s | %s |" % (k, a["n"], a["us"], a["us"] / a["n"], 100 * a["us"] / total2,
+                                                                           a["grid"], a["block"]))
+        lines.append("")
+        for c in full_capture(tag, suffix):
+            lines.append(f"**{c['kernel']}** (`ncu --set full`)\n")
+            lines.append("| metric | value | unit |")
+            lines.append("|---|---|---|")
+            for m in METRICS:
+                if m in c:
+                    lines.append(f"| `{m}` | {c[m][0]} | {c[m][1]} |")
+            lines.append("")
     with open(os.path.join(DST, f"{tag}_summary.md"), "w") as f:
         f.write("\n".join(lines) + "\n")
     print("\n".join(lines))

@@ -248,3 +248,58 @@ def test_many_requests_per_execute_are_served_in_one_pass(wdl_gpu):
         assert st["failed_requests"] == 1 and st["ok_requests"] == 5 + 3 + 20
         inst.close()
         model.close()
+
+
+def test_two_models_with_two_instances_each_run_concurrently(tmp_path, cuda_device):
+    """configs[4] shape (multi-model HPS): a DCN-like and a Wide&Deep-like model on one parameter server, two
+    instances per model sharing that model's cache (include/model_state.hpp:76-84), four Triton worker threads
+    issuing mixed batch sizes at once.  Every response is bit-exact."""
+    import threading
+
+    import torch
+    dirs_a, tabs_a = write_tables(str(tmp_path / "dcn"), [(30000, 32)], seed=21)
+    dirs_b, tabs_b = write_tables(str(tmp_path / "wdl"), [(400, 1), (15000, 16)], seed=22)
+    ps = ps_json(str(tmp_path / "ps.json"), [
+        model_entry("dcn", dirs_a, [32], [26], gpucache=True, max_batch=512, hit_rate_threshold=1.0, gpucacheper=0.2,
+                    enable_pagelock=True, workers=2),
+        model_entry("wdl", dirs_b, [1, 16], [2, 26], gpucache=True, defaults=[0.0, 1.5], max_batch=512,
+                    hit_rate_threshold=1.0, gpucacheper=0.3, workers=2)])
+    ref_a = [O.NumpyTable(32, 0.0)]
+    ref_a[0].insert(*tabs_a[0])
+    ref_b = []
+    for (k, v), d in zip(tabs_b, [0.0, 1.5]):
+        t = O.NumpyTable(v.shape[1], d)
+        t.insert(k, v)
+        ref_b.append(t)
+    with FT.Backend(ps) as be:
+        ma = be.model("dcn", FT.model_config("dcn", gpus=[0], count=2, max_batch_size=512))
+        mb = be.model("wdl", FT.model_config("wdl", gpus=[0], count=2, max_batch_size=512))
+        insts = [ma.instance(name="dcn_0_0", kind=FT.KIND_GPU, device=0), ma.instance(name="dcn_0_1", kind=FT.KIND_GPU, device=0),
+                 mb.instance(name="wdl_0_0", kind=FT.KIND_GPU, device=0), mb.instance(name="wdl_0_1", kind=FT.KIND_GPU, device=0)]
+        results = {}
+
+        def work(i):
+            rng = np.random.default_rng(50 + i)
+            ok = True
+            for it in range(25):
+                samples = int(rng.choice([1, 8, 64, 512]))
+                if i < 2:
+                    keys = rng.choice(tabs_a[0][0], size=samples * 26)
+                    numkeys = np.array([[samples * 26]], dtype=np.int32)
+                    want = O.request(ref_a, keys, numkeys.ravel())
+                else:
+                    keys, numkeys = wdl_request(tabs_b, samples, rng)
+                    want = O.request(ref_b, keys, numkeys.ravel())
+                out = torch.full((len(want),), float("nan"), device="cuda")
+                r = insts[i].infer(keys, numkeys, gpu_out=out)
+                ok &= r.error_code is None and np.array_equal(out.cpu().numpy(), want)
+            results[i] = ok
+
+        threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+        [t.start() for t in threads]
+        [t.join(120) for t in threads]
+        assert results == {0: True, 1: True, 2: True, 3: True}
+        for x in insts:
+            x.close()
+        ma.close()
+        mb.close()
