@@ -1,15 +1,15 @@
 #!/bin/bash
-# configs[2] shape: 100M-row table, 50 % measured hit rate (host-miss path stressed)
 mkdir -p gpurun_out
-free -g | tee gpurun_out/free.txt
-AVAIL=$(free -g | awk '/^Mem:/ {print $7}')
-if [ "$AVAIL" -lt 120 ]; then echo "not enough host memory ($AVAIL GB): skipping"; exit 0; fi
-timeout 900 python bench.py --rows 100000000 --hit 0.42 --prefill 80 --steps 8 --warmup 3 --no-cpu-baseline --core-arms-only --skip-triton-arm \
-  > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
-echo "exit $?"
-tail -3 gpurun_out/bench_c3.err
-python - <<PY
+run() {
+  tag=$1; shift
+  env "$@" timeout 300 python bench.py --no-cpu-baseline --core-arms-only --skip-triton-arm --steps 20 > gpurun_out/exp_$tag.json 2> gpurun_out/exp_$tag.err
+  grep "L2 persist" gpurun_out/exp_$tag.err | head -1
+  python - <<PY
 import json
-d=json.loads([l for l in open('gpurun_out/bench_c3.json').read().splitlines() if l.startswith('{')][-1])
-print('C3: value %.1f M/s step %.3f ms hit %.4f | e2e(session) %.1f M/s | probe frac %.3f | link %.1f GB/s frac %.3f | setup %.1f s' % (d['value']/1e6, d['ms_per_step'], d['config']['hit_rate_measured'], d['e2e_session']['value']/1e6, d['roofline']['frac'], d['roofline_host_link']['achieved'], d['roofline_host_link']['frac'], d['config']['setup_s']))
+d=json.loads([l for l in open('gpurun_out/exp_$tag.json').read().splitlines() if l.startswith('{')][-1]); r=d['roofline']; c=d['cache_hit']
+print('$tag: step %.3f ms probe %.3f ms (%.3f) | all-hit %.3f ms (%.3f)' % (d['ms_per_step'], r['avg_launch_ms'], r['frac'], c['kernel_ms'], c['frac_of_peak']))
 PY
+}
+run base HPSX_L2_PERSIST=0
+run persist HPSX_L2_PERSIST=1
+run ldg_persist HPSX_L2_PERSIST=1 HPSX_PROBE=ldg
