@@ -113,6 +113,7 @@ SYMBOLS = {
     "hpsx_shard_group_connect_local": (_int, [_vp, _vpp]),
     "hpsx_shard_group_lookup": (_int, [_vp, _vp, _sz, _vpp]),
     "hpsx_shard_group_get_stats": (_int, [_vp, ctypes.POINTER(ShardStatsC)]),
+    "hpsx_shard_group_capacity": (_int, [_vp, c_size_p]),
     "hpsx_shard_group_set_timeout_ms": (_int, [_vp, ctypes.c_uint64]),
     "hpsx_shard_group_destroy": (_int, [_vp]),
     "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),

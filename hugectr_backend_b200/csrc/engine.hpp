@@ -154,7 +154,9 @@ struct hpsx_shard_group {
   hpsx_shard_stats last{};
 
   // control words (uint32 index into the arena)
-  static constexpr uint32_t kCnt = 0, kFlagDispatch = 16, kFlagReturn = 32, kCursor = 48, kStatus = 64, kWords = 80;
+  // [kCursor, kDone] are local scratch, zeroed with one memset per lookup
+  static constexpr uint32_t kCnt = 0, kFlagDispatch = 16, kFlagReturn = 32, kCursor = 48, kStatus = 64, kMissCount = 65,
+                            kDone = 66, kWords = 80;
   uint32_t* ctrl() const { return reinterpret_cast<uint32_t*>(arena); }
   ~hpsx_shard_group();
 };

@@ -1007,14 +1007,14 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
   const double tr0 = now_ms();
   uint32_t* ctrl = g->ctrl();
   uint32_t* d_status = ctrl + G::kStatus;
-  uint32_t* d_miss_count = s->d_counters + t;
+  uint32_t* d_miss_count = ctrl + G::kMissCount;
   const DeviceTable& dt = c->tables[t];
   ++s->stats.lookups;
   s->stats.keys += n;
 
-  HPSX_CU(cudaMemsetAsync(d_status, 0, sizeof(uint32_t), s->stream));
-  HPSX_CU(cudaMemsetAsync(d_miss_count, 0, sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(ctrl + G::kCursor, 0, (G::kDone + 1 - G::kCursor) * sizeof(uint32_t), s->stream));
   uint32_t m = 0, status = 0;
+  bool returned = false;  // the speculative return wave ran on the device
   {
     std::shared_lock<std::shared_mutex> rlock(c->rw);
     HPSX_CU(launch_shard_dispatch(d_keys, n, g->world, g->peers, ctrl + G::kCursor, s->stream));
@@ -1028,15 +1028,18 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
                                       epoch, !c->is_static, d_miss_count, g->d_miss_pos, g->d_miss_keys, g->hd_miss_keys,
                                       n, s->stream));
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
-    s->stats.kernel_launches += 3;
+    // return wave, speculatively: it runs only if the gather recorded no miss (else the host resolves them below)
+    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
+                                     d_status, g->timeout_ns, s->stream, d_miss_count, ctrl + G::kDone));
+    s->stats.kernel_launches += 4;
     HPSX_CU(cudaMemcpyAsync(g->h_ctrl, ctrl, G::kWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kWords, d_miss_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
     status = g->h_ctrl[G::kStatus];
-    m = status ? 0u : g->h_ctrl[G::kWords];
+    returned = g->h_ctrl[G::kDone] != 0u;
+    m = (status || returned) ? 0u : g->h_ctrl[G::kMissCount];
   }
   const double tr1 = now_ms();
-  s->stats.d2h_bytes += (G::kWords + 1) * sizeof(uint32_t);
+  s->stats.d2h_bytes += G::kWords * sizeof(uint32_t);
   hpsx_shard_stats& st = g->last;
   st = hpsx_shard_stats{};
   for (uint32_t p = 0; p < g->world; ++p) {
@@ -1108,15 +1111,17 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     if (wlock.owns_lock()) cudaStreamSynchronize(s->stream);  // slots are rewritten under the exclusive lock only
   }
   const double tr2 = now_ms();
-  // after a timeout nobody is listening any more: publish, do not wait again
-  const unsigned long long wait_ns = (status & 2u) ? 0ull : g->timeout_ns;
   const std::string keep = g_err;
-  HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
-                                   d_status, wait_ns, s->stream));
-  ++s->stats.kernel_launches;
-  HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  HPSX_CU(cudaStreamSynchronize(s->stream));
-  status |= g->h_ctrl[G::kStatus];
+  if (!returned) {
+    // after a timeout nobody is listening any more: publish, do not wait again
+    const unsigned long long wait_ns = (status & 2u) ? 0ull : g->timeout_ns;
+    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
+                                     d_status, wait_ns, s->stream));
+    ++s->stats.kernel_launches;
+    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    status |= g->h_ctrl[G::kStatus];
+  }
   st.status = status;
   if (trace_on())
     std::fprintf(stderr, "[hpsx] shard lookup rank %u n=%zu: dispatch+wait+gather+sync %.3f ms | misses %u: %.3f ms | return wave %.3f ms\n",
@@ -1924,7 +1929,7 @@ int hpsx_shard_group_create(hpsx_session* s, size_t table, uint32_t rank, uint32
     HPSX_CU(cudaHostAlloc(&g->h_miss_keys, g->miss_cap * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable));
     HPSX_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->hd_miss_keys), g->h_miss_keys, 0));
   }
-  HPSX_CU(cudaMallocHost(&g->h_ctrl, (hpsx_shard_group::kWords + 1) * sizeof(uint32_t)));
+  HPSX_CU(cudaMallocHost(&g->h_ctrl, hpsx_shard_group::kWords * sizeof(uint32_t)));
   if (const char* env = std::getenv("HPSX_SHARD_TIMEOUT_MS")) {
     const long long v = std::atoll(env);
     if (v > 0) g->timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
@@ -2004,6 +2009,12 @@ int hpsx_shard_group_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n
 int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out) {
   if (!g || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
   *out = g->last;
+  return HPSX_OK;
+}
+
+int hpsx_shard_group_capacity(const hpsx_shard_group* g, size_t* rows) {
+  if (!g || !rows) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  *rows = g->slot_cap;
   return HPSX_OK;
 }
 

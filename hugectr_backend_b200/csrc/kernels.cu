@@ -1841,7 +1841,13 @@ __global__ void __launch_bounds__(kBlock) shard_dispatch_kernel(const int64_t* _
 //   phase 1 (rows returned): flag carries this rank's error bit so that requesters learn about it.
 __global__ void shard_signal_wait_kernel(const ShardPeers peers, uint32_t world, uint32_t seq, int phase,
                                          const uint32_t* cursor, const uint32_t* my_cnt, const uint32_t* my_flags,
-                                         uint32_t capacity, uint32_t* status, unsigned long long timeout_ns) {
+                                         uint32_t capacity, uint32_t* status, unsigned long long timeout_ns,
+                                         const uint32_t* skip_if_nonzero, uint32_t* done) {
+  // speculative return wave: enqueued right behind the gather so that a request without misses needs no host
+  // round trip in between; when the gather did record misses the host resolves them first and signals later
+  if (skip_if_nonzero != nullptr && *reinterpret_cast<const volatile uint32_t*>(skip_if_nonzero) != 0u) return;
+  // after a timeout in the dispatch wave nobody is listening any more: publish, do not wait again
+  if (phase == 1 && (*reinterpret_cast<volatile uint32_t*>(status) & 2u) != 0u) timeout_ns = 0;
   const uint32_t p = threadIdx.x;
   const bool active = p < world;
   uint32_t err = phase == 1 ? (*reinterpret_cast<volatile uint32_t*>(status) & 1u) : 0u;
@@ -1882,6 +1888,7 @@ __global__ void shard_signal_wait_kernel(const ShardPeers peers, uint32_t world,
     if (timed_out) st |= 3u;
     if (phase == 0 && cnt > capacity) st |= 5u;  // bit 2: this rank received more keys than it has room for
     if (st) atomicOr(status, st);
+    if (done != nullptr) *done = 1u;
   }
   __threadfence_system();
 }
@@ -2013,8 +2020,7 @@ __global__ void __launch_bounds__(kBlock) shard_scatter_stage_kernel(const float
 cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t world, const ShardPeers& peers,
                                   uint32_t* d_cursor, cudaStream_t stream) {
   if (world == 0 || world > kMaxPeers) return cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(d_cursor, 0, kMaxPeers * sizeof(uint32_t), stream);
-  if (e != cudaSuccess || n == 0) return e;
+  if (n == 0) return cudaSuccess;  // d_cursor was zeroed by the caller
   const unsigned grid = static_cast<unsigned>((n + kRouteChunk - 1) / kRouteChunk);
   shard_dispatch_kernel<<<grid, kBlock, 0, stream>>>(d_keys, n, world, peers, d_cursor);
   return cudaGetLastError();
@@ -2023,10 +2029,10 @@ cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t worl
 cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, uint32_t seq, int phase,
                                      const uint32_t* d_cursor, const uint32_t* d_my_cnt, const uint32_t* d_my_flags,
                                      uint32_t capacity, uint32_t* d_status, unsigned long long timeout_ns,
-                                     cudaStream_t stream) {
+                                     cudaStream_t stream, const uint32_t* d_skip_if_nonzero, uint32_t* d_done) {
   if (world == 0 || world > kMaxPeers) return cudaErrorInvalidValue;
   shard_signal_wait_kernel<<<1, 32, 0, stream>>>(peers, world, seq, phase, d_cursor, d_my_cnt, d_my_flags, capacity,
-                                                 d_status, timeout_ns);
+                                                 d_status, timeout_ns, d_skip_if_nonzero, d_done);
   return cudaGetLastError();
 }
 

@@ -143,7 +143,7 @@ struct ShardPeers {
 };
 
 // Step 1: bucket keys by owner_of(key, world) and store (key, position) into the owners' inboxes.
-// d_cursor[kMaxPeers] (local) receives the per-owner counts.
+// d_cursor[kMaxPeers] (local, zeroed by the caller) receives the per-owner counts.
 cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t world, const ShardPeers& peers,
                                   uint32_t* d_cursor, cudaStream_t stream);
 // Steps 2 and 4: publish (phase 0: counts + dispatch flag, phase 1: return flag with this rank's error bit)
@@ -152,7 +152,10 @@ cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t worl
 cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, uint32_t seq, int phase,
                                      const uint32_t* d_cursor, const uint32_t* d_my_cnt, const uint32_t* d_my_flags,
                                      uint32_t capacity, uint32_t* d_status, unsigned long long timeout_ns,
-                                     cudaStream_t stream);
+                                     cudaStream_t stream, const uint32_t* d_skip_if_nonzero = nullptr,
+                                     uint32_t* d_done = nullptr);
+// d_skip_if_nonzero: the kernel does nothing when that word is non-zero (speculative return wave behind a gather
+// that may have recorded misses); d_done is set to 1 when the wave ran.
 // Step 3: probe the cache for every key in the local inbox and store the rows (or the default vector) into
 // row pos of the SENDER's output buffer; misses are appended to the miss list with kShardPosBits-encoded
 // destinations.  Does nothing when *d_status != 0.

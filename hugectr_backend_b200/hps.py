@@ -333,6 +333,12 @@ class ShardGroup:
         N.check(self._L.hpsx_shard_group_lookup(self._h, _addr(d_keys), n, ctypes.byref(out)))
         return _DeviceRows(out.value or 0, n, self.dim, self)
 
+    @property
+    def capacity(self) -> int:
+        c = ctypes.c_size_t()
+        N.check(self._L.hpsx_shard_group_capacity(self._h, ctypes.byref(c)))
+        return c.value
+
     def lookup_ptr(self, d_keys, n: int) -> int:
         out = ctypes.c_void_p()
         N.check(self._L.hpsx_shard_group_lookup(self._h, _addr(d_keys), n, ctypes.byref(out)))

@@ -70,7 +70,8 @@ class ShardedLookup:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.session = hps.session(model, device)
         self.on_gpu = device >= 0
-        self.last = {}
+        self._last = {}
+        self._rows, self._rows_ptr = None, 0
         self.mode = mode
         self.p2p = None
         if mode == "p2p":
@@ -98,18 +99,29 @@ class ShardedLookup:
         torch = self.torch
         n = keys.numel()
         torch.cuda.current_stream().synchronize()  # the session launches on its own stream
-        view = self.p2p.lookup(keys, n)
-        st = self.p2p.stats()
-        self.last = {"sent_keys": int(st["keys_sent_remote"]), "received_keys": int(st["keys_received_remote"]),
-                     "send_counts": st["sent"], "recv_counts": st["received"], "misses": int(st["misses"])}
-        if n == 0:
-            rows = torch.empty((0, self.dim), dtype=torch.float32, device=keys.device)
-        else:
-            rows = torch.as_tensor(view, device=keys.device)
+        ptr = self.p2p.lookup_ptr(keys, n)
+        self._last = None  # exchange statistics are fetched on demand (`last`)
+        if self._rows is None or self._rows_ptr != ptr:
+            # the group's output buffer never moves: wrap it once, slice per request
+            self._rows = torch.as_tensor(H._DeviceRows(ptr, self.p2p.capacity, self.dim, self.p2p), device=keys.device)
+            self._rows_ptr = ptr
+        rows = self._rows[:n]
         if out is not None:
             out.copy_(rows)
             return out
         return rows
+
+    @property
+    def last(self):
+        if self._last is None and self.p2p is not None:
+            st = self.p2p.stats()
+            self._last = {"sent_keys": int(st["keys_sent_remote"]), "received_keys": int(st["keys_received_remote"]),
+                          "send_counts": st["sent"], "recv_counts": st["received"], "misses": int(st["misses"])}
+        return self._last or {}
+
+    @last.setter
+    def last(self, value):
+        self._last = value
 
     # -- step 1: bucket keys by owner ---------------------------------------------------------------------
     def _route(self, keys):

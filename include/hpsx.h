@@ -284,6 +284,8 @@ int hpsx_shard_group_connect_local(hpsx_shard_group* g, hpsx_shard_group* const*
  * buffer [n, dim] (owned by the group, valid until the next lookup), rows in request order. */
 int hpsx_shard_group_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out);
 int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out);
+/* Rows of the group's output buffer (= keys one request may hold); the buffer address never changes. */
+int hpsx_shard_group_capacity(const hpsx_shard_group* g, size_t* rows);
 int hpsx_shard_group_set_timeout_ms(hpsx_shard_group* g, uint64_t ms);
 int hpsx_shard_group_destroy(hpsx_shard_group* g);
 
