@@ -520,6 +520,7 @@ def run_ours(a):
         ev1.synchronize()
         ms_d = ev0.elapsed_time(ev1) / a.steps
         flops = 2.0 * a.batch * sum(dims[l] * dims[l + 1] for l in range(4))
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0))
         # library baseline for the same GEMMs: torch (cuBLAS) bf16 matmuls on pre-converted operands
         xb = out.view(a.batch, -1).to(torch.bfloat16)
         wb = [torch.from_numpy(w).cuda().to(torch.bfloat16) for w in weights[:3]]
@@ -537,7 +538,29 @@ def run_ours(a):
         ev1.synchronize()
         ms_lib = ev0.elapsed_time(ev1) / a.steps
         peak_tf = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 2250.0))
-        dense_head = {"dims": dims, "batch": a.batch, "ms_per_step": ms_d, "tflops": flops / (ms_d / 1e3) / 1e12,
+        # fused form: the lookup writes a bf16 mirror from its own kernels, the head skips the conversion pass
+        mirror = torch.empty((n, a.dim), dtype=torch.bfloat16, device="cuda")
+        for _ in range(3):
+            mlp.forward_bf16(mirror, a.batch, logit, stream=cur.cuda_stream)
+        ev0.record()
+        for _ in range(a.steps):
+            mlp.forward_bf16(mirror, a.batch, logit, stream=cur.cuda_stream)
+        ev1.record()
+        ev1.synchronize()
+        ms_fused = ev0.elapsed_time(ev1) / a.steps
+        mirror_step = lambda i: sess.lookup_bf16_mirror(0, hit_reqs[i % 4], n, out, mirror, device_keys=True)
+        for i in range(a.warmup):
+            mirror_step(i)
+        sess.reset_stats()
+        timed(mirror_step, a.steps)
+        st_m = sess.stats()
+        mirror_probe_ms = st_m.probe_kernel_ms / max(1, st_m.probe_kernel_launches)
+        dense_head = {"dims": dims, "batch": a.batch, "ms_per_step": ms_d,
+                      "fused_bf16": {"head_ms_per_step": ms_fused, "head_tflops": flops / (ms_fused / 1e3) / 1e12,
+                                     "head_frac_of_peak": flops / (ms_fused / 1e3) / 1e12 / peak_tf,
+                                     "gather_with_mirror_kernel_ms": mirror_probe_ms, "gather_kernel_ms": cache_hit["kernel_ms"],
+                                     "note": "hpsx_session_lookup_bf16_mirror + hpsx_mlp_forward_bf16: the all-hit gather kernel also "
+                                             "writes the bf16 rows (+0.44 GB of stores), the head runs without its conversion pass"}, "tflops": flops / (ms_d / 1e3) / 1e12,
                       "peak_tflops": peak_tf, "frac_of_peak": flops / (ms_d / 1e3) / 1e12 / peak_tf,
                       "includes": "fp32 -> bf16 conversion of the lookup output (0.87 GB read), 3 tcgen05 GEMM layers with fused bias+ReLU, final dot-product layer",
                       "cublas_bf16_gemms_ms": ms_lib,

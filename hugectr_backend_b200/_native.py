@@ -146,7 +146,9 @@ SYMBOLS = {
     "hpsx_cache_drain_async": (_int, [_vp]),
     "hpsx_mlp_create": (_int, [_int, _sz, c_size_p, _vpp, _vpp, ctypes.POINTER(_int), _vpp]),
     "hpsx_mlp_forward": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "hpsx_mlp_forward_bf16": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "hpsx_mlp_destroy": (_int, [_vp]),
+    "hpsx_session_lookup_bf16_mirror": (_int, [_vp, _sz, _vp, _int, _sz, _vp, _vp]),
     "hpsx_unique": (_int, [_int, _vp, _sz, _vp, _vp, c_size_p, _vp]),
     "hpsx_owner": (ctypes.c_uint32, [ctypes.c_int64, ctypes.c_uint32]),
     "hpsx_owner_batch": (_int, [_vp, _sz, ctypes.c_uint32, _vp]),

@@ -447,8 +447,9 @@ void mlp_destroy(DenseMlp* m) {
   delete m;
 }
 
-cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_out, cudaStream_t stream) {
-  if (!m || !d_in || !d_out) {
+cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_out, cudaStream_t stream,
+                        const void* d_in_bf16) {
+  if (!m || (!d_in && !d_in_bf16) || !d_out) {
     g_mlp_err = "null argument";
     return cudaErrorInvalidValue;
   }
@@ -465,14 +466,18 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
     m->act_rows = batch;
   }
   const size_t L = m->w.size();
-  // input fp32 (the lookup's output) -> bf16
-  {
+  // input fp32 (the lookup's output) -> bf16, unless the lookup already wrote a bf16 mirror
+  if (d_in_bf16 == nullptr) {
     const size_t n = batch * m->dims[0], n8 = n / 8;
     if (n8) to_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, stream>>>(d_in, m->act[0], n8);
     if (n8 * 8 < n) to_bf16_tail_kernel<<<1, 8, 0, stream>>>(d_in, m->act[0], n8 * 8, n);
+  } else if ((reinterpret_cast<uintptr_t>(d_in_bf16) & 15u) != 0) {
+    g_mlp_err = "the bf16 input must be 16-byte aligned";
+    return cudaErrorInvalidValue;
   }
   int cur = 0;
   for (size_t l = 0; l < L; ++l) {
+    const __nv_bfloat16* x_in = (l == 0 && d_in_bf16 != nullptr) ? static_cast<const __nv_bfloat16*>(d_in_bf16) : m->act[cur];
     const size_t K = m->dims[l], N = m->dims[l + 1];
     const bool last = l + 1 == L;
     if (N == 1) {
@@ -482,13 +487,13 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
         g_mlp_err = "a layer with one output unit must be the last layer";
         return cudaErrorInvalidValue;
       }
-      mlp_dot_kernel<<<static_cast<unsigned>((batch * 32 + 255) / 256), 256, 0, stream>>>(m->act[cur], m->w[l], m->b[l],
+      mlp_dot_kernel<<<static_cast<unsigned>((batch * 32 + 255) / 256), 256, 0, stream>>>(x_in, m->w[l], m->b[l],
                                                                                           static_cast<int>(batch), static_cast<int>(K),
                                                                                           m->relu[l], dst);
       continue;
     }
     CUtensorMap map_x, map_w;
-    if (!make_map(&map_x, m->act[cur], batch, K, kBlockM) || !make_map(&map_w, m->w[l], N, K, kBlockN)) {
+    if (!make_map(&map_x, x_in, batch, K, kBlockM) || !make_map(&map_w, m->w[l], N, K, kBlockN)) {
       g_mlp_err = "cuTensorMapEncodeTiled failed";
       return cudaErrorInvalidValue;
     }

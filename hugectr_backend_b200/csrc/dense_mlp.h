@@ -15,7 +15,10 @@ cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const 
 void mlp_destroy(DenseMlp* m);
 // d_in: device fp32 [batch, dims[0]] (e.g. the lookup's OUTPUT0 viewed as [batch, slots * dim]); d_out: device fp32
 // [batch, dims[L]].  Asynchronous on `stream`.
-cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_out, cudaStream_t stream);
+cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_out, cudaStream_t stream,
+                        const void* d_in_bf16 = nullptr);
+// With d_in_bf16 (device bf16 [batch, dims[0]], 16-B aligned: the lookup's bf16 mirror) the conversion pass is
+// skipped and d_in is ignored.
 const char* mlp_last_error();
 
 }  // namespace hpsx

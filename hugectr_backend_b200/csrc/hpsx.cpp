@@ -381,6 +381,12 @@ void run_async_insert(AsyncJob job) {
 // reuse a stage.  With `d_all_stage` the rows land at d_all_stage + i*dim and stay there for the
 // caller (pooled path).  The first kernel that rewrites cache slots takes `wlock` (exclusive) and
 // keeps it; the caller synchronises the stream before releasing it.
+// bf16 mirror destination of rows [row_off, ...) of virtual table t, or nullptr (no mirror requested / other table)
+void* bf16_dst(const hpsx_session* s, size_t t, size_t row_off, size_t dim) {
+  if (s->bf16_out == nullptr || t != s->bf16_table) return nullptr;
+  return static_cast<unsigned char*>(s->bf16_out) + row_off * dim * 2u;
+}
+
 // `mb` (nullable) replaces the session's own miss list (model-parallel groups keep a larger one).
 struct MissBufs {
   const int64_t* h_keys;
@@ -419,7 +425,7 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
     if (d_out != nullptr || insert) {
       if (insert && wlock != nullptr && !wlock->owns_lock()) wlock->lock();
       HPSX_CU(launch_insert_merge(c->tables[rt], d_mkeys + off, d_mpos + off, d_rows, mc, d_out, insert, epoch,
-                                  d_inserted, s->stream));
+                                  d_inserted, s->stream, d_out ? bf16_dst(s, t, 0, dim) : nullptr));
       ++s->stats.kernel_launches;
     }
     HPSX_CU(cudaEventRecord(s->stage_free[b], s->stream));
@@ -644,7 +650,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
         which = t;
       }
     const bool always_sync = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
-    if (busy == 1 && sorted && always_sync && pos_per_table == nullptr && s->pipe_chunks >= 2 &&
+    if (busy == 1 && sorted && always_sync && pos_per_table == nullptr && s->bf16_out == nullptr && s->pipe_chunks >= 2 &&
         n_per_table[which] >= kPipelineMinKeys)
       return gpu_lookup_direct_pipelined(s, which % T, keys_per_table[which], keys_on_device, out_per_table[which],
                                          n_per_table[which], epoch);
@@ -658,7 +664,8 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
                               n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + s->vt + t,
                               s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
-                              use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream);
+                              use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream, 0,
+                              bf16_dst(s, t, 0, c->tables[t % T].dim));
   };
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t n = n_per_table[t];
@@ -695,7 +702,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
         HPSX_CU(launch_probe_gather(c->tables[t % T], s->d_keys + off[t] + o, nc, out_per_table[t] + o * dim, epoch,
                                     !c->is_static, s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
                                     nullptr, s->probe_variant, s->stream, nullptr, s->d_src ? s->d_src + off[t] + o : nullptr,
-                                    static_cast<uint32_t>(o)));
+                                    static_cast<uint32_t>(o), bf16_dst(s, t, o, dim)));
         ++s->stats.kernel_launches;
       }
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
@@ -718,7 +725,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                 s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t], nullptr,
                                 s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr,
-                                s->d_src ? s->d_src + off[t] : nullptr));
+                                s->d_src ? s->d_src + off[t] : nullptr, 0, bf16_dst(s, t, 0, dim)));
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
     ++s->stats.kernel_launches;
     if (!sorted) {
@@ -826,7 +833,8 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
       HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
                                   s->hd_miss_keys + off[t], s->probe_variant, s->stream,
-                                  pos_per_table ? pos_per_table[t] : nullptr, s->d_src ? s->d_src + off[t] : nullptr));
+                                  pos_per_table ? pos_per_table[t] : nullptr, s->d_src ? s->d_src + off[t] : nullptr, 0,
+                                  bf16_dst(s, t, 0, c->tables[t % T].dim)));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
     }
@@ -2111,6 +2119,40 @@ int hpsx_session_lookup_batch(hpsx_session* s, size_t num_requests, const void* 
   HPSX_GUARD_END
 }
 
+int hpsx_session_lookup_bf16_mirror(hpsx_session* s, size_t table, const int64_t* keys, int key_memory, size_t n,
+                                    float* d_vectors, void* d_vectors_bf16) {
+  HPSX_GUARD_BEGIN
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  if (!s->cache) return fail(HPSX_ERR_UNSUPPORTED, "the bf16 mirror needs a GPU session (gpucache = true)");
+  const size_t T = s->model->tables.size();
+  if (table >= T) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
+  if (n > s->cap_per_table[table])
+    return fail(HPSX_ERR_INVALID_ARG, "lookup exceeds the table's key capacity (max_batch_size * maxnum_catfeature)");
+  if (n == 0) return HPSX_OK;
+  if (!keys || !d_vectors || !d_vectors_bf16) return fail(HPSX_ERR_INVALID_ARG, "null argument");
+  if (s->model->tables[table]->dim() % 8 != 0)
+    return fail(HPSX_ERR_UNSUPPORTED, "the bf16 mirror needs rows that are multiples of 8 floats");
+  // synchronous insertion only: a row that arrives after the response has no defined place in the mirror
+  std::vector<const void*> kp(T, nullptr);
+  std::vector<float*> op(T, nullptr);
+  std::vector<size_t> np(T, 0);
+  kp[table] = keys;
+  op[table] = d_vectors;
+  np[table] = n;
+  std::lock_guard<std::mutex> lk(s->mu);
+  const int saved_mode = s->insert_mode;
+  s->insert_mode = 1;
+  s->bf16_table = table;
+  s->bf16_out = d_vectors_bf16;
+  const int rc = gpu_lookup(s, kp.data(), key_memory == HPSX_MEM_DEVICE, op.data(), np.data(), T);
+  s->bf16_out = nullptr;
+  s->insert_mode = saved_mode;
+  if (rc == HPSX_ERR_CUDA && std::string(g_err).find("not supported") != std::string::npos)
+    return fail(HPSX_ERR_UNSUPPORTED, "the bf16 mirror needs 32-byte aligned fp32 output and 16-byte aligned bf16 output");
+  return rc;
+  HPSX_GUARD_END
+}
+
 static int pooled_common(hpsx_session* s, size_t table, const int64_t* keys, bool on_device,
                          size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
@@ -2293,6 +2335,17 @@ int hpsx_mlp_forward(hpsx_mlp* m, const float* d_in, size_t batch, float* d_out,
   DeviceGuard guard(m->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   const cudaError_t e = hpsx::mlp_forward(m->impl, d_in, batch, d_out, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
+  return HPSX_OK;
+  HPSX_GUARD_END
+}
+
+int hpsx_mlp_forward_bf16(hpsx_mlp* m, const void* d_in_bf16, size_t batch, float* d_out, void* stream) {
+  HPSX_GUARD_BEGIN
+  if (!m) return fail(HPSX_ERR_INVALID_ARG, "null mlp");
+  DeviceGuard guard(m->device);
+  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
+  const cudaError_t e = hpsx::mlp_forward(m->impl, nullptr, batch, d_out, static_cast<cudaStream_t>(stream), d_in_bf16);
   if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
   return HPSX_OK;
   HPSX_GUARD_END

@@ -3,6 +3,7 @@
 // None of this is a contraction: every kernel is HBM-bound integer hashing + row copies, so the
 // design rules are coalescing, 16-B vector accesses, many independent loads in flight per warp,
 // bulk-async (TMA engine) row staging where rows are >= 16 B, and warp ballot/prefix compaction.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -157,6 +158,7 @@ struct ProbeArgs {
   uint32_t* src;  // probe_index only
   const uint32_t* pos;  // optional: key i is delivered to row pos[i] of `out` (which may be peer memory)
   uint32_t pos_base;    // added to the positions recorded in the miss list (this launch covers keys [pos_base, pos_base + n))
+  __nv_bfloat16* out_bf16;  // optional mirror of `out` in bf16 (same row order), feeds the dense head without a conversion pass
 };
 
 // Append the misses of one warp tile to the global miss list: ballot -> popc prefix -> one atomic.
@@ -259,6 +261,18 @@ __device__ __forceinline__ void st_stream256(Vec8* p, const Vec8& r) {
                "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
                : "memory");
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 8 floats -> 8 bf16 (16 B), streaming store
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const Vec8& r) {
+  __stcs(reinterpret_cast<uint4*>(p), make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
+                                                 pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7])));
+}
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, const float4& r) {
+  __stcs(reinterpret_cast<uint2*>(p), make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w)));
+}
 __device__ __forceinline__ BucketKeys load_bucket_keys_keep(const Bucket* __restrict__ buckets, uint32_t b) {
   BucketKeys r;
   const long long* kp = reinterpret_cast<const long long*>(buckets[b].keys);
@@ -271,7 +285,7 @@ __device__ __forceinline__ BucketKeys load_bucket_keys_keep(const Bucket* __rest
   return r;
 }
 
-template <int kV8, int kUnroll>
+template <int kV8, int kUnroll, bool kMirror = false>
 __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const size_t tile = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
@@ -321,6 +335,14 @@ __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
       if (i < total) st_stream256(outv + i, buf[u]);
+    }
+    if (kMirror) {
+      __nv_bfloat16* __restrict__ ob = a.out_bf16 + tile_base * static_cast<size_t>(V) * 8u;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t i = i0 + u * 32u + lane;
+        if (i < total) st_bf16x8(ob + static_cast<size_t>(i) * 8u, buf[u]);
+      }
     }
   }
   if (is_miss) {
@@ -605,6 +627,7 @@ struct InsertArgs {
   int insert;
   uint32_t epoch;
   uint32_t* inserted;
+  __nv_bfloat16* out_bf16;  // optional bf16 mirror of `out` (float4 instantiation only)
 };
 
 // Claims the cache slot for `key`.  Called by a whole warp.  Both candidate buckets (primary and second
@@ -708,6 +731,9 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
       const VecT x = src[v];
       if (dst_out) dst_out[v] = x;
       if (dst_slab) dst_slab[v] = x;
+      if constexpr (sizeof(VecT) == 16) {
+        if (dst_out && a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(a.miss_pos[i]) * V + v) * 4u, x);
+      }
     }
     if (claim.lo != nullptr) {
       release_claim(claim, lane);
@@ -830,6 +856,7 @@ struct PullArgs {
   // is miss sorted_idx[i] and its row lives at sorted_addr[i] (0: key absent from the host table)
   const unsigned long long* sorted_addr;
   const uint32_t* sorted_idx;
+  __nv_bfloat16* out_bf16;  // optional bf16 mirror of `out` (float4 instantiation only)
 };
 
 // Step 1 of the sorted pull: host address of every missed key (8 lanes per key, one 128-B index line each)
@@ -952,6 +979,9 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
         if (dst_out) st_stream(dst_out + v, x);
         if (dst_stage) dst_stage[v] = x;
         if (dst_slab) dst_slab[v] = x;
+        if constexpr (sizeof(VecT) == 16) {
+          if (dst_out && a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(a.miss_pos[i]) * V + v) * 4u, x);
+        }
       }
       if (claim.lo != nullptr) {
         release_claim(claim, lane);
@@ -1405,10 +1435,18 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
                                 int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t* d_slot_scratch,
-                                uint32_t pos_base) {
+                                uint32_t pos_base, void* d_out_bf16) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.pos_base = pos_base;
+  a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
+  if (d_out_bf16 != nullptr) {
+    // the bf16 mirror is written by the 256-bit kernel only
+    if (d_pos != nullptr || t.dim % 8 != 0 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 15u) != 0 ||
+        ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(t.values)) & 31u) != 0)
+      return cudaErrorNotSupported;
+    variant = kProbeV8;
+  }
   a.buckets = t.buckets;
   a.values = t.values;
   a.num_buckets = t.num_buckets;
@@ -1446,6 +1484,13 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
       if (const char* env = getenv("HPSX_V8_UNROLL")) unroll = atoi(env) == 2 ? 2 : (atoi(env) == 8 ? 8 : 4);
     }
     const unsigned grid = grid_for(n);
+    if (a.out_bf16 != nullptr) {
+      if (t.dim == 128)
+        probe_gather_v8_kernel<16, 4, true><<<grid, kBlock, 0, stream>>>(a);
+      else
+        probe_gather_v8_kernel<0, 2, true><<<grid, kBlock, 0, stream>>>(a);
+      return cudaGetLastError();
+    }
     if (t.dim == 128 && unroll == 4)
       probe_gather_v8_kernel<16, 4><<<grid, kBlock, 0, stream>>>(a);
     else if (t.dim == 128 && unroll == 8)
@@ -1497,9 +1542,10 @@ cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size
 cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys,
                                 const uint32_t* d_miss_pos, const float* d_stage, size_t m,
                                 float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, void* d_out_bf16) {
   if (m == 0) return cudaSuccess;
   InsertArgs a{};
+  a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
   a.buckets = t.buckets;
   a.values = t.values;
   a.num_buckets = t.num_buckets;
@@ -1516,6 +1562,7 @@ cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys
   const unsigned grid = static_cast<unsigned>(
       min(static_cast<size_t>(148 * 32), (warps * 32 + kBlock - 1) / kBlock));
   const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
+  if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
   if (vb == 16)
     insert_merge_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 8)
@@ -1543,10 +1590,12 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                const uint32_t* d_miss_count, size_t n_keys, float* d_out, float* d_stage,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
-                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream, int max_ctas_per_sm) {
+                               const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream, int max_ctas_per_sm,
+                               void* d_out_bf16) {
   if (n_keys == 0) return cudaSuccess;
   if (t.index == nullptr) return cudaErrorInvalidValue;
   PullArgs a{};
+  a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
   a.sorted_addr = d_sorted_addr;
   a.sorted_idx = d_sorted_idx;
   a.buckets = t.buckets;
@@ -1590,6 +1639,7 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
       min(static_cast<size_t>(148 * ctas), (warps_needed * 32 + kBlock - 1) / kBlock));
   // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
   const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
+  if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
   if (vb == 16 && rows_per_warp == 2)
     pull_misses_kernel<float4, 2><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 16)

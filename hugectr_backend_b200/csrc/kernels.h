@@ -42,7 +42,9 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
                                 int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr,
-                                uint32_t* d_slot_scratch = nullptr, uint32_t pos_base = 0);
+                                uint32_t* d_slot_scratch = nullptr, uint32_t pos_base = 0, void* d_out_bf16 = nullptr);
+// `d_out_bf16` (nullable, 16-B aligned): a bf16 mirror of d_out in the same row order, written by the same kernel
+// (and by the miss kernels below), so the dense head reads bf16 activations without a conversion pass.
 // `pos_base`: this launch covers keys [pos_base, pos_base + n) of a larger request whose chunks share one miss
 // list (d_out / d_keys already point at the chunk; recorded miss positions are request-relative).
 // With `d_pos`, key i is delivered to row d_pos[i] of d_out instead of row i, and d_out may be another
@@ -60,7 +62,7 @@ cudaError_t launch_probe_index(const DeviceTable& t, const int64_t* d_keys, size
 cudaError_t launch_insert_merge(const DeviceTable& t, const int64_t* d_miss_keys,
                                 const uint32_t* d_miss_pos, const float* d_stage, size_t m,
                                 float* d_out, bool insert, uint32_t epoch, uint32_t* d_inserted,
-                                cudaStream_t stream);
+                                cudaStream_t stream, void* d_out_bf16 = nullptr);
 
 // K9 (cache refresh): for every key that is still resident overwrite its cached row with d_stage[i*dim..);
 // *d_updated (nullable) counts the rows rewritten.  Caller holds the cache's host lock exclusively.
@@ -80,7 +82,7 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
                                const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream,
-                               int max_ctas_per_sm = 0);
+                               int max_ctas_per_sm = 0, void* d_out_bf16 = nullptr);
 // max_ctas_per_sm > 0 caps the persistent grid so that other kernels (the probes of later request chunks) keep
 // SM resources while the pull waits on PCIe.
 

@@ -273,6 +273,11 @@ class LookupSession:
         N.check(self._L.hpsx_session_lookup_batch(self._h, len(requests), K, 1 if device_keys else 0, O_,
                                                   1 if device_vectors else 0, Nn))
 
+    def lookup_bf16_mirror(self, table: int, keys, n: int, d_vectors, d_vectors_bf16, device_keys: bool = False) -> None:
+        """Lookup of one table that also writes a bf16 copy of the vectors (feeds ``DenseMlp.forward_bf16``)."""
+        N.check(self._L.hpsx_session_lookup_bf16_mirror(self._h, table, _addr(keys), 1 if device_keys else 0, n,
+                                                        _addr(d_vectors), _addr(d_vectors_bf16)))
+
     def lookup_pooled(self, table: int, keys, num_bags: int, hotness: int, d_pooled, combiner: str = "sum",
                       device_keys: bool = False) -> None:
         comb = 1 if combiner == "mean" else 0
@@ -387,6 +392,9 @@ class DenseMlp:
 
     def forward(self, d_in, batch: int, d_out, stream: int = 0) -> None:
         N.check(self._L.hpsx_mlp_forward(self._h, _addr(d_in), batch, _addr(d_out), stream))
+
+    def forward_bf16(self, d_in_bf16, batch: int, d_out, stream: int = 0) -> None:
+        N.check(self._L.hpsx_mlp_forward_bf16(self._h, _addr(d_in_bf16), batch, _addr(d_out), stream))
 
     def close(self) -> None:
         if getattr(self, "_h", None):

@@ -236,6 +236,12 @@ int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, i
 #define HPSX_MAX_BATCH_REQUESTS 16
 int hpsx_session_lookup_batch(hpsx_session* s, size_t num_requests, const void* const* keys, int key_memory,
                               float* const* vectors, int vector_memory, const size_t* num_keys);
+/* Lookup of one table that ALSO writes a bf16 mirror of the vectors (d_vectors_bf16: device, [n, vecsize] bf16,
+ * 16-byte aligned; d_vectors: device fp32, 32-byte aligned), produced by the same kernels that write the fp32 rows
+ * (probe+gather and the miss kernels) — the elementwise conversion the dense head needs is fused into the
+ * producer.  Insertion is synchronous for this call.  Rows must be multiples of 8 floats. */
+int hpsx_session_lookup_bf16_mirror(hpsx_session* s, size_t table, const int64_t* keys, int key_memory, size_t n,
+                                    float* d_vectors, void* d_vectors_bf16);
 /* Model-parallel return leg fused into the gather: key i of `table` is delivered to row
  * d_pos[i] of d_out_base, which may be ANOTHER GPU's buffer opened with hpsx_ipc_open — the rows then leave
  * the owner's gather kernel as NVLink peer stores, no all-to-all of vectors and no scatter pass.  Misses are
@@ -338,6 +344,9 @@ int hpsx_mlp_create(int device, size_t num_layers, const size_t* dims, const flo
 /* d_in: device fp32 [batch, dims[0]]; d_out: device fp32 [batch, dims[num_layers]].  Asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream). */
 int hpsx_mlp_forward(hpsx_mlp* m, const float* d_in, size_t batch, float* d_out, void* stream);
+/* Same with bf16 activations [batch, dims[0]] (16-byte aligned) written by hpsx_session_lookup_bf16_mirror: no
+ * conversion pass. */
+int hpsx_mlp_forward_bf16(hpsx_mlp* m, const void* d_in_bf16, size_t batch, float* d_out, void* stream);
 int hpsx_mlp_destroy(hpsx_mlp* m);
 
 /* ---------------------------------------------------------------------------------------------

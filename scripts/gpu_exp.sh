@@ -1,11 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 \
-  bench.py --workload c4 --gpus 8 --exchange p2p --steps 30 --warmup 5 > gpurun_out/bench_c4_p2p_8.json 2> gpurun_out/bench_c4_p2p_8.err
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -25 gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --no-cpu-baseline --steps 10 > gpurun_out/exp_mlp.json 2> gpurun_out/exp_mlp.err
 python - <<PY
 import json
-txt=open('gpurun_out/bench_c4_p2p_8.json').read()
-d=json.loads([l for l in txt.splitlines() if l.startswith("{")][-1]); r=d['roofline']
-print('p2p N=8: value %.2f G/s step %.3f ms, kernel %.3f ms, nvlink out %.0f GB/s, e2e %.3f ms (%.2f G/s)' % (d['value']/1e9, d['ms_per_step'], r['avg_launch_ms'], r['nvlink_out_gbs_per_gpu'], d['e2e']['ms_per_step'], d['e2e']['value']/1e9))
+d=json.loads([l for l in open('gpurun_out/exp_mlp.json').read().splitlines() if l.startswith('{')][-1])
+print('value %.1f step %.3f probe %.3f (%.3f) e2e %.3f' % (d['value']/1e6, d['ms_per_step'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['e2e']['ms_per_step']))
+print(json.dumps(d['dense_head'], indent=1))
 PY
-tail -2 gpurun_out/bench_c4_p2p_8.err
+tail -3 gpurun_out/exp_mlp.err

@@ -93,3 +93,45 @@ def test_rejects_bad_shapes(cuda_device):
         hb.DenseMlp(0, [np.ones((1, 16), np.float32), np.ones((8, 1), np.float32)])  # a single unit cannot feed a GEMM layer
     with pytest.raises(ValueError):
         hb.DenseMlp(0, [np.ones((8, 16), np.float32), np.ones((8, 16), np.float32)])  # widths do not chain
+
+
+@pytest.mark.parametrize("pagelock", [False, True])
+def test_bf16_mirror_is_the_rounded_fp32_output_and_feeds_the_head(cuda_device, pagelock, monkeypatch):
+    """The lookup writes a bf16 copy of its rows from the same kernels (hits: probe+gather, misses: pull / merge):
+    bit-exact round-to-nearest-even of the fp32 rows, in both miss paths, and the dense head gives the same logits
+    from it as from the fp32 output (no conversion pass)."""
+    torch = _torch()
+    monkeypatch.setenv("HPSX_DIRECT_PULL", "1" if pagelock else "0")
+    slots, dim, batch, rows = 26, 128, 1500, 60_000
+    n = batch * slots
+    hps = hb.HPS(num_partitions=4)
+    hps.add_model(hb.ModelParams("m", batch, [dim], [slots], [0.75], hit_rate_threshold=0.5, cache_size_percentage=0.3,
+                                 enable_pagelock=pagelock))
+    hps.load_table_procedural("m", 0, rows, 3)
+    hps.create_embedding_cache("m")
+    table = O.NumpyTable(dim, 0.75)
+    table.fill_procedural(rows, 3)
+    s = hps.session("m", 0)
+    rng = np.random.default_rng(8)
+    dims = [slots * dim, 512, 1]
+    weights = [(rng.standard_normal((dims[l + 1], dims[l])) / np.sqrt(dims[l])).astype(np.float32) for l in range(2)]
+    mlp = hb.DenseMlp(0, weights, None, [1, 0])
+    for it in range(3):
+        keys = rng.integers(-3, rows + 3, size=n)
+        out = torch.full((n, dim), float("nan"), device="cuda")
+        mirror = torch.zeros((n, dim), dtype=torch.bfloat16, device="cuda")
+        if it == 1:
+            dk = torch.from_numpy(keys).cuda()
+            torch.cuda.synchronize()
+            s.lookup_bf16_mirror(0, dk, n, out, mirror, device_keys=True)
+        else:
+            s.lookup_bf16_mirror(0, keys, n, out, mirror)
+        assert s.stats().misses > 0
+        assert np.array_equal(out.cpu().numpy(), table.lookup(keys))  # fp32 contract unchanged (sync insert forced)
+        assert torch.equal(mirror, out.to(torch.bfloat16))
+        a = torch.empty((batch, 1), device="cuda")
+        b = torch.empty((batch, 1), device="cuda")
+        mlp.forward(out, batch, a)
+        mlp.forward_bf16(mirror, batch, b)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
