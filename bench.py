@@ -499,6 +499,69 @@ def run_ours(a):
                        "batched_ms_per_request": ms_b / a.steps / 16, "one_by_one_ms_per_request": ms_s / a.steps / 16,
                        "call": "hpsx_session_lookup_batch vs 16 x hpsx_session_lookup, pinned host keys -> device vectors"}
 
+    # ---- two instances of the model on this GPU sharing the cache (configs[4]: concurrent instances, one EmbeddingCache):
+    # probes of one instance run beside the PCIe pull of the other; aggregate throughput over both
+    two_instances = None
+    if not a.core_arms_only:
+        conc = make_requests(a, hot, warm_rows, 2 * a.steps, SEED + 2000 + rank)
+        d_conc = [torch.from_numpy(k).cuda() for k in conc]
+        sess2 = hps.session("dcn", local)
+        sess2.set_probe_variant(a.variant)
+        out2 = torch.empty((n, a.dim), device="cuda", dtype=torch.float32)
+
+        def worker(sx, ox, base):
+            for i in range(a.steps):
+                sx.lookup_device_keys([d_conc[base + i]], [ox], [n])
+
+        for sx, ox in ((sess, out), (sess2, out2)):
+            sx.lookup_device_keys([d_reqs[0]], [ox], [n])
+        barrier()
+        tw0 = time.perf_counter()
+        th = [threading.Thread(target=worker, args=(sess, out, 0)), threading.Thread(target=worker, args=(sess2, out2, a.steps))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        torch.cuda.synchronize()
+        wall2 = time.perf_counter() - tw0
+        barrier()
+        if world > 1:
+            tt = torch.tensor([wall2], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            wall2 = float(tt[0])
+        # latency isolation: instance 2 serves small requests (batch/16) while instance 1 streams full-size ones
+        small_k = n // 16
+        lat, stop = [], threading.Event()
+
+        def small_worker():
+            j = 0
+            while not stop.is_set():
+                k = d_conc[a.steps + j % a.steps][:small_k]
+                t0 = time.perf_counter()
+                sess2.lookup_device_keys([k], [out2[:small_k]], [small_k])
+                lat.append(time.perf_counter() - t0)
+                j += 1
+
+        big = threading.Thread(target=worker, args=(sess, out, 0))
+        sm = threading.Thread(target=small_worker)
+        sm.start()
+        big.start()
+        big.join()
+        stop.set()
+        sm.join()
+        t0 = time.perf_counter()
+        for j in range(20):
+            sess2.lookup_device_keys([d_conc[a.steps + j % a.steps][:small_k]], [out2[:small_k]], [small_k])
+        alone = (time.perf_counter() - t0) / 20
+        two_instances = {"vectors_per_s": world * 2 * a.steps * n / wall2, "ms_per_request_pair": wall2 / a.steps * 1e3,
+                         "vs_one_instance": (2 * a.steps * n / wall2) / (a.steps * n / (ms / 1e3)),
+                         "small_request_ms_beside_large_stream": {"mean": float(np.mean(lat)) * 1e3 if lat else None,
+                                                                  "p95": float(np.percentile(lat, 95)) * 1e3 if lat else None,
+                                                                  "alone": alone * 1e3, "requests": len(lat)},
+                         "split_lock": os.environ.get("HPSX_SPLIT_LOCK", "1") != "0",
+                         "note": "two lookup sessions (Triton model instances) of one model on one GPU sharing the HBM cache: shared "
+                                 "lock for probes, lock-free PCIe pull, short exclusive insert; aggregate throughput stays PCIe-bound, "
+                                 "the split keeps a small request from waiting behind another instance's 2 ms pull"}
+        del sess2, out2
+
     # ---- dense head: the MLP that follows the lookup in the reference's ensembles, fed in place
     # from the lookup's device output; Criteo-shape [26 x 128 -> 1024 -> 512 -> 256 -> 1], bf16 tensor cores
     dense_head = None
@@ -548,7 +611,9 @@ def run_ours(a):
         ev1.record()
         ev1.synchronize()
         ms_fused = ev0.elapsed_time(ev1) / a.steps
-        mirror_step = lambda i: sess.lookup_bf16_mirror(0, hit_reqs[i % 4], n, out, mirror, device_keys=True)
+        hot_m = hps.cache_keys("dcn", local, 0)  # the cache content moved on since the all-hit arm
+        hit_m = [torch.from_numpy(hot_m[rng.integers(0, len(hot_m), size=n)]).cuda() for _ in range(4)]
+        mirror_step = lambda i: sess.lookup_bf16_mirror(0, hit_m[i % 4], n, out, mirror, device_keys=True)
         for i in range(a.warmup):
             mirror_step(i)
         sess.reset_stats()
@@ -591,7 +656,7 @@ def run_ours(a):
                    "load_factor": a.load_factor, "miss_path": a.miss_path,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_session": e2e_session,
-        "cache_hit": cache_hit, "small_batch": small_batch, "dense_head": dense_head,
+        "cache_hit": cache_hit, "small_batch": small_batch, "two_instances": two_instances, "dense_head": dense_head,
         "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,

@@ -41,6 +41,7 @@ struct hpsx_cache {
   bool direct_pull = false;             // enable_pagelock: misses are pulled by kernels from pinned host rows
   std::vector<hpsx::IndexSlot*> indexes;  // HBM mirrors of the host tables' key -> row-address index
   std::atomic<uint32_t> epoch{1};       // one tick per lookup call; LRU stamps are epochs
+  std::atomic<int> sessions{0};         // lookup sessions (model instances) attached to this cache
   // Probes (readers) run concurrently; a kernel that rewrites slots (insert) excludes them, so a
   // row is never copied while it is being replaced.
   std::shared_mutex rw;

@@ -636,10 +636,20 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   }
   const double tr0 = now_ms();
 
-  // the pull kernel rewrites cache slots: exclusive unless the cache is static (never inserts)
+  // The fused pull kernel rewrites cache slots: exclusive unless the cache is static (never inserts).  When several
+  // instances share the cache (include/model_state.hpp:76-84) the call splits instead: probes under the SHARED lock,
+  // the PCIe pull (which then only writes the output) under no lock at all, and a short exclusive section that
+  // inserts the pulled rows from the output buffer — so one instance's probes run beside another instance's pull.
+  const bool always_sync_mode = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
+  static const bool split_allowed = [] {
+    const char* e = std::getenv("HPSX_SPLIT_LOCK");
+    return e == nullptr || e[0] != '0';
+  }();
+  const bool split = split_allowed && !c->is_static && sorted && always_sync_mode && pos_per_table == nullptr &&
+                     c->sessions.load(std::memory_order_relaxed) > 1;
   std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
   std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
-  if (c->is_static) rlock.lock(); else wlock.lock();
+  if (c->is_static || split) rlock.lock(); else wlock.lock();
 
   // one large slice, synchronous insertion, rows delivered in place: overlap the PCIe pull with the probes
   {
@@ -650,7 +660,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
         which = t;
       }
     const bool always_sync = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
-    if (busy == 1 && sorted && always_sync && pos_per_table == nullptr && s->bf16_out == nullptr && s->pipe_chunks >= 2 &&
+    if (busy == 1 && sorted && always_sync && !split && pos_per_table == nullptr && s->bf16_out == nullptr && s->pipe_chunks >= 2 &&
         n_per_table[which] >= kPipelineMinKeys)
       return gpu_lookup_direct_pipelined(s, which % T, keys_per_table[which], keys_on_device, out_per_table[which],
                                          n_per_table[which], epoch);
@@ -661,11 +671,11 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   auto pull = [&](size_t t, size_t m_hint) -> cudaError_t {
     const bool use_sorted = sorted && m_hint >= std::max<size_t>(pull_sort_min(), 1);
     return launch_pull_misses(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
-                              n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
+                              n_per_table[t], out_per_table[t], nullptr, !c->is_static && !split, s->insert_mode,
                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + s->vt + t,
                               s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
                               use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream, 0,
-                              bf16_dst(s, t, 0, c->tables[t % T].dim));
+                              bf16_dst(s, t, 0, c->tables[t % T].dim), split ? s->d_miss_keys + off[t] : nullptr);
   };
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t n = n_per_table[t];
@@ -740,6 +750,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     s->stats.d2h_bytes += T * sizeof(uint32_t);
     for (size_t t = 0; t < num_tables; ++t)
       if (n_per_table[t] != 0) account_probe_time(s, t, n_per_table[t]);
+    if (split) rlock.unlock();  // every probe has completed: nothing below reads the cache
     for (size_t t = 0; t < num_tables; ++t) {
       const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
       if (m == 0) continue;
@@ -753,6 +764,22 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       HPSX_CU(pull(t, m));
       HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
+    }
+  }
+  if (split) {
+    // the pulls are done with the host link; insert what they brought, from the output rows, exclusively
+    bool any = false;
+    for (size_t t = 0; t < num_tables; ++t) any = any || (n_per_table[t] != 0 && s->h_counters[t] != 0);
+    if (any) {
+      HPSX_CU(cudaStreamSynchronize(s->stream));
+      wlock.lock();
+      for (size_t t = 0; t < num_tables; ++t) {
+        const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
+        if (m == 0) continue;
+        HPSX_CU(launch_insert_merge(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], nullptr, m,
+                                    out_per_table[t], true, epoch, s->d_counters + s->vt + t, s->stream));
+        ++s->stats.kernel_launches;
+      }
     }
   }
   HPSX_CU(cudaMemcpyAsync(s->h_counters + s->vt, s->d_counters + s->vt, 2 * s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -1167,6 +1194,7 @@ hpsx_cache::~hpsx_cache() {
 }
 
 hpsx_session::~hpsx_session() {
+  if (cache) cache->sessions.fetch_sub(1, std::memory_order_relaxed);
   if (device >= 0 && cache) {
     DeviceGuard guard(device);
     if (stream) cudaStreamSynchronize(stream);
@@ -1722,6 +1750,7 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   int rc = hpsx_ps_get_embedding_cache(ps, model, device, &c);
   if (rc != HPSX_OK) return rc;
   s->cache = c;
+  c->sessions.fetch_add(1, std::memory_order_relaxed);
   s->device = device;
   if (const char* env = std::getenv("HPSX_PROBE"))
     s->probe_variant = std::strcmp(env, "tma") == 0     ? kProbeTma

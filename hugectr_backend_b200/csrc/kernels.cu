@@ -677,8 +677,11 @@ __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buc
   if (empties != 0u) {
     pick = __ffs(empties) - 1;  // primary ways come first
   } else {
-    // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted
-    const uint32_t age = lane < nways ? epoch - st : 0u;
+    // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted.  Instances that share the
+    // cache run with interleaved epochs: a stamp NEWER than this call's epoch is age 0 too (signed difference),
+    // not a huge unsigned age that would make the most recently used rows the first victims.
+    const int32_t diff = static_cast<int32_t>(epoch - st);
+    const uint32_t age = (lane < nways && diff > 0) ? static_cast<uint32_t>(diff) : 0u;
     unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
 #pragma unroll
     for (int off = 8; off > 0; off >>= 1) {
@@ -857,6 +860,8 @@ struct PullArgs {
   const unsigned long long* sorted_addr;
   const uint32_t* sorted_idx;
   __nv_bfloat16* out_bf16;  // optional bf16 mirror of `out` (float4 instantiation only)
+  int64_t* mark_absent;     // optional (= miss_keys): keys that are not in the host table are overwritten with kEmptyKey,
+                            // so that a later insert-from-output pass skips them
 };
 
 // Step 1 of the sorted pull: host address of every missed key (8 lanes per key, one 128-B index line each)
@@ -987,7 +992,10 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
         release_claim(claim, lane);
         if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
       }
-      if (lane == 0 && src[r] == nullptr && a.absent != nullptr) atomicAdd(a.absent, 1u);
+      if (lane == 0 && src[r] == nullptr) {
+        if (a.absent != nullptr) atomicAdd(a.absent, 1u);
+        if (a.mark_absent != nullptr) a.mark_absent[i] = kEmptyKey;
+      }
     }
   }
 }
@@ -1591,11 +1599,12 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
                                const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream, int max_ctas_per_sm,
-                               void* d_out_bf16) {
+                               void* d_out_bf16, int64_t* d_mark_absent) {
   if (n_keys == 0) return cudaSuccess;
   if (t.index == nullptr) return cudaErrorInvalidValue;
   PullArgs a{};
   a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
+  a.mark_absent = d_mark_absent;
   a.sorted_addr = d_sorted_addr;
   a.sorted_idx = d_sorted_idx;
   a.buckets = t.buckets;

@@ -82,7 +82,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
                                const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream,
-                               int max_ctas_per_sm = 0, void* d_out_bf16 = nullptr);
+                               int max_ctas_per_sm = 0, void* d_out_bf16 = nullptr, int64_t* d_mark_absent = nullptr);
+// d_mark_absent (= d_miss_keys, writable): keys missing from the host table are replaced by the empty marker, so
+// that launch_insert_merge(d_stage = nullptr), which inserts the pulled rows from the output buffer, skips them.
 // max_ctas_per_sm > 0 caps the persistent grid so that other kernels (the probes of later request chunks) keep
 // SM resources while the pull waits on PCIe.
 

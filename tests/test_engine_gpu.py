@@ -501,3 +501,39 @@ def test_pipelined_direct_pull_large_request(cuda_device, miss_path, monkeypatch
     s.lookup([keys], [out], [n])
     assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
     assert s.stats().misses < 0.05 * n
+
+
+def test_two_sessions_with_interleaved_epochs_keep_the_hot_set(cuda_device, miss_path):
+    """Instances that share a cache run with interleaved LRU epochs (an older call may insert after a newer call has
+    touched rows).  A stamp newer than the inserting call's epoch must count as most-recently-used, not as the oldest
+    (unsigned wrap): the hot set stays resident while two sessions stream cold keys through the cache at once."""
+    import threading
+
+    torch = _torch()
+    rows, dim, n = 200_000, 32, 40_000
+    hps, ref = make_server(rows, dim, cache_pct=0.2, thr=1.0, max_batch=n, load_factor=0.5)  # 40 k rows warmed, 80 k slots
+    hot = hps.cache_keys("m", 0, 0)
+    assert len(hot) > 35_000
+    sessions = [hps.session("m", 0), hps.session("m", 0)]
+    ok = {}
+
+    def work(i):
+        rng = np.random.default_rng(70 + i)
+        out = torch.empty((n, dim), device="cuda")
+        good = True
+        for it in range(12):
+            keys = rng.choice(hot, size=n)
+            cold = rng.integers(len(hot), rows, size=n // 10)  # 10 % cold keys: constant insertion pressure
+            keys[rng.choice(n, size=len(cold), replace=False)] = cold
+            sessions[i].lookup([keys], [out], [n])
+            good &= bool(np.array_equal(out.cpu().numpy(), ref.lookup(keys)))
+        ok[i] = good
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join(120) for t in threads]
+    assert ok == {0: True, 1: True}
+    res = hps.cache_keys("m", 0, 0)
+    assert len(res) == len(set(res.tolist()))
+    still_hot = np.isin(hot, res).mean()
+    assert still_hot > 0.9, f"only {still_hot:.2f} of the hot set survived"
