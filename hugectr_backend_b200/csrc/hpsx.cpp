@@ -8,6 +8,7 @@
 //
 // The reference performs the same stages inside libhuge_ctr_hps.so behind
 // LookupSessionBase::lookup (call site hps_backend/src/model_instance_state.cpp:194-195).
+#include <cuda.h>
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -49,6 +50,25 @@ int fail(int code, std::string msg) {
     return fail(HPSX_ERR_INTERNAL, e.what());                  \
   }
 
+// Is the primary context of `dev` alive in this process?  (A thread that never selected a device reports device 0;
+// switching "back" to it would CREATE a context on GPU 0 — ~0.4 s and some HBM — in a process that only serves
+// another GPU, e.g. one rank of a one-process-per-GPU deployment calling from a worker thread.)
+bool primary_context_active(int dev) {
+  typedef CUresult (*Fn)(CUdevice, unsigned int*, int*);
+  static Fn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<Fn>(p);
+  }();
+  if (fn == nullptr) return true;
+  unsigned int flags = 0;
+  int active = 0;
+  return fn(static_cast<CUdevice>(dev), &flags, &active) != CUDA_SUCCESS || active != 0;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = true;
@@ -58,7 +78,7 @@ struct DeviceGuard {
   }
   ~DeviceGuard() {
     int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev && primary_context_active(prev)) cudaSetDevice(prev);
   }
 };
 
