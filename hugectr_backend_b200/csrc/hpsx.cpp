@@ -19,6 +19,8 @@
 #include <cstring>
 #include <stdexcept>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "dense_mlp.h"
 #include "engine.hpp"
 
@@ -68,6 +70,13 @@ bool primary_context_active(int dev) {
   int active = 0;
   return fn(static_cast<CUdevice>(dev), &flags, &active) != CUDA_SUCCESS || active != 0;
 }
+
+// NVTX range around the phases of a lookup (the reference marks the same places: hps_backend/src/hps.cc:375,671,
+// 674,701, src/model_instance_state.cpp:179; opt-in there, free here when no tool is attached).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DeviceGuard {
   int prev = -1;
@@ -771,6 +780,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     for (size_t t = 0; t < num_tables; ++t)
       if (n_per_table[t] != 0) account_probe_time(s, t, n_per_table[t]);
     if (split) rlock.unlock();  // every probe has completed: nothing below reads the cache
+    NvtxRange miss_range("hpsx_direct_pull_misses");
     for (size_t t = 0; t < num_tables; ++t) {
       const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
       if (m == 0) continue;
@@ -843,6 +853,7 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
                float* const* out_per_table, const size_t* n_per_table, size_t num_tables,
                const uint32_t* const* pos_per_table = nullptr) {
   hpsx_cache* c = s->cache;
+  NvtxRange range("hpsx_lookup");
   DeviceGuard guard(s->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   if (c->direct_pull)
@@ -948,6 +959,7 @@ int ensure_pool_stage(hpsx_session* s, size_t m) {
 
 int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool keys_on_device,
                       size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
+  NvtxRange range("hpsx_lookup_pooled");
   hpsx_cache* c = s->cache;
   DeviceGuard guard(s->device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
@@ -1052,6 +1064,7 @@ void shard_fill_peers(hpsx_shard_group* g) {
 
 int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out) {
   using G = hpsx_shard_group;
+  NvtxRange range("hpsx_shard_group_lookup");
   hpsx_session* s = g->s;
   hpsx_cache* c = s->cache;
   const size_t t = g->table;
