@@ -779,6 +779,15 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     s->stats.d2h_bytes += T * sizeof(uint32_t);
     for (size_t t = 0; t < num_tables; ++t)
       if (n_per_table[t] != 0) account_probe_time(s, t, n_per_table[t]);
+    {
+      // no table missed anything: the rows are all delivered, nothing to pull, no second host wait
+      bool any_miss = false;
+      for (size_t t = 0; t < num_tables; ++t) any_miss = any_miss || (n_per_table[t] != 0 && s->h_counters[t] != 0);
+      if (!any_miss) {
+        for (size_t t = 0; t < num_tables; ++t) s->stats.hits += n_per_table[t];
+        return HPSX_OK;
+      }
+    }
     if (split) rlock.unlock();  // every probe has completed: nothing below reads the cache
     NvtxRange miss_range("hpsx_direct_pull_misses");
     for (size_t t = 0; t < num_tables; ++t) {
