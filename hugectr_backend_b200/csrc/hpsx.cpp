@@ -504,6 +504,14 @@ size_t pull_sort_min() {
   return v;
 }
 
+bool batch_merge_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("HPSX_BATCH_MERGE");
+    return e != nullptr && e[0] == '1';  // opt-in until measured on the GPU
+  }();
+  return on;
+}
+
 bool pull_sort_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("HPSX_PULL_SORT");
@@ -639,6 +647,94 @@ int gpu_lookup_direct_pipelined(hpsx_session* s, size_t t, const void* keys, boo
   return HPSX_OK;
 }
 
+// Batch of requests (virtual tables v = request * T + table) on the direct-pull path, synchronous insertion: the
+// probes of all requests that touch real table t append to ONE miss list (positions carry the request index in
+// their high bits), so every table needs one address sort and one pull launch for the whole batch instead of one
+// unsorted pull per request — small requests then get the sorted link rate too.  Caller holds c->rw exclusively.
+int gpu_lookup_direct_batch_merged(hpsx_session* s, const void* const* keys_v, bool keys_on_device, float* const* out_v,
+                                   const size_t* n_v, size_t num_v, uint32_t epoch) {
+  hpsx_cache* c = s->cache;
+  const size_t T = s->model->tables.size();
+  const size_t R = num_v / T;
+  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * s->vt * sizeof(uint32_t), s->stream));
+  // per real table: contiguous region of the miss list / sort workspace, sized by all requests' keys of that table
+  std::vector<size_t> tbase(T + 1, 0), tkeys(T, 0);
+  for (size_t t = 0; t < T; ++t) {
+    for (size_t r = 0; r < R; ++r) tkeys[t] += n_v[r * T + t];
+    tbase[t + 1] = tbase[t] + tkeys[t];
+  }
+  std::vector<size_t> koff(T, 0);  // running offset inside the table's region (also the staging offset of the keys)
+  for (size_t r = 0; r < R; ++r) {
+    for (size_t t = 0; t < T; ++t) {
+      const size_t v = r * T + t, n = n_v[v];
+      if (n == 0) continue;
+      const size_t at = tbase[t] + koff[t];
+      koff[t] += n;
+      const int64_t* d_keys;
+      if (keys_on_device) {
+        d_keys = static_cast<const int64_t*>(keys_v[v]);
+      } else {
+        HPSX_CU(cudaMemcpyAsync(s->d_keys + at, keys_v[v], n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+        s->stats.h2d_bytes += n * sizeof(int64_t);
+        d_keys = s->d_keys + at;
+      }
+      HPSX_CU(cudaEventRecord(s->ev[2 * v], s->stream));
+      HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_v[v], epoch, !c->is_static, s->d_counters + t,
+                                  s->d_miss_pos + tbase[t], s->d_miss_keys + tbase[t], nullptr, s->probe_variant, s->stream,
+                                  nullptr, s->d_src ? s->d_src + at : nullptr, static_cast<uint32_t>(r) << kShardPosBits));
+      HPSX_CU(cudaEventRecord(s->ev[2 * v + 1], s->stream));
+      ++s->stats.kernel_launches;
+    }
+  }
+  HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));
+  s->stats.d2h_bytes += T * sizeof(uint32_t);
+  for (size_t v = 0; v < num_v; ++v)
+    if (n_v[v] != 0) account_probe_time(s, v, n_v[v]);
+  bool any = false;
+  for (size_t t = 0; t < T; ++t) any = any || (tkeys[t] != 0 && s->h_counters[t] != 0);
+  if (any) {
+    NvtxRange miss_range("hpsx_direct_pull_misses");
+    std::vector<float*> outs(R, nullptr);
+    HPSX_CU(cudaEventRecord(s->ev_pull[0], s->stream));
+    for (size_t t = 0; t < T; ++t) {
+      const uint32_t m = tkeys[t] ? s->h_counters[t] : 0;
+      if (m == 0) continue;
+      const bool use_sorted = m >= std::max<size_t>(pull_sort_min(), 1);
+      if (use_sorted) {
+        HPSX_CU(launch_resolve_and_sort_misses(c->tables[t], s->d_miss_keys + tbase[t], m, s->d_addr[0] + tbase[t],
+                                               s->d_sidx[0] + tbase[t], s->d_addr[1] + tbase[t], s->d_sidx[1] + tbase[t],
+                                               s->d_sort_temp, s->sort_temp_bytes, s->stream));
+        ++s->stats.kernel_launches;
+      }
+      for (size_t r = 0; r < R; ++r) outs[r] = out_v[r * T + t];
+      HPSX_CU(launch_pull_misses(c->tables[t], s->d_miss_keys + tbase[t], s->d_miss_pos + tbase[t], s->d_counters + t,
+                                 tkeys[t], nullptr, nullptr, !c->is_static, 1, 0.f, epoch, s->d_counters + s->vt + t,
+                                 s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + tbase[t] : nullptr,
+                                 use_sorted ? s->d_sidx[1] + tbase[t] : nullptr, m, s->stream, 0, nullptr, nullptr,
+                                 outs.data(), static_cast<int>(R)));
+      ++s->stats.kernel_launches;
+    }
+    HPSX_CU(cudaEventRecord(s->ev_pull[1], s->stream));
+    HPSX_CU(cudaMemcpyAsync(s->h_counters + 2 * s->vt, s->d_counters + 2 * s->vt, T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes += T * sizeof(uint32_t);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[1]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+  }
+  for (size_t t = 0; t < T; ++t) {
+    if (tkeys[t] == 0) continue;
+    const uint32_t m = s->h_counters[t];
+    const uint32_t absent = any ? s->h_counters[2 * s->vt + t] : 0u;
+    s->stats.hits += tkeys[t] - m;
+    s->stats.misses += m;
+    s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * s->model->tables[t]->dim() * sizeof(float);
+    s->stats.default_filled += absent;
+  }
+  return HPSX_OK;
+}
+
 // Direct-pull lookup (enable_pagelock): probe+gather, then the misses are resolved ON THE GPU: their
 // rows are read straight from the page-locked host table over PCIe and inserted.  No CPU gather, no
 // staging copy.  With HPSX_PULL_SORT (default) the host reads the miss counts once, and the misses
@@ -693,6 +789,13 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
         n_per_table[which] >= kPipelineMinKeys)
       return gpu_lookup_direct_pipelined(s, which % T, keys_per_table[which], keys_on_device, out_per_table[which],
                                          n_per_table[which], epoch);
+  }
+  if (num_tables > T && num_tables % T == 0 && num_tables / T <= static_cast<size_t>(kMaxBatchOuts) && sorted &&
+      always_sync_mode && !split && pos_per_table == nullptr && s->bf16_out == nullptr && batch_merge_enabled()) {
+    bool fits = true;  // request-relative rows must fit below the request index bits
+    for (size_t v = 0; v < num_tables; ++v) fits = fits && n_per_table[v] < (1ull << kShardPosBits);
+    if (fits)
+      return gpu_lookup_direct_batch_merged(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables, epoch);
   }
   HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
   HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));

@@ -862,6 +862,9 @@ struct PullArgs {
   __nv_bfloat16* out_bf16;  // optional bf16 mirror of `out` (float4 instantiation only)
   int64_t* mark_absent;     // optional (= miss_keys): keys that are not in the host table are overwritten with kEmptyKey,
                             // so that a later insert-from-output pass skips them
+  // merged miss list of a batch of requests: miss_pos = (request << kShardPosBits) | row, one output base per request
+  int batch;
+  float* batch_out[kMaxBatchOuts];
 };
 
 // Step 1 of the sorted pull: host address of every missed key (8 lanes per key, one 128-B index line each)
@@ -924,7 +927,7 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
     const double hit_rate = 1.0 - static_cast<double>(m) / static_cast<double>(a.n_keys);
     sync_mode = hit_rate < static_cast<double>(a.hit_rate_threshold);
   }
-  const bool write_out = a.out != nullptr && sync_mode;
+  const bool write_out = (a.out != nullptr || a.batch != 0) && sync_mode;
   const VecT defv = splat<VecT>(a.default_value);
   for (size_t i0 = warp * kRows; i0 < m; i0 += nwarps * kRows) {
     int64_t key[kRows];
@@ -964,8 +967,13 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
     for (int r = 0; r < kRows; ++r) {
       if (i0 + r >= m) break;
       const size_t i = idx[r];  // position in the miss list (stage row, miss_pos entry)
-      VecT* dst_out =
-          write_out ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V : nullptr;
+      VecT* dst_out = nullptr;
+      if (write_out) {
+        const uint32_t p = a.miss_pos[i];
+        dst_out = a.batch ? reinterpret_cast<VecT*>(a.batch_out[p >> kShardPosBits]) +
+                                static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
+                          : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(p) * V;
+      }
       VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
       VecT* dst_slab = nullptr;
       Claim claim{nullptr, nullptr};
@@ -1299,9 +1307,11 @@ __global__ void __launch_bounds__(kBlock) synth_rows_kernel(const int64_t* __res
 }
 
 // widest vector (bytes) usable for rows of `dim` floats given the pointer alignments involved
-inline int vec_bytes(uint32_t dim, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr) {
+inline int vec_bytes(uint32_t dim, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr,
+                     const void* p3 = nullptr) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1) |
-                      reinterpret_cast<uintptr_t>(p2) | (static_cast<uintptr_t>(dim) * 4u);
+                      reinterpret_cast<uintptr_t>(p2) | reinterpret_cast<uintptr_t>(p3) |
+                      (static_cast<uintptr_t>(dim) * 4u);
   if ((a & 15u) == 0) return 16;
   if ((a & 7u) == 0) return 8;
   return 4;
@@ -1599,10 +1609,14 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
                                const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream, int max_ctas_per_sm,
-                               void* d_out_bf16, int64_t* d_mark_absent) {
+                               void* d_out_bf16, int64_t* d_mark_absent, float* const* batch_outs, int batch_count) {
   if (n_keys == 0) return cudaSuccess;
   if (t.index == nullptr) return cudaErrorInvalidValue;
+  if (batch_count < 0 || batch_count > kMaxBatchOuts || (batch_count > 0 && (batch_outs == nullptr || d_out_bf16 != nullptr)))
+    return cudaErrorInvalidValue;
   PullArgs a{};
+  a.batch = batch_count;
+  for (int r = 0; r < batch_count; ++r) a.batch_out[r] = batch_outs[r];
   a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
   a.mark_absent = d_mark_absent;
   a.sorted_addr = d_sorted_addr;
@@ -1647,7 +1661,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
   const unsigned grid = static_cast<unsigned>(
       min(static_cast<size_t>(148 * ctas), (warps_needed * 32 + kBlock - 1) / kBlock));
   // host rows are only guaranteed 4-B aligned relative to dim; slabs are 4096-B aligned, rows dim*4 apart
-  const int vb = vec_bytes(t.dim, d_out, d_stage, t.values);
+  uintptr_t batch_bits = 0;
+  for (int r = 0; r < batch_count; ++r) batch_bits |= reinterpret_cast<uintptr_t>(batch_outs[r]);
+  const int vb = vec_bytes(t.dim, d_out, d_stage, t.values, reinterpret_cast<const void*>(batch_bits & 15u));
   if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
   if (vb == 16 && rows_per_warp == 2)
     pull_misses_kernel<float4, 2><<<grid, kBlock, 0, stream>>>(a);

@@ -82,7 +82,10 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
                                bool insert, int insert_mode, float hit_rate_threshold, uint32_t epoch,
                                uint32_t* d_inserted, uint32_t* d_absent, const unsigned long long* d_sorted_addr,
                                const uint32_t* d_sorted_idx, size_t m_hint, cudaStream_t stream,
-                               int max_ctas_per_sm = 0, void* d_out_bf16 = nullptr, int64_t* d_mark_absent = nullptr);
+                               int max_ctas_per_sm = 0, void* d_out_bf16 = nullptr, int64_t* d_mark_absent = nullptr,
+                               float* const* batch_outs = nullptr, int batch_count = 0);
+// batch_outs/batch_count: the miss list merges the misses of `batch_count` requests of one table; entry i goes to
+// row (pos & (2^26 - 1)) of batch_outs[pos >> 26] (d_out is ignored).
 // d_mark_absent (= d_miss_keys, writable): keys missing from the host table are replaced by the empty marker, so
 // that launch_insert_merge(d_stage = nullptr), which inserts the pulled rows from the output buffer, skips them.
 // max_ctas_per_sm > 0 caps the persistent grid so that other kernels (the probes of later request chunks) keep
@@ -134,6 +137,7 @@ cudaError_t launch_scatter_rows(const float* d_rows, const uint32_t* d_perm, siz
 // Fused model-parallel exchange over NVLink peer memory (hpsx_shard_group in hpsx.h).
 // ------------------------------------------------------------------------------------------------
 constexpr int kMaxPeers = 16;            // GPUs of one box
+constexpr int kMaxBatchOuts = 16;        // requests whose misses one pull launch may serve (= kMaxBatchRequests)
 constexpr uint32_t kShardPosBits = 26;   // miss destination = (requester << 26) | row in its output
 
 // What rank r knows about every rank p of the group (entry r = its own arena).  Passed to kernels by value.
