@@ -95,6 +95,7 @@ struct hpsx_session {
   // bf16 mirror of the current lookup's output (hpsx_session_lookup_bf16_mirror): table index and device buffer
   size_t bf16_table = 0;
   void* bf16_out = nullptr;
+  double miss_ratio = 1.0;             // running miss ratio of this session's lookups (predicts the next miss count)
   int copy_chunks = 4;                 // host keys of a large request: H2D of chunk c+1 overlaps the probe of chunk c
   int pipe_chunks = 0;                 // chunks of the opt-in pipelined direct pull (HPSX_PIPE_CHUNKS; < 2: off)
   int probe_variant = hpsx::kProbeV8;  // falls back to the LDG.128 variant for rows that are not 32-B multiples

@@ -754,7 +754,12 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   for (size_t t = 0; t < num_tables; ++t)
     if (n_per_table[t] != 0 && (!keys_per_table[t] || !out_per_table[t]))
       return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
-  const bool sorted = pull_sort_enabled();
+  // A small request whose predicted miss count (from this session's recent miss ratio) is below the sort threshold
+  // would pull in miss-list order anyway: it then takes the device-driven form — probe and pull back to back, the
+  // pull reads the miss count on the device, ONE host wait — instead of reading the count back first.
+  const bool speculative = num_tables <= T && total < kPipelineMinKeys && pos_per_table == nullptr &&
+                           s->miss_ratio * static_cast<double>(total) < static_cast<double>(pull_sort_min());
+  const bool sorted = pull_sort_enabled() && !speculative;
   if (sorted) {
     const int rc = ensure_sort_workspace(s);
     if (rc != HPSX_OK) return rc;
@@ -888,6 +893,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       for (size_t t = 0; t < num_tables; ++t) any_miss = any_miss || (n_per_table[t] != 0 && s->h_counters[t] != 0);
       if (!any_miss) {
         for (size_t t = 0; t < num_tables; ++t) s->stats.hits += n_per_table[t];
+        s->miss_ratio *= 0.5;
         return HPSX_OK;
       }
     }
@@ -948,6 +954,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     const uint32_t absent = s->h_counters[2 * s->vt + t];
     s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * row_bytes;  // rows pulled over PCIe by the kernel
     s->stats.default_filled += (m != 0 && !decide_sync(s, n, m)) ? m : absent;
+    s->miss_ratio = 0.5 * s->miss_ratio + 0.5 * static_cast<double>(m) / static_cast<double>(n);
     if (trace_on()) {
       float p_ms = 0.f, q_ms = 0.f;
       cudaEventElapsedTime(&p_ms, s->ev[2 * t], s->ev[2 * t + 1]);
