@@ -19,14 +19,13 @@
 #include <cstring>
 #include <stdexcept>
 
-#include <nvtx3/nvToolsExt.h>
-
-#include "dense_mlp.h"
 #include "engine.hpp"
+#include "engine_internal.hpp"
 
 using namespace hpsx;
 
-namespace {
+namespace hpsx {
+namespace eng {
 
 thread_local std::string g_err;
 
@@ -35,26 +34,6 @@ int fail(int code, std::string msg) {
   return code;
 }
 
-#define HPSX_CU(call)                                                                         \
-  do {                                                                                        \
-    const cudaError_t e__ = (call);                                                           \
-    if (e__ != cudaSuccess)                                                                   \
-      return fail(HPSX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));        \
-  } while (0)
-
-#define HPSX_GUARD_BEGIN try {
-#define HPSX_GUARD_END                                         \
-  }                                                            \
-  catch (const std::bad_alloc&) {                              \
-    return fail(HPSX_ERR_INTERNAL, "out of host memory");      \
-  }                                                            \
-  catch (const std::exception& e) {                            \
-    return fail(HPSX_ERR_INTERNAL, e.what());                  \
-  }
-
-// Is the primary context of `dev` alive in this process?  (A thread that never selected a device reports device 0;
-// switching "back" to it would CREATE a context on GPU 0 — ~0.4 s and some HBM — in a process that only serves
-// another GPU, e.g. one rank of a one-process-per-GPU deployment calling from a worker thread.)
 bool primary_context_active(int dev) {
   typedef CUresult (*Fn)(CUdevice, unsigned int*, int*);
   static Fn fn = [] {
@@ -71,38 +50,11 @@ bool primary_context_active(int dev) {
   return fn(static_cast<CUdevice>(dev), &flags, &active) != CUDA_SUCCESS || active != 0;
 }
 
-// NVTX range around the phases of a lookup (the reference marks the same places: hps_backend/src/hps.cc:375,671,
-// 674,701, src/model_instance_state.cpp:179; opt-in there, free here when no tool is attached).
-struct NvtxRange {
-  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-  ~NvtxRange() { nvtxRangePop(); }
-};
+}  // namespace eng
+}  // namespace hpsx
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev && primary_context_active(prev)) cudaSetDevice(prev);
-  }
-};
-
-Model* find_model(hpsx_ps* ps, const char* name) {
-  if (!ps || !name) return nullptr;
-  std::lock_guard<std::mutex> lk(ps->mu);
-  auto it = ps->models.find(name);
-  return it == ps->models.end() ? nullptr : it->second.get();
-}
-
-size_t resolve_partitions(size_t requested) {
-  if (requested > 0) return requested;
-  // docs/hierarchical_parameter_server.md:410-412: min(number of cores, 16)
-  return std::max<size_t>(1, std::min<size_t>(ThreadPool::default_concurrency(), 16));
-}
+namespace hpsx {
+namespace eng {
 
 double now_ms() {
   using namespace std::chrono;
@@ -122,6 +74,27 @@ bool trace_on() {
 // sparse model files: <dir>/key (int64 | uint32) + <dir>/emb_vector (fp32 row-major)
 // (docs/architecture.md:185-218; writer samples/hps-triton-ensemble/01_model_training.ipynb:498-505)
 // ------------------------------------------------------------------------------------------------
+
+}  // namespace eng
+}  // namespace hpsx
+
+using namespace hpsx::eng;
+
+namespace {
+
+Model* find_model(hpsx_ps* ps, const char* name) {
+  if (!ps || !name) return nullptr;
+  std::lock_guard<std::mutex> lk(ps->mu);
+  auto it = ps->models.find(name);
+  return it == ps->models.end() ? nullptr : it->second.get();
+}
+
+size_t resolve_partitions(size_t requested) {
+  if (requested > 0) return requested;
+  // docs/hierarchical_parameter_server.md:410-412: min(number of cores, 16)
+  return std::max<size_t>(1, std::min<size_t>(ThreadPool::default_concurrency(), 16));
+}
+
 int load_sparse_dir(hpsx_ps* ps, HostTable* table, const std::string& dir) {
   // engine extension for benchmarks: "synthetic:rows=<N>,seed=<S>" names a procedural table
   // (keys [0,N), rows from synth_value()) instead of a directory, so that a 10 M-row table needs no 5 GB file
@@ -416,16 +389,14 @@ void* bf16_dst(const hpsx_session* s, size_t t, size_t row_off, size_t dim) {
   return static_cast<unsigned char*>(s->bf16_out) + row_off * dim * 2u;
 }
 
-// `mb` (nullable) replaces the session's own miss list (model-parallel groups keep a larger one).
-struct MissBufs {
-  const int64_t* h_keys;
-  const int64_t* d_keys;
-  const uint32_t* d_pos;
-};
+}  // namespace
+
+namespace hpsx {
+namespace eng {
 
 int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, float* d_out, bool insert,
                      uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock,
-                     const MissBufs* mb = nullptr) {
+                     const MissBufs* mb) {
   hpsx_cache* c = s->cache;
   const size_t rt = t % s->model->tables.size();  // t may be a virtual table (request * T + table)
   const HostTable& ht = *s->model->tables[rt];
@@ -462,6 +433,11 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
   return HPSX_OK;
 }
 
+}  // namespace eng
+}  // namespace hpsx
+
+namespace {
+
 // Asynchronous insertion: this response already carries the default vector for the misses (written
 // by the probe kernel); a pool worker fetches + inserts later (docs/architecture.md:65-67).
 void post_async_insert(hpsx_session* s, size_t t, size_t key_off, uint32_t m) {
@@ -494,6 +470,11 @@ void account_probe_time(hpsx_session* s, size_t t, size_t n) {
   }
 }
 
+}  // namespace
+
+namespace hpsx {
+namespace eng {
+
 // Miss lists shorter than this are pulled in miss-list order: the resolve + radix sort costs ~70 us of launches,
 // more than the sorted order saves on a few thousand rows (HPSX_PULL_SORT_MIN overrides).
 size_t pull_sort_min() {
@@ -504,6 +485,11 @@ size_t pull_sort_min() {
   return v;
 }
 
+}  // namespace eng
+}  // namespace hpsx
+
+namespace {
+
 bool batch_merge_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("HPSX_BATCH_MERGE");
@@ -512,6 +498,11 @@ bool batch_merge_enabled() {
   return on;
 }
 
+}  // namespace
+
+namespace hpsx {
+namespace eng {
+
 bool pull_sort_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("HPSX_PULL_SORT");
@@ -519,6 +510,16 @@ bool pull_sort_enabled() {
   }();
   return on;
 }
+
+}  // namespace eng
+}  // namespace hpsx
+
+namespace {
+
+}  // namespace
+
+namespace hpsx {
+namespace eng {
 
 // Workspace of the address-sorted pull, allocated on first use.
 int ensure_sort_workspace(hpsx_session* s) {
@@ -532,6 +533,11 @@ int ensure_sort_workspace(hpsx_session* s) {
   HPSX_CU(cudaMalloc(&s->d_sort_temp, std::max<size_t>(s->sort_temp_bytes, 16)));
   return HPSX_OK;
 }
+
+}  // namespace eng
+}  // namespace hpsx
+
+namespace {
 
 // Opt-in (HPSX_PIPE_CHUNKS >= 2) pipelined form of the direct-pull lookup for one large table slice: the request is
 // cut into chunks; stream A copies the keys of chunk c and probes it while stream B resolves, sorts and pulls the
@@ -1062,6 +1068,11 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
   return HPSX_OK;
 }
 
+}  // namespace
+
+namespace hpsx {
+namespace eng {
+
 // The per-call stage that keeps all miss rows of one request (pooled path, model-parallel groups).
 // Stream-ordered (cudaMallocAsync/cudaFreeAsync): growing it never synchronises the device, which matters when
 // another rank's flag-wait kernel is resident on the same GPU.
@@ -1075,6 +1086,11 @@ int ensure_pool_stage(hpsx_session* s, size_t m) {
   s->pool_stage_rows = rows;
   return HPSX_OK;
 }
+
+}  // namespace eng
+}  // namespace hpsx
+
+namespace {
 
 int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool keys_on_device,
                       size_t num_bags, size_t hotness, int combiner, float* d_pooled) {
@@ -1163,167 +1179,6 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
 }
 
 
-size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-void shard_fill_peers(hpsx_shard_group* g) {
-  using G = hpsx_shard_group;
-  for (uint32_t p = 0; p < g->world; ++p) {
-    unsigned char* base = g->peer_arena[p];
-    uint32_t* ctrl = reinterpret_cast<uint32_t*>(base);
-    // the slot / cells of rank p that belong to THIS rank
-    g->peers.inbox_keys[p] = reinterpret_cast<int64_t*>(base + g->off_keys) + static_cast<size_t>(g->rank) * g->slot_cap;
-    g->peers.inbox_pos[p] = reinterpret_cast<uint32_t*>(base + g->off_pos) + static_cast<size_t>(g->rank) * g->slot_cap;
-    g->peers.inbox_cnt[p] = ctrl + G::kCnt + g->rank;
-    g->peers.flag_dispatch[p] = ctrl + G::kFlagDispatch + g->rank;
-    g->peers.flag_return[p] = ctrl + G::kFlagReturn + g->rank;
-    g->peers.out[p] = reinterpret_cast<float*>(base + g->off_out);
-  }
-  g->connected = true;
-}
-
-int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out) {
-  using G = hpsx_shard_group;
-  NvtxRange range("hpsx_shard_group_lookup");
-  hpsx_session* s = g->s;
-  hpsx_cache* c = s->cache;
-  const size_t t = g->table;
-  DeviceGuard guard(s->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  const uint32_t seq = ++g->seq;
-  const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
-  const double tr0 = now_ms();
-  uint32_t* ctrl = g->ctrl();
-  uint32_t* d_status = ctrl + G::kStatus;
-  uint32_t* d_miss_count = ctrl + G::kMissCount;
-  const DeviceTable& dt = c->tables[t];
-  ++s->stats.lookups;
-  s->stats.keys += n;
-
-  HPSX_CU(cudaMemsetAsync(ctrl + G::kCursor, 0, (G::kDone + 1 - G::kCursor) * sizeof(uint32_t), s->stream));
-  uint32_t m = 0, status = 0;
-  bool returned = false;  // the speculative return wave ran on the device
-  {
-    std::shared_lock<std::shared_mutex> rlock(c->rw);
-    HPSX_CU(launch_shard_dispatch(d_keys, n, g->world, g->peers, ctrl + G::kCursor, s->stream));
-    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 0, ctrl + G::kCursor, ctrl + G::kCnt,
-                                     ctrl + G::kFlagDispatch, static_cast<uint32_t>(std::min<size_t>(g->miss_cap, 0xFFFFFFFFu)),
-                                     d_status, g->timeout_ns, s->stream));
-    HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
-    HPSX_CU(launch_probe_gather_inbox(dt, g->peers, g->world, g->rank, g->slot_cap,
-                                      reinterpret_cast<const int64_t*>(g->arena + g->off_keys),
-                                      reinterpret_cast<const uint32_t*>(g->arena + g->off_pos), ctrl + G::kCnt, d_status,
-                                      epoch, !c->is_static, d_miss_count, g->d_miss_pos, g->d_miss_keys, g->hd_miss_keys,
-                                      n, s->stream));
-    HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
-    // return wave, speculatively: it runs only if the gather recorded no miss (else the host resolves them below)
-    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
-                                     d_status, g->timeout_ns, s->stream, d_miss_count, ctrl + G::kDone));
-    s->stats.kernel_launches += 4;
-    HPSX_CU(cudaMemcpyAsync(g->h_ctrl, ctrl, G::kWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    HPSX_CU(cudaStreamSynchronize(s->stream));
-    status = g->h_ctrl[G::kStatus];
-    returned = g->h_ctrl[G::kDone] != 0u;
-    m = (status || returned) ? 0u : g->h_ctrl[G::kMissCount];
-  }
-  const double tr1 = now_ms();
-  s->stats.d2h_bytes += G::kWords * sizeof(uint32_t);
-  hpsx_shard_stats& st = g->last;
-  st = hpsx_shard_stats{};
-  for (uint32_t p = 0; p < g->world; ++p) {
-    st.sent[p] = g->h_ctrl[G::kCursor + p];
-    st.received[p] = status ? 0u : g->h_ctrl[G::kCnt + p];
-    st.keys_received += st.received[p];
-    if (p != g->rank) {
-      st.keys_sent_remote += st.sent[p];
-      st.keys_received_remote += st.received[p];
-    }
-  }
-  st.misses = m;
-  if (status == 0) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev[2 * t], s->ev[2 * t + 1]) == cudaSuccess) {
-      s->stats.probe_kernel_ms += ms;
-      ++s->stats.probe_kernel_launches;
-      s->stats.probe_kernel_keys += st.keys_received;
-    }
-    s->stats.hits += st.keys_received - m;
-  }
-
-  int rc = HPSX_OK;
-  if (m > 0) {
-    // resolve the misses into a local stage, forward the rows to their requesters, insert them here
-    rc = ensure_pool_stage(s, m);
-    std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
-    if (rc == HPSX_OK && c->direct_pull) {
-      if (!c->is_static) wlock.lock();
-      const bool use_sorted = pull_sort_enabled() && m <= s->cap_keys;
-      cudaError_t e = cudaMemsetAsync(s->d_counters + 2 * s->vt + t, 0, sizeof(uint32_t), s->stream);
-      if (e == cudaSuccess && use_sorted) {
-        rc = ensure_sort_workspace(s);
-        if (rc == HPSX_OK)
-          e = launch_resolve_and_sort_misses(dt, g->d_miss_keys, m, s->d_addr[0], s->d_sidx[0], s->d_addr[1],
-                                             s->d_sidx[1], s->d_sort_temp, s->sort_temp_bytes, s->stream);
-      }
-      if (rc == HPSX_OK && e == cudaSuccess)
-        e = launch_pull_misses(dt, g->d_miss_keys, g->d_miss_pos, d_miss_count, st.keys_received, nullptr,
-                               s->d_pool_stage, !c->is_static, 1, 0.f, epoch, s->d_counters + s->vt + t,
-                               s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] : nullptr,
-                               use_sorted ? s->d_sidx[1] : nullptr, m, s->stream);
-      if (rc == HPSX_OK && e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("direct pull: ") + cudaGetErrorString(e));
-      s->stats.kernel_launches += use_sorted ? 2 : 1;
-      s->stats.misses += m;
-      s->stats.h2d_bytes += static_cast<uint64_t>(m) * g->dim * sizeof(float);
-    } else if (rc == HPSX_OK) {
-      const MissBufs mb{g->h_miss_keys, g->d_miss_keys, g->d_miss_pos};
-      s->stats.d2h_bytes += static_cast<uint64_t>(m) * sizeof(int64_t);
-      rc = stream_miss_rows(s, t, 0, m, nullptr, false, epoch, s->d_pool_stage, nullptr, &mb);
-      if (rc == HPSX_OK && !c->is_static) {
-        wlock.lock();
-        const cudaError_t e = launch_insert_merge(dt, g->d_miss_keys, nullptr, s->d_pool_stage, m, nullptr, true, epoch,
-                                                  s->d_counters + s->vt + t, s->stream);
-        if (e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("insert: ") + cudaGetErrorString(e));
-        ++s->stats.kernel_launches;
-      }
-    }
-    if (rc == HPSX_OK) {
-      const cudaError_t e = launch_shard_scatter_stage(s->d_pool_stage, g->d_miss_pos, m, g->dim, g->peers, g->world, s->stream);
-      if (e != cudaSuccess) rc = fail(HPSX_ERR_CUDA, std::string("scatter: ") + cudaGetErrorString(e));
-      ++s->stats.kernel_launches;
-    }
-    if (rc != HPSX_OK) {
-      // the peers still wait for this rank's return flag: raise the error bit and fall through
-      const uint32_t one = 1;
-      cudaMemcpyAsync(d_status, &one, sizeof(one), cudaMemcpyHostToDevice, s->stream);
-    }
-    if (wlock.owns_lock()) cudaStreamSynchronize(s->stream);  // slots are rewritten under the exclusive lock only
-  }
-  const double tr2 = now_ms();
-  const std::string keep = g_err;
-  if (!returned) {
-    // after a timeout nobody is listening any more: publish, do not wait again
-    const unsigned long long wait_ns = (status & 2u) ? 0ull : g->timeout_ns;
-    HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
-                                     d_status, wait_ns, s->stream));
-    ++s->stats.kernel_launches;
-    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-    HPSX_CU(cudaStreamSynchronize(s->stream));
-    status |= g->h_ctrl[G::kStatus];
-  }
-  st.status = status;
-  if (trace_on())
-    std::fprintf(stderr, "[hpsx] shard lookup rank %u n=%zu: dispatch+wait+gather+sync %.3f ms | misses %u: %.3f ms | return wave %.3f ms\n",
-                 g->rank, n, tr1 - tr0, m, tr2 - tr1, now_ms() - tr2);
-  if (rc != HPSX_OK) return fail(rc, keep);
-  if (status != 0) {
-    std::string why = (status & 2u) ? "a rank did not arrive before the timeout"
-                      : (status & 4u) ? "this rank received more keys than its miss list can hold"
-                                      : "another rank of the group reported a failure";
-    return fail(HPSX_ERR_INTERNAL, "model-parallel lookup failed: " + why);
-  }
-  if (d_out) *d_out = reinterpret_cast<float*>(g->arena + g->off_out);
-  return HPSX_OK;
-}
-
 }  // namespace
 
 hpsx_cache::~hpsx_cache() {
@@ -1377,19 +1232,6 @@ hpsx_session::~hpsx_session() {
   }
 }
 
-
-hpsx_shard_group::~hpsx_shard_group() {
-  if (!s || s->device < 0) return;
-  DeviceGuard guard(s->device);
-  if (s->stream) cudaStreamSynchronize(s->stream);
-  for (uint32_t p = 0; p < peer_arena.size(); ++p)
-    if (p != rank && peer_arena[p] != nullptr && peer_ipc[p]) cudaIpcCloseMemHandle(peer_arena[p]);
-  cudaFree(arena);
-  cudaFree(d_miss_pos);
-  cudaFree(d_miss_keys);
-  if (h_miss_keys) cudaFreeHost(h_miss_keys);
-  if (h_ctrl) cudaFreeHost(h_ctrl);
-}
 
 // ================================================================================================
 // C ABI
@@ -2082,144 +1924,6 @@ int hpsx_ipc_close(int device, void* d_ptr) {
   return HPSX_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// model-parallel group
-// ------------------------------------------------------------------------------------------------
-int hpsx_shard_group_create(hpsx_session* s, size_t table, uint32_t rank, uint32_t world, hpsx_shard_group** out,
-                            void* handle64) {
-  HPSX_GUARD_BEGIN
-  if (!s || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  if (!s->cache) return fail(HPSX_ERR_UNSUPPORTED, "a model-parallel group needs a GPU session (gpucache = true)");
-  if (table >= s->model->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
-  if (world == 0 || world > static_cast<uint32_t>(kMaxPeers) || rank >= world)
-    return fail(HPSX_ERR_INVALID_ARG, "need rank < world <= " + std::to_string(kMaxPeers));
-  const size_t cap = s->cap_per_table[table];
-  if (cap == 0 || cap >= (1ull << kShardPosBits))
-    return fail(HPSX_ERR_UNSUPPORTED, "keys per request of the sharded table must be in [1, 2^26)");
-  DeviceGuard guard(s->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  std::unique_ptr<hpsx_shard_group> g(new hpsx_shard_group());
-  g->s = s;
-  g->table = table;
-  g->rank = rank;
-  g->world = world;
-  g->slot_cap = static_cast<uint32_t>(cap);
-  g->dim = s->model->tables[table]->dim();
-  g->off_keys = 4096;
-  g->off_pos = align_up(g->off_keys + static_cast<size_t>(world) * cap * sizeof(int64_t), 512);
-  g->off_out = align_up(g->off_pos + static_cast<size_t>(world) * cap * sizeof(uint32_t), 512);
-  g->arena_bytes = g->off_out + cap * g->dim * sizeof(float);
-  HPSX_CU(cudaMalloc(&g->arena, g->arena_bytes));
-  HPSX_CU(cudaMemset(g->arena, 0, 4096));
-  g->miss_cap = static_cast<size_t>(world) * cap;
-  HPSX_CU(cudaMalloc(&g->d_miss_pos, g->miss_cap * sizeof(uint32_t)));
-  HPSX_CU(cudaMalloc(&g->d_miss_keys, g->miss_cap * sizeof(int64_t)));
-  if (!s->cache->direct_pull) {
-    HPSX_CU(cudaHostAlloc(&g->h_miss_keys, g->miss_cap * sizeof(int64_t), cudaHostAllocMapped | cudaHostAllocPortable));
-    HPSX_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->hd_miss_keys), g->h_miss_keys, 0));
-  }
-  HPSX_CU(cudaMallocHost(&g->h_ctrl, hpsx_shard_group::kWords * sizeof(uint32_t)));
-  if (const char* env = std::getenv("HPSX_SHARD_TIMEOUT_MS")) {
-    const long long v = std::atoll(env);
-    if (v > 0) g->timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
-  }
-  g->peer_arena.assign(world, nullptr);
-  g->peer_ipc.assign(world, false);
-  g->peer_arena[rank] = g->arena;
-  if (handle64) {
-    cudaIpcMemHandle_t h;
-    HPSX_CU(cudaIpcGetMemHandle(&h, g->arena));
-    std::memcpy(handle64, &h, sizeof(h));
-  }
-  if (world == 1) shard_fill_peers(g.get());
-  *out = g.release();
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_shard_group_connect_ipc(hpsx_shard_group* g, const void* all_handles) {
-  HPSX_GUARD_BEGIN
-  if (!g || !all_handles) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  DeviceGuard guard(g->s->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  const unsigned char* hs = static_cast<const unsigned char*>(all_handles);
-  for (uint32_t p = 0; p < g->world; ++p) {
-    if (p == g->rank || g->peer_arena[p] != nullptr) continue;
-    cudaIpcMemHandle_t h;
-    std::memcpy(&h, hs + static_cast<size_t>(p) * sizeof(h), sizeof(h));
-    void* ptr = nullptr;
-    HPSX_CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-    g->peer_arena[p] = static_cast<unsigned char*>(ptr);
-    g->peer_ipc[p] = true;
-  }
-  shard_fill_peers(g);
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_shard_group_connect_local(hpsx_shard_group* g, hpsx_shard_group* const* groups) {
-  HPSX_GUARD_BEGIN
-  if (!g || !groups) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  DeviceGuard guard(g->s->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  for (uint32_t p = 0; p < g->world; ++p) {
-    if (p == g->rank) continue;
-    const hpsx_shard_group* o = groups[p];
-    if (!o || o->world != g->world || o->rank != p || o->slot_cap != g->slot_cap || o->dim != g->dim)
-      return fail(HPSX_ERR_INVALID_ARG, "group " + std::to_string(p) + " does not match (world, rank, capacity, dim)");
-    if (o->s->device != g->s->device) {
-      int can = 0;
-      HPSX_CU(cudaDeviceCanAccessPeer(&can, g->s->device, o->s->device));
-      if (!can) return fail(HPSX_ERR_UNSUPPORTED, "no peer access between the devices of the group");
-      const cudaError_t e = cudaDeviceEnablePeerAccess(o->s->device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) HPSX_CU(e);
-      cudaGetLastError();
-    }
-    g->peer_arena[p] = o->arena;
-  }
-  shard_fill_peers(g);
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_shard_group_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d_out) {
-  HPSX_GUARD_BEGIN
-  if (!g) return fail(HPSX_ERR_INVALID_ARG, "null group");
-  if (!g->connected) return fail(HPSX_ERR_INVALID_ARG, "the group is not connected to its peers yet");
-  if (n > g->slot_cap)
-    return fail(HPSX_ERR_INVALID_ARG, std::to_string(n) + " keys exceed max_batch_size * maxnum_catfeature_query_per_table_per_sample = " +
-                                          std::to_string(g->slot_cap));
-  if (n > 0 && !d_keys) return fail(HPSX_ERR_INVALID_ARG, "null keys");
-  std::lock_guard<std::mutex> lk(g->s->mu);
-  return shard_lookup(g, d_keys, n, d_out);
-  HPSX_GUARD_END
-}
-
-int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out) {
-  if (!g || !out) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  *out = g->last;
-  return HPSX_OK;
-}
-
-int hpsx_shard_group_capacity(const hpsx_shard_group* g, size_t* rows) {
-  if (!g || !rows) return fail(HPSX_ERR_INVALID_ARG, "null argument");
-  *rows = g->slot_cap;
-  return HPSX_OK;
-}
-
-int hpsx_shard_group_set_timeout_ms(hpsx_shard_group* g, uint64_t ms) {
-  if (!g || ms == 0) return fail(HPSX_ERR_INVALID_ARG, "null group / zero timeout");
-  g->timeout_ns = ms * 1000000ull;
-  return HPSX_OK;
-}
-
-int hpsx_shard_group_destroy(hpsx_shard_group* g) {
-  HPSX_GUARD_BEGIN
-  delete g;
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
 int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, int key_memory,
                            float* const* vectors_per_table, int vector_memory,
                            const size_t* num_keys_per_table, size_t num_tables) {
@@ -2483,63 +2187,6 @@ int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   }
   s->probe_variant = variant;
   return HPSX_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
-// dense MLP head
-// ------------------------------------------------------------------------------------------------
-struct hpsx_mlp {
-  hpsx::DenseMlp* impl = nullptr;
-  int device = 0;
-};
-
-int hpsx_mlp_create(int device, size_t num_layers, const size_t* dims, const float* const* weights,
-                    const float* const* biases, const int* relu, hpsx_mlp** out) {
-  HPSX_GUARD_BEGIN
-  if (!out) return fail(HPSX_ERR_INVALID_ARG, "null output handle");
-  DeviceGuard guard(device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  hpsx::DenseMlp* impl = nullptr;
-  const cudaError_t e = hpsx::mlp_create(device, num_layers, dims, weights, biases, relu, &impl);
-  if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
-  hpsx_mlp* m = new hpsx_mlp();
-  m->impl = impl;
-  m->device = device;
-  *out = m;
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_mlp_forward(hpsx_mlp* m, const float* d_in, size_t batch, float* d_out, void* stream) {
-  HPSX_GUARD_BEGIN
-  if (!m) return fail(HPSX_ERR_INVALID_ARG, "null mlp");
-  DeviceGuard guard(m->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  const cudaError_t e = hpsx::mlp_forward(m->impl, d_in, batch, d_out, static_cast<cudaStream_t>(stream));
-  if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_mlp_forward_bf16(hpsx_mlp* m, const void* d_in_bf16, size_t batch, float* d_out, void* stream) {
-  HPSX_GUARD_BEGIN
-  if (!m) return fail(HPSX_ERR_INVALID_ARG, "null mlp");
-  DeviceGuard guard(m->device);
-  if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-  const cudaError_t e = hpsx::mlp_forward(m->impl, nullptr, batch, d_out, static_cast<cudaStream_t>(stream), d_in_bf16);
-  if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
-  return HPSX_OK;
-  HPSX_GUARD_END
-}
-
-int hpsx_mlp_destroy(hpsx_mlp* m) {
-  HPSX_GUARD_BEGIN
-  if (!m) return HPSX_OK;
-  DeviceGuard guard(m->device);
-  hpsx::mlp_destroy(m->impl);
-  delete m;
-  return HPSX_OK;
-  HPSX_GUARD_END
 }
 
 // ------------------------------------------------------------------------------------------------
