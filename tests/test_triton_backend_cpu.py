@@ -379,3 +379,25 @@ def test_new_version_reloads_the_database_unless_frozen(tmp_path, freeze):
         assert np.array_equal(i1.infer(q, nk).data, O.request([want], q, [len(q)]))
         i1.close()
         m1.close()
+
+
+def test_periodic_refresh_thread_lifecycle_on_a_cpu_model(tmp_path):
+    """`refresh_interval` starts the model's refresh timer (model_state.cpp:422-427); on a CPU model there is no cache to
+    refresh, the thread just ticks beside the lookups and ModelFinalize stops and joins it promptly."""
+    import time
+    dirs, tabs = write_tables(str(tmp_path), [(120, 4)], seed=5)
+    ps = ps_json(str(tmp_path / "ps.json"), [model_entry("m", dirs, [4], [3], defaults=[0.5])])
+    t = O.NumpyTable(4, 0.5)
+    t.insert(*tabs[0])
+    with FT.Backend(ps) as be:
+        m = be.model("m", FT.model_config("m", kind="KIND_CPU", parameters={"refresh_interval": "0.02", "refresh_delay": "0"}))
+        inst = m.instance(kind=FT.KIND_CPU)
+        q = np.array([1, 4, 7, 100000], dtype=np.int64)
+        for _ in range(10):
+            r = inst.infer(q, np.array([[4]], dtype=np.int32))
+            assert r.error_code is None and np.array_equal(r.data, O.request([t], q, [4]))
+            time.sleep(0.01)
+        inst.close()
+        t0 = time.perf_counter()
+        m.close()
+        assert time.perf_counter() - t0 < 1.0
