@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zipf", type=float, default=0.0,
+                    help="> 1: draw keys Zipf(alpha)-distributed over the rows instead of the hot/cold mixture (popular rows are the "
+                         "warmed ones); config.unique_over_keys reports the duplication U/N of a request")
     ap.add_argument("--skip-triton-arm", action="store_true",
                     help="e2e falls back to the session-level arm (used for very large tables: the Triton arm loads a second copy)")
     ap.add_argument("--core-arms-only", action="store_true",
@@ -76,6 +79,9 @@ def parse_args():
 
 
 def workload_name(a) -> str:
+    if a.zipf > 1.0:
+        return (f"Criteo-shape: {a.slots} slots, {a.rows // 1_000_000}M-row table, dim {a.dim}, batch {a.batch}, "
+                f"Zipf({a.zipf}) keys (see config.hit_rate_measured, config.unique_over_keys)")
     if a.rows == 10_000_000 and abs(a.hit - 0.87) < 1e-9:
         return (f"DCN Criteo-shape: {a.slots} slots, {a.rows // 1_000_000}M-row table, dim {a.dim}, batch {a.batch}, "
                 f"90% cache-hit")
@@ -90,6 +96,9 @@ def make_requests(a, hot_keys: np.ndarray, cold_lo: int, count: int, seed: int):
     rng = np.random.default_rng(seed)
     reqs = []
     for _ in range(count):
+        if a.zipf > 1.0:
+            reqs.append(((rng.zipf(a.zipf, size=n) - 1) % a.rows).astype(np.int64))
+            continue
         is_hot = rng.random(n) < a.hit
         k = rng.integers(cold_lo, a.rows, size=n, dtype=np.int64)
         k[is_hot] = hot_keys[rng.integers(0, len(hot_keys), size=int(is_hot.sum()))]
@@ -652,6 +661,7 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
                    "gpucacheper": a.gpucacheper, "hit_rate_measured": st_pipe.hits / max(1, st_pipe.keys),
                    "pipeline_chunks": int(os.environ.get("HPSX_PIPE_CHUNKS", "0")),
+                   "unique_over_keys": float(len(np.unique(reqs[0])) / n),
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches per arm",
                    "hot_draw_probability": a.hit, "prefill_requests": a.prefill,
