@@ -63,7 +63,18 @@ def test_world1_group_matches_oracle(cuda_device, pagelock, dim):
 
 @pytest.mark.parametrize("pagelock", [False, True])
 def test_world2_same_device_threads(cuda_device, pagelock):
-    """Two ranks of one process on one GPU: every cross-rank key/row moves through the peer pointers."""
+    """Two ranks of one process on one GPU: every cross-rank key/row moves through the peer pointers.
+    This arrangement needs the two ranks' kernels (different streams of one process) to be co-resident on the single
+    device, which CUDA does not guarantee (under compute-sanitizer, for one, they are serialised and the flag waits
+    time out — by design, not a hang).  A timeout therefore gets ONE retry with fresh groups; wrong rows never do."""
+    for attempt in range(2):
+        verdict = _world2_same_device(pagelock)
+        if verdict != "timeout":
+            break
+    assert verdict == "ok", verdict
+
+
+def _world2_same_device(pagelock):
     torch = _torch()
     rows, dim, world = 80_000, 128, 2
     ref = O.NumpyTable(dim, 0.25)
@@ -86,7 +97,11 @@ def test_world2_same_device_threads(cuda_device, pagelock):
             keys = rng.integers(-5, rows + 5, size=n)
             dk = torch.from_numpy(keys).cuda()
             torch.cuda.current_stream().synchronize()
-            view = groups[rank].lookup(dk, n)
+            try:
+                view = groups[rank].lookup(dk, n)
+            except hb.HpsxError as e:
+                results[rank] = "timeout" if "timeout" in str(e) else f"error: {e}"
+                return
             st = groups[rank].stats()
             ok &= st["status"] == 0
             ok &= bool(np.array_equal(st["sent"], np.bincount(O.owner(keys, world), minlength=world)))
@@ -99,12 +114,19 @@ def test_world2_same_device_threads(cuda_device, pagelock):
     [t.start() for t in threads]
     [t.join(180) for t in threads]
     assert not any(t.is_alive() for t in threads), "a rank hung"
-    assert results == {0: True, 1: True}
+    if "timeout" in results.values():
+        for g in groups:
+            g.close()
+        return "timeout"
+    if results != {0: True, 1: True}:
+        return f"wrong result: {results}"
     # what one rank received is what the other sent
     a, b = groups[0].stats(), groups[1].stats()
-    assert a["received"][1] == b["sent"][0] and b["received"][0] == a["sent"][1]
+    if not (a["received"][1] == b["sent"][0] and b["received"][0] == a["sent"][1]):
+        return "send/receive counts disagree"
     for g in groups:
         g.close()
+    return "ok"
 
 
 def test_absent_peer_times_out(cuda_device):
