@@ -57,7 +57,10 @@ def parse_args():
                     help="direct: enable_pagelock, kernels pull missing rows from pinned host tables over PCIe; "
                          "staged: CPU gather + cudaMemcpyAsync")
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
-    ap.add_argument("--variant", default=os.environ.get("HPSX_PROBE", "v8"), choices=["ldg", "tma", "pipe", "split", "v8"])
+    ap.add_argument("--variant", default="v8", choices=["ldg", "tma", "v8"])
+    ap.add_argument("--chunks", type=int, default=0, help="request_chunks of the model (0: engine default 4)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 296)")
+    ap.add_argument("--value-only", action="store_true", help="device-resident arm only (kernel experiments)")
     ap.add_argument("--workload", default="dcn", choices=["dcn", "c4"],
                     help="dcn: BASELINE.json configs[1] (default, replicas over --gpus); c4: DLRM-shaped model-parallel table "
                          "(configs[3]): rows sharded over the GPUs by owner(key), global batch split over the ranks, 100 %% HBM-resident")
@@ -219,6 +222,33 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def _splitmix64_torch(torch, x):
+    """splitmix64 on int64 tensors (two's complement wrap-around, logical shifts emulated)."""
+    lsr = lambda v, sh: (v >> sh) & ((1 << (64 - sh)) - 1)
+    c = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+    x = x + c(0x9E3779B97F4A7C15)
+    x = (x ^ lsr(x, 30)) * c(0xBF58476D1CE4E5B9)
+    x = (x ^ lsr(x, 27)) * c(0x94D049BB133111EB)
+    return x ^ lsr(x, 31)
+
+
+def verify_rows(torch, d_keys, out, dim: int, seed: int, what: str) -> int:
+    """Self-check of a timed arm: every row of `out` must equal the closed-form synthetic row of its key
+    (hpsx_common.h synth_value; keys outside the table would be the default 0.0 — the bench draws none).  Runs on the
+    device in row blocks, after the timed region; returns the number of rows verified, raises on any mismatch."""
+    n = d_keys.numel()
+    j = torch.arange(dim, device=out.device, dtype=torch.int64)
+    for b0 in range(0, n, 1 << 18):
+        k = d_keys[b0:b0 + (1 << 18)]
+        r = _splitmix64_torch(torch, k[:, None] * 131 + j[None, :] + seed)
+        bits = ((r >> 41) & ((1 << 23) - 1)) | 0x3F800000
+        expect = bits.to(torch.int32).view(torch.float32) - 1.5
+        if not torch.equal(out[b0:b0 + (1 << 18)], expect):
+            bad = int((out[b0:b0 + (1 << 18)] != expect).any(dim=1).sum())
+            raise SystemExit(f"bench self-check FAILED ({what}): {bad} wrong rows in block {b0}")
+    return n
+
+
 def measure_host_link_gbs(torch) -> float:
     src = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
     dst = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
@@ -295,6 +325,7 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
         wall = time.perf_counter() - t0
         barrier()
         assert r.error_code is None and r.memory_type == FT.MEM_GPU and r.params["NumSample"] == a.batch
+        verified = verify_rows(torch, torch.from_numpy(h_keys[(a.steps - 1) % R]).cuda(), out, a.dim, SEED, "Triton arm")
         if world > 1:
             t = torch.tensor([wall], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,7 +337,8 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
     return {"value": world * a.steps * n / wall, "unit": UNIT, "ms_per_step": wall / a.steps * 1e3,
             "call": "TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so): host KEYS/NUMKEYS -> GPU OUTPUT0",
             "timer": "host wall clock around the blocking Execute calls, max over ranks (the backend's stream is private)",
-            "output": "device memory (Triton GPU output buffer contract)", "requests_ok": stats["ok_requests"]}
+            "output": "device memory (Triton GPU output buffer contract)", "requests_ok": stats["ok_requests"],
+            "verified_rows": verified}
 
 
 def run_ours(a):
@@ -339,7 +371,8 @@ def run_ours(a):
     hps = hb.HPS(num_partitions=16)
     hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
                                  cache_size_percentage=a.gpucacheper, deployed_devices=[local],
-                                 cache_load_factor=a.load_factor, enable_pagelock=(a.miss_path == "direct")))
+                                 cache_load_factor=a.load_factor, enable_pagelock=(a.miss_path == "direct"),
+                                 request_chunks=a.chunks, pull_grid_ctas=a.pull_ctas))
     hps.load_table_procedural("dcn", 0, a.rows, SEED)
     hps.create_embedding_cache("dcn")
     setup_s = time.perf_counter() - t0
@@ -396,6 +429,7 @@ def run_ours(a):
     ms, wall = timed(dev_step, a.steps)
     st_pipe = sess.stats()
     value = world * a.steps * n / (ms / 1e3)
+    verified_rows = verify_rows(torch, d_reqs[(a.steps - 1) % R], out, a.dim, SEED, "value arm")
 
     st = st_pipe
     ms_serial = ms
@@ -404,7 +438,8 @@ def run_ours(a):
     hits_per, miss_per = st.hits / a.steps, st.misses / a.steps
     # algorithmic bytes of one probe+gather launch: key read + row read + row write for a hit; key read +
     # default-row write for a miss (its row arrives later through the merge kernel)
-    alg_bytes = hits_per * (8 + 8 * a.dim) + miss_per * (8 + 4 * a.dim)
+    # (a miss costs this kernel its 8-B key read only; its row is delivered by the pull kernel)
+    alg_bytes = hits_per * (8 + 8 * a.dim) + miss_per * 8
     achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:
@@ -418,7 +453,30 @@ def run_ours(a):
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
                 "traffic_source": traffic_src, "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": probe_ms / (ms_serial / a.steps), "serial_ms_per_step": ms_serial / a.steps,
+                "step_fraction_of_hbm_roofline": (n * (8 + 8 * a.dim) / (ms_serial / a.steps / 1e3) / 1e9) / peak_gbs,
+                "step_note": "whole step: keys x 1032 algorithmic bytes / step time, against the HBM peak; the step is bound by the "
+                             "host link (roofline_host_link), the probes run beside the pulls",
                 "note": "the HBM-bound kernel of the path; the rest of the step is the PCIe-bound miss kernel, see roofline_host_link"}
+    if a.value_only:
+        rng = np.random.default_rng(SEED + 77 + rank)
+        hot_now = hps.cache_keys("dcn", local, 0)
+        hit_reqs = [torch.from_numpy(hot_now[rng.integers(0, len(hot_now), size=n)]).cuda() for _ in range(4)]
+        for i in range(a.warmup):
+            sess.lookup_device_keys([hit_reqs[i % 4]], [out], [n])
+        sess.reset_stats()
+        ms_h, _ = timed(lambda i: sess.lookup_device_keys([hit_reqs[i % 4]], [out], [n]), a.steps)
+        st_h = sess.stats()
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / a.steps, "probe_ms": probe_ms, "probe_frac": achieved / peak_gbs,
+                              "pull_ms": st.pull_kernel_ms / a.steps, "miss_phase_ms": st.insert_kernel_ms / a.steps,
+                              "link_gbs": (st.h2d_bytes / a.steps) / (max(st.pull_kernel_ms, 1e-9) / a.steps / 1e3) / 1e9,
+                              "misses": miss_per, "chunks": a.chunks, "pull_ctas": a.pull_ctas, "verified_rows": verified_rows,
+                              "all_hit_kernel_ms": st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches),
+                              "all_hit_frac": (n * (8 + 8 * a.dim)) / (st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches) / 1e3) / 1e9 / peak_gbs,
+                              "all_hit_step_ms": ms_h / a.steps}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     ceiling = measure_random_gather_gbs(torch, hb, local, n, a.dim)
     roofline["random_gather_ceiling_gbs"] = ceiling
     roofline["frac_of_random_gather_ceiling"] = achieved / ceiling if ceiling > 0 else None
@@ -426,7 +484,7 @@ def run_ours(a):
                                 "measured in this run: what HBM3e delivers for random 512-B rows, vs `peak` = streaming copy")
     # the miss kernel is bound by the host link, not HBM: judge it against a pinned cudaMemcpyAsync measured here
     link_gbs = measure_host_link_gbs(torch)
-    pull_ms = st.insert_kernel_ms / a.steps
+    pull_ms = (st.pull_kernel_ms if st.pull_kernel_ms > 0 else st.insert_kernel_ms) / a.steps  # first pull start -> last pull end
     miss_bytes = (st.h2d_bytes - 0) / a.steps  # device-key arm: every H2D byte is a missed row crossing PCIe
     roofline_host_link = {"bound": "pcie", "kernel": "pull_misses" if a.miss_path == "direct" else "host gather + cudaMemcpyAsync + insert_merge",
                           "achieved": miss_bytes / (pull_ms / 1e3) / 1e9 if pull_ms > 0 else 0.0, "peak": link_gbs,
@@ -441,9 +499,11 @@ def run_ours(a):
     sess.reset_stats()
     ms_e, wall_e = timed(e2e_step, a.steps)
     st_e = sess.stats()
+    verified_e2e_session = verify_rows(torch, h_reqs[(a.steps - 1) % R].cuda(), out, a.dim, SEED, "e2e session arm")
     e2e_session = {"value": world * a.steps * n / (ms_e / 1e3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
                    "h2d_bytes_per_step": st_e.h2d_bytes / a.steps, "d2h_bytes_per_step": st_e.d2h_bytes / a.steps,
                    "hit_rate": st_e.hits / max(1, st_e.keys), "host_gather_ms_per_step": st_e.host_gather_ms / a.steps,
+                   "verified_rows": verified_e2e_session,
                    "call": "hpsx_session_lookup (host keys -> device vectors), CUDA events on the session stream"}
 
     # ---- end-to-end arm 2 (headline e2e): the reference-facing plugin call ------------------------------
@@ -471,7 +531,7 @@ def run_ours(a):
     ms_h, _ = timed(hit_step, a.steps)
     st_h = sess.stats()
     probe_h = st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches)
-    hit_alg = (st_h.hits * (8 + 8 * a.dim) + st_h.misses * (8 + 4 * a.dim)) / a.steps
+    hit_alg = (st_h.hits * (8 + 8 * a.dim) + st_h.misses * 8) / a.steps
     cache_hit = {"vectors_per_s": world * a.steps * n / (ms_h / 1e3), "ms_per_step": ms_h / a.steps,
                  "kernel_ms": probe_h, "hbm_gbs": hit_alg / (probe_h / 1e3) / 1e9 if probe_h > 0 else 0.0,
                  "hit_rate": st_h.hits / max(1, st_h.keys)}
@@ -566,7 +626,7 @@ def run_ours(a):
                          "small_request_ms_beside_large_stream": {"mean": float(np.mean(lat)) * 1e3 if lat else None,
                                                                   "p95": float(np.percentile(lat, 95)) * 1e3 if lat else None,
                                                                   "alone": alone * 1e3, "requests": len(lat)},
-                         "split_lock": os.environ.get("HPSX_SPLIT_LOCK", "1") != "0",
+                         "split_lock": True,
                          "note": "two lookup sessions (Triton model instances) of one model on one GPU sharing the HBM cache: shared "
                                  "lock for probes, lock-free PCIe pull, short exclusive insert; aggregate throughput stays PCIe-bound, "
                                  "the split keeps a small request from waiting behind another instance's 2 ms pull"}
@@ -660,7 +720,7 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
                    "gpucacheper": a.gpucacheper, "hit_rate_measured": st_pipe.hits / max(1, st_pipe.keys),
-                   "pipeline_chunks": int(os.environ.get("HPSX_PIPE_CHUNKS", "0")),
+                   "request_chunks": a.chunks or 4,
                    "unique_over_keys": float(len(np.unique(reqs[0])) / n),
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches per arm",
@@ -669,7 +729,7 @@ def run_ours(a):
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_session": e2e_session,
         "cache_hit": cache_hit, "small_batch": small_batch, "two_instances": two_instances, "dense_head": dense_head,
-        "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks,
+        "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks, "verified_rows": verified_rows,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,
                       "insert_phase_ms_per_step": st.insert_kernel_ms / a.steps,

@@ -39,6 +39,11 @@ class ModelParamsC(ctypes.Structure):
         ("embedding_cache_type", ctypes.c_int),
         ("cache_load_factor", ctypes.c_float),
         ("enable_pagelock", ctypes.c_int),
+        ("split_lock", ctypes.c_int),
+        ("request_chunks", ctypes.c_int),
+        ("pull_grid_ctas", ctypes.c_int),
+        ("probe_variant", ctypes.c_int),
+        ("probe_variant_set", ctypes.c_int),
     ]
 
 
@@ -67,6 +72,7 @@ class SessionStatsC(ctypes.Structure):
         ("probe_kernel_keys", ctypes.c_uint64),
         ("insert_kernel_ms", ctypes.c_double),
         ("host_gather_ms", ctypes.c_double),
+        ("pull_kernel_ms", ctypes.c_double),
     ]
 
 

@@ -45,6 +45,10 @@ struct hpsx_cache {
   // Probes (readers) run concurrently; a kernel that rewrites slots (insert) excludes them, so a
   // row is never copied while it is being replaced.
   std::shared_mutex rw;
+  // Direct pull: kernels read the page-locked host rows and their HBM index.  Lookups hold this shared for the whole
+  // call (also where they run outside `rw`), a database reload holds it exclusively while it rewrites rows,
+  // re-registers slabs and rebuilds the index.  Lock order: async_mu, pull_rw, rw.
+  std::shared_mutex pull_rw;
   // asynchronous insertion (hit_rate >= hit_rate_threshold): one workspace, jobs serialised
   std::mutex async_mu;
   std::condition_variable async_cv;
@@ -65,7 +69,12 @@ namespace hpsx {
 struct Model {
   ModelConfig cfg;
   float load_factor = 0.5f;
-  bool direct_pull = false;  // cfg.enable_pagelock (or HPSX_DIRECT_PULL=0/1)
+  bool direct_pull = false;  // cfg.enable_pagelock
+  // engine extensions of ps.json / hpsx_model_params (ps_config.hpp: hpsx_*)
+  bool split_lock = true;
+  int request_chunks = 4;
+  int pull_grid_ctas = 296;
+  int probe_variant = kProbeV8;
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
   std::vector<std::string> table_names;
@@ -90,14 +99,28 @@ struct hpsx_session {
   hpsx_cache* cache = nullptr;  // nullptr: CPU session
   int device = -1;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream_b = nullptr;     // pipelined direct pull: misses of chunk c are pulled while chunk c+1 is probed
-  std::vector<cudaEvent_t> ev_chunk;   // one per chunk: its probe (and miss count copy) has completed
+  cudaStream_t stream_b = nullptr;     // binned direct pull: misses of chunk c are pulled while chunk c+1 is probed
+  std::vector<cudaEvent_t> ev_chunk;   // untimed events of the binned pipeline: keys copied / probed / pulled, per group
   // bf16 mirror of the current lookup's output (hpsx_session_lookup_bf16_mirror): table index and device buffer
   size_t bf16_table = 0;
   void* bf16_out = nullptr;
   double miss_ratio = 1.0;             // running miss ratio of this session's lookups (predicts the next miss count)
-  int copy_chunks = 4;                 // host keys of a large request: H2D of chunk c+1 overlaps the probe of chunk c
-  int pipe_chunks = 0;                 // chunks of the opt-in pipelined direct pull (HPSX_PIPE_CHUNKS; < 2: off)
+  cudaStream_t stream_c = nullptr;     // key copies of the chunks of a request (copy engine)
+  cudaStream_t stream_d = nullptr;     // host-output requests: D2H of a chunk's rows while later chunks are served
+  // set by hpsx_session_lookup_ex around a lookup whose vectors go to HOST memory: per-table host destinations; the
+  // binned pipeline copies every chunk as soon as it is complete and sets host_out_done
+  float* const* host_out = nullptr;
+  bool host_out_done = false;
+  int request_chunks = 4;              // a request of >= kPipelineMinKeys keys is cut into this many chunks: the pull of
+                                       // chunk c (and the key copy of chunk c+1) overlaps the probe of chunk c+1
+  int pull_grid_ctas = 296;            // CTAs of the persistent binned pull kernel
+  // binned miss lists (MissBins) of the groups of one request
+  uint32_t* d_bin_count = nullptr;
+  uint32_t* h_bin_count = nullptr;     // pinned mirror
+  size_t bin_count_cap = 0;            // words
+  int64_t* d_bin_keys = nullptr;
+  uint32_t* d_bin_pos = nullptr;
+  size_t bin_entry_cap = 0;
   int probe_variant = hpsx::kProbeV8;  // falls back to the LDG.128 variant for rows that are not 32-B multiples
   int insert_mode = -1;
 
@@ -160,8 +183,9 @@ struct hpsx_shard_group {
 
   // control words (uint32 index into the arena)
   // [kCursor, kDone] are local scratch, zeroed with one memset per lookup
+  // [kSeen, kSeen + 16): after a flag-wait timeout, the last value read from every peer's flag cell (diagnosis)
   static constexpr uint32_t kCnt = 0, kFlagDispatch = 16, kFlagReturn = 32, kCursor = 48, kStatus = 64, kMissCount = 65,
-                            kDone = 66, kWords = 80;
+                            kDone = 66, kSeen = 67, kWords = 96;
   uint32_t* ctrl() const { return reinterpret_cast<uint32_t*>(arena); }
   ~hpsx_shard_group();
 };

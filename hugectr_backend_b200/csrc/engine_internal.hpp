@@ -58,7 +58,6 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
                      float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock, const MissBufs* mb = nullptr);
 int ensure_pool_stage(hpsx_session* s, size_t m);
 int ensure_sort_workspace(hpsx_session* s);
-bool pull_sort_enabled();
 size_t pull_sort_min();
 
 }  // namespace eng

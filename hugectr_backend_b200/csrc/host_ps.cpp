@@ -27,6 +27,10 @@ ThreadPool::ThreadPool(size_t num_threads) {
   if (num_threads == 0) num_threads = default_concurrency();
   // the caller of parallel_for is one of the lanes, so spawn one fewer
   for (size_t i = 1; i < num_threads; ++i) workers_.emplace_back([this] { worker_loop(); });
+  // A pool of one lane has no worker; post() must still not run its job on the poster's thread (the poster may
+  // hold locks the job needs: an asynchronous cache insertion posted from inside a lookup), so such a pool keeps
+  // one thread that serves jobs only.
+  if (workers_.empty()) job_thread_ = std::thread([this] { job_loop(); });
 }
 
 ThreadPool::~ThreadPool() {
@@ -36,6 +40,21 @@ ThreadPool::~ThreadPool() {
   }
   cv_.notify_all();
   for (auto& t : workers_) t.join();
+  if (job_thread_.joinable()) job_thread_.join();
+}
+
+void ThreadPool::job_loop() {
+  while (true) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [this] { return stop_ || !jobs_.empty(); });
+      if (jobs_.empty()) return;  // stop_ and drained
+      job = std::move(jobs_.front());
+      jobs_.pop_front();
+    }
+    job();
+  }
 }
 
 void ThreadPool::run_batch(const std::shared_ptr<Batch>& b) {
@@ -98,15 +117,11 @@ void ThreadPool::parallel_for(size_t num_tasks, const std::function<void(size_t)
 }
 
 void ThreadPool::post(std::function<void()> job) {
-  if (workers_.empty()) {
-    job();
-    return;
-  }
   {
     std::lock_guard<std::mutex> lk(mu_);
     jobs_.push_back(std::move(job));
   }
-  cv_.notify_one();
+  cv_.notify_all();  // workers and the job thread share the condition variable
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -116,6 +131,7 @@ HostTable::HostTable(size_t dim, float default_value, size_t num_partitions, siz
     : dim_(dim), default_value_(default_value) {
   if (dim == 0) throw std::invalid_argument("embedding vector size must be > 0");
   if (num_partitions == 0) num_partitions = 1;
+  requested_partitions_ = num_partitions;
   if (allocation_rate == 0) allocation_rate = 256ull << 20;
   const size_t row_bytes = dim * sizeof(float);
   size_t rows_per_slab = std::max<size_t>(1, allocation_rate / row_bytes);
@@ -147,7 +163,8 @@ bool HostTable::pagelock(std::string* err) {
     p.slab_device.resize(p.slabs.size(), nullptr);
     for (size_t i = 0; i < p.slabs.size(); ++i) {
       const size_t used_rows = std::min(rows_per_slab, p.rows_used - std::min(p.rows_used, i * rows_per_slab));
-      const size_t want = (used_rows * row_bytes + 4095) & ~static_cast<size_t>(4095);
+      // slabs are allocated in whole 4-KiB pages (alloc_row), so the rounded length never leaves the allocation
+      const size_t want = std::min(slab_bytes(), (used_rows * row_bytes + 4095) & ~static_cast<size_t>(4095));
       if (want == 0 || want <= p.locked_bytes[i]) continue;
       if (p.locked_bytes[i] != 0) {
         cudaHostUnregister(p.slabs[i]);
@@ -204,8 +221,7 @@ uint64_t HostTable::alloc_row(Partition& p) {
   const uint64_t row = p.rows_used++;
   if ((row >> slab_shift_) >= p.slabs.size()) {
     void* mem = nullptr;
-    const size_t bytes = (static_cast<size_t>(1) << slab_shift_) * dim_ * sizeof(float);
-    if (posix_memalign(&mem, 4096, bytes) != 0 || mem == nullptr) throw std::bad_alloc();
+    if (posix_memalign(&mem, 4096, slab_bytes()) != 0 || mem == nullptr) throw std::bad_alloc();
     p.slabs.push_back(static_cast<float*>(mem));
   }
   return row;
@@ -275,8 +291,24 @@ void HostTable::warm_keys(size_t count, std::vector<int64_t>& out) const {
   for (size_t i = 0; i < load_order_.size() && out.size() < count; ++i) out.push_back(load_order_[i]);
 }
 
+void HostTable::repartition_for(size_t expected_rows) {
+  // caller holds rw_ exclusively
+  if (partitions_sized_ || rows_.load(std::memory_order_relaxed) != 0) return;
+  partitions_sized_ = true;  // the first bulk load (or reserve) decides
+  const size_t bytes = expected_rows * dim_ * sizeof(float);
+  size_t want = std::max(requested_partitions_, (bytes + kPullWindowBytes - 1) / kPullWindowBytes);
+  want = std::min<size_t>(std::max<size_t>(want, 1), 4096);
+  if (want == parts_.size()) return;
+  parts_.clear();
+  for (size_t p = 0; p < want; ++p) {
+    parts_.emplace_back(new Partition());
+    parts_.back()->slots.assign(1024, Slot{kEmpty, 0});
+  }
+}
+
 void HostTable::reserve(size_t rows) {
   std::unique_lock<std::shared_mutex> lk(rw_);
+  repartition_for(rows);
   const size_t per_part = rows / parts_.size() + rows / (parts_.size() * 8) + 64;
   for (auto& pp : parts_) {
     Partition& p = *pp;
@@ -284,61 +316,99 @@ void HostTable::reserve(size_t rows) {
   }
 }
 
+template <typename KeyAt, typename Keep>
+void HostTable::group_by_partition(size_t n, const KeyAt& key_at, const Keep& keep, ThreadPool& pool,
+                                   std::vector<uint32_t>& order, std::vector<size_t>& offsets) const {
+  const size_t P = parts_.size();
+  const size_t tasks = std::max<size_t>(1, std::min(pool.size() * 2, (n + 65535) / 65536));
+  const size_t per = (n + tasks - 1) / tasks;
+  std::vector<size_t> counts(tasks * P, 0);
+  pool.parallel_for(tasks, [&](size_t t) {
+    size_t* c = counts.data() + t * P;
+    const size_t e = std::min(n, (t + 1) * per);
+    for (size_t i = t * per; i < e; ++i)
+      if (keep(i)) ++c[partition_of(mix64(static_cast<uint64_t>(key_at(i))))];
+  });
+  offsets.assign(P + 1, 0);
+  for (size_t p = 0; p < P; ++p) {
+    size_t run = offsets[p];
+    for (size_t t = 0; t < tasks; ++t) {
+      const size_t c = counts[t * P + p];
+      counts[t * P + p] = run;  // becomes the task's write cursor for this partition
+      run += c;
+    }
+    offsets[p + 1] = run;
+  }
+  order.resize(offsets[P]);
+  pool.parallel_for(tasks, [&](size_t t) {
+    size_t* c = counts.data() + t * P;
+    const size_t e = std::min(n, (t + 1) * per);
+    for (size_t i = t * per; i < e; ++i)
+      if (keep(i)) order[c[partition_of(mix64(static_cast<uint64_t>(key_at(i))))]++] = static_cast<uint32_t>(i);
+  });
+}
+
+// Bulk loads run in chunks of kLoadChunk keys: the chunk is grouped by partition in parallel, then one task per
+// partition (the maps are not concurrent) inserts its group.  Cost O(n) whatever the partition count.
+static constexpr size_t kLoadChunk = static_cast<size_t>(1) << 24;
+
 void HostTable::insert(const int64_t* keys, const float* vectors, size_t n, ThreadPool& pool) {
   std::unique_lock<std::shared_mutex> lk(rw_);
+  repartition_for(n);
   note_loaded(keys, n);
-  const size_t P = parts_.size();
-  // every partition task scans the whole batch and takes its own keys: no locks, no sorting
-  pool.parallel_for(P, [&](size_t p) {
-    Partition& part = *parts_[p];
-    for (size_t i = 0; i < n; ++i) {
-      const uint64_t h = mix64(static_cast<uint64_t>(keys[i]));
-      if (partition_of(h) != p) continue;
-      float* dst = upsert(part, keys[i], h);
-      std::memcpy(dst, vectors + i * dim_, dim_ * sizeof(float));
-    }
-  });
+  std::vector<uint32_t> order;
+  std::vector<size_t> offsets;
+  for (size_t base = 0; base < n; base += kLoadChunk) {
+    const size_t m = std::min(kLoadChunk, n - base);
+    const int64_t* k = keys + base;
+    group_by_partition(m, [&](size_t i) { return k[i]; }, [](size_t) { return true; }, pool, order, offsets);
+    pool.parallel_for(parts_.size(), [&](size_t p) {
+      Partition& part = *parts_[p];
+      for (size_t j = offsets[p]; j < offsets[p + 1]; ++j) {
+        const size_t i = order[j];
+        float* dst = upsert(part, k[i], mix64(static_cast<uint64_t>(k[i])));
+        std::memcpy(dst, vectors + (base + i) * dim_, dim_ * sizeof(float));
+      }
+    });
+  }
 }
 
 void HostTable::fill_procedural(size_t n, uint64_t seed, ThreadPool& pool, uint32_t shard,
                                 uint32_t num_shards) {
   std::unique_lock<std::shared_mutex> lk(rw_);
   const bool sharded = num_shards > 1;
+  const size_t mine = sharded ? n / num_shards + n / (8 * num_shards) : n;
+  repartition_for(mine);
   if (!sharded) procedural_rows_ = std::max(procedural_rows_, n);
   const size_t P = parts_.size();
   {
-    const size_t mine = sharded ? n / num_shards + n / (8 * num_shards) : n;
     const size_t per_part = mine / P + mine / (P * 8) + 64;
     for (auto& pp : parts_)
       while ((pp->count + per_part) * 2 > pp->slots.size()) grow(*pp);
   }
-  // pass 1 (one task per partition: the maps are not concurrent): claim a row for every key
-  std::vector<float*> dst(n, nullptr);
-  pool.parallel_for(P, [&](size_t p) {
-    Partition& part = *parts_[p];
-    for (size_t k = 0; k < n; ++k) {
-      const int64_t key = static_cast<int64_t>(k);
-      const uint64_t h = mix64(static_cast<uint64_t>(key));
-      if (partition_of(h) != p) continue;
-      if (sharded && owner_of(key, num_shards) != shard) continue;
-      dst[k] = upsert(part, key, h);
+  std::vector<uint32_t> order;
+  std::vector<size_t> offsets;
+  for (size_t base = 0; base < n; base += kLoadChunk) {
+    const size_t m = std::min(kLoadChunk, n - base);
+    auto key_at = [&](size_t i) { return static_cast<int64_t>(base + i); };
+    auto keep = [&](size_t i) { return !sharded || owner_of(key_at(i), num_shards) == shard; };
+    group_by_partition(m, key_at, keep, pool, order, offsets);
+    // one task per partition claims the rows of its keys and generates them in place
+    pool.parallel_for(P, [&](size_t p) {
+      Partition& part = *parts_[p];
+      for (size_t j = offsets[p]; j < offsets[p + 1]; ++j) {
+        const int64_t key = key_at(order[j]);
+        float* dst = upsert(part, key, mix64(static_cast<uint64_t>(key)));
+        for (size_t d = 0; d < dim_; ++d) dst[d] = synth_value(key, static_cast<uint32_t>(d), seed);
+      }
+    });
+    if (sharded) {
+      // model-parallel shard: only the keys this shard owns exist here; they are also the warm-up order
+      std::vector<uint32_t> kept(order);
+      std::sort(kept.begin(), kept.end());
+      for (uint32_t i : kept) load_order_.push_back(key_at(i));
     }
-  });
-  if (sharded) {
-    // model-parallel shard: only the keys this shard owns exist here; they are also the warm-up order
-    for (size_t k = 0; k < n; ++k)
-      if (dst[k] != nullptr) load_order_.push_back(static_cast<int64_t>(k));
   }
-  // pass 2 (all threads): generate the rows
-  constexpr size_t kRowsPerTask = 4096;
-  pool.parallel_for((n + kRowsPerTask - 1) / kRowsPerTask, [&](size_t task) {
-    const size_t e = std::min(n, (task + 1) * kRowsPerTask);
-    for (size_t k = task * kRowsPerTask; k < e; ++k) {
-      if (dst[k] == nullptr) continue;
-      for (size_t j = 0; j < dim_; ++j)
-        dst[k][j] = synth_value(static_cast<int64_t>(k), static_cast<uint32_t>(j), seed);
-    }
-  });
 }
 
 size_t HostTable::fetch_range(const int64_t* keys, size_t begin, size_t end, float* out,

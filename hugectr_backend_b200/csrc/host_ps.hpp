@@ -17,6 +17,8 @@
 #include <thread>
 #include <vector>
 
+#include "hpsx_common.h"
+
 namespace hpsx {
 
 // Fixed pool; size follows the reference (HCTR_DEFAULT_CONCURRENCY, else hardware_concurrency:
@@ -42,9 +44,11 @@ class ThreadPool {
     std::condition_variable cv;
   };
   void worker_loop();
+  void job_loop();
   static void run_batch(const std::shared_ptr<Batch>& b);
 
   std::vector<std::thread> workers_;
+  std::thread job_thread_;  // only when workers_ is empty: serves post()ed jobs
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<std::shared_ptr<Batch>> batches_;
@@ -75,13 +79,19 @@ class HostTable {
   // out[i*stride .. +dim) = row(keys[i]) or default.  Returns the number of absent keys.
   // Multi-threaded over key ranges; software-prefetched probe + row gather.
   size_t fetch(const int64_t* keys, size_t n, float* out, size_t stride, ThreadPool& pool) const;
-  // Single-threaded variant used from worker threads that already fan out themselves.
-  size_t fetch_range(const int64_t* keys, size_t begin, size_t end, float* out, size_t stride) const;
 
   // The first min(count, rows) keys in load order (cache warm-up, a9).
   void warm_keys(size_t count, std::vector<int64_t>& out) const;
-  // Pre-size the partition maps for `rows` more rows (avoids rehashing during bulk loads).
+  // Pre-size the partition maps for `rows` more rows (avoids rehashing during bulk loads).  On a still EMPTY table
+  // this also fixes the partition count: at least the configured `num_partitions`, and enough of them that one
+  // partition's rows fill at most kPullWindowBytes of host memory (see below).
   void reserve(size_t rows);
+
+  // Direct pull reads rows over PCIe at 39 GB/s when the rows in flight are spread over the whole table and at
+  // 51 GB/s when they stay inside a window of <= 256 MiB (tools/pcie_probe2.cu, profiles/pcie_probe2_r02.txt).
+  // A partition therefore doubles as a locality bin: its rows live in slabs of its own, partition_of(key) needs
+  // no memory access, and the probe kernel appends a missed key straight to its partition's miss list.
+  static constexpr size_t kPullWindowBytes = 192ull << 20;
 
   // enable_pagelock (reference key: src/backend.cpp:506-511): page-lock the used part of every value
   // slab and map it into the CUDA address space, so kernels can read rows straight from host DRAM
@@ -112,7 +122,15 @@ class HostTable {
   };
 
   static constexpr int64_t kEmpty = INT64_MIN;
-  size_t partition_of(uint64_t h) const { return ((h >> 32) * parts_.size()) >> 32; }
+  size_t partition_of(uint64_t h) const { return host_partition_of_hash(h, static_cast<uint32_t>(parts_.size())); }
+  // [begin, end) of `keys`, single-threaded; the caller holds rw_ (shared)
+  size_t fetch_range(const int64_t* keys, size_t begin, size_t end, float* out, size_t stride) const;
+  // Only while the table is empty: partition count for a table of `expected_rows` rows.
+  void repartition_for(size_t expected_rows);
+  // order[offsets[p] .. offsets[p+1]) = the indices i in [0, n) with keep(i) whose key_at(i) lives in partition p
+  template <typename KeyAt, typename Keep>
+  void group_by_partition(size_t n, const KeyAt& key_at, const Keep& keep, ThreadPool& pool, std::vector<uint32_t>& order,
+                          std::vector<size_t>& offsets) const;
   float* row_ptr(const Partition& p, uint64_t row) const {
     return p.slabs[row >> slab_shift_] + (row & slab_mask_) * dim_;
   }
@@ -125,10 +143,15 @@ class HostTable {
   const float* find(const Partition& p, int64_t key, uint64_t h) const;
   void grow(Partition& p);
   uint64_t alloc_row(Partition& p);
+  size_t slab_bytes() const {  // whole 4-KiB pages, so that a page-locked prefix never leaves the allocation
+    return ((static_cast<size_t>(1) << slab_shift_) * dim_ * sizeof(float) + 4095) & ~static_cast<size_t>(4095);
+  }
   void note_loaded(const int64_t* keys, size_t n);
 
   size_t dim_;
   float default_value_;
+  size_t requested_partitions_ = 1;
+  bool partitions_sized_ = false;
   std::vector<std::unique_ptr<Partition>> parts_;
   size_t slab_shift_;  // rows per slab = 1 << slab_shift_
   uint64_t slab_mask_;

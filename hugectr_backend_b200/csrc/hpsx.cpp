@@ -239,6 +239,7 @@ int sync_direct_pull_index(hpsx_cache* c, cudaStream_t stream) {
     c->tables[t].index = slots;
     c->tables[t].index_mask = cap - 1;
     c->tables[t].sentinel_row = ht.sentinel_row_device();
+    c->tables[t].host_parts = static_cast<uint32_t>(ht.num_partitions());
   }
   cudaFree(d_ikeys);
   cudaFree(d_iaddrs);
@@ -476,47 +477,11 @@ namespace hpsx {
 namespace eng {
 
 // Miss lists shorter than this are pulled in miss-list order: the resolve + radix sort costs ~70 us of launches,
-// more than the sorted order saves on a few thousand rows (HPSX_PULL_SORT_MIN overrides).
-size_t pull_sort_min() {
-  static const size_t v = [] {
-    const char* e = std::getenv("HPSX_PULL_SORT_MIN");
-    return e ? static_cast<size_t>(std::atoll(e)) : static_cast<size_t>(16384);
-  }();
-  return v;
-}
+// more than the sorted order saves on a few thousand rows.
+size_t pull_sort_min() { return 16384; }
 
 }  // namespace eng
 }  // namespace hpsx
-
-namespace {
-
-bool batch_merge_enabled() {
-  static const bool on = [] {
-    const char* e = std::getenv("HPSX_BATCH_MERGE");
-    return e == nullptr || e[0] != '0';  // measured: 0.245 -> 0.196 ms per batch-4096 request in a batch of 16
-  }();
-  return on;
-}
-
-}  // namespace
-
-namespace hpsx {
-namespace eng {
-
-bool pull_sort_enabled() {
-  static const bool on = [] {
-    const char* e = std::getenv("HPSX_PULL_SORT");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
-}
-
-}  // namespace eng
-}  // namespace hpsx
-
-namespace {
-
-}  // namespace
 
 namespace hpsx {
 namespace eng {
@@ -539,213 +504,323 @@ int ensure_sort_workspace(hpsx_session* s) {
 
 namespace {
 
-// Opt-in (HPSX_PIPE_CHUNKS >= 2) pipelined form of the direct-pull lookup for one large table slice: the request is
-// cut into chunks; stream A copies the keys of chunk c and probes it while stream B resolves, sorts and pulls the
-// misses of chunk c-1 over PCIe.  The pulls only write the output rows: the cache is left untouched until every
-// probe has finished, then the pulled rows are inserted from the output buffer (HBM to HBM).  The PCIe transfer,
-// which is ~80 % of the step, so starts after the first chunk's probe instead of after the whole probe, and the
-// key copy of later chunks hides behind it.  Caller holds c->rw exclusively.
-// HPSX_PIPE_CHUNKS (read when a session is created): chunks per request, 0 or 1 = no pipelining (default).
-// Measured on B200 (DCN step, 130 k misses): 4 chunks 2.27 ms vs 1.78 ms serial — every chunk pays its own
-// resolve + radix sort (~70 us) and host hand-off, the chunked address sort walks the host table four times, and
-// the probes take SM resources from the pull; the overlap it buys (0.3 ms) is smaller than what it costs.  Kept
-// opt-in as a measured negative.
-int pipeline_chunks_from_env() {
-  const char* e = std::getenv("HPSX_PIPE_CHUNKS");
-  const int v = e ? std::atoi(e) : 0;
-  return v < 0 ? 0 : std::min(v, static_cast<int>(kMaxBatchRequests));
-}
+// ------------------------------------------------------------------------------------------------
+// Binned direct pull: the miss path of enable_pagelock models with synchronous insertion.
+//
+//   stream A   [keys c0 ready] probe c0 | probe c1 | probe c2 | probe c3 | insert c0 .. c3 | counters D2H
+//   stream B                    wait c0: pull c0 | pull c1 | pull c2 | pull c3
+//   stream C   H2D keys c0 | c1 | c2 | c3          (host keys only; copy engine)
+//
+// A probe appends every miss to the list of its host-table partition (MissBins) and stores nothing for it; the
+// pull kernel of the chunk walks those lists bin by bin — the PCIe reads in flight stay inside one <= 256-MiB
+// window of host memory, which is what the host link rewards (51 vs 39 GB/s) — and writes the rows into the
+// output; it never touches the cache, so it runs beside the probes of the following chunks.  When all probes are
+// done the rows are inserted from the output buffer (HBM to HBM).  Nothing is sorted, no count crosses to the host
+// in between: the whole request is enqueued at once and the host waits exactly once.
+// A "group" = the probe launches that share one set of bins, one pull and one insert: one chunk of one table of a
+// plain request, or table t of ALL requests of a batch (positions then carry the request index in their high bits).
+// ------------------------------------------------------------------------------------------------
+struct BinGroup {
+  size_t table = 0;  // real table
+  size_t n = 0;      // keys probing into the group
+  MissBins bins;
+  size_t count_off = 0;       // first word of the group's counts in s->d_bin_count
+  float* out = nullptr;       // plain request: base of the table's output rows
+  size_t row_off = 0;         // plain request: the chunk covers rows [row_off, row_off + n) of virtual table v
+  size_t v = 0;
+  std::vector<float*> outs;   // batch: one base per request
+  void* out_bf16 = nullptr;
+};
 
-int gpu_lookup_direct_pipelined(hpsx_session* s, size_t t, const void* keys, bool keys_on_device, float* out, size_t n,
-                                uint32_t epoch) {
-  hpsx_cache* c = s->cache;
-  const DeviceTable& dt = c->tables[t];
-  const size_t dim = dt.dim;
-  const int K = s->pipe_chunks;
-  const size_t csz = ((n + K - 1) / K + 31) / 32 * 32;
-  if (!s->stream_b) HPSX_CU(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
-  while (s->ev_chunk.size() < static_cast<size_t>(K)) {
+struct ProbeLaunch {
+  size_t group = 0, v = 0;  // v = virtual table (request * T + table): timing events
+  const int64_t* keys = nullptr;  // this slice, host or device
+  size_t n = 0, stage_off = 0;
+  float* out = nullptr;  // where row 0 of this slice goes
+  uint32_t pos_base = 0;
+  void* out_bf16 = nullptr;
+  bool first_of_v = false, last_of_v = false;
+};
+
+int ensure_binned_workspace(hpsx_session* s, size_t count_words, size_t entries, size_t events) {
+  if (!s->stream_b) {
+    // the pull kernels are few CTAs that must get onto the SMs AHEAD of the thousands of queued probe CTAs of the next
+    // chunk (the link, not the SMs, is the scarce resource): highest stream priority
+    int lo = 0, hi = 0;
+    HPSX_CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HPSX_CU(cudaStreamCreateWithPriority(&s->stream_b, cudaStreamNonBlocking, hi));
+  }
+  if (!s->stream_c) HPSX_CU(cudaStreamCreateWithFlags(&s->stream_c, cudaStreamNonBlocking));
+  if (!s->stream_d) HPSX_CU(cudaStreamCreateWithFlags(&s->stream_d, cudaStreamNonBlocking));
+  if (count_words > s->bin_count_cap) {
+    if (s->d_bin_count) HPSX_CU(cudaFree(s->d_bin_count));
+    if (s->h_bin_count) HPSX_CU(cudaFreeHost(s->h_bin_count));
+    s->d_bin_count = nullptr;
+    s->h_bin_count = nullptr;
+    s->bin_count_cap = 0;
+    const size_t cap = count_words + count_words / 2 + 64;
+    HPSX_CU(cudaMalloc(&s->d_bin_count, cap * sizeof(uint32_t)));
+    HPSX_CU(cudaMallocHost(&s->h_bin_count, cap * sizeof(uint32_t)));
+    s->bin_count_cap = cap;
+  }
+  if (entries > s->bin_entry_cap) {
+    if (s->d_bin_keys) HPSX_CU(cudaFree(s->d_bin_keys));
+    if (s->d_bin_pos) HPSX_CU(cudaFree(s->d_bin_pos));
+    s->d_bin_keys = nullptr;
+    s->d_bin_pos = nullptr;
+    s->bin_entry_cap = 0;
+    const size_t cap = entries + entries / 8 + 1024;
+    HPSX_CU(cudaMalloc(&s->d_bin_keys, cap * sizeof(int64_t)));
+    HPSX_CU(cudaMalloc(&s->d_bin_pos, cap * sizeof(uint32_t)));
+    s->bin_entry_cap = cap;
+  }
+  while (s->ev_chunk.size() < events) {
     cudaEvent_t e;
     HPSX_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     s->ev_chunk.push_back(e);
   }
-  cudaStream_t A = s->stream, B = s->stream_b;
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * s->vt * sizeof(uint32_t), A));
-  // stream A: key copy + probe per chunk
-  for (int ci = 0; ci < K; ++ci) {
-    const size_t off = ci * csz;
-    if (off >= n) break;
-    const size_t nc = std::min(csz, n - off);
-    const int64_t* d_keys;
-    if (keys_on_device) {
-      d_keys = static_cast<const int64_t*>(keys) + off;
-    } else {
-      HPSX_CU(cudaMemcpyAsync(s->d_keys + off, static_cast<const int64_t*>(keys) + off, nc * sizeof(int64_t),
-                              cudaMemcpyHostToDevice, A));
-      s->stats.h2d_bytes += nc * sizeof(int64_t);
-      d_keys = s->d_keys + off;
-    }
-    HPSX_CU(cudaEventRecord(s->ev[2 * ci], A));
-    HPSX_CU(launch_probe_gather(dt, d_keys, nc, out + off * dim, epoch, !c->is_static, s->d_counters + ci,
-                                s->d_miss_pos + off, s->d_miss_keys + off, nullptr, s->probe_variant, A, nullptr,
-                                s->d_src ? s->d_src + off : nullptr));
-    HPSX_CU(cudaEventRecord(s->ev[2 * ci + 1], A));
-    HPSX_CU(cudaMemcpyAsync(s->h_counters + ci, s->d_counters + ci, sizeof(uint32_t), cudaMemcpyDeviceToHost, A));
-    HPSX_CU(cudaEventRecord(s->ev_chunk[ci], A));
-    ++s->stats.kernel_launches;
-  }
-  // stream B: as soon as the host knows a chunk's miss count, resolve + sort + pull it
-  uint64_t misses = 0;
-  bool first = true;
-  int last_chunk = -1;
-  for (int ci = 0; ci < K; ++ci) {
-    const size_t off = ci * csz;
-    if (off >= n) break;
-    last_chunk = ci;
-    const size_t nc = std::min(csz, n - off);
-    HPSX_CU(cudaEventSynchronize(s->ev_chunk[ci]));
-    const uint32_t m = s->h_counters[ci];
-    misses += m;
-    if (m == 0) continue;
-    HPSX_CU(cudaStreamWaitEvent(B, s->ev_chunk[ci], 0));
-    if (first) HPSX_CU(cudaEventRecord(s->ev_pull[0], B));
-    first = false;
-    HPSX_CU(launch_resolve_and_sort_misses(dt, s->d_miss_keys + off, m, s->d_addr[0] + off, s->d_sidx[0] + off,
-                                           s->d_addr[1] + off, s->d_sidx[1] + off, s->d_sort_temp, s->sort_temp_bytes, B));
-    HPSX_CU(launch_pull_misses(dt, s->d_miss_keys + off, s->d_miss_pos + off, s->d_counters + ci, nc, out + off * dim,
-                               nullptr, false, 1, 0.f, epoch, nullptr, s->d_counters + 2 * s->vt + ci,
-                               s->d_addr[1] + off, s->d_sidx[1] + off, m, B, 3));
-    s->stats.kernel_launches += 2;
-  }
-  if (!first) {
-    if (!c->is_static) {
-      // every probe is done (the host saw the last chunk's event): insert the pulled rows from the output buffer
-      HPSX_CU(cudaStreamWaitEvent(B, s->ev_chunk[last_chunk], 0));
-      for (int ci = 0; ci <= last_chunk; ++ci) {
-        const size_t off = ci * csz;
-        const uint32_t m = s->h_counters[ci];
-        if (m == 0) continue;
-        HPSX_CU(launch_insert_merge(dt, s->d_miss_keys + off, s->d_miss_pos + off, nullptr, m, out + off * dim, true,
-                                    epoch, s->d_counters + s->vt + ci, B));
-        ++s->stats.kernel_launches;
-      }
-    }
-    HPSX_CU(cudaEventRecord(s->ev_pull[1], B));
-    HPSX_CU(cudaMemcpyAsync(s->h_counters + 2 * s->vt, s->d_counters + 2 * s->vt, K * sizeof(uint32_t),
-                            cudaMemcpyDeviceToHost, B));
-    HPSX_CU(cudaStreamSynchronize(B));
-  }
-  HPSX_CU(cudaStreamSynchronize(A));
-  s->stats.d2h_bytes += 2 * K * sizeof(uint32_t);
-  for (int ci = 0; ci <= last_chunk; ++ci) account_probe_time(s, ci, std::min(csz, n - ci * csz));
-  // the probes of the chunks ran back to back: count them as ONE launch of the probe kernel over the request
-  if (last_chunk > 0) s->stats.probe_kernel_launches -= last_chunk;
-  uint64_t absent = 0;
-  if (!first) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[1]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
-    for (int ci = 0; ci <= last_chunk; ++ci) absent += s->h_counters[2 * s->vt + ci];
-  }
-  s->stats.hits += n - misses;
-  s->stats.misses += misses;
-  s->stats.h2d_bytes += (misses - absent) * dim * sizeof(float);
-  s->stats.default_filled += absent;
   return HPSX_OK;
 }
 
-// Batch of requests (virtual tables v = request * T + table) on the direct-pull path, synchronous insertion: the
-// probes of all requests that touch real table t append to ONE miss list (positions carry the request index in
-// their high bits), so every table needs one address sort and one pull launch for the whole batch instead of one
-// unsorted pull per request — small requests then get the sorted link rate too.  Caller holds c->rw exclusively.
-int gpu_lookup_direct_batch_merged(hpsx_session* s, const void* const* keys_v, bool keys_on_device, float* const* out_v,
-                                   const size_t* n_v, size_t num_v, uint32_t epoch) {
+// Is this request one the binned path serves?  (Everything else takes gpu_lookup_direct's general form.)
+bool binned_path_applies(const hpsx_session* s, const size_t* n_v, size_t num_v, const uint32_t* const* pos_per_table) {
+  const hpsx_cache* c = s->cache;
+  const size_t T = s->model->tables.size();
+  const bool always_sync = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
+  if (!always_sync || pos_per_table != nullptr) return false;
+  for (size_t t = 0; t < T; ++t)
+    if (c->tables[t].host_parts == 0 || c->tables[t].host_parts > 4096) return false;
+  if (num_v > T) {
+    if (num_v % T != 0 || num_v / T > static_cast<size_t>(kMaxBatchOuts) || s->bf16_out != nullptr) return false;
+    for (size_t v = 0; v < num_v; ++v)
+      if (n_v[v] >= (1ull << kShardPosBits)) return false;  // request-relative rows must fit below the request bits
+  }
+  for (size_t v = 0; v < num_v; ++v)
+    if (n_v[v] > 0xFFFFFFFFull) return false;
+  return true;
+}
+
+// Caller holds c->rw (exclusive, or shared when `split`) and c->pull_rw (shared).
+int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool keys_on_device, float* const* out_v,
+                             const size_t* n_v, size_t num_v, uint32_t epoch, bool split,
+                             std::shared_lock<std::shared_mutex>& rlock, std::unique_lock<std::shared_mutex>& wlock) {
   hpsx_cache* c = s->cache;
   const size_t T = s->model->tables.size();
-  const size_t R = num_v / T;
-  HPSX_CU(cudaMemsetAsync(s->d_counters, 0, 3 * s->vt * sizeof(uint32_t), s->stream));
-  // per real table: contiguous region of the miss list / sort workspace, sized by all requests' keys of that table
-  std::vector<size_t> tbase(T + 1, 0), tkeys(T, 0);
-  for (size_t t = 0; t < T; ++t) {
-    for (size_t r = 0; r < R; ++r) tkeys[t] += n_v[r * T + t];
-    tbase[t + 1] = tbase[t] + tkeys[t];
-  }
-  std::vector<size_t> koff(T, 0);  // running offset inside the table's region (also the staging offset of the keys)
-  for (size_t r = 0; r < R; ++r) {
+  const bool batch = num_v > T;
+  const size_t R = batch ? num_v / T : 1;
+  const double tr0 = now_ms();
+
+  // ---- plan: groups and probe launches
+  std::vector<BinGroup> groups;
+  std::vector<ProbeLaunch> launches;
+  size_t stage_off = 0;
+  if (batch) {
     for (size_t t = 0; t < T; ++t) {
-      const size_t v = r * T + t, n = n_v[v];
+      BinGroup g;
+      g.table = t;
+      g.outs.assign(R, nullptr);
+      for (size_t r = 0; r < R; ++r) {
+        const size_t v = r * T + t, n = n_v[v];
+        g.outs[r] = out_v[v];
+        if (n == 0) continue;
+        ProbeLaunch L;
+        L.group = groups.size();
+        L.v = v;
+        L.keys = static_cast<const int64_t*>(keys_v[v]);
+        L.n = n;
+        L.stage_off = stage_off;
+        L.out = out_v[v];
+        L.pos_base = static_cast<uint32_t>(r) << kShardPosBits;
+        L.first_of_v = L.last_of_v = true;
+        launches.push_back(L);
+        stage_off += n;
+        g.n += n;
+      }
+      if (g.n != 0) groups.push_back(std::move(g));
+    }
+  } else {
+    for (size_t v = 0; v < num_v; ++v) {
+      const size_t n = n_v[v];
       if (n == 0) continue;
-      const size_t at = tbase[t] + koff[t];
-      koff[t] += n;
-      const int64_t* d_keys;
-      if (keys_on_device) {
-        d_keys = static_cast<const int64_t*>(keys_v[v]);
-      } else {
-        HPSX_CU(cudaMemcpyAsync(s->d_keys + at, keys_v[v], n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
-        s->stats.h2d_bytes += n * sizeof(int64_t);
-        d_keys = s->d_keys + at;
+      const size_t dim = c->tables[v].dim;
+      const size_t K = n >= kPipelineMinKeys ? static_cast<size_t>(std::max(1, s->request_chunks)) : 1;
+      const size_t csz = ((n + K - 1) / K + 31) / 32 * 32;
+      for (size_t o = 0; o < n; o += csz) {
+        const size_t nc = std::min(csz, n - o);
+        BinGroup g;
+        g.table = v;
+        g.n = nc;
+        g.out = out_v[v];
+        g.row_off = o;
+        g.v = v;
+        g.out_bf16 = bf16_dst(s, v, 0, dim);
+        ProbeLaunch L;
+        L.group = groups.size();
+        L.v = v;
+        L.keys = static_cast<const int64_t*>(keys_v[v]) + o;
+        L.n = nc;
+        L.stage_off = stage_off;
+        L.out = out_v[v] + o * dim;
+        L.pos_base = static_cast<uint32_t>(o);
+        L.out_bf16 = bf16_dst(s, v, o, dim);
+        L.first_of_v = o == 0;
+        L.last_of_v = o + csz >= n;
+        launches.push_back(L);
+        groups.push_back(std::move(g));
+        stage_off += nc;
       }
-      HPSX_CU(cudaEventRecord(s->ev[2 * v], s->stream));
-      HPSX_CU(launch_probe_gather(c->tables[t], d_keys, n, out_v[v], epoch, !c->is_static, s->d_counters + t,
-                                  s->d_miss_pos + tbase[t], s->d_miss_keys + tbase[t], nullptr, s->probe_variant, s->stream,
-                                  nullptr, s->d_src ? s->d_src + at : nullptr, static_cast<uint32_t>(r) << kShardPosBits));
-      HPSX_CU(cudaEventRecord(s->ev[2 * v + 1], s->stream));
-      ++s->stats.kernel_launches;
     }
   }
-  HPSX_CU(cudaMemcpyAsync(s->h_counters, s->d_counters, T * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-  HPSX_CU(cudaStreamSynchronize(s->stream));
-  s->stats.d2h_bytes += T * sizeof(uint32_t);
-  for (size_t v = 0; v < num_v; ++v)
-    if (n_v[v] != 0) account_probe_time(s, v, n_v[v]);
-  bool any = false;
-  for (size_t t = 0; t < T; ++t) any = any || (tkeys[t] != 0 && s->h_counters[t] != 0);
-  if (any) {
-    NvtxRange miss_range("hpsx_direct_pull_misses");
-    std::vector<float*> outs(R, nullptr);
-    HPSX_CU(cudaEventRecord(s->ev_pull[0], s->stream));
-    for (size_t t = 0; t < T; ++t) {
-      const uint32_t m = tkeys[t] ? s->h_counters[t] : 0;
-      if (m == 0) continue;
-      const bool use_sorted = m >= std::max<size_t>(pull_sort_min(), 1);
-      if (use_sorted) {
-        HPSX_CU(launch_resolve_and_sort_misses(c->tables[t], s->d_miss_keys + tbase[t], m, s->d_addr[0] + tbase[t],
-                                               s->d_sidx[0] + tbase[t], s->d_addr[1] + tbase[t], s->d_sidx[1] + tbase[t],
-                                               s->d_sort_temp, s->sort_temp_bytes, s->stream));
-        ++s->stats.kernel_launches;
-      }
-      for (size_t r = 0; r < R; ++r) outs[r] = out_v[r * T + t];
-      HPSX_CU(launch_pull_misses(c->tables[t], s->d_miss_keys + tbase[t], s->d_miss_pos + tbase[t], s->d_counters + t,
-                                 tkeys[t], nullptr, nullptr, !c->is_static, 1, 0.f, epoch, s->d_counters + s->vt + t,
-                                 s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + tbase[t] : nullptr,
-                                 use_sorted ? s->d_sidx[1] + tbase[t] : nullptr, m, s->stream, 0, nullptr, nullptr,
-                                 outs.data(), static_cast<int>(R)));
+  const size_t G = groups.size();
+  if (G > s->vt) return fail(HPSX_ERR_INTERNAL, "binned lookup: more groups than counters");
+  size_t count_words = 0, entries = 0;
+  for (BinGroup& g : groups) {
+    const uint32_t P = c->tables[g.table].host_parts;
+    g.count_off = count_words;
+    count_words += P + 1;
+    g.bins.num_bins = P;
+    // uniform hashing keeps the bins within a few per cent of n/P; a bin that still overflows (one key repeated
+    // thousands of times) spills into the group's overflow list, which can take every key of the group
+    g.bins.bin_cap = static_cast<uint32_t>(g.n / P + g.n / (4 * P) + 256);
+    g.bins.spill_cap = static_cast<uint32_t>(g.n);
+    entries += static_cast<size_t>(P) * g.bins.bin_cap + g.bins.spill_cap;
+  }
+  {
+    const int rc = ensure_binned_workspace(s, count_words, entries, launches.size() + 2 * G + 2);
+    if (rc != HPSX_OK) return rc;
+  }
+  {
+    size_t e = 0;
+    for (BinGroup& g : groups) {
+      g.bins.count = s->d_bin_count + g.count_off;
+      g.bins.keys = s->d_bin_keys + e;
+      g.bins.pos = s->d_bin_pos + e;
+      e += static_cast<size_t>(g.bins.num_bins) * g.bins.bin_cap + g.bins.spill_cap;
+    }
+  }
+  cudaStream_t A = s->stream, B = s->stream_b, C = s->stream_c;
+  const bool host_out = s->host_out != nullptr && !batch;
+  cudaEvent_t* ev_keys = s->ev_chunk.data();
+  cudaEvent_t* ev_probe = ev_keys + launches.size();
+  cudaEvent_t* ev_pulled = ev_probe + G;
+  uint32_t* d_absent = s->d_counters + 2 * s->vt;
+  uint32_t* d_inserted = s->d_counters + s->vt;
+
+  // ---- enqueue
+  HPSX_CU(cudaMemsetAsync(s->d_bin_count, 0, count_words * sizeof(uint32_t), A));
+  HPSX_CU(cudaMemsetAsync(d_absent, 0, G * sizeof(uint32_t), A));
+  if (!keys_on_device) {
+    for (size_t i = 0; i < launches.size(); ++i) {
+      const ProbeLaunch& L = launches[i];
+      HPSX_CU(cudaMemcpyAsync(s->d_keys + L.stage_off, L.keys, L.n * sizeof(int64_t), cudaMemcpyHostToDevice, C));
+      HPSX_CU(cudaEventRecord(ev_keys[i], C));
+      s->stats.h2d_bytes += L.n * sizeof(int64_t);
+    }
+  }
+  size_t li = 0;
+  for (size_t g = 0; g < G; ++g) {
+    const BinGroup& grp = groups[g];
+    const DeviceTable& dt = c->tables[grp.table];
+    for (; li < launches.size() && launches[li].group == g; ++li) {
+      const ProbeLaunch& L = launches[li];
+      if (!keys_on_device) HPSX_CU(cudaStreamWaitEvent(A, ev_keys[li], 0));
+      if (L.first_of_v) HPSX_CU(cudaEventRecord(s->ev[2 * L.v], A));
+      HPSX_CU(launch_probe_gather(dt, keys_on_device ? L.keys : s->d_keys + L.stage_off, L.n, L.out, epoch, !c->is_static,
+                                  nullptr, nullptr, nullptr, nullptr, s->probe_variant, A, nullptr, L.pos_base, L.out_bf16,
+                                  &grp.bins, true));
+      if (L.last_of_v) HPSX_CU(cudaEventRecord(s->ev[2 * L.v + 1], A));
       ++s->stats.kernel_launches;
     }
-    HPSX_CU(cudaEventRecord(s->ev_pull[1], s->stream));
-    HPSX_CU(cudaMemcpyAsync(s->h_counters + 2 * s->vt, s->d_counters + 2 * s->vt, T * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                            s->stream));
-    HPSX_CU(cudaStreamSynchronize(s->stream));
-    s->stats.d2h_bytes += T * sizeof(uint32_t);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[1]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    HPSX_CU(cudaEventRecord(ev_probe[g], A));
+    HPSX_CU(cudaStreamWaitEvent(B, ev_probe[g], 0));
+    if (g == 0) HPSX_CU(cudaEventRecord(s->ev_pull[0], B));
+    HPSX_CU(launch_pull_binned(dt, grp.bins, grp.out, grp.out_bf16, batch ? grp.outs.data() : nullptr,
+                               batch ? static_cast<int>(R) : 0, d_absent + g, s->pull_grid_ctas, B));
+    HPSX_CU(cudaEventRecord(ev_pulled[g], B));
+    ++s->stats.kernel_launches;
+    if (host_out) {
+      // the chunk's rows are complete (hits by its probe, misses by its pull): start their trip to host memory now,
+      // on the other direction of the link, while the next chunks are probed and pulled
+      const size_t dim = dt.dim;
+      HPSX_CU(cudaStreamWaitEvent(s->stream_d, ev_pulled[g], 0));
+      HPSX_CU(cudaMemcpyAsync(s->host_out[grp.v] + grp.row_off * dim, grp.out + grp.row_off * dim, grp.n * dim * sizeof(float),
+                              cudaMemcpyDeviceToHost, s->stream_d));
+      s->stats.d2h_bytes += grp.n * dim * sizeof(float);
+    }
   }
-  for (size_t t = 0; t < T; ++t) {
-    if (tkeys[t] == 0) continue;
-    const uint32_t m = s->h_counters[t];
-    const uint32_t absent = any ? s->h_counters[2 * s->vt + t] : 0u;
-    s->stats.hits += tkeys[t] - m;
+  HPSX_CU(cudaEventRecord(s->ev_pull[2], B));
+  auto enqueue_inserts = [&]() -> int {
+    for (size_t g = 0; g < G; ++g) {
+      const BinGroup& grp = groups[g];
+      HPSX_CU(cudaStreamWaitEvent(A, ev_pulled[g], 0));
+      HPSX_CU(launch_insert_binned(c->tables[grp.table], grp.bins, grp.out, batch ? grp.outs.data() : nullptr,
+                                   batch ? static_cast<int>(R) : 0, epoch, d_inserted + g, A));
+      ++s->stats.kernel_launches;
+    }
+    return HPSX_OK;
+  };
+  if (!c->is_static && !split) {
+    const int rc = enqueue_inserts();
+    if (rc != HPSX_OK) return rc;
+  } else if (G > 0) {
+    HPSX_CU(cudaStreamWaitEvent(A, ev_pulled[G - 1], 0));
+  }
+  HPSX_CU(cudaEventRecord(s->ev_pull[1], A));
+  HPSX_CU(cudaMemcpyAsync(s->h_bin_count, s->d_bin_count, count_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, A));
+  HPSX_CU(cudaMemcpyAsync(s->h_counters + 2 * s->vt, d_absent, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, A));
+  HPSX_CU(cudaStreamSynchronize(A));
+  if (host_out) {
+    HPSX_CU(cudaStreamSynchronize(s->stream_d));
+    s->host_out_done = true;
+  }
+  s->stats.d2h_bytes += (count_words + G) * sizeof(uint32_t);
+  if (split && !c->is_static) {
+    // several instances share the cache: the probes and pulls above ran under the SHARED lock; the rows they
+    // brought are inserted in a short exclusive section
+    rlock.unlock();
+    wlock.lock();
+    const int rc = enqueue_inserts();
+    if (rc != HPSX_OK) return rc;
+    HPSX_CU(cudaStreamSynchronize(A));
+  }
+
+  // ---- account
+  for (const ProbeLaunch& L : launches)
+    if (L.last_of_v) account_probe_time(s, L.v, n_v[L.v]);
+  uint64_t total_keys = 0, total_miss = 0;
+  for (size_t g = 0; g < G; ++g) {
+    const BinGroup& grp = groups[g];
+    const uint32_t* cnt = s->h_bin_count + grp.count_off;
+    uint64_t m = std::min<uint32_t>(cnt[grp.bins.num_bins], grp.bins.spill_cap);
+    for (uint32_t b = 0; b < grp.bins.num_bins; ++b) m += std::min<uint32_t>(cnt[b], grp.bins.bin_cap);
+    const uint32_t absent = s->h_counters[2 * s->vt + g];
+    s->stats.hits += grp.n - m;
     s->stats.misses += m;
-    s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * s->model->tables[t]->dim() * sizeof(float);
+    s->stats.h2d_bytes += (m - absent) * c->tables[grp.table].dim * sizeof(float);  // rows pulled over PCIe by the kernel
     s->stats.default_filled += absent;
+    total_keys += grp.n;
+    total_miss += m;
   }
+  float ms = 0.f;
+  if (total_miss != 0) {
+    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[1]) == cudaSuccess) s->stats.insert_kernel_ms += ms;
+    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[2]) == cudaSuccess) s->stats.pull_kernel_ms += ms;
+  }
+  if (total_keys != 0)
+    s->miss_ratio = 0.5 * s->miss_ratio + 0.5 * static_cast<double>(total_miss) / static_cast<double>(total_keys);
+  if (trace_on())
+    std::fprintf(stderr, "[hpsx] binned lookup: %zu keys (%s), %zu group(s), %llu misses, host total %.3f ms\n", static_cast<size_t>(total_keys),
+                 keys_on_device ? "device" : "host", G, static_cast<unsigned long long>(total_miss), now_ms() - tr0);
   return HPSX_OK;
 }
 
-// Direct-pull lookup (enable_pagelock): probe+gather, then the misses are resolved ON THE GPU: their
-// rows are read straight from the page-locked host table over PCIe and inserted.  No CPU gather, no
-// staging copy.  With HPSX_PULL_SORT (default) the host reads the miss counts once, and the misses
-// are walked in ascending host-address order, which the host link rewards with ~1.5x the bandwidth;
-// with HPSX_PULL_SORT=0 the miss list never leaves the device and the host waits exactly once.
+// Direct-pull lookup (enable_pagelock): probe+gather, then the misses are resolved ON THE GPU: their rows are read
+// straight from the page-locked host table over PCIe.  No CPU gather, no staging copy.  Requests with synchronous
+// insertion (hit_rate_threshold >= 1, the samples' setting) take the binned pipeline above.  What remains here is
+// the general form: insertion mode decided per request from the hit rate (the miss rows may then have to stay the
+// default vector), and scattered delivery (`pos_per_table`, model-parallel return leg).  Large miss lists are
+// resolved to host addresses and radix-sorted by host page first; short ones are pulled in list order with the miss
+// count read on the device.
 int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool keys_on_device,
                       float* const* out_per_table, const size_t* n_per_table, size_t num_tables,
                       const uint32_t* const* pos_per_table) {
@@ -760,65 +835,47 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   for (size_t t = 0; t < num_tables; ++t)
     if (n_per_table[t] != 0 && (!keys_per_table[t] || !out_per_table[t]))
       return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer for table " + std::to_string(t));
+  // the pull kernels read the page-locked host rows and their HBM index: a database reload waits for them
+  std::shared_lock<std::shared_mutex> pull_lock(c->pull_rw);
+  std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
+  std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
+
+  if (binned_path_applies(s, n_per_table, num_tables, pos_per_table)) {
+    // The insert pass rewrites cache slots: exclusive unless the cache is static (never inserts).  When several
+    // instances share the cache (include/model_state.hpp:76-84) the call splits instead: probes and pulls under
+    // the SHARED lock, then a short exclusive section for the inserts — one instance's probes run beside
+    // another instance's pull.
+    const bool split = s->model->split_lock && !c->is_static && c->sessions.load(std::memory_order_relaxed) > 1;
+    if (c->is_static || split) rlock.lock(); else wlock.lock();
+    return gpu_lookup_direct_binned(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables, epoch, split,
+                                    rlock, wlock);
+  }
+
   // A small request whose predicted miss count (from this session's recent miss ratio) is below the sort threshold
   // would pull in miss-list order anyway: it then takes the device-driven form — probe and pull back to back, the
   // pull reads the miss count on the device, ONE host wait — instead of reading the count back first.
   const bool speculative = num_tables <= T && total < kPipelineMinKeys && pos_per_table == nullptr &&
                            s->miss_ratio * static_cast<double>(total) < static_cast<double>(pull_sort_min());
-  const bool sorted = pull_sort_enabled() && !speculative;
+  const bool sorted = !speculative;
   if (sorted) {
     const int rc = ensure_sort_workspace(s);
     if (rc != HPSX_OK) return rc;
   }
   const double tr0 = now_ms();
+  // the fused pull kernel rewrites cache slots: exclusive unless the cache is static
+  if (c->is_static) rlock.lock(); else wlock.lock();
 
-  // The fused pull kernel rewrites cache slots: exclusive unless the cache is static (never inserts).  When several
-  // instances share the cache (include/model_state.hpp:76-84) the call splits instead: probes under the SHARED lock,
-  // the PCIe pull (which then only writes the output) under no lock at all, and a short exclusive section that
-  // inserts the pulled rows from the output buffer — so one instance's probes run beside another instance's pull.
-  const bool always_sync_mode = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
-  static const bool split_allowed = [] {
-    const char* e = std::getenv("HPSX_SPLIT_LOCK");
-    return e == nullptr || e[0] != '0';
-  }();
-  const bool split = split_allowed && !c->is_static && sorted && always_sync_mode && pos_per_table == nullptr &&
-                     c->sessions.load(std::memory_order_relaxed) > 1;
-  std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
-  std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
-  if (c->is_static || split) rlock.lock(); else wlock.lock();
-
-  // one large slice, synchronous insertion, rows delivered in place: overlap the PCIe pull with the probes
-  {
-    size_t busy = 0, which = 0;
-    for (size_t t = 0; t < num_tables; ++t)
-      if (n_per_table[t] != 0) {
-        ++busy;
-        which = t;
-      }
-    const bool always_sync = s->insert_mode > 0 || (s->insert_mode < 0 && s->model->cfg.hit_rate_threshold >= 1.0f);
-    if (busy == 1 && sorted && always_sync && !split && pos_per_table == nullptr && s->bf16_out == nullptr && s->pipe_chunks >= 2 &&
-        n_per_table[which] >= kPipelineMinKeys)
-      return gpu_lookup_direct_pipelined(s, which % T, keys_per_table[which], keys_on_device, out_per_table[which],
-                                         n_per_table[which], epoch);
-  }
-  if (num_tables > T && num_tables % T == 0 && num_tables / T <= static_cast<size_t>(kMaxBatchOuts) && sorted &&
-      always_sync_mode && !split && pos_per_table == nullptr && s->bf16_out == nullptr && batch_merge_enabled()) {
-    bool fits = true;  // request-relative rows must fit below the request index bits
-    for (size_t v = 0; v < num_tables; ++v) fits = fits && n_per_table[v] < (1ull << kShardPosBits);
-    if (fits)
-      return gpu_lookup_direct_batch_merged(s, keys_per_table, keys_on_device, out_per_table, n_per_table, num_tables, epoch);
-  }
   HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
   HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
   std::vector<size_t> off(num_tables + 1, 0);
   auto pull = [&](size_t t, size_t m_hint) -> cudaError_t {
     const bool use_sorted = sorted && m_hint >= std::max<size_t>(pull_sort_min(), 1);
     return launch_pull_misses(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], s->d_counters + t,
-                              n_per_table[t], out_per_table[t], nullptr, !c->is_static && !split, s->insert_mode,
+                              n_per_table[t], out_per_table[t], nullptr, !c->is_static, s->insert_mode,
                               s->model->cfg.hit_rate_threshold, epoch, s->d_counters + s->vt + t,
                               s->d_counters + 2 * s->vt + t, use_sorted ? s->d_addr[1] + off[t] : nullptr,
                               use_sorted ? s->d_sidx[1] + off[t] : nullptr, m_hint, s->stream, 0,
-                              bf16_dst(s, t, 0, c->tables[t % T].dim), split ? s->d_miss_keys + off[t] : nullptr);
+                              bf16_dst(s, t, 0, c->tables[t % T].dim), nullptr);
   };
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t n = n_per_table[t];
@@ -826,46 +883,6 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     if (n == 0) continue;
     const int64_t* d_keys;
     const size_t dim = c->tables[t % T].dim;
-    if (!keys_on_device && n >= kPipelineMinKeys && s->copy_chunks >= 2 && pos_per_table == nullptr) {
-      // Large request with host keys: the copy engine moves the keys of chunk c+1 (second stream) while the SMs
-      // probe chunk c.  All chunks append to ONE miss list (request-relative positions), so the pull below is
-      // unchanged; the cache is only read here.
-      const size_t K = static_cast<size_t>(s->copy_chunks);
-      const size_t csz = ((n + K - 1) / K + 31) / 32 * 32;
-      if (!s->stream_b) HPSX_CU(cudaStreamCreateWithFlags(&s->stream_b, cudaStreamNonBlocking));
-      while (s->ev_chunk.size() < K) {
-        cudaEvent_t e;
-        HPSX_CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        s->ev_chunk.push_back(e);
-      }
-      const int64_t* h_keys = static_cast<const int64_t*>(keys_per_table[t]);
-      size_t nchunks = 0;
-      for (size_t o = 0; o < n; o += csz, ++nchunks) {
-        const size_t nc = std::min(csz, n - o);
-        HPSX_CU(cudaMemcpyAsync(s->d_keys + off[t] + o, h_keys + o, nc * sizeof(int64_t), cudaMemcpyHostToDevice,
-                                s->stream_b));
-        HPSX_CU(cudaEventRecord(s->ev_chunk[nchunks], s->stream_b));
-      }
-      s->stats.h2d_bytes += n * sizeof(int64_t);
-      HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
-      size_t ci = 0;
-      for (size_t o = 0; o < n; o += csz, ++ci) {
-        const size_t nc = std::min(csz, n - o);
-        HPSX_CU(cudaStreamWaitEvent(s->stream, s->ev_chunk[ci], 0));
-        HPSX_CU(launch_probe_gather(c->tables[t % T], s->d_keys + off[t] + o, nc, out_per_table[t] + o * dim, epoch,
-                                    !c->is_static, s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
-                                    nullptr, s->probe_variant, s->stream, nullptr, s->d_src ? s->d_src + off[t] + o : nullptr,
-                                    static_cast<uint32_t>(o), bf16_dst(s, t, o, dim)));
-        ++s->stats.kernel_launches;
-      }
-      HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
-      if (!sorted) {
-        HPSX_CU(pull(t, 0));
-        HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
-        ++s->stats.kernel_launches;
-      }
-      continue;
-    }
     if (keys_on_device) {
       d_keys = static_cast<const int64_t*>(keys_per_table[t]);
     } else {
@@ -877,8 +894,8 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
     HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                 s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t], nullptr,
-                                s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr,
-                                s->d_src ? s->d_src + off[t] : nullptr, 0, bf16_dst(s, t, 0, dim)));
+                                s->probe_variant, s->stream, pos_per_table ? pos_per_table[t] : nullptr, 0,
+                                bf16_dst(s, t, 0, dim)));
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
     ++s->stats.kernel_launches;
     if (!sorted) {
@@ -903,7 +920,6 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
         return HPSX_OK;
       }
     }
-    if (split) rlock.unlock();  // every probe has completed: nothing below reads the cache
     NvtxRange miss_range("hpsx_direct_pull_misses");
     for (size_t t = 0; t < num_tables; ++t) {
       const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
@@ -918,22 +934,6 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       HPSX_CU(pull(t, m));
       HPSX_CU(cudaEventRecord(s->ev_pull[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
-    }
-  }
-  if (split) {
-    // the pulls are done with the host link; insert what they brought, from the output rows, exclusively
-    bool any = false;
-    for (size_t t = 0; t < num_tables; ++t) any = any || (n_per_table[t] != 0 && s->h_counters[t] != 0);
-    if (any) {
-      HPSX_CU(cudaStreamSynchronize(s->stream));
-      wlock.lock();
-      for (size_t t = 0; t < num_tables; ++t) {
-        const uint32_t m = n_per_table[t] ? s->h_counters[t] : 0;
-        if (m == 0) continue;
-        HPSX_CU(launch_insert_merge(c->tables[t % T], s->d_miss_keys + off[t], s->d_miss_pos + off[t], nullptr, m,
-                                    out_per_table[t], true, epoch, s->d_counters + s->vt + t, s->stream));
-        ++s->stats.kernel_launches;
-      }
     }
   }
   HPSX_CU(cudaMemcpyAsync(s->h_counters + s->vt, s->d_counters + s->vt, 2 * s->vt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
@@ -1016,7 +1016,7 @@ int gpu_lookup(hpsx_session* s, const void* const* keys_per_table, bool keys_on_
       HPSX_CU(launch_probe_gather(c->tables[t % T], d_keys, n, out_per_table[t], epoch, !c->is_static,
                                   s->d_counters + t, s->d_miss_pos + off[t], s->d_miss_keys + off[t],
                                   s->hd_miss_keys + off[t], s->probe_variant, s->stream,
-                                  pos_per_table ? pos_per_table[t] : nullptr, s->d_src ? s->d_src + off[t] : nullptr, 0,
+                                  pos_per_table ? pos_per_table[t] : nullptr, 0,
                                   bf16_dst(s, t, 0, c->tables[t % T].dim)));
       HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
       ++s->stats.kernel_launches;
@@ -1106,6 +1106,8 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
   if (!keys || !d_pooled) return fail(HPSX_ERR_INVALID_ARG, "null key/vector pointer");
   if (!s->d_src) HPSX_CU(cudaMalloc(&s->d_src, s->cap_keys * sizeof(uint32_t)));
   const uint32_t epoch = c->epoch.fetch_add(1, std::memory_order_relaxed);
+  std::shared_lock<std::shared_mutex> pull_lock(c->pull_rw, std::defer_lock);
+  if (c->direct_pull) pull_lock.lock();  // the pull below reads the page-locked host rows and their HBM index
   HPSX_CU(cudaMemsetAsync(s->d_counters, 0, s->vt * sizeof(uint32_t), s->stream));
   const int64_t* d_keys = keys;
   uint32_t m = 0;
@@ -1139,7 +1141,7 @@ int gpu_lookup_pooled(hpsx_session* s, size_t table, const int64_t* keys, bool k
       if (c->direct_pull) {
         // rows pulled by the GPU straight from the page-locked host table into the stage
         HPSX_CU(cudaMemsetAsync(s->d_counters + 2 * s->vt, 0, s->vt * sizeof(uint32_t), s->stream));
-        const bool use_sorted = pull_sort_enabled();
+        const bool use_sorted = m >= pull_sort_min();
         if (use_sorted) {
           const int wrc = ensure_sort_workspace(s);
           if (wrc != HPSX_OK) return wrc;
@@ -1215,6 +1217,10 @@ hpsx_session::~hpsx_session() {
       cudaFree(d_sidx[i]);
     }
     cudaFree(d_sort_temp);
+    cudaFree(d_bin_count);
+    cudaFree(d_bin_keys);
+    cudaFree(d_bin_pos);
+    if (h_bin_count) cudaFreeHost(h_bin_count);
     cudaFree(d_result);
     cudaFree(d_pool_stage);
     if (h_counters) cudaFreeHost(h_counters);
@@ -1228,6 +1234,8 @@ hpsx_session::~hpsx_session() {
     for (cudaEvent_t e : ev_pull) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_chunk) cudaEventDestroy(e);
     if (stream_b) cudaStreamDestroy(stream_b);
+    if (stream_c) cudaStreamDestroy(stream_c);
+    if (stream_d) cudaStreamDestroy(stream_d);
     if (stream) cudaStreamDestroy(stream);
   }
 }
@@ -1308,7 +1316,10 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
   m->cfg = cfg;
   m->load_factor = load_factor > 0.f ? load_factor : 0.5f;
   m->direct_pull = cfg.enable_pagelock;
-  if (const char* env = std::getenv("HPSX_DIRECT_PULL")) m->direct_pull = env[0] == '1';
+  m->split_lock = cfg.hpsx_split_lock;
+  m->request_chunks = cfg.hpsx_request_chunks > 0 ? std::min<int>(cfg.hpsx_request_chunks, kMaxBatchRequests) : 4;
+  m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 296;
+  m->probe_variant = cfg.hpsx_probe == "ldg" ? kProbeLdg : cfg.hpsx_probe == "tma" ? kProbeTma : kProbeV8;
   for (size_t t = 0; t < T; ++t) {
     if (cfg.embedding_vecsize_per_table[t] == 0)
       return fail(HPSX_ERR_INVALID_ARG, "embedding_vecsize_per_table must be > 0");
@@ -1367,6 +1378,10 @@ int hpsx_ps_add_model(hpsx_ps* ps, const hpsx_model_params* p) {
   cfg.embedding_cache_type = p->embedding_cache_type == HPSX_CACHE_STATIC ? CacheType::Static
                                                                           : CacheType::Dynamic;
   cfg.enable_pagelock = p->enable_pagelock != 0;
+  cfg.hpsx_split_lock = p->split_lock >= 0;
+  cfg.hpsx_request_chunks = p->request_chunks;
+  cfg.hpsx_pull_grid_ctas = p->pull_grid_ctas;
+  cfg.hpsx_probe = p->probe_variant == kProbeLdg && p->probe_variant_set ? "ldg" : p->probe_variant == kProbeTma ? "tma" : "";
   return add_model_cfg(ps, cfg, p->cache_load_factor);
   HPSX_GUARD_END
 }
@@ -1478,6 +1493,11 @@ int hpsx_ps_get_model_params(hpsx_ps* ps, const char* model, hpsx_model_params* 
   out->embedding_cache_type = c.embedding_cache_type == CacheType::Static ? HPSX_CACHE_STATIC : HPSX_CACHE_DYNAMIC;
   out->cache_load_factor = m->load_factor;
   out->enable_pagelock = c.enable_pagelock ? 1 : 0;
+  out->split_lock = m->split_lock ? 0 : -1;
+  out->request_chunks = m->request_chunks;
+  out->pull_grid_ctas = m->pull_grid_ctas;
+  out->probe_variant = m->probe_variant;
+  out->probe_variant_set = 1;
   return HPSX_OK;
 }
 
@@ -1567,11 +1587,15 @@ int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model) {
     std::lock_guard<std::mutex> lk(m->mu);
     for (auto& kv : m->caches) caches.push_back(kv.second.get());
   }
-  // lock order everywhere: async_mu (workspace owner) before rw
+  // lock order everywhere: async_mu (workspace owner), then pull_rw, then rw
   std::vector<std::unique_lock<std::mutex>> held_ws;
   std::vector<std::unique_lock<std::shared_mutex>> held;
   for (hpsx_cache* c : caches)
     if (c->direct_pull) held_ws.emplace_back(c->async_mu);
+  // pull kernels of in-flight lookups read the page-locked rows and the HBM index (some of them outside c->rw:
+  // the split-lock form, static caches of shard groups): wait for them, keep new ones out
+  for (hpsx_cache* c : caches)
+    if (c->direct_pull) held.emplace_back(c->pull_rw);
   for (hpsx_cache* c : caches)
     if (c->direct_pull) held.emplace_back(c->rw);
   for (size_t t = 0; t < m->tables.size() && t < m->cfg.sparse_files.size(); ++t) {
@@ -1746,12 +1770,9 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
   s->cache = c;
   c->sessions.fetch_add(1, std::memory_order_relaxed);
   s->device = device;
-  if (const char* env = std::getenv("HPSX_PROBE"))
-    s->probe_variant = std::strcmp(env, "tma") == 0     ? kProbeTma
-                       : std::strcmp(env, "pipe") == 0  ? kProbePipe
-                       : std::strcmp(env, "split") == 0 ? kProbeSplit
-                       : std::strcmp(env, "ldg") == 0   ? kProbeLdg
-                                                        : kProbeV8;
+  s->probe_variant = m->probe_variant;
+  s->request_chunks = m->request_chunks;
+  s->pull_grid_ctas = m->pull_grid_ctas;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   HPSX_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
@@ -1775,9 +1796,6 @@ int hpsx_session_create(hpsx_ps* ps, const char* model, int device, hpsx_session
     HPSX_CU(cudaMalloc(&s->d_stage[b], stage_rows * s->max_dim * sizeof(float)));
     HPSX_CU(cudaEventCreateWithFlags(&s->stage_free[b], cudaEventDisableTiming));
   }
-  if (s->probe_variant == kProbeSplit) HPSX_CU(cudaMalloc(&s->d_src, cap * sizeof(uint32_t)));
-  s->pipe_chunks = pipeline_chunks_from_env();
-  if (const char* e = std::getenv("HPSX_COPY_CHUNKS")) s->copy_chunks = std::max(0, std::min(std::atoi(e), 64));
   HPSX_CU(cudaStreamSynchronize(s->stream));
   s->ev.resize(2 * s->vt);
   for (auto& e : s->ev) HPSX_CU(cudaEventCreate(&e));
@@ -1959,8 +1977,15 @@ int hpsx_session_lookup_ex(hpsx_session* s, const void* const* keys_per_table, i
     d_out[t] = s->d_result + off;
     off += num_keys_per_table[t] * s->model->tables[t]->dim();
   }
+  for (size_t t = 0; t < num_tables; ++t)
+    if (num_keys_per_table[t] != 0 && !vectors_per_table[t])
+      return fail(HPSX_ERR_INVALID_ARG, "null vector pointer for table " + std::to_string(t));
+  s->host_out = vectors_per_table;
+  s->host_out_done = false;
   rc = gpu_lookup(s, keys_per_table, keys_dev, d_out.data(), num_keys_per_table, num_tables);
+  s->host_out = nullptr;
   if (rc != HPSX_OK) return rc;
+  if (s->host_out_done) return HPSX_OK;  // the binned pipeline copied every chunk as it completed
   for (size_t t = 0; t < num_tables; ++t) {
     const size_t bytes = num_keys_per_table[t] * s->model->tables[t]->dim() * sizeof(float);
     if (bytes == 0) continue;
@@ -2176,15 +2201,8 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
 
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
-  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbePipe && variant != kProbeSplit && variant != kProbeV8)
+  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbeV8)
     return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
-  if (variant == kProbeSplit && s->cache && !s->d_src) {
-    // the split variant keeps one slot index per key between its two launches
-    DeviceGuard guard(s->device);
-    if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-    std::lock_guard<std::mutex> lk(s->mu);
-    HPSX_CU(cudaMalloc(&s->d_src, std::max<size_t>(s->cap_keys, 1) * sizeof(uint32_t)));
-  }
   s->probe_variant = variant;
   return HPSX_OK;
 }

@@ -59,6 +59,15 @@ HPSX_HD uint32_t bucket2_of(int64_t key, uint32_t num_buckets) {
   return static_cast<uint32_t>(((h >> 32) * static_cast<uint64_t>(num_buckets)) >> 32);
 }
 
+// Partition of the HOST table a key lives in (host_ps.hpp): high 32 hash bits, multiply-shift.  Shared with the
+// device because a partition doubles as the locality bin of the direct-pull miss lists.
+HPSX_HD uint32_t host_partition_of_hash(uint64_t h, uint32_t num_partitions) {
+  return static_cast<uint32_t>(((h >> 32) * static_cast<uint64_t>(num_partitions)) >> 32);
+}
+HPSX_HD uint32_t host_partition_of(int64_t key, uint32_t num_partitions) {
+  return host_partition_of_hash(mix64(static_cast<uint64_t>(key)), num_partitions);
+}
+
 // Owning shard of a key in the model-parallel mode: low 32 hash bits, so that the bucket index
 // (high bits) stays uniform inside one shard.
 HPSX_HD uint32_t owner_of(int64_t key, uint32_t num_shards) {

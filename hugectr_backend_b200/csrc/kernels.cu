@@ -43,16 +43,19 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
   uint32_t slot = kMissSlot;
   if (valid) slot = probe_bucket(a.buckets, a.num_buckets, key, a.epoch, a.touch != 0);
   const bool is_miss = valid && slot == kMissSlot;
-  unsigned miss_mask;
-  const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+  unsigned miss_mask = 0;
+  uint32_t miss_base = 0;
+  if (a.bins.count == nullptr) miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
 
   const VecT* __restrict__ vals = reinterpret_cast<const VecT*>(a.values);
   VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + (kScatter ? 0 : tile_base * V);
   const uint32_t dst = (kScatter && valid) ? a.pos[tile_base + lane] : static_cast<uint32_t>(tile_base + lane);
   const VecT defv = splat<VecT>(a.default_value);
   const uint32_t total = nk * V;
+  const bool skip = a.skip_miss_rows != 0;
   for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
     VecT buf[kUnroll];
+    bool live[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
       const uint32_t s = __shfl_sync(kFull, slot, kk);
       const uint32_t v = i - kk * V;
       buf[u] = defv;
+      live[u] = i < total && (s != kMissSlot || !skip);
       if (i < total && s != kMissSlot) buf[u] = ld_stream(vals + static_cast<size_t>(s) * V + v);
     }
 #pragma unroll
@@ -68,18 +72,22 @@ __global__ void __launch_bounds__(kBlock) probe_gather_ldg_kernel(const ProbeArg
       if (kScatter) {
         const uint32_t kk = min(i / V, 31u);
         const uint32_t d = __shfl_sync(kFull, dst, kk);
-        if (i < total) st_stream(outv + static_cast<size_t>(d) * V + (i - kk * V), buf[u]);
+        if (live[u]) st_stream(outv + static_cast<size_t>(d) * V + (i - kk * V), buf[u]);
       } else {
-        if (i < total) st_stream(outv + i, buf[u]);
+        if (live[u]) st_stream(outv + i, buf[u]);
       }
     }
   }
 
   if (is_miss) {
-    const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = kScatter ? dst : dst + a.pos_base;
-    a.miss_keys[r] = key;
-    if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
+    if (a.bins.count != nullptr) {
+      append_miss_binned(a.bins, key, kScatter ? dst : dst + a.pos_base);
+    } else {
+      const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
+      a.miss_pos[r] = kScatter ? dst : dst + a.pos_base;
+      a.miss_keys[r] = key;
+      if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
+    }
   }
 }
 
@@ -151,14 +159,13 @@ __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs
       bk = load_bucket_keys_keep(a.buckets, b);
       way = match_way(bk, key);
     }
-    if (way >= 0) {
-      if (a.touch) a.buckets[b].stamp[way] = a.epoch;
-      slot = b * kWays + static_cast<uint32_t>(way);
-    }
+    if (way >= 0) slot = b * kWays + static_cast<uint32_t>(way);
   }
   const bool is_miss = valid && slot == kMissSlot;
-  unsigned miss_mask;
-  const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+  unsigned miss_mask = 0;
+  uint32_t miss_base = 0;
+  if (a.bins.count == nullptr) miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
+  const bool skip = a.skip_miss_rows != 0;
 
   const Vec8* __restrict__ vals = reinterpret_cast<const Vec8*>(a.values);
   Vec8* __restrict__ outv = reinterpret_cast<Vec8*>(a.out) + tile_base * V;
@@ -168,111 +175,43 @@ __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs
   const uint32_t total = nk * V;
   for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
     Vec8 buf[kUnroll];
+    bool live[kUnroll];  // false: the row of a missed key that the pull kernel will deliver (nothing is stored here)
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
       const uint32_t kk = min(i / V, 31u);
       const uint32_t s = __shfl_sync(kFull, slot, kk);
       buf[u] = defv;
+      live[u] = i < total && (s != kMissSlot || !skip);
       if (i < total && s != kMissSlot) buf[u] = ld_stream256(vals + static_cast<size_t>(s) * V + (i - kk * V));
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
       const uint32_t i = i0 + u * 32u + lane;
-      if (i < total) st_stream256(outv + i, buf[u]);
+      if (live[u]) st_stream256(outv + i, buf[u]);
     }
     if (kMirror) {
       __nv_bfloat16* __restrict__ ob = a.out_bf16 + tile_base * static_cast<size_t>(V) * 8u;
 #pragma unroll
       for (int u = 0; u < kUnroll; ++u) {
         const uint32_t i = i0 + u * 32u + lane;
-        if (i < total) st_bf16x8(ob + static_cast<size_t>(i) * 8u, buf[u]);
+        if (live[u]) st_bf16x8(ob + static_cast<size_t>(i) * 8u, buf[u]);
       }
     }
   }
+  // LRU touch last: its read-compare-store chain (device_helpers.cuh touch_stamp) must not sit between the probe and
+  // the row loads of the tile
+  if (a.touch && valid && slot != kMissSlot) touch_stamp(&a.buckets[slot / kWays].stamp[slot % kWays], a.epoch);
   if (is_miss) {
-    const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-    a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
-    a.miss_keys[r] = key;
-    if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2 pipelined variant.  Persistent grid (a multiple of the SM count); a warp strides over tiles and
-// software-pipelines the dependent chain key -> bucket -> rows across tiles: while it copies the rows
-// of tile t, the bucket lines of tile t+1 and the keys of tile t+2 are already in flight, so the two
-// latency hops at the head of a tile no longer idle the warp.
-// ------------------------------------------------------------------------------------------------
-template <typename VecT, int kV, int kUnroll>
-__global__ void __launch_bounds__(kBlock) probe_gather_pipe_kernel(const ProbeArgs a) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const size_t warp_global = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
-  const size_t total_warps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
-  const size_t num_tiles = (a.n + 31) / 32;
-  if (warp_global >= num_tiles) return;
-  constexpr uint32_t V = static_cast<uint32_t>(kV);
-  const VecT* __restrict__ vals = reinterpret_cast<const VecT*>(a.values);
-  const VecT defv = splat<VecT>(a.default_value);
-
-  auto load_key = [&](size_t tile) -> int64_t {
-    const size_t i = tile * 32 + lane;
-    return (tile < num_tiles && i < a.n) ? __ldcs(reinterpret_cast<const long long*>(a.keys) + i) : kEmptyKey;
-  };
-
-  size_t tile = warp_global;
-  int64_t key_cur = load_key(tile);
-  int64_t key_nxt = load_key(tile + total_warps);
-  uint32_t b_cur = bucket_of(key_cur, a.num_buckets);
-  BucketKeys bk_cur = load_bucket_keys(a.buckets, b_cur);
-  for (; tile < num_tiles; tile += total_warps) {
-    // stage A (tile t+1): bucket lines, (tile t+2): keys — in flight during the copy below
-    const uint32_t b_nxt = bucket_of(key_nxt, a.num_buckets);
-    const BucketKeys bk_nxt = load_bucket_keys(a.buckets, b_nxt);
-    const int64_t key_nn = load_key(tile + 2 * total_warps);
-
-    // stage B (tile t): resolve slots, claim miss-list space
-    const size_t tile_base = tile * 32;
-    const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), a.n - tile_base));
-    const bool valid = lane < nk;
-    uint32_t slot = kMissSlot;
-    if (valid && key_cur != kEmptyKey)
-      slot = resolve_slot(a.buckets, a.num_buckets, key_cur, b_cur, bk_cur, a.epoch, a.touch != 0);
-    const bool is_miss = valid && slot == kMissSlot;
-    unsigned miss_mask;
-    const uint32_t miss_base = warp_claim_misses(is_miss, lane, a.miss_count, &miss_mask);
-
-    // stage C (tile t): cooperative row copy, kUnroll independent 16-B loads per lane in flight
-    VecT* __restrict__ outv = reinterpret_cast<VecT*>(a.out) + tile_base * V;
-    const uint32_t total = nk * V;
-#pragma unroll 1
-    for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
-      VecT buf[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = i0 + u * 32u + lane;
-        const uint32_t kk = min(i / V, 31u);
-        const uint32_t s = __shfl_sync(kFull, slot, kk);
-        const uint32_t v = i - kk * V;
-        buf[u] = defv;
-        if (i < total && s != kMissSlot) buf[u] = ld_stream(vals + static_cast<size_t>(s) * V + v);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t i = i0 + u * 32u + lane;
-        if (i < total) st_stream(outv + i, buf[u]);
-      }
-    }
-    if (is_miss) {
+    const uint32_t p = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
+    if (a.bins.count != nullptr) {
+      append_miss_binned(a.bins, key, p);
+    } else {
       const uint32_t r = miss_base + __popc(miss_mask & ((1u << lane) - 1u));
-      a.miss_pos[r] = static_cast<uint32_t>(tile_base + lane) + a.pos_base;
-      a.miss_keys[r] = key_cur;
-      if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key_cur;
+      a.miss_pos[r] = p;
+      a.miss_keys[r] = key;
+      if (a.miss_keys_host != nullptr) a.miss_keys_host[r] = key;
     }
-    key_cur = key_nxt;
-    key_nxt = key_nn;
-    b_cur = b_nxt;
-    bk_cur = bk_nxt;
   }
 }
 
@@ -854,6 +793,158 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Binned miss path: the probe kernels appended every miss to the list of its host-table partition;
+// the kernels below walk those lists bin by bin.  A CTA first builds the exclusive prefix of the (clamped) bin
+// counts in shared memory, then every warp takes flat entry indices warp, warp + nwarps, ... and maps them back to
+// (bin, j) by binary search — so the whole grid works on one or two neighbouring bins at any moment, which is what
+// keeps the PCIe reads in flight inside a <= 256-MiB window of host memory.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMaxBins = 4096;  // HostTable caps its partition count at this
+
+// prefix[b] = entries in bins [0, b), b in [0, nb]; nb = num_bins + 1 (the spill list is the last bin)
+__device__ __forceinline__ uint32_t build_bin_prefix(const MissBins& bins, uint32_t* prefix, uint32_t* warp_sums) {
+  const uint32_t nb = bins.num_bins + 1;
+  const uint32_t per = (nb + kBlock - 1) / kBlock;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t b0 = threadIdx.x * per;
+  uint32_t local = 0;
+  for (uint32_t b = b0; b < min(nb, b0 + per); ++b) {
+    const uint32_t c = __ldcg(bins.count + b);
+    local += b < bins.num_bins ? min(c, bins.bin_cap) : min(c, bins.spill_cap);
+  }
+  uint32_t incl = local;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t o = __shfl_up_sync(kFull, incl, off);
+    if (lane >= static_cast<uint32_t>(off)) incl += o;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t base = 0;
+  for (uint32_t w = 0; w < warp; ++w) base += warp_sums[w];
+  uint32_t run = base + incl - local;
+  for (uint32_t b = b0; b < min(nb, b0 + per); ++b) {
+    prefix[b] = run;
+    const uint32_t c = __ldcg(bins.count + b);
+    run += b < bins.num_bins ? min(c, bins.bin_cap) : min(c, bins.spill_cap);
+  }
+  if (threadIdx.x == kBlock - 1) prefix[nb] = base + incl;  // total (threads past nb contribute 0)
+  __syncthreads();
+  return prefix[nb];
+}
+
+// flat index -> slot of the entry in bins.keys / bins.pos
+__device__ __forceinline__ size_t bin_entry(const MissBins& bins, const uint32_t* prefix, uint32_t i) {
+  uint32_t lo = 0, hi = bins.num_bins + 1;  // find the last b with prefix[b] <= i
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (prefix[mid] <= i) lo = mid; else hi = mid;
+  }
+  return static_cast<size_t>(lo) * bins.bin_cap + (i - prefix[lo]);
+}
+
+struct PullBinnedArgs {
+  MissBins bins;
+  const IndexSlot* index;
+  uint64_t index_mask;
+  const float* sentinel_row;
+  uint32_t dim;
+  float default_value;
+  float* out;
+  __nv_bfloat16* out_bf16;
+  uint32_t* absent;
+  int batch;
+  float* batch_out[kMaxBatchOuts];
+};
+
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArgs a) {
+  __shared__ uint32_t prefix[kMaxBins + 2];
+  __shared__ uint32_t warp_sums[kBlock / 32];
+  const uint32_t total = build_bin_prefix(a.bins, prefix, warp_sums);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * kBlock) >> 5;
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  const VecT defv = splat<VecT>(a.default_value);
+  for (uint32_t i = warp; i < total; i += nwarps) {
+    const size_t r = bin_entry(a.bins, prefix, i);
+    const int64_t key = a.bins.keys[r];
+    const uint32_t p = a.bins.pos[r];
+    const float* row = key == kEmptyKey ? a.sentinel_row : index_find(a.index, a.index_mask, key, lane);
+    const VecT* src = reinterpret_cast<const VecT*>(row);
+    VecT* dst = a.batch ? reinterpret_cast<VecT*>(a.batch_out[p >> kShardPosBits]) +
+                              static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
+                        : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(p) * V;
+    // all PCIe reads of the row first (up to 4 per lane in flight), then the stores
+    for (uint32_t v0 = 0; v0 < V; v0 += 128u) {
+      VecT x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v = v0 + u * 32u + lane;
+        x[u] = defv;
+        if (src != nullptr && v < V) x[u] = src[v];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t v = v0 + u * 32u + lane;
+        if (v < V) {
+          st_stream(dst + v, x[u]);
+          if constexpr (sizeof(VecT) == 16) {
+            if (a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(p) * V + v) * 4u, x[u]);
+          }
+        }
+      }
+    }
+    if (lane == 0 && src == nullptr) {
+      atomicAdd(a.absent, 1u);
+      a.bins.keys[r] = kEmptyKey;  // the insert pass skips it
+    }
+  }
+}
+
+struct InsertBinnedArgs {
+  MissBins bins;
+  Bucket* buckets;
+  float* values;
+  uint32_t num_buckets;
+  uint32_t dim;
+  const float* out;
+  uint32_t epoch;
+  uint32_t* inserted;
+  int batch;
+  float* batch_out[kMaxBatchOuts];
+};
+
+template <typename VecT>
+__global__ void __launch_bounds__(kBlock) insert_binned_kernel(const InsertBinnedArgs a) {
+  __shared__ uint32_t prefix[kMaxBins + 2];
+  __shared__ uint32_t warp_sums[kBlock / 32];
+  const uint32_t total = build_bin_prefix(a.bins, prefix, warp_sums);
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+  const uint32_t nwarps = (gridDim.x * kBlock) >> 5;
+  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
+  for (uint32_t i = warp; i < total; i += nwarps) {
+    const size_t r = bin_entry(a.bins, prefix, i);
+    const int64_t key = a.bins.keys[r];
+    if (key == kEmptyKey) continue;  // not in the host table (or the key that is never cached)
+    const uint32_t p = a.bins.pos[r];
+    const VecT* src = a.batch ? reinterpret_cast<const VecT*>(a.batch_out[p >> kShardPosBits]) +
+                                    static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
+                              : reinterpret_cast<const VecT*>(a.out) + static_cast<size_t>(p) * V;
+    Claim claim{nullptr, nullptr};
+    const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+    if (slot != kMissSlot) {
+      VecT* dst = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
+      for (uint32_t v = lane; v < V; v += 32u) dst[v] = ld_stream(src + v);
+    }
+    release_claim(claim, lane);
+    if (lane == 0 && slot != kMissSlot && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // a8 pooled gather + reduce.  A group of `kGroup` lanes owns one bag; fp32 adds in ascending j.
 // ------------------------------------------------------------------------------------------------
 template <typename VecT, int kGroup>
@@ -1107,40 +1198,6 @@ __global__ void __launch_bounds__(kBlock) gather_rows_kernel(const float4* __res
   }
 }
 
-// Second half of the split probe/gather variant: out[i] = slab[src[i]], or the default vector when src[i]
-// carries kSrcMissBit.  No hashing and no dependent bucket hop in this kernel: it runs at the random-gather
-// ceiling, and the probe that feeds it (probe_index_kernel) only moves 76 B per key.
-template <int kV, int kUnroll>
-__global__ void __launch_bounds__(kBlock) gather_src_kernel(const float4* __restrict__ table,
-                                                            const uint32_t* __restrict__ src, size_t n,
-                                                            float default_value, float4* __restrict__ out) {
-  const uint32_t lane = threadIdx.x & 31u;
-  const size_t tile_base = ((static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5) * 32;
-  if (tile_base >= n) return;
-  const uint32_t nk = static_cast<uint32_t>(min(static_cast<size_t>(32), n - tile_base));
-  const uint32_t slot = lane < nk ? __ldcs(src + tile_base + lane) : kSrcMissBit;
-  constexpr uint32_t V = kV;
-  const float4 defv = make_float4(default_value, default_value, default_value, default_value);
-  float4* __restrict__ outv = out + tile_base * V;
-  const uint32_t total = nk * V;
-  for (uint32_t i0 = 0; i0 < total; i0 += 32u * kUnroll) {
-    float4 buf[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint32_t i = i0 + u * 32u + lane;
-      const uint32_t kk = min(i / V, 31u);
-      const uint32_t s = __shfl_sync(kFull, slot, kk);
-      buf[u] = defv;
-      if (i < total && (s & kSrcMissBit) == 0u) buf[u] = ld_stream(table + static_cast<size_t>(s) * V + (i - kk * V));
-    }
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const uint32_t i = i0 + u * 32u + lane;
-      if (i < total) st_stream(outv + i, buf[u]);
-    }
-  }
-}
-
 __global__ void __launch_bounds__(kBlock) synth_rows_kernel(const int64_t* __restrict__ keys, size_t n,
                                                             uint32_t dim, uint64_t seed, float* rows) {
   const size_t i = static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x;
@@ -1197,43 +1254,6 @@ cudaError_t launch_probe_ldg_vec(const ProbeArgs& a, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// HPSX_PIPE_CFG="<unroll>x<ctas_per_sm>" tunes the pipelined variant (defaults 8x4).
-template <typename VecT>
-cudaError_t launch_probe_pipe(const ProbeArgs& a, cudaStream_t stream) {
-  static int cfg_u = 0, cfg_c = 0;
-  if (cfg_u == 0) {
-    cfg_u = 8;
-    cfg_c = 4;
-    if (const char* env = getenv("HPSX_PIPE_CFG")) {
-      int u = 0, c = 0;
-      if (sscanf(env, "%dx%d", &u, &c) == 2 && (u == 4 || u == 8) && c > 0 && c <= 8) {
-        cfg_u = u;
-        cfg_c = c;
-      }
-    }
-  }
-  const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
-  const size_t num_tiles = (a.n + 31) / 32;
-  const unsigned grid = static_cast<unsigned>(
-      min(static_cast<size_t>(148 * cfg_c), (num_tiles * 32 + kBlock - 1) / kBlock));
-#define HPSX_PIPE(VV)                                                                   \
-  do {                                                                                  \
-    if (cfg_u == 4)                                                                     \
-      probe_gather_pipe_kernel<VecT, VV, 4><<<grid, kBlock, 0, stream>>>(a);            \
-    else                                                                                \
-      probe_gather_pipe_kernel<VecT, VV, 8><<<grid, kBlock, 0, stream>>>(a);            \
-    return cudaGetLastError();                                                          \
-  } while (0)
-  switch (V) {
-    case 32: HPSX_PIPE(32);
-    case 16: HPSX_PIPE(16);
-    case 8: HPSX_PIPE(8);
-    case 4: HPSX_PIPE(4);
-    default: return cudaErrorNotSupported;
-  }
-#undef HPSX_PIPE
-}
-
 template <int kWarps, int kStages>
 cudaError_t launch_probe_tma_cfg(const ProbeArgs& a, uint32_t tiles_per_warp, cudaStream_t stream) {
   const uint32_t row_bytes = a.dim * 4u;
@@ -1255,36 +1275,12 @@ cudaError_t launch_probe_tma_cfg(const ProbeArgs& a, uint32_t tiles_per_warp, cu
   return cudaGetLastError();
 }
 
-// HPSX_TMA_CFG="<warps>x<stages>x<tiles_per_warp>" selects the ring shape (tuning knob).
+// Ring shape: 4 warps x 3 stages x 8 tiles per warp (the best of the shapes measured in round 1); rows too large
+// for that ring fall back to 2 x 2, then to the LDG variant.
 cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
-  static int cfg_w = 0, cfg_s = 0, cfg_t = 0;
-  if (cfg_w == 0) {
-    cfg_w = 4;
-    cfg_s = 3;
-    cfg_t = 8;
-    if (const char* env = getenv("HPSX_TMA_CFG")) {
-      int w = 0, s = 0, t = 0;
-      if (sscanf(env, "%dx%dx%d", &w, &s, &t) == 3 && w > 0 && s > 1 && t > 0) {
-        cfg_w = w;
-        cfg_s = s;
-        cfg_t = t;
-      }
-    }
-  }
-  const uint32_t tpw = static_cast<uint32_t>(cfg_t);
   const uint32_t row_bytes = a.dim * 4u;
-  // rows too large for the configured ring fall back to fewer warps/stages, then to LDG
-  if (cfg_w == 8 && cfg_s == 3 && 8u * 3u * 32u * row_bytes <= 200u * 1024u)
-    return launch_probe_tma_cfg<8, 3>(a, tpw, stream);
-  if (cfg_w == 8 && cfg_s == 2 && 8u * 2u * 32u * row_bytes <= 200u * 1024u)
-    return launch_probe_tma_cfg<8, 2>(a, tpw, stream);
-  if (cfg_w == 6 && cfg_s == 2 && 6u * 2u * 32u * row_bytes <= 200u * 1024u)
-    return launch_probe_tma_cfg<6, 2>(a, tpw, stream);
-  if (cfg_w == 4 && cfg_s == 2) return launch_probe_tma_cfg<4, 2>(a, tpw, stream);
-  if (cfg_w == 2 && cfg_s == 3) return launch_probe_tma_cfg<2, 3>(a, tpw, stream);
-  if (cfg_w == 2 && cfg_s == 2) return launch_probe_tma_cfg<2, 2>(a, tpw, stream);
-  if (4u * 3u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<4, 3>(a, tpw, stream);
-  if (2u * 2u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<2, 2>(a, tpw, stream);
+  if (4u * 3u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<4, 3>(a, 8, stream);
+  if (2u * 2u * 32u * row_bytes <= 200u * 1024u) return launch_probe_tma_cfg<2, 2>(a, 8, stream);
   return cudaErrorNotSupported;
 }
 
@@ -1293,12 +1289,15 @@ cudaError_t launch_probe_tma(const ProbeArgs& a, cudaStream_t stream) {
 cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out,
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
-                                int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t* d_slot_scratch,
-                                uint32_t pos_base, void* d_out_bf16) {
+                                int variant, cudaStream_t stream, const uint32_t* d_pos, uint32_t pos_base,
+                                void* d_out_bf16, const MissBins* bins, bool skip_miss_rows) {
   if (n == 0) return cudaSuccess;
   ProbeArgs a{};
   a.pos_base = pos_base;
   a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
+  if (bins != nullptr) a.bins = *bins;
+  a.skip_miss_rows = skip_miss_rows ? 1 : 0;
+  if (bins != nullptr && variant == kProbeTma) variant = kProbeV8;  // the TMA variant only knows the flat miss list
   if (d_out_bf16 != nullptr) {
     // the bf16 mirror is written by the 256-bit kernel only
     if (d_pos != nullptr || t.dim % 8 != 0 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 15u) != 0 ||
@@ -1328,20 +1327,8 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
     if (vb == 8) return launch_probe_ldg_scatter<float2>(a, stream);
     return launch_probe_ldg_scatter<float>(a, stream);
   }
-  if (variant == kProbeSplit && vb == 16 && t.dim == 128 && d_slot_scratch != nullptr) {
-    a.src = d_slot_scratch;
-    probe_index_kernel<<<grid_for(n), kBlock, 0, stream>>>(a);
-    gather_src_kernel<32, 8><<<grid_for(n), kBlock, 0, stream>>>(reinterpret_cast<const float4*>(t.values), d_slot_scratch,
-                                                                  n, t.default_value, reinterpret_cast<float4*>(d_out));
-    return cudaGetLastError();
-  }
   if (variant == kProbeV8 && t.dim % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(t.values)) & 31u) == 0) {
-    static int unroll = 0;
-    if (unroll == 0) {
-      unroll = 4;
-      if (const char* env = getenv("HPSX_V8_UNROLL")) unroll = atoi(env) == 2 ? 2 : (atoi(env) == 8 ? 8 : 4);
-    }
     const unsigned grid = grid_for(n);
     if (a.out_bf16 != nullptr) {
       if (t.dim == 128)
@@ -1350,22 +1337,14 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
         probe_gather_v8_kernel<0, 2, true><<<grid, kBlock, 0, stream>>>(a);
       return cudaGetLastError();
     }
-    if (t.dim == 128 && unroll == 4)
+    if (t.dim == 128)
       probe_gather_v8_kernel<16, 4><<<grid, kBlock, 0, stream>>>(a);
-    else if (t.dim == 128 && unroll == 8)
-      probe_gather_v8_kernel<16, 8><<<grid, kBlock, 0, stream>>>(a);
-    else if (t.dim == 128)
-      probe_gather_v8_kernel<16, 2><<<grid, kBlock, 0, stream>>>(a);
     else
       probe_gather_v8_kernel<0, 2><<<grid, kBlock, 0, stream>>>(a);
     return cudaGetLastError();
   }
   if (variant == kProbeTma && vb == 16) {
     const cudaError_t e = launch_probe_tma(a, stream);
-    if (e != cudaErrorNotSupported) return e;
-  }
-  if (variant == kProbePipe && vb == 16) {
-    const cudaError_t e = launch_probe_pipe<float4>(a, stream);
     if (e != cudaErrorNotSupported) return e;
   }
   if (vb == 16) return launch_probe_ldg_vec<float4>(a, stream);
@@ -1482,20 +1461,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
   a.epoch = epoch;
   a.inserted = d_inserted;
   a.absent = d_absent;
-  // The miss count is only known on the device: a fixed grid of 4 CTAs per SM loops over the list.
-  // PCIe needs ~100 KB in flight (51 GB/s x ~2 us); 4736 warps x 512 B is far more than enough.
-  // tuning knobs: HPSX_PULL_CTAS (CTAs of 256 threads per SM), HPSX_PULL_LD (0 ld.global, 1 .nc.L1::no_allocate,
-  // 2 .cg), HPSX_PULL_ROWS (host rows in flight per warp: 1 or 2)
-  static int ctas_per_sm = 0, load_mode = 0, rows_per_warp = 1;
-  if (ctas_per_sm == 0) {
-    ctas_per_sm = 8;
-    if (const char* env = getenv("HPSX_PULL_CTAS")) {
-      const int v = atoi(env);
-      if (v >= 1 && v <= 32) ctas_per_sm = v;
-    }
-    if (const char* env = getenv("HPSX_PULL_LD")) load_mode = atoi(env);
-    if (const char* env = getenv("HPSX_PULL_ROWS")) rows_per_warp = atoi(env) == 2 ? 2 : 1;
-  }
+  // The miss count is only known on the device: a fixed grid of 8 CTAs per SM loops over the list.
+  // PCIe needs ~130 KB in flight (51 GB/s x ~2.5 us); 9472 warps x 512 B is far more than enough.
+  const int ctas_per_sm = 8, load_mode = 0, rows_per_warp = 1;
   a.load_mode = load_mode;
   const size_t warps_needed = m_hint > 0 ? m_hint : n_keys;
   const int ctas = max_ctas_per_sm > 0 ? std::min(max_ctas_per_sm, ctas_per_sm) : ctas_per_sm;
@@ -1538,6 +1506,104 @@ cudaError_t launch_resolve_and_sort_misses(const DeviceTable& t, const int64_t* 
   // 4-KiB page number and above: bits [12, 48) of the host virtual address
   return cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_addr_tmp, d_addr_sorted, d_idx_tmp, d_idx_sorted,
                                          static_cast<int>(m), 12, 48, stream);
+}
+
+cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
+                               float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
+                               cudaStream_t stream) {
+  if (t.index == nullptr || bins.count == nullptr || bins.num_bins == 0 || bins.num_bins > kMaxBins || d_absent == nullptr)
+    return cudaErrorInvalidValue;
+  if (batch_count < 0 || batch_count > kMaxBatchOuts || (batch_count > 0 && (batch_outs == nullptr || d_out_bf16 != nullptr)))
+    return cudaErrorInvalidValue;
+  PullBinnedArgs a{};
+  a.bins = bins;
+  a.index = t.index;
+  a.index_mask = t.index_mask;
+  a.sentinel_row = t.sentinel_row;
+  a.dim = t.dim;
+  a.default_value = t.default_value;
+  a.out = d_out;
+  a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
+  a.absent = d_absent;
+  a.batch = batch_count;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(d_out);
+  for (int r = 0; r < batch_count; ++r) {
+    a.batch_out[r] = batch_outs[r];
+    bits |= reinterpret_cast<uintptr_t>(batch_outs[r]);
+  }
+  // The miss count is only known on the device: a persistent grid walks the lists.  PCIe needs ~130 KB in flight
+  // (51 GB/s x ~2.5 us); one CTA per SM already keeps 1184 rows of 512 B in flight, two reach the full link rate
+  // with 16-B loads (profiles/pcie_probe2_r02.txt) and leave the SMs to the probes that run beside this kernel.
+  const unsigned grid = static_cast<unsigned>(std::max(1, std::min(grid_ctas, 148 * 8)));
+  const int vb = vec_bytes(t.dim, reinterpret_cast<const void*>(bits & 15u));
+  if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
+  // host rows: slabs are 4096-B aligned and rows dim*4 apart, so the row alignment is that of dim*4
+  if (vb == 16)
+    pull_binned_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 8)
+    pull_binned_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+  else
+    pull_binned_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_insert_binned(const DeviceTable& t, const MissBins& bins, const float* d_out,
+                                 float* const* batch_outs, int batch_count, uint32_t epoch, uint32_t* d_inserted,
+                                 cudaStream_t stream) {
+  if (bins.count == nullptr || bins.num_bins == 0 || bins.num_bins > kMaxBins) return cudaErrorInvalidValue;
+  if (batch_count < 0 || batch_count > kMaxBatchOuts || (batch_count > 0 && batch_outs == nullptr)) return cudaErrorInvalidValue;
+  InsertBinnedArgs a{};
+  a.bins = bins;
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.dim = t.dim;
+  a.out = d_out;
+  a.epoch = epoch;
+  a.inserted = d_inserted;
+  a.batch = batch_count;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(t.values);
+  for (int r = 0; r < batch_count; ++r) {
+    a.batch_out[r] = batch_outs[r];
+    bits |= reinterpret_cast<uintptr_t>(batch_outs[r]);
+  }
+  const unsigned grid = 148u * 8u;
+  const int vb = vec_bytes(t.dim, reinterpret_cast<const void*>(bits & 15u));
+  if (vb == 16)
+    insert_binned_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 8)
+    insert_binned_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+  else
+    insert_binned_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+namespace {
+template <typename K>
+void preload_one(K kernel, cudaError_t* e) {
+  cudaFuncAttributes a;
+  const cudaError_t r = cudaFuncGetAttributes(&a, reinterpret_cast<const void*>(kernel));
+  if (*e == cudaSuccess) *e = r;
+}
+}  // namespace
+
+cudaError_t preload_miss_path_kernels() {
+  cudaError_t e = cudaSuccess;
+  preload_one(insert_merge_kernel<float4>, &e);
+  preload_one(insert_merge_kernel<float2>, &e);
+  preload_one(insert_merge_kernel<float>, &e);
+  preload_one(pull_misses_kernel<float4, 2>, &e);
+  preload_one(pull_misses_kernel<float4, 1>, &e);
+  preload_one(pull_misses_kernel<float2, 1>, &e);
+  preload_one(pull_misses_kernel<float, 1>, &e);
+  preload_one(pull_binned_kernel<float4>, &e);
+  preload_one(pull_binned_kernel<float2>, &e);
+  preload_one(pull_binned_kernel<float>, &e);
+  preload_one(insert_binned_kernel<float4>, &e);
+  preload_one(insert_binned_kernel<float2>, &e);
+  preload_one(insert_binned_kernel<float>, &e);
+  preload_one(resolve_rows_kernel, &e);
+  return e;
 }
 
 cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t stream) {

@@ -19,17 +19,30 @@ struct DeviceTable {
   const IndexSlot* index = nullptr;  // [index_mask + 1]
   uint64_t index_mask = 0;
   const float* sentinel_row = nullptr;  // row of the key that doubles as the empty marker, if loaded
+  uint32_t host_parts = 1;              // partitions of the host table = bins of the miss lists
+};
+
+// Binned miss list of ONE probe launch sequence against one table (DESIGN.md §3 "Miss path").  Bin b < num_bins holds
+// the misses whose row lives in partition b of the host table — a window of <= 256 MiB of host memory, inside which
+// zero-copy PCIe reads run at the link's full rate; bin num_bins is the spill list for entries that found their bin
+// full.  Appended to by the probe kernels, consumed by launch_pull_binned / launch_insert_binned without any sort
+// and without the host learning a count in between.
+struct MissBins {
+  uint32_t* count = nullptr;  // [num_bins + 1], zeroed by the caller; count[b] may run past bin_cap (consumers clamp)
+  int64_t* keys = nullptr;    // [num_bins * bin_cap + spill_cap]
+  uint32_t* pos = nullptr;    // same layout: destination row (| request << kShardPosBits when requests are merged)
+  uint32_t num_bins = 0;      // partitions of the host table
+  uint32_t bin_cap = 0;
+  uint32_t spill_cap = 0;
 };
 
 constexpr uint32_t kMissSlot = 0xFFFFFFFFu;
 constexpr uint32_t kSrcMissBit = 0x80000000u;  // pooled path: src index refers to the miss stage
 
 enum ProbeVariant : int {
-  kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers
+  kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers (any row size)
   kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
-  kProbePipe = 2, // persistent grid, key -> bucket -> rows chain software-pipelined across tiles
-  kProbeV8 = 4,   // 256-bit row vectors with L2 evict_first, bucket keys kept in L2 (evict_last)
-  kProbeSplit = 3, // two launches: probe (slot per key, 76 B/key) then a hash-free gather at the random-gather ceiling
+  kProbeV8 = 4,   // default: 256-bit row vectors with L2 evict_first, bucket keys kept in L2 (evict_last)
 };
 
 // K2+K3+K6 fused: probe the cache for keys[0..n), copy hit rows to out[i*dim..),
@@ -42,7 +55,10 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
                                 uint32_t epoch, bool touch, uint32_t* d_miss_count,
                                 uint32_t* d_miss_pos, int64_t* d_miss_keys, int64_t* hd_miss_keys,
                                 int variant, cudaStream_t stream, const uint32_t* d_pos = nullptr,
-                                uint32_t* d_slot_scratch = nullptr, uint32_t pos_base = 0, void* d_out_bf16 = nullptr);
+                                uint32_t pos_base = 0, void* d_out_bf16 = nullptr, const MissBins* bins = nullptr,
+                                bool skip_miss_rows = false);
+// `bins` (nullable): misses are appended to the binned lists (d_miss_count / d_miss_pos / d_miss_keys are unused);
+// with `skip_miss_rows` the kernel stores nothing for a missed key — launch_pull_binned writes that row.
 // `d_out_bf16` (nullable, 16-B aligned): a bf16 mirror of d_out in the same row order, written by the same kernel
 // (and by the miss kernels below), so the dense head reads bf16 activations without a conversion pass.
 // `pos_base`: this launch covers keys [pos_base, pos_base + n) of a larger request whose chunks share one miss
@@ -90,6 +106,21 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
 // that launch_insert_merge(d_stage = nullptr), which inserts the pulled rows from the output buffer, skips them.
 // max_ctas_per_sm > 0 caps the persistent grid so that other kernels (the probes of later request chunks) keep
 // SM resources while the pull waits on PCIe.
+
+// Binned pull (the default miss path with enable_pagelock and synchronous insertion): for every entry of `bins`,
+// walking the bins in ascending order so that the PCIe reads in flight stay inside one or two host-memory windows:
+// find the key in the HBM index of the page-locked host table, read its row over PCIe and store it to row `pos` of
+// `d_out` (of batch_outs[pos >> kShardPosBits] when requests are merged); a key that is not in the host table gets
+// the default vector, is counted in *d_absent and is replaced by kEmptyKey in the list.  The cache is NOT touched:
+// probes of later chunks of the request run beside this kernel.  Grid: `grid_ctas` CTAs, persistent.
+cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
+                               float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
+                               cudaStream_t stream);
+// Inserts the rows the binned pull delivered, reading them back from the output buffer (HBM to HBM); entries whose
+// key was replaced by kEmptyKey are skipped.  Caller excludes probes (they would copy rows while slots are rewritten).
+cudaError_t launch_insert_binned(const DeviceTable& t, const MissBins& bins, const float* d_out,
+                                 float* const* batch_outs, int batch_count, uint32_t epoch, uint32_t* d_inserted,
+                                 cudaStream_t stream);
 
 // Locality for the host link: random 512-B reads over a multi-GB pinned table run at ~32-42 GB/s, the same
 // reads in ascending address order at ~51 GB/s (tools/pcie_probe.cu: page-table / IOTLB reach).  So when the
@@ -161,7 +192,8 @@ cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, ui
                                      const uint32_t* d_cursor, const uint32_t* d_my_cnt, const uint32_t* d_my_flags,
                                      uint32_t capacity, uint32_t* d_status, unsigned long long timeout_ns,
                                      cudaStream_t stream, const uint32_t* d_skip_if_nonzero = nullptr,
-                                     uint32_t* d_done = nullptr);
+                                     uint32_t* d_done = nullptr, uint32_t* d_seen = nullptr);
+// d_seen (nullable, [kMaxPeers]): after a timeout, the last value read from every peer's flag cell.
 // d_skip_if_nonzero: the kernel does nothing when that word is non-zero (speculative return wave behind a gather
 // that may have recorded misses); d_done is set to 1 when the wave ran.
 // Step 3: probe the cache for every key in the local inbox and store the rows (or the default vector) into
@@ -176,6 +208,16 @@ cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& pe
 // Rows of resolved misses (d_stage[i]) to their requesters' outputs.
 cudaError_t launch_shard_scatter_stage(const float* d_stage, const uint32_t* d_miss_pos, size_t m, size_t dim,
                                        const ShardPeers& peers, uint32_t world, cudaStream_t stream);
+
+// CUDA loads a kernel lazily, at its first launch, and that load can stall until the kernels already running on the
+// device have finished.  A flag-wait kernel of the model-parallel exchange spins until ANOTHER stream's kernels have
+// published; if one of those is launched for the first time at that moment (two ranks of one process on one device:
+// tests/test_shard_group_gpu.py), the load waits for the spinner and the spinner for the load — until the timeout.
+// (Measured with tools/stream_alias_probe.cu: of 552 stream pairs only the very first, the one that loads the
+// setter kernel, is serialised; more hardware queues change nothing.)  These load every kernel a lookup of a
+// shard group can launch, on the current device; hpsx_shard_group_create calls them.
+cudaError_t preload_miss_path_kernels();  // kernels.cu
+cudaError_t preload_shard_kernels();      // shard_kernels.cu
 
 // Measurement primitive: out[i] = table[idx[i]] for 128-float rows (the random-gather ceiling the
 // probe+gather kernel is compared with in bench.py).

@@ -311,6 +311,14 @@ void parse_model(const json::Value& j, bool i64, ModelConfig* m) {
   need(j, "init_ec", &m->init_ec, false);
   need(j, "fp8_quant", &m->fp8_quant, false);
   need(j, "enable_pagelock", &m->enable_pagelock, false);
+  // engine extensions
+  need(j, "hpsx_split_lock", &m->hpsx_split_lock, false);
+  need(j, "hpsx_request_chunks", &m->hpsx_request_chunks, false);
+  need(j, "hpsx_pull_grid_ctas", &m->hpsx_pull_grid_ctas, false);
+  need(j, "hpsx_probe", &m->hpsx_probe, false);
+  m->hpsx_probe = lower(m->hpsx_probe);
+  if (!m->hpsx_probe.empty() && m->hpsx_probe != "v8" && m->hpsx_probe != "ldg" && m->hpsx_probe != "tma")
+    throw std::invalid_argument("The parameter 'hpsx_probe' of model '" + m->model_name + "' must be v8, ldg or tma.");
   need(j, "refresh_delay", &m->refresh_delay, false);
   need(j, "refresh_interval", &m->refresh_interval, false);
 

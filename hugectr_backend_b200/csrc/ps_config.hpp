@@ -79,6 +79,11 @@ struct ModelConfig {
   bool init_ec = true;
   bool fp8_quant = false;
   bool enable_pagelock = false;
+  // engine extensions (optional keys, not in the reference's surface): see include/hpsx.h hpsx_model_params
+  bool hpsx_split_lock = true;
+  int hpsx_request_chunks = 0;
+  int hpsx_pull_grid_ctas = 0;
+  std::string hpsx_probe;  // "", "v8", "ldg", "tma"
   // refresh knobs: carried for the Triton shell (model_state.cpp:312-335)
   float refresh_delay = 0.0f, refresh_interval = 0.0f;
 };

@@ -49,15 +49,18 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
   ++s->stats.lookups;
   s->stats.keys += n;
 
-  HPSX_CU(cudaMemsetAsync(ctrl + G::kCursor, 0, (G::kDone + 1 - G::kCursor) * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaMemsetAsync(ctrl + G::kCursor, 0, (G::kSeen + kMaxPeers - G::kCursor) * sizeof(uint32_t), s->stream));
   uint32_t m = 0, status = 0;
   bool returned = false;  // the speculative return wave ran on the device
+  // the miss path below may pull rows from the page-locked host table: keep a database reload out for the whole call
+  std::shared_lock<std::shared_mutex> pull_lock(c->pull_rw, std::defer_lock);
+  if (c->direct_pull) pull_lock.lock();
   {
     std::shared_lock<std::shared_mutex> rlock(c->rw);
     HPSX_CU(launch_shard_dispatch(d_keys, n, g->world, g->peers, ctrl + G::kCursor, s->stream));
     HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 0, ctrl + G::kCursor, ctrl + G::kCnt,
                                      ctrl + G::kFlagDispatch, static_cast<uint32_t>(std::min<size_t>(g->miss_cap, 0xFFFFFFFFu)),
-                                     d_status, g->timeout_ns, s->stream));
+                                     d_status, g->timeout_ns, s->stream, nullptr, nullptr, ctrl + G::kSeen));
     HPSX_CU(cudaEventRecord(s->ev[2 * t], s->stream));
     HPSX_CU(launch_probe_gather_inbox(dt, g->peers, g->world, g->rank, g->slot_cap,
                                       reinterpret_cast<const int64_t*>(g->arena + g->off_keys),
@@ -67,7 +70,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     HPSX_CU(cudaEventRecord(s->ev[2 * t + 1], s->stream));
     // return wave, speculatively: it runs only if the gather recorded no miss (else the host resolves them below)
     HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
-                                     d_status, g->timeout_ns, s->stream, d_miss_count, ctrl + G::kDone));
+                                     d_status, g->timeout_ns, s->stream, d_miss_count, ctrl + G::kDone, ctrl + G::kSeen));
     s->stats.kernel_launches += 4;
     HPSX_CU(cudaMemcpyAsync(g->h_ctrl, ctrl, G::kWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
@@ -106,7 +109,7 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
     if (rc == HPSX_OK && c->direct_pull) {
       if (!c->is_static) wlock.lock();
-      const bool use_sorted = pull_sort_enabled() && m <= s->cap_keys;
+      const bool use_sorted = m >= pull_sort_min() && m <= s->cap_keys;
       cudaError_t e = cudaMemsetAsync(s->d_counters + 2 * s->vt + t, 0, sizeof(uint32_t), s->stream);
       if (e == cudaSuccess && use_sorted) {
         rc = ensure_sort_workspace(s);
@@ -155,7 +158,8 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
     HPSX_CU(launch_shard_signal_wait(g->peers, g->world, seq, 1, ctrl + G::kCursor, ctrl + G::kCnt, ctrl + G::kFlagReturn, 0,
                                      d_status, wait_ns, s->stream));
     ++s->stats.kernel_launches;
-    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaMemcpyAsync(g->h_ctrl + G::kStatus, d_status, (G::kSeen + kMaxPeers - G::kStatus) * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, s->stream));
     HPSX_CU(cudaStreamSynchronize(s->stream));
     status |= g->h_ctrl[G::kStatus];
   }
@@ -165,7 +169,14 @@ int shard_lookup(hpsx_shard_group* g, const int64_t* d_keys, size_t n, float** d
                  g->rank, n, tr1 - tr0, m, tr2 - tr1, now_ms() - tr2);
   if (rc != HPSX_OK) return fail(rc, keep);
   if (status != 0) {
-    std::string why = (status & 2u) ? "a rank did not arrive before the timeout"
+    std::string seen;
+    if (status & 2u) {
+      // which peer was late, and by how much: its flag cell still held an older sequence number
+      seen = " (this rank is at sequence " + std::to_string(seq) + "; last flag seen per peer:";
+      for (uint32_t p = 0; p < g->world; ++p) seen += " " + std::to_string(g->h_ctrl[G::kSeen + p] >> 1);
+      seen += ")";
+    }
+    std::string why = (status & 2u) ? "a rank did not arrive before the timeout" + seen
                       : (status & 4u) ? "this rank received more keys than its miss list can hold"
                                       : "another rank of the group reported a failure";
     return fail(HPSX_ERR_INTERNAL, "model-parallel lookup failed: " + why);
@@ -228,9 +239,28 @@ int hpsx_shard_group_create(hpsx_session* s, size_t table, uint32_t rank, uint32
     HPSX_CU(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g->hd_miss_keys), g->h_miss_keys, 0));
   }
   HPSX_CU(cudaMallocHost(&g->h_ctrl, hpsx_shard_group::kWords * sizeof(uint32_t)));
-  if (const char* env = std::getenv("HPSX_SHARD_TIMEOUT_MS")) {
-    const long long v = std::atoll(env);
-    if (v > 0) g->timeout_ns = static_cast<unsigned long long>(v) * 1000000ull;
+  // Nothing a lookup launches may be loaded lazily while a peer's flag-wait kernel spins (kernels.h): load this
+  // library's kernels now, and run one tiny address sort so that the CUB kernels of the sorted pull are loaded too.
+  HPSX_CU(cudaMemsetAsync(g->ctrl() + hpsx_shard_group::kCursor, 0,
+                          (hpsx_shard_group::kSeen + kMaxPeers - hpsx_shard_group::kCursor) * sizeof(uint32_t), s->stream));
+  HPSX_CU(cudaStreamSynchronize(s->stream));  // the driver's own memset kernel of that size is loaded now, too
+  {
+    // the stream-ordered allocator behind the miss stage creates its pool at first use
+    const int prc = ensure_pool_stage(s, std::min<size_t>(cap, 4096));
+    if (prc != HPSX_OK) return prc;
+  }
+  HPSX_CU(preload_shard_kernels());
+  HPSX_CU(preload_miss_path_kernels());
+  if (s->cache->direct_pull) {
+    const int wrc = ensure_sort_workspace(s);
+    if (wrc != HPSX_OK) return wrc;
+    // CUB picks its kernels by problem size (one tile, or histogram + onesweep passes): sort once at each size
+    for (size_t m : {static_cast<size_t>(1), std::min<size_t>(cap, 1u << 16)}) {
+      HPSX_CU(cudaMemsetAsync(g->d_miss_keys, 0, m * sizeof(int64_t), s->stream));
+      HPSX_CU(launch_resolve_and_sort_misses(s->cache->tables[table], g->d_miss_keys, m, s->d_addr[0], s->d_sidx[0],
+                                             s->d_addr[1], s->d_sidx[1], s->d_sort_temp, s->sort_temp_bytes, s->stream));
+    }
+    HPSX_CU(cudaStreamSynchronize(s->stream));
   }
   g->peer_arena.assign(world, nullptr);
   g->peer_ipc.assign(world, false);

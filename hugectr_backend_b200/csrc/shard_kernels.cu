@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kBlock) shard_dispatch_kernel(const int64_t* _
 __global__ void shard_signal_wait_kernel(const ShardPeers peers, uint32_t world, uint32_t seq, int phase,
                                          const uint32_t* cursor, const uint32_t* my_cnt, const uint32_t* my_flags,
                                          uint32_t capacity, uint32_t* status, unsigned long long timeout_ns,
-                                         const uint32_t* skip_if_nonzero, uint32_t* done) {
+                                         const uint32_t* skip_if_nonzero, uint32_t* done, uint32_t* seen) {
   // speculative return wave: enqueued right behind the gather so that a request without misses needs no host
   // round trip in between; when the gather did record misses the host resolves them first and signals later
   if (skip_if_nonzero != nullptr && *reinterpret_cast<const volatile uint32_t*>(skip_if_nonzero) != 0u) return;
@@ -114,6 +114,7 @@ __global__ void shard_signal_wait_kernel(const ShardPeers peers, uint32_t world,
       __nanosleep(64);
     }
   }
+  if (active && timed_out && seen != nullptr) seen[p] = got;
   uint32_t bad = active ? (got & 1u) : 0u;
   uint32_t cnt = (active && phase == 0 && !timed_out) ? *reinterpret_cast<const volatile uint32_t*>(my_cnt + p) : 0u;
 #pragma unroll
@@ -257,6 +258,24 @@ __global__ void __launch_bounds__(kBlock) shard_scatter_stage_kernel(const float
 
 }  // namespace
 
+cudaError_t preload_shard_kernels() {
+  cudaError_t e = cudaSuccess;
+  auto one = [&e](const void* k) {
+    cudaFuncAttributes a;
+    const cudaError_t r = cudaFuncGetAttributes(&a, k);
+    if (e == cudaSuccess) e = r;
+  };
+  one(reinterpret_cast<const void*>(shard_dispatch_kernel));
+  one(reinterpret_cast<const void*>(shard_signal_wait_kernel));
+  one(reinterpret_cast<const void*>(probe_gather_inbox_kernel<float4, 32, 8, true>));
+  one(reinterpret_cast<const void*>(probe_gather_inbox_kernel<float4, 32, 8>));
+  one(reinterpret_cast<const void*>(probe_gather_inbox_kernel<float4, 0, 4>));
+  one(reinterpret_cast<const void*>(probe_gather_inbox_kernel<float, 0, 4>));
+  one(reinterpret_cast<const void*>(shard_scatter_stage_kernel<float4>));
+  one(reinterpret_cast<const void*>(shard_scatter_stage_kernel<float>));
+  return e;
+}
+
 cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t world, const ShardPeers& peers,
                                   uint32_t* d_cursor, cudaStream_t stream) {
   if (world == 0 || world > kMaxPeers) return cudaErrorInvalidValue;
@@ -269,10 +288,11 @@ cudaError_t launch_shard_dispatch(const int64_t* d_keys, size_t n, uint32_t worl
 cudaError_t launch_shard_signal_wait(const ShardPeers& peers, uint32_t world, uint32_t seq, int phase,
                                      const uint32_t* d_cursor, const uint32_t* d_my_cnt, const uint32_t* d_my_flags,
                                      uint32_t capacity, uint32_t* d_status, unsigned long long timeout_ns,
-                                     cudaStream_t stream, const uint32_t* d_skip_if_nonzero, uint32_t* d_done) {
+                                     cudaStream_t stream, const uint32_t* d_skip_if_nonzero, uint32_t* d_done,
+                                     uint32_t* d_seen) {
   if (world == 0 || world > kMaxPeers) return cudaErrorInvalidValue;
   shard_signal_wait_kernel<<<1, 32, 0, stream>>>(peers, world, seq, phase, d_cursor, d_my_cnt, d_my_flags, capacity,
-                                                 d_status, timeout_ns, d_skip_if_nonzero, d_done);
+                                                 d_status, timeout_ns, d_skip_if_nonzero, d_done, d_seen);
   return cudaGetLastError();
 }
 
@@ -304,22 +324,14 @@ cudaError_t launch_probe_gather_inbox(const DeviceTable& t, const ShardPeers& pe
   a.miss_keys_host = hd_miss_keys;
   // the received count is only known on the device: the grid is sized for an even split of the request
   const size_t tiles = (std::max<size_t>(expected_keys, 32) + 31) / 32 + world;
-  static int ctas_per_sm = -1;
-  if (ctas_per_sm < 0) {
-    // measured (profiles/): one tile per warp + 3 % slack beats a persistent grid of 4-8 CTAs/SM by ~10 %; under
-    // heavier skew the surplus tiles are picked up by the stride loop.  HPSX_INBOX_CTAS=<n> forces n CTAs per SM.
-    ctas_per_sm = 0;
-    if (const char* env = getenv("HPSX_INBOX_CTAS")) ctas_per_sm = atoi(env);
-  }
+  // measured (profiles/): one tile per warp + 3 % slack beats a persistent grid of 4-8 CTAs/SM by ~10 %; under
+  // heavier skew the surplus tiles are picked up by the stride loop
+  const int ctas_per_sm = 0;
   const size_t want = ((tiles + tiles / 32) * 32 + kBlock - 1) / kBlock;
   const unsigned grid = static_cast<unsigned>(ctas_per_sm > 0 ? std::min<size_t>(148 * ctas_per_sm, want) : want);
   bool aligned = ((reinterpret_cast<uintptr_t>(t.values) | (static_cast<uintptr_t>(t.dim) * 4u)) & 15u) == 0;
   for (uint32_t p = 0; p < world; ++p) aligned = aligned && (reinterpret_cast<uintptr_t>(peers.out[p]) & 15u) == 0;
-  static int stream_stores = -1;
-  if (stream_stores < 0) {
-    stream_stores = 1;  // st.global.cs: output rows are written once and not re-read by this kernel
-    if (const char* env = getenv("HPSX_INBOX_ST")) stream_stores = atoi(env);
-  }
+  const bool stream_stores = true;  // st.global.cs: output rows are written once and not re-read by this kernel
   if (aligned && t.dim == 128 && stream_stores)
     probe_gather_inbox_kernel<float4, 32, 8, true><<<grid, kBlock, 0, stream>>>(a, peers);
   else if (aligned && t.dim == 128)

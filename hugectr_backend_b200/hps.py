@@ -34,6 +34,9 @@ def _addr(x) -> int:
     raise TypeError(f"cannot take the address of {type(x)!r}")
 
 
+PROBE_VARIANTS = {"ldg": 0, "tma": 1, "v8": 4}
+
+
 @dataclass
 class ModelParams:
     """~ ``HugeCTR::InferenceParams`` as filled from ps.json (hps_backend/src/backend.cpp:318-523)."""
@@ -51,6 +54,11 @@ class ModelParams:
     embedding_cache_type: str = "dynamic"
     cache_load_factor: float = 0.0
     enable_pagelock: bool = False
+    # engine extensions (include/hpsx.h hpsx_model_params)
+    split_lock: bool = True
+    request_chunks: int = 0
+    pull_grid_ctas: int = 0
+    probe_variant: Optional[str] = None  # "v8" (default), "ldg", "tma"
 
 
 @dataclass
@@ -69,6 +77,7 @@ class SessionStats:
     probe_kernel_keys: int
     insert_kernel_ms: float
     host_gather_ms: float
+    pull_kernel_ms: float = 0.0
 
 
 class HPS:
@@ -142,6 +151,11 @@ class HPS:
         c.embedding_cache_type = 1 if p.embedding_cache_type.lower() == "static" else 0
         c.cache_load_factor = p.cache_load_factor
         c.enable_pagelock = 1 if p.enable_pagelock else 0
+        c.split_lock = 0 if p.split_lock else -1
+        c.request_chunks = int(p.request_chunks)
+        c.pull_grid_ctas = int(p.pull_grid_ctas)
+        c.probe_variant_set = 0 if p.probe_variant is None else 1
+        c.probe_variant = PROBE_VARIANTS[p.probe_variant] if p.probe_variant is not None else 0
         N.check(self._L.hpsx_ps_add_model(self._h, ctypes.byref(c)))
         self._dims[p.model_name] = [int(v) for v in p.embedding_vecsize_per_table]
 
@@ -296,7 +310,7 @@ class LookupSession:
         N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
 
     def set_probe_variant(self, variant: str) -> None:
-        N.check(self._L.hpsx_session_set_probe_variant(self._h, {"ldg": 0, "tma": 1, "pipe": 2, "split": 3, "v8": 4}[variant]))
+        N.check(self._L.hpsx_session_set_probe_variant(self._h, PROBE_VARIANTS[variant]))
 
 
 class _DeviceRows:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HPSX_ABI_VERSION 3
+#define HPSX_ABI_VERSION 4
 
 typedef enum hpsx_status {
   HPSX_OK = 0,
@@ -77,6 +77,16 @@ typedef struct hpsx_model_params {
                                               kernels read the missing rows straight from host DRAM over
                                               PCIe through an HBM-resident key index ("direct pull"),
                                               instead of CPU gather + cudaMemcpyAsync */
+  /* further engine extensions; ps.json spells them "hpsx_split_lock", "hpsx_request_chunks",
+   * "hpsx_pull_grid_ctas", "hpsx_probe" (all optional) */
+  int split_lock;                          /* >= 0 (default): instances that share a cache probe and pull under a shared
+                                              lock and insert in a short exclusive section; < 0: whole-call exclusive lock */
+  int request_chunks;                      /* a direct-pull request of >= 2^18 keys is cut into this many chunks so that
+                                              the PCIe pull of chunk c overlaps the probe of chunk c+1; 0 -> 4 */
+  int pull_grid_ctas;                      /* CTAs (of 256 threads) of the persistent binned pull kernel; 0 -> 296 */
+  int probe_variant;                       /* probe+gather kernel, see hpsx_session_set_probe_variant; used when
+                                              probe_variant_set != 0, else the default (4) */
+  int probe_variant_set;
 } hpsx_model_params;
 
 /* ~ HugeCTR::VolatileDatabaseParams, hash_map / parallel_hash_map only (src/backend.cpp:129-216). */
@@ -101,8 +111,10 @@ typedef struct hpsx_session_stats {
   double probe_kernel_ms;      /* CUDA-event time of the probe+gather kernels (sum) */
   uint64_t probe_kernel_launches;
   uint64_t probe_kernel_keys;  /* keys those launches processed */
-  double insert_kernel_ms;     /* CUDA-event time of the merge+insert kernels (sum) */
+  double insert_kernel_ms;     /* CUDA-event time of the miss phase: first pull/merge kernel start to last insert end (sum) */
   double host_gather_ms;       /* wall time spent in the host parameter-server gather */
+  double pull_kernel_ms;       /* binned direct pull: first pull kernel start to last pull kernel end (sum); the pulls of a
+                                  chunked request run beside the probes of its later chunks */
 } hpsx_session_stats;
 
 /* ---------------------------------------------------------------------------------------------
@@ -319,11 +331,9 @@ int hpsx_session_reset_stats(hpsx_session* s);
 /* Force the insertion mode of subsequent lookups: <0 use hit_rate_threshold (default), 0 always
  * asynchronous (misses answered with the default vector), 1 always synchronous. */
 int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
-/* Select the probe+gather kernel (default 4): 4 = 256-bit row vectors with L2 evict_first and bucket keys kept in
- * L2 (rows must be multiples of 32 B, else 0 is used), 0 = LDG.128 register copies, 1 = bulk-async (TMA engine) row
- * staging through shared memory, 2 = persistent grid with the key->bucket->row chain software-pipelined
- * across tiles, 3 = two launches (probe to slot indices, then a hash-free row gather).  The environment variable
- * HPSX_PROBE=v8|ldg|tma|pipe|split sets the default. */
+/* Select the probe+gather kernel (default 4, or the model's "hpsx_probe"): 4 = 256-bit row vectors with L2
+ * evict_first and bucket keys kept in L2 (rows must be multiples of 32 B, else 0 is used), 0 = LDG.128 register
+ * copies (any row size), 1 = bulk-async (TMA engine) row staging through shared memory. */
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);

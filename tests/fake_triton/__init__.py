@@ -54,6 +54,7 @@ _SIGS = {
     "ft_request_input_append_buffer": (None, [_vp, _int, _vp, _u64, _int, _i64]),
     "ft_request_add_requested_output": (None, [_vp, _cp]),
     "ft_request_set_gpu_output": (None, [_vp, _vp, _u64, _i64]),
+    "ft_request_set_cpu_output": (None, [_vp, _vp, _u64, _int]),
     "ft_request_force_output_memory": (None, [_vp, _int]),
     "ft_request_fail_output_buffer": (None, [_vp, _int]),
     "ft_execute": (_int, [_vp, _vpp, _u32]),
@@ -152,6 +153,7 @@ class Instance:
         _check(self._L.ft_instance_create(model._h, name.encode(), kind, device, ctypes.byref(h)))
         self._h = h
         self.device = device
+        self._caller_cpu_out = False
 
     def close(self) -> None:
         if self._h:
@@ -167,6 +169,7 @@ class Instance:
 
     def _make_request(self, keys, numkeys, *, numkeys_shape=None, keys_shape=None, gpu_out=None, out_device=0,
                       key_buffers: int = 1, keys_device_ptr: Optional[int] = None, numkeys_device_ptr: Optional[int] = None,
+                      cpu_out=None, cpu_out_pinned: bool = False,
                       requested_output: Optional[str] = "OUTPUT0", force_output_memory: Optional[int] = None,
                       fail_output_buffer: bool = False, input_names=("KEYS", "NUMKEYS"), keys_dtype=TYPE_INT64,
                       numkeys_dtype=TYPE_INT32, request_id: str = "req", keep: Optional[list] = None):
@@ -199,6 +202,11 @@ class Instance:
             L.ft_request_add_requested_output(r, requested_output.encode())
         if gpu_out is not None:
             L.ft_request_set_gpu_output(r, gpu_out.data_ptr(), gpu_out.numel() * gpu_out.element_size(), out_device)
+        if cpu_out is not None:
+            # a caller-owned host buffer (torch CPU tensor, pinned or not) that the harness hands out for a CPU output
+            L.ft_request_set_cpu_output(r, cpu_out.data_ptr(), cpu_out.numel() * cpu_out.element_size(),
+                                        MEM_CPU_PINNED if cpu_out_pinned else MEM_CPU)
+            keep.append(cpu_out)
         if force_output_memory is not None:
             L.ft_request_force_output_memory(r, force_output_memory)
         if fail_output_buffer:
@@ -223,6 +231,8 @@ class Instance:
             assert dtype.value == TYPE_FP32
             if mt.value == MEM_GPU:
                 resp.device_ptr = buf.value
+            elif self._caller_cpu_out:
+                pass  # the rows are in the caller's own buffer: no copy
             elif nbytes.value:
                 resp.data = np.ctypeslib.as_array(ctypes.cast(buf, ctypes.POINTER(ctypes.c_float)),
                                                   shape=(nbytes.value // 4,)).copy()
@@ -237,6 +247,7 @@ class Instance:
     def infer_many(self, requests: Sequence[dict]) -> List[Response]:
         """One TRITONBACKEND_ModelInstanceExecute call carrying len(requests) requests."""
         keep: list = []
+        self._caller_cpu_out = any(kw.get("cpu_out") is not None for kw in requests)
         handles = [self._make_request(keep=keep, **kw) for kw in requests]
         arr = (ctypes.c_void_p * len(handles))(*handles)
         try:

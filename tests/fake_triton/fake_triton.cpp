@@ -115,6 +115,9 @@ struct TRITONBACKEND_Request {
   void* gpu_out = nullptr;
   uint64_t gpu_out_cap = 0;
   int64_t gpu_out_device = 0;
+  void* cpu_out = nullptr;  // caller-owned host buffer handed out when the output ends up in CPU memory
+  uint64_t cpu_out_cap = 0;
+  int cpu_out_mt = 0;       // TRITONSERVER_MEMORY_CPU or TRITONSERVER_MEMORY_CPU_PINNED, as the caller allocated it
   int force_output_memory = -1;  // -1: honour the backend's preference when possible
   bool fail_output_buffer = false;
 };
@@ -441,6 +444,12 @@ TRITONSERVER_Error* TRITONBACKEND_OutputBuffer(TRITONBACKEND_Output* o, void** b
     o->mt = TRITONSERVER_MEMORY_GPU;
     o->mt_id = req->gpu_out_device;
     o->owned = false;
+  } else if (req != nullptr && req->cpu_out != nullptr && buffer_byte_size <= req->cpu_out_cap) {
+    // Triton may override the preference: CPU memory, here a buffer of the caller (e.g. from the pinned pool)
+    o->buffer = req->cpu_out;
+    o->mt = static_cast<TRITONSERVER_MemoryType>(req->cpu_out_mt);
+    o->mt_id = 0;
+    o->owned = false;
   } else {
     // Triton may override the preference: CPU memory
     o->buffer = buffer_byte_size ? std::malloc(buffer_byte_size) : nullptr;
@@ -615,6 +624,11 @@ void ft_request_set_gpu_output(TRITONBACKEND_Request* r, void* d_ptr, uint64_t c
   r->gpu_out = d_ptr;
   r->gpu_out_cap = capacity;
   r->gpu_out_device = device;
+}
+void ft_request_set_cpu_output(TRITONBACKEND_Request* r, void* h_ptr, uint64_t capacity, int memory_type) {
+  r->cpu_out = h_ptr;
+  r->cpu_out_cap = capacity;
+  r->cpu_out_mt = memory_type;
 }
 void ft_request_force_output_memory(TRITONBACKEND_Request* r, int memory_type) { r->force_output_memory = memory_type; }
 void ft_request_fail_output_buffer(TRITONBACKEND_Request* r, int fail) { r->fail_output_buffer = fail != 0; }

@@ -96,12 +96,11 @@ def test_rejects_bad_shapes(cuda_device):
 
 
 @pytest.mark.parametrize("pagelock", [False, True])
-def test_bf16_mirror_is_the_rounded_fp32_output_and_feeds_the_head(cuda_device, pagelock, monkeypatch):
+def test_bf16_mirror_is_the_rounded_fp32_output_and_feeds_the_head(cuda_device, pagelock):
     """The lookup writes a bf16 copy of its rows from the same kernels (hits: probe+gather, misses: pull / merge):
     bit-exact round-to-nearest-even of the fp32 rows, in both miss paths, and the dense head gives the same logits
     from it as from the fp32 output (no conversion pass)."""
     torch = _torch()
-    monkeypatch.setenv("HPSX_DIRECT_PULL", "1" if pagelock else "0")
     slots, dim, batch, rows = 26, 128, 1500, 60_000
     n = batch * slots
     hps = hb.HPS(num_partitions=4)
