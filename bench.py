@@ -59,8 +59,9 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
     ap.add_argument("--variant", default="v8", choices=["ldg", "tma", "v8"])
     ap.add_argument("--chunks", type=int, default=0, help="request_chunks of the model (0: engine default 4)")
-    ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 296)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 370)")
     ap.add_argument("--value-only", action="store_true", help="device-resident arm only (kernel experiments)")
+    ap.add_argument("--debug-flags", type=int, default=0, help="hpsx_session_set_debug bits 0-1 for the timed arm (experiments)")
     ap.add_argument("--workload", default="dcn", choices=["dcn", "c4"],
                     help="dcn: BASELINE.json configs[1] (default, replicas over --gpus); c4: DLRM-shaped model-parallel table "
                          "(configs[3]): rows sharded over the GPUs by owner(key), global batch split over the ranks, 100 %% HBM-resident")
@@ -78,6 +79,10 @@ def parse_args():
     ap.add_argument("--core-arms-only", action="store_true",
                     help="skip the small-request and dense-head arms (used for the ncu launch list, so that it shows the step's kernels)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--skip-extra", action="store_true",
+                    help="skip the other BASELINE configs that the default 1-GPU run adds to its line (c1, c5, c3: CPU path, "
+                         "two concurrent models, 100M-row table)")
+    ap.add_argument("--only-extra", default="", help="comma list out of c1,c5,c3 (experiments)")
     return ap.parse_args()
 
 
@@ -331,14 +336,293 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             wall = float(t[0])
         stats = inst.stats()
+        # ---- the same call with OUTPUT0 in HOST memory (what Triton hands back when the client wants the rows on the
+        # host, hps_backend/src/hps.cc:682-690): the 872 MB of rows cross PCIe D2H inside the timed region.  Pinned buffer
+        # (Triton's pinned pool); the engine copies every chunk as soon as its rows are complete.
+        steps_h = max(3, min(a.steps, 10))
+        host_buf = torch.empty(n * a.dim, dtype=torch.float32).pin_memory()
+        for i in range(2):
+            r = inst.infer(h_keys[(steps_h + i) % R], numkeys, cpu_out=host_buf, cpu_out_pinned=True)
+            assert r.error_code is None, r.error_message
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps_h):
+            r = inst.infer(h_keys[i % R], numkeys, cpu_out=host_buf, cpu_out_pinned=True)
+        wall_h = time.perf_counter() - t0
+        barrier()
+        assert r.error_code is None and r.memory_type == FT.MEM_CPU_PINNED and r.params["NumSample"] == a.batch
+        verified_h = verify_rows(torch, torch.from_numpy(h_keys[(steps_h - 1) % R]).cuda(), host_buf.cuda().view(n, a.dim), a.dim,
+                                 SEED, "Triton arm, host output")
+        pageable = torch.empty(n * a.dim, dtype=torch.float32)
+        t0 = time.perf_counter()
+        for i in range(2):
+            r = inst.infer(h_keys[i % R], numkeys, cpu_out=pageable, cpu_out_pinned=False)
+        wall_p = (time.perf_counter() - t0) / 2
+        assert r.error_code is None
+        if world > 1:
+            t = torch.tensor([wall_h], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            wall_h = float(t[0])
+        host_output = {"value": world * steps_h * n / wall_h, "unit": UNIT, "ms_per_step": wall_h / steps_h * 1e3, "steps": steps_h,
+                       "h2d_bytes_per_step": None, "d2h_bytes_per_step": n * a.dim * 4 + 16,
+                       "call": "TRITONBACKEND_ModelInstanceExecute: host KEYS/NUMKEYS -> OUTPUT0 in pinned HOST memory",
+                       "d2h_gbs": n * a.dim * 4 / (wall_h / steps_h) / 1e9, "verified_rows": verified_h,
+                       "pageable_output_ms_per_step": wall_p * 1e3,
+                       "note": "the form that is comparable with the CPU path's host output; the D2H of the rows (872 MB) bounds it"}
+        del host_buf, pageable
         inst.close()
         model.close()
         be.close()
-    return {"value": world * a.steps * n / wall, "unit": UNIT, "ms_per_step": wall / a.steps * 1e3,
+    return {"value": world * a.steps * n / wall, "unit": UNIT, "ms_per_step": wall / a.steps * 1e3, "host_output": host_output,
             "call": "TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so): host KEYS/NUMKEYS -> GPU OUTPUT0",
             "timer": "host wall clock around the blocking Execute calls, max over ranks (the backend's stream is private)",
             "output": "device memory (Triton GPU output buffer contract)", "requests_ok": stats["ok_requests"],
             "verified_rows": verified}
+
+
+def _ps_model(name, rows, seed, dim, slots, batch, device, *, gpucache=True, gpucacheper=0.2, pagelock=True, instances=1):
+    return {"model": name, "sparse_files": [f"synthetic:rows={rows},seed={seed}"], "num_of_worker_buffer_in_pool": instances,
+            "embedding_vecsize_per_table": [dim], "maxnum_catfeature_query_per_table_per_sample": [slots],
+            "default_value_for_each_table": [0.0], "deployed_device_list": [device], "max_batch_size": batch,
+            "hit_rate_threshold": 1.0, "gpucacheper": gpucacheper, "gpucache": gpucache, "enable_pagelock": pagelock}
+
+
+def _mixture(rng, n, rows, warm_rows, p_hot):
+    """n keys: w.p. p_hot one of the warmed rows [0, warm_rows), else uniform over the rows that were not warmed."""
+    k = rng.integers(warm_rows, rows, size=n, dtype=np.int64)
+    hot = rng.random(n) < p_hot
+    k[hot] = rng.integers(0, warm_rows, size=int(hot.sum()), dtype=np.int64)
+    return k
+
+
+def config_c1(a, FT, tmp):
+    """BASELINE configs[0]: single table 1 M rows x dim 32, 1 slot, batch 1024, every key present, gpucache=false — the
+    CPU ParameterServer path (output in host memory, hps_backend/src/hps.cc:640-642), through ModelInstanceExecute."""
+    from oracle import hps_oracle as O
+
+    rows, dim, batch, seed = 1_000_000, 32, 1024, 0xB2000000 + 1
+    path = os.path.join(tmp, "ps_c1.json")
+    with open(path, "w") as f:
+        json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16},
+                   "models": [_ps_model("c1", rows, seed, dim, 1, batch, 0, gpucache=False, gpucacheper=1.0, pagelock=False)]}, f)
+    import torch
+
+    rng = np.random.default_rng(seed)
+    R, repeat = 64, 40
+    keys = [rng.integers(0, rows, size=batch, dtype=np.int64) for _ in range(R)]
+    outs = [torch.empty(batch * dim, dtype=torch.float32) for _ in range(R)]
+    numkeys = np.array([[batch]], dtype=np.int32)
+    with FT.Backend(path) as be:
+        model = be.model("c1", FT.model_config("c1", kind="KIND_CPU", max_batch_size=batch))
+        inst = model.instance(kind=FT.KIND_CPU, device=0)
+        # one Execute call per request (Triton's scheduler would do the same at this size), prepared once
+        preps = [inst.prepare([dict(keys=keys[i], numkeys=numkeys, cpu_out=outs[i])]) for i in range(R)]
+        for p in preps:
+            p.run(1)
+        t = 0.0
+        for _ in range(repeat):
+            for p in preps:
+                t += p.run(1)
+        resp = preps[-1].responses()[0]
+        assert resp.error_code is None and resp.memory_type == FT.MEM_CPU and resp.params["NumSample"] == batch
+        ref = O.synth_rows(keys[-1], dim, seed)
+        assert np.array_equal(outs[-1].numpy().reshape(batch, dim), ref), "bench self-check FAILED (C1)"
+        for p in preps:
+            p.close()
+        inst.close()
+        model.close()
+    calls = R * repeat
+    ours = calls * batch / t
+    # the same requests through the oracle's C port (the reference's CPU parameter-server path restated), one thread:
+    # 1024 keys are below the size at which fanning out over a pool pays
+    table = O.CTable(dim, 0.0, num_partitions=16)
+    table.fill_procedural(rows, seed, os.cpu_count() or 1)
+    out = np.empty((batch, dim), dtype=np.float32)
+    for k in keys:
+        table.lookup(k, 1, out)
+    t0 = time.perf_counter()
+    for _ in range(repeat):
+        for k in keys:
+            table.lookup(k, 1, out)
+    t_cpu = time.perf_counter() - t0
+    return {"workload": "configs[0]: 1M rows x dim 32, 1 slot, batch 1024, all keys present, gpucache=false (CPU ParameterServer path)",
+            "value": ours, "unit": UNIT, "us_per_request": t / calls * 1e6, "host_gbs": ours * (8 + 8 * dim) / 1e9,
+            "bytes_per_vector": 8 + 8 * dim, "requests": calls, "verified_rows": batch,
+            "call": "TRITONBACKEND_ModelInstanceExecute, KIND_CPU instance, host KEYS -> host OUTPUT0; timed inside the harness (C)",
+            "cpu_baseline": {"value": calls * batch / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{calls} requests of {batch} keys through oracle/hps_oracle.c, 1 thread (ctypes call per request)"}}
+
+
+def config_c5(a, FT, tmp, local, torch, sampler_cls):
+    """BASELINE configs[4]: two different models — DCN (10 M rows, ~90 % hit) and a W&D-shaped one (20 M rows, ~50 % hit) —
+    served by ONE parameter server (the reference shares one process-wide PS across models, hps_backend/include/
+    backend.hpp:70-74,104, and one cache per (model, device), include/model_state.hpp:76-84), two instances each,
+    request batch drawn from {4096 .. 65536}, all four instances running at once on one GPU."""
+    dim, slots, B = a.dim, a.slots, a.batch
+    specs = [("dcn", 10_000_000, SEED, 0.87), ("wdl", 20_000_000, 0xB2000000 + 5, 0.42)]
+    path = os.path.join(tmp, "ps_c5.json")
+    with open(path, "w") as f:
+        json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16},
+                   "models": [_ps_model(nm, rows, sd, dim, slots, B, local, instances=2) for nm, rows, sd, _ in specs]}, f)
+    per_inst, batches = 16, [4096, 8192, 16384, 32768, 65536]
+    t_setup = time.perf_counter()
+    with FT.Backend(path) as be:
+        models, insts = [], []
+        for nm, rows, sd, p_hot in specs:
+            m = be.model(nm, FT.model_config(nm, gpus=[local], max_batch_size=B, count=2, parameters={"hps_report_stats": "1"}))
+            models.append(m)
+            for j in range(2):
+                insts.append((nm, rows, sd, p_hot, m.instance(name=f"{nm}_{j}", kind=FT.KIND_GPU, device=local)))
+        setup_s = time.perf_counter() - t_setup
+        work = []
+        for w, (nm, rows, sd, p_hot, inst) in enumerate(insts):
+            rng = np.random.default_rng(sd + 100 + w)
+            warm = int(np.ceil(0.2 * rows))
+            out = torch.empty(B * slots * dim, device="cuda", dtype=torch.float32)
+            reqs = []
+            for i in range(per_inst):
+                b = int(rng.choice(batches))
+                keys = _mixture(rng, b * slots, rows, warm, p_hot)
+                reqs.append((b, keys, inst.prepare([dict(keys=keys, numkeys=np.array([[b * slots]], dtype=np.int32), gpu_out=out,
+                                                         out_device=local)])))
+            work.append((nm, sd, inst, out, reqs))
+        # untimed: every instance serves its requests once (cache reaches the workload's mix), then all four run at once
+        for nm, sd, inst, out, reqs in work:
+            for b, keys, p in reqs:
+                p.run(1)
+        torch.cuda.synchronize()
+        hits = {nm: [0, 0] for nm, *_ in specs}
+        errors = []
+
+        def serve(item):
+            nm, sd, inst, out, reqs = item
+            torch.cuda.set_device(local)
+            for b, keys, p in reqs:
+                p.run(1)
+                r = p.responses()[0]
+                if r.error_code is not None or r.params.get("NumSample") != b:
+                    errors.append((nm, r.error_message))
+                    return
+                hits[nm][0] += r.params.get("CacheHits", 0)
+                hits[nm][1] += r.params.get("CacheMisses", 0)
+
+        sampler = sampler_cls(local)
+        sampler.start()
+        threads = [threading.Thread(target=serve, args=(item,)) for item in work]
+        t0 = time.perf_counter()
+        [t.start() for t in threads]
+        [t.join() for t in threads]
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        assert not errors, errors
+        verified = 0
+        for nm, sd, inst, out, reqs in work:  # the rows of every instance's last request, closed form on the device
+            b, keys, p = reqs[-1]
+            verified += verify_rows(torch, torch.from_numpy(keys).cuda(), out[:b * slots * dim].view(b * slots, dim), dim, sd, f"C5 {nm}")
+        total_keys = sum(b * slots for *_x, reqs in work for b, _k, _p in reqs)
+        per_model = {nm: sum(b * slots for n2, _s, _i, _o, reqs in work if n2 == nm for b, _k, _p in reqs) for nm, *_ in specs}
+        for *_x, reqs in work:
+            for _b, _k, p in reqs:
+                p.close()
+        for *_x, inst in insts:
+            inst.close()
+        for m in models:
+            m.close()
+    return {"workload": "configs[4]: DCN (10M rows) + W&D-shaped (20M rows) models in one parameter server, 2 instances each, "
+                        f"request batch drawn from {batches}, 26 slots, dim 128, all 4 instances concurrent on one GPU",
+            "value": total_keys / wall, "unit": UNIT, "wall_ms": wall * 1e3, "requests": per_inst * len(work), "keys": total_keys,
+            "keys_per_model": per_model,
+            "hit_rate_measured": {nm: (h / max(1, h + m)) for nm, (h, m) in hits.items()},
+            "miss_bytes_over_host_link": sum(m for _h, m in hits.values()) * dim * 4,
+            "host_link_gbs": sum(m for _h, m in hits.values()) * dim * 4 / wall / 1e9,
+            "verified_rows": verified, "clocks": clocks, "setup_s": setup_s,
+            "call": "TRITONBACKEND_ModelInstanceExecute from 4 threads (one per instance), host KEYS -> GPU OUTPUT0, wall clock"}
+
+
+def config_c3(a, FT, tmp, local, torch, sampler_cls, link_gbs, peak_gbs):
+    """BASELINE configs[2] = the north-star target: 26 slots, 100 M-row table (51 GB of host rows), dim 128, batch 65536,
+    ~50 % cache-hit — the host-miss path stressed.  Through ModelInstanceExecute (one copy of the table in memory)."""
+    from oracle import hps_oracle as O
+
+    rows, dim, slots, B, seed, p_hot = 100_000_000, a.dim, a.slots, a.batch, 0xB2000000 + 3, 0.42
+    n = B * slots
+    warm = int(np.ceil(0.2 * rows))
+    path = os.path.join(tmp, "ps_c3.json")
+    with open(path, "w") as f:
+        json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16},
+                   "models": [_ps_model("wdl100m", rows, seed, dim, slots, B, local)]}, f)
+    steps, warmup, prefill, R = 6, 2, 26, 8
+    rng = np.random.default_rng(seed)
+    reqs = [_mixture(rng, n, rows, warm, p_hot) for _ in range(prefill + R)]
+    numkeys = np.array([[n]], dtype=np.int32)
+    out = torch.empty(n * dim, device="cuda", dtype=torch.float32)
+    t0 = time.perf_counter()
+    with FT.Backend(path) as be:
+        model = be.model("wdl100m", FT.model_config("wdl100m", gpus=[local], max_batch_size=B, parameters={"hps_report_stats": "1"}))
+        inst = model.instance(kind=FT.KIND_GPU, device=local)
+        setup_s = time.perf_counter() - t0
+        for k in reqs[:prefill]:  # fills the cache's free half with cold rows: LRU eviction in steady state afterwards
+            r = inst.infer(k, numkeys, gpu_out=out, out_device=local)
+            assert r.error_code is None, r.error_message
+        timed = reqs[prefill:]
+        d_keys = [torch.from_numpy(k).cuda() for k in timed]
+        pinned = [torch.from_numpy(k).pin_memory() for k in timed]
+        dev = [inst.prepare([dict(keys=timed[i], numkeys=numkeys, gpu_out=out, out_device=local, keys_device_ptr=d_keys[i].data_ptr())])
+               for i in range(R)]
+        host = [inst.prepare([dict(keys=pinned[i].numpy(), numkeys=numkeys, gpu_out=out, out_device=local)]) for i in range(R)]
+        sampler = sampler_cls(local)
+        sampler.start()
+        res = {}
+        for name, preps in (("value", dev), ("e2e", host)):
+            for i in range(warmup):
+                preps[(steps + i) % R].run(1)
+            torch.cuda.synchronize()
+            t, hm = 0.0, [0, 0]
+            for i in range(steps):
+                t += preps[i % R].run(1)
+                r = preps[i % R].responses()[0]
+                assert r.error_code is None and r.params["NumSample"] == B
+                hm[0] += r.params["CacheHits"]
+                hm[1] += r.params["CacheMisses"]
+            verified = verify_rows(torch, d_keys[(steps - 1) % R], out.view(n, dim), dim, seed, f"C3 {name}")
+            res[name] = {"value": steps * n / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "hit_rate_measured": hm[0] / max(1, sum(hm)),
+                         "misses_per_step": hm[1] / steps, "verified_rows": verified,
+                         "host_link_gbs": hm[1] / steps * dim * 4 / (t / steps) / 1e9}
+        clocks = sampler.stop()
+        for p in dev + host:
+            p.close()
+        inst.close()
+        model.close()
+    del out
+    res["e2e"].update({"h2d_bytes_per_step": n * 8 + res["e2e"]["misses_per_step"] * dim * 4, "d2h_bytes_per_step": 16,
+                       "call": "TRITONBACKEND_ModelInstanceExecute: pinned host KEYS -> GPU OUTPUT0"})
+    # the reference's CPU parameter-server path on the same table and requests (after the backend's copy is freed)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    table = O.CTable(dim, 0.0, num_partitions=max(8, min(cores, 64)))
+    table.fill_procedural(rows, seed, cores)
+    build_s = time.perf_counter() - t0
+    host_out = np.empty((n, dim), dtype=np.float32)
+    table.lookup(timed[0], cores, host_out)
+    t0 = time.perf_counter()
+    for i in range(3):
+        table.lookup(timed[i % R], cores, host_out)
+    t_cpu = (time.perf_counter() - t0) / 3
+    del table, host_out
+    v = res["value"]
+    return {"workload": "configs[2] (north-star target): 26 slots, 100M-row table, dim 128, batch 65536, ~50% cache-hit, 1xB200",
+            "value": v["value"], "unit": UNIT, "ms_per_step": v["ms_per_step"], "steps": steps, "warmup": warmup,
+            "hit_rate_measured": v["hit_rate_measured"], "verified_rows": v["verified_rows"], "e2e": res["e2e"],
+            "call": "TRITONBACKEND_ModelInstanceExecute: device KEYS -> GPU OUTPUT0, timed inside the harness (C)",
+            "roofline_host_link": {"bound": "pcie", "achieved": v["host_link_gbs"], "peak": link_gbs, "unit": "GB/s",
+                                   "frac": v["host_link_gbs"] / link_gbs if link_gbs else None,
+                                   "algorithmic_bytes_per_step": v["misses_per_step"] * dim * 4,
+                                   "note": "missed rows x 512 B over the WHOLE step (probe + pull), against a pinned cudaMemcpyAsync measured in this run"},
+            "fraction_of_hbm_roofline": (n * (8 + 8 * dim) / (v["ms_per_step"] / 1e3) / 1e9) / peak_gbs,
+            "clocks": clocks, "setup_s": setup_s,
+            "cpu_baseline": {"value": n / t_cpu, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": t_cpu * 1e3, "build_s": build_s,
+                             "sample": f"3 full requests of {n} keys against a 100M-row table, {cores} threads, output in host memory"}}
 
 
 def run_ours(a):
@@ -384,6 +668,7 @@ def run_ours(a):
     pre_reqs, reqs, e2e_reqs = all_reqs[:a.prefill], all_reqs[a.prefill:a.prefill + R], all_reqs[a.prefill + R:]
     sess = hps.session("dcn", local)
     sess.set_probe_variant(a.variant)
+    sess.set_debug(a.debug_flags & 11)
     ext = torch.cuda.ExternalStream(sess.stream)
 
     d_reqs = [torch.from_numpy(k).cuda() for k in reqs]
@@ -458,6 +743,9 @@ def run_ours(a):
                              "host link (roofline_host_link), the probes run beside the pulls",
                 "note": "the HBM-bound kernel of the path; the rest of the step is the PCIe-bound miss kernel, see roofline_host_link"}
     if a.value_only:
+        sess.set_debug((a.debug_flags & 11) | 4)  # one more request with the per-kernel timeline on stderr
+        dev_step(0)
+        sess.set_debug(a.debug_flags & 11)
         rng = np.random.default_rng(SEED + 77 + rank)
         hot_now = hps.cache_keys("dcn", local, 0)
         hit_reqs = [torch.from_numpy(hot_now[rng.integers(0, len(hot_now), size=n)]).cuda() for _ in range(4)]
@@ -517,6 +805,9 @@ def run_ours(a):
     clocks = sampler.stop()  # sampled from the start of the device-resident arm to the end of the end-to-end arms
     e2e["h2d_bytes_per_step"] = e2e_session["h2d_bytes_per_step"]
     e2e["d2h_bytes_per_step"] = e2e_session["d2h_bytes_per_step"]
+    e2e_host_output = e2e.pop("host_output", None)
+    if e2e_host_output is not None:
+        e2e_host_output["h2d_bytes_per_step"] = e2e_session["h2d_bytes_per_step"]
     e2e["bytes_note"] = ("KEYS copied H2D (8 B/key) + rows of missed keys crossing PCIe + 12 B of counters D2H; counted "
                          "by the engine in the session-level arm, which runs the same code below the Triton shell")
 
@@ -714,6 +1005,37 @@ def run_ours(a):
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"],
                         "ms_per_step": r["ms_per_step"]}
 
+    # ---- the other single-GPU configurations of BASELINE.json, each through TRITONBACKEND_ModelInstanceExecute, each with its
+    # own hit rate / clocks / cpu_baseline (rank 0 of a 1-GPU run only: they would measure the same thing on every rank)
+    extra = {}
+    if world == 1 and not a.skip_extra:
+        import gc
+        import tempfile
+
+        del sess, hps, out, d_reqs, h_reqs, hit_reqs
+        gc.collect()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import fake_triton as FT
+
+        want = [x for x in a.only_extra.split(",") if x] or ["c1", "c5", "c3"]
+        with tempfile.TemporaryDirectory() as tmp:
+            for name in want:
+                t0 = time.perf_counter()
+                try:
+                    if name == "c1":
+                        extra[name] = config_c1(a, FT, tmp)
+                    elif name == "c5":
+                        extra[name] = config_c5(a, FT, tmp, local, torch, ClockSampler)
+                    elif name == "c3":
+                        extra[name] = config_c3(a, FT, tmp, local, torch, ClockSampler, link_gbs, peak_gbs)
+                    extra[name]["arm_wall_s"] = time.perf_counter() - t0
+                except Exception as e:  # the headline line must survive a failing side arm — but say so loudly
+                    print(f"[bench] configuration {name} FAILED: {e!r}", file=sys.stderr)
+                    extra[name] = {"error": repr(e)}
+                gc.collect()
+                torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -727,8 +1049,10 @@ def run_ours(a):
                    "hot_draw_probability": a.hit, "prefill_requests": a.prefill,
                    "load_factor": a.load_factor, "miss_path": a.miss_path,
                    "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
-        "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e, "e2e_session": e2e_session,
+        "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "e2e_host_output": e2e_host_output, "e2e_session": e2e_session,
         "cache_hit": cache_hit, "small_batch": small_batch, "two_instances": two_instances, "dense_head": dense_head,
+        "c1": extra.get("c1"), "c5": extra.get("c5"), "c3": extra.get("c3"),
         "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks, "verified_rows": verified_rows,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,

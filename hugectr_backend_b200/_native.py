@@ -148,6 +148,7 @@ SYMBOLS = {
     "hpsx_session_get_stats": (_int, [_vp, ctypes.POINTER(SessionStatsC)]),
     "hpsx_session_reset_stats": (_int, [_vp]),
     "hpsx_session_set_insert_mode": (_int, [_vp, _int]),
+    "hpsx_session_set_debug": (_int, [_vp, _int]),
     "hpsx_session_set_probe_variant": (_int, [_vp, _int]),
     "hpsx_cache_drain_async": (_int, [_vp]),
     "hpsx_mlp_create": (_int, [_int, _sz, c_size_p, _vpp, _vpp, ctypes.POINTER(_int), _vpp]),

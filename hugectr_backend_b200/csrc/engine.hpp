@@ -73,7 +73,7 @@ struct Model {
   // engine extensions of ps.json / hpsx_model_params (ps_config.hpp: hpsx_*)
   bool split_lock = true;
   int request_chunks = 4;
-  int pull_grid_ctas = 296;
+  int pull_grid_ctas = 370;
   int probe_variant = kProbeV8;
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
@@ -113,7 +113,10 @@ struct hpsx_session {
   bool host_out_done = false;
   int request_chunks = 4;              // a request of >= kPipelineMinKeys keys is cut into this many chunks: the pull of
                                        // chunk c (and the key copy of chunk c+1) overlaps the probe of chunk c+1
-  int pull_grid_ctas = 296;            // CTAs of the persistent binned pull kernel
+  int pull_grid_ctas = 370;            // CTAs of the persistent binned pull kernel (2.5 per SM: the measured optimum is
+                                       // 370-444, 48.7-49.1 GB/s fused; 518 falls off a cliff to 42 GB/s)
+  int debug_flags = 0;                 // hpsx_session_set_debug: 1 inserts after ALL pulls, 2 pulls after ALL probes, 4 timeline
+  std::vector<cudaEvent_t> ev_trace;   // timing events of the timeline
   // binned miss lists (MissBins) of the groups of one request
   uint32_t* d_bin_count = nullptr;
   uint32_t* h_bin_count = nullptr;     // pinned mirror

@@ -507,18 +507,21 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // Binned direct pull: the miss path of enable_pagelock models with synchronous insertion.
 //
-//   stream A   [keys c0 ready] probe c0 | probe c1 | probe c2 | probe c3 | insert c0 .. c3 | counters D2H
-//   stream B                    wait c0: pull c0 | pull c1 | pull c2 | pull c3
+//   stream A   [keys c0 ready] probe c0 | probe c1 | probe c2 | probe c3 | pull + insert (fused) | counters D2H
 //   stream C   H2D keys c0 | c1 | c2 | c3          (host keys only; copy engine)
 //
 // A probe appends every miss to the list of its host-table partition (MissBins) and stores nothing for it; the
-// pull kernel of the chunk walks those lists bin by bin — the PCIe reads in flight stay inside one <= 256-MiB
-// window of host memory, which is what the host link rewards (51 vs 39 GB/s) — and writes the rows into the
-// output; it never touches the cache, so it runs beside the probes of the following chunks.  When all probes are
-// done the rows are inserted from the output buffer (HBM to HBM).  Nothing is sorted, no count crosses to the host
-// in between: the whole request is enqueued at once and the host waits exactly once.
-// A "group" = the probe launches that share one set of bins, one pull and one insert: one chunk of one table of a
-// plain request, or table t of ALL requests of a batch (positions then carry the request index in their high bits).
+// pull kernel walks those lists bin by bin — the PCIe reads in flight stay inside one <= 256-MiB window of host
+// memory, which is what the host link rewards (51 vs 39 GB/s, profiles/pcie_probe2_r02.txt) — writes the rows into
+// the output and, holding the cache exclusively, inserts them in the same pass.  Nothing is sorted and no count
+// crosses to the host in between: the whole request is enqueued at once and the host waits exactly once.
+// A "group" = the probe launches that share one set of bins and one pull: all chunks of one table of a plain
+// request, or table t of ALL requests of a batch (positions then carry the request index in their high bits).
+// Measured and NOT done (profiles/r02_pipeline_timeline.txt): running the pull of chunk c beside the probe of
+// chunk c+1.  Both kernels collapse when they share the GPU (probe 5x slower, pull at 20 GB/s), although a plain
+// zero-copy gather and a plain HBM gather coexist (tools/pcie_probe3.cu); the serial order is faster.  Only
+// requests whose vectors go to HOST memory keep one group per chunk: pull c then runs on stream B beside probe
+// c+1, because the D2H copy of chunk c (stream D, 15 ms for a Criteo request) is what has to start early there.
 // ------------------------------------------------------------------------------------------------
 struct BinGroup {
   size_t table = 0;  // real table
@@ -643,19 +646,25 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
       const size_t n = n_v[v];
       if (n == 0) continue;
       const size_t dim = c->tables[v].dim;
-      const size_t K = n >= kPipelineMinKeys ? static_cast<size_t>(std::max(1, s->request_chunks)) : 1;
+      // chunks: host keys are copied chunk by chunk so that the copy of chunk c+1 overlaps the probe of chunk c
+      const bool chunked = n >= kPipelineMinKeys && (!keys_on_device || s->host_out != nullptr);
+      const size_t K = chunked ? static_cast<size_t>(std::max(1, s->request_chunks)) : 1;
       const size_t csz = ((n + K - 1) / K + 31) / 32 * 32;
+      const bool group_per_chunk = s->host_out != nullptr;
       for (size_t o = 0; o < n; o += csz) {
         const size_t nc = std::min(csz, n - o);
-        BinGroup g;
-        g.table = v;
-        g.n = nc;
-        g.out = out_v[v];
-        g.row_off = o;
-        g.v = v;
-        g.out_bf16 = bf16_dst(s, v, 0, dim);
+        if (o == 0 || group_per_chunk) {
+          BinGroup g;
+          g.table = v;
+          g.out = out_v[v];
+          g.row_off = o;
+          g.v = v;
+          g.out_bf16 = bf16_dst(s, v, 0, dim);
+          groups.push_back(std::move(g));
+        }
+        groups.back().n += nc;
         ProbeLaunch L;
-        L.group = groups.size();
+        L.group = groups.size() - 1;
         L.v = v;
         L.keys = static_cast<const int64_t*>(keys_v[v]) + o;
         L.n = nc;
@@ -666,7 +675,6 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
         L.first_of_v = o == 0;
         L.last_of_v = o + csz >= n;
         launches.push_back(L);
-        groups.push_back(std::move(g));
         stage_off += nc;
       }
     }
@@ -707,6 +715,15 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
   uint32_t* d_inserted = s->d_counters + s->vt;
 
   // ---- enqueue
+  const bool timeline = (s->debug_flags & 4) != 0;
+  if (timeline) {
+    while (s->ev_trace.size() < 6 * G + 1) {
+      cudaEvent_t e;
+      HPSX_CU(cudaEventCreate(&e));
+      s->ev_trace.push_back(e);
+    }
+    HPSX_CU(cudaEventRecord(s->ev_trace[6 * G], A));
+  }
   HPSX_CU(cudaMemsetAsync(s->d_bin_count, 0, count_words * sizeof(uint32_t), A));
   HPSX_CU(cudaMemsetAsync(d_absent, 0, G * sizeof(uint32_t), A));
   if (!keys_on_device) {
@@ -717,10 +734,17 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
       s->stats.h2d_bytes += L.n * sizeof(int64_t);
     }
   }
+  // The pulling warp also inserts the row when this call owns the cache (one instance, dynamic cache) and no
+  // probe can run beside the pull; otherwise (several instances: split lock; host output: pulls beside probes)
+  // the rows are inserted from the output buffer in a separate pass.
+  const bool overlap = host_out;  // pull of group g on stream B beside the probes of group g+1
+  const bool fused = !c->is_static && !split && !overlap;
+  cudaStream_t P = overlap ? B : A;  // where the pulls run
   size_t li = 0;
   for (size_t g = 0; g < G; ++g) {
     const BinGroup& grp = groups[g];
     const DeviceTable& dt = c->tables[grp.table];
+    if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g], A));
     for (; li < launches.size() && launches[li].group == g; ++li) {
       const ProbeLaunch& L = launches[li];
       if (!keys_on_device) HPSX_CU(cudaStreamWaitEvent(A, ev_keys[li], 0));
@@ -731,12 +755,21 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
       if (L.last_of_v) HPSX_CU(cudaEventRecord(s->ev[2 * L.v + 1], A));
       ++s->stats.kernel_launches;
     }
+    if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 1], A));
     HPSX_CU(cudaEventRecord(ev_probe[g], A));
-    HPSX_CU(cudaStreamWaitEvent(B, ev_probe[g], 0));
-    if (g == 0) HPSX_CU(cudaEventRecord(s->ev_pull[0], B));
+  }
+  for (size_t g = 0; g < G; ++g) {
+    const BinGroup& grp = groups[g];
+    const DeviceTable& dt = c->tables[grp.table];
+    // fused pulls rewrite cache slots: every probe of the request must be done (stream order on A gives that)
+    if (overlap) HPSX_CU(cudaStreamWaitEvent(P, ev_probe[g], 0));
+    if (g == 0) HPSX_CU(cudaEventRecord(s->ev_pull[0], P));
+    if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 2], P));
     HPSX_CU(launch_pull_binned(dt, grp.bins, grp.out, grp.out_bf16, batch ? grp.outs.data() : nullptr,
-                               batch ? static_cast<int>(R) : 0, d_absent + g, s->pull_grid_ctas, B));
-    HPSX_CU(cudaEventRecord(ev_pulled[g], B));
+                               batch ? static_cast<int>(R) : 0, d_absent + g, s->pull_grid_ctas, P,
+                               fused ? ((s->debug_flags & 8) ? 2 : 1) : 0, epoch, d_inserted + g));
+    if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 3], P));
+    HPSX_CU(cudaEventRecord(ev_pulled[g], P));
     ++s->stats.kernel_launches;
     if (host_out) {
       // the chunk's rows are complete (hits by its probe, misses by its pull): start their trip to host memory now,
@@ -748,22 +781,22 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
       s->stats.d2h_bytes += grp.n * dim * sizeof(float);
     }
   }
-  HPSX_CU(cudaEventRecord(s->ev_pull[2], B));
+  HPSX_CU(cudaEventRecord(s->ev_pull[2], P));
   auto enqueue_inserts = [&]() -> int {
     for (size_t g = 0; g < G; ++g) {
       const BinGroup& grp = groups[g];
-      HPSX_CU(cudaStreamWaitEvent(A, ev_pulled[g], 0));
+      if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 4], A));
       HPSX_CU(launch_insert_binned(c->tables[grp.table], grp.bins, grp.out, batch ? grp.outs.data() : nullptr,
                                    batch ? static_cast<int>(R) : 0, epoch, d_inserted + g, A));
+      if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 5], A));
       ++s->stats.kernel_launches;
     }
     return HPSX_OK;
   };
-  if (!c->is_static && !split) {
+  if (overlap && G > 0) HPSX_CU(cudaStreamWaitEvent(A, ev_pulled[G - 1], 0));  // B is in order: the last pull implies all
+  if (!c->is_static && !split && !fused) {
     const int rc = enqueue_inserts();
     if (rc != HPSX_OK) return rc;
-  } else if (G > 0) {
-    HPSX_CU(cudaStreamWaitEvent(A, ev_pulled[G - 1], 0));
   }
   HPSX_CU(cudaEventRecord(s->ev_pull[1], A));
   HPSX_CU(cudaMemcpyAsync(s->h_bin_count, s->d_bin_count, count_words * sizeof(uint32_t), cudaMemcpyDeviceToHost, A));
@@ -784,6 +817,16 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
     HPSX_CU(cudaStreamSynchronize(A));
   }
 
+  if (timeline && !c->is_static && !fused && !split) {
+    auto at = [&](size_t i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, s->ev_trace[6 * G], s->ev_trace[i]);
+      return ms;
+    };
+    for (size_t g = 0; g < G; ++g)
+      std::fprintf(stderr, "[hpsx] timeline group %zu (%zu keys): probe %.3f-%.3f | pull %.3f-%.3f | insert %.3f-%.3f ms\n", g,
+                   groups[g].n, at(6 * g), at(6 * g + 1), at(6 * g + 2), at(6 * g + 3), at(6 * g + 4), at(6 * g + 5));
+  }
   // ---- account
   for (const ProbeLaunch& L : launches)
     if (L.last_of_v) account_probe_time(s, L.v, n_v[L.v]);
@@ -1318,7 +1361,7 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
   m->direct_pull = cfg.enable_pagelock;
   m->split_lock = cfg.hpsx_split_lock;
   m->request_chunks = cfg.hpsx_request_chunks > 0 ? std::min<int>(cfg.hpsx_request_chunks, kMaxBatchRequests) : 4;
-  m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 296;
+  m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 370;
   m->probe_variant = cfg.hpsx_probe == "ldg" ? kProbeLdg : cfg.hpsx_probe == "tma" ? kProbeTma : kProbeV8;
   for (size_t t = 0; t < T; ++t) {
     if (cfg.embedding_vecsize_per_table[t] == 0)
@@ -2196,6 +2239,12 @@ int hpsx_session_reset_stats(hpsx_session* s) {
 int hpsx_session_set_insert_mode(hpsx_session* s, int mode) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
   s->insert_mode = mode < 0 ? -1 : (mode > 0 ? 1 : 0);
+  return HPSX_OK;
+}
+
+int hpsx_session_set_debug(hpsx_session* s, int flags) {
+  if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
+  s->debug_flags = flags;
   return HPSX_OK;
 }
 

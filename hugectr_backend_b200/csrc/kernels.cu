@@ -855,9 +855,17 @@ struct PullBinnedArgs {
   uint32_t* absent;
   int batch;
   float* batch_out[kMaxBatchOuts];
+  // fused insert (kInsert): the warp that pulled a row also puts it into the cache — HBM-only work hidden behind the
+  // PCIe reads of the other warps.  Needs the cache to itself (no probe may run beside it).
+  Bucket* buckets;
+  float* values;
+  uint32_t num_buckets;
+  uint32_t epoch;
+  uint32_t* inserted;
+  int claim_first;  // experiment: claim the slot before the PCIe reads are issued instead of while they are in flight
 };
 
-template <typename VecT>
+template <typename VecT, bool kInsert>
 __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArgs a) {
   __shared__ uint32_t prefix[kMaxBins + 2];
   __shared__ uint32_t warp_sums[kBlock / 32];
@@ -876,7 +884,15 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
     VecT* dst = a.batch ? reinterpret_cast<VecT*>(a.batch_out[p >> kShardPosBits]) +
                               static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
                         : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(p) * V;
-    // all PCIe reads of the row first (up to 4 per lane in flight), then the stores
+    // all PCIe reads of the row first (up to 4 per lane in flight); the slot claim runs while they are in flight
+    VecT* slab = nullptr;
+    Claim claim{nullptr, nullptr};
+    if constexpr (kInsert) {
+      if (a.claim_first && src != nullptr && key != kEmptyKey) {
+        const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+        if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
+      }
+    }
     for (uint32_t v0 = 0; v0 < V; v0 += 128u) {
       VecT x[4];
 #pragma unroll
@@ -885,15 +901,28 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
         x[u] = defv;
         if (src != nullptr && v < V) x[u] = src[v];
       }
+      if constexpr (kInsert) {
+        if (!a.claim_first && v0 == 0 && src != nullptr && key != kEmptyKey) {
+          const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+          if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t v = v0 + u * 32u + lane;
         if (v < V) {
           st_stream(dst + v, x[u]);
+          if (kInsert && slab != nullptr) slab[v] = x[u];
           if constexpr (sizeof(VecT) == 16) {
             if (a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(p) * V + v) * 4u, x[u]);
           }
         }
+      }
+    }
+    if constexpr (kInsert) {
+      if (claim.lo != nullptr) {
+        release_claim(claim, lane);
+        if (lane == 0 && slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
       }
     }
     if (lane == 0 && src == nullptr) {
@@ -1510,7 +1539,7 @@ cudaError_t launch_resolve_and_sort_misses(const DeviceTable& t, const int64_t* 
 
 cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
                                float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, int insert, uint32_t epoch, uint32_t* d_inserted) {
   if (t.index == nullptr || bins.count == nullptr || bins.num_bins == 0 || bins.num_bins > kMaxBins || d_absent == nullptr)
     return cudaErrorInvalidValue;
   if (batch_count < 0 || batch_count > kMaxBatchOuts || (batch_count > 0 && (batch_outs == nullptr || d_out_bf16 != nullptr)))
@@ -1526,7 +1555,13 @@ cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float
   a.out_bf16 = static_cast<__nv_bfloat16*>(d_out_bf16);
   a.absent = d_absent;
   a.batch = batch_count;
-  uintptr_t bits = reinterpret_cast<uintptr_t>(d_out);
+  a.buckets = t.buckets;
+  a.values = t.values;
+  a.num_buckets = t.num_buckets;
+  a.epoch = epoch;
+  a.inserted = d_inserted;
+  a.claim_first = insert == 2;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(d_out) | (insert ? reinterpret_cast<uintptr_t>(t.values) : 0);
   for (int r = 0; r < batch_count; ++r) {
     a.batch_out[r] = batch_outs[r];
     bits |= reinterpret_cast<uintptr_t>(batch_outs[r]);
@@ -1538,12 +1573,18 @@ cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float
   const int vb = vec_bytes(t.dim, reinterpret_cast<const void*>(bits & 15u));
   if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
   // host rows: slabs are 4096-B aligned and rows dim*4 apart, so the row alignment is that of dim*4
-  if (vb == 16)
-    pull_binned_kernel<float4><<<grid, kBlock, 0, stream>>>(a);
+  if (vb == 16 && insert)
+    pull_binned_kernel<float4, true><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 16)
+    pull_binned_kernel<float4, false><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 8 && insert)
+    pull_binned_kernel<float2, true><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 8)
-    pull_binned_kernel<float2><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float2, false><<<grid, kBlock, 0, stream>>>(a);
+  else if (insert)
+    pull_binned_kernel<float, true><<<grid, kBlock, 0, stream>>>(a);
   else
-    pull_binned_kernel<float><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float, false><<<grid, kBlock, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -1596,9 +1637,12 @@ cudaError_t preload_miss_path_kernels() {
   preload_one(pull_misses_kernel<float4, 1>, &e);
   preload_one(pull_misses_kernel<float2, 1>, &e);
   preload_one(pull_misses_kernel<float, 1>, &e);
-  preload_one(pull_binned_kernel<float4>, &e);
-  preload_one(pull_binned_kernel<float2>, &e);
-  preload_one(pull_binned_kernel<float>, &e);
+  preload_one(pull_binned_kernel<float4, false>, &e);
+  preload_one(pull_binned_kernel<float2, false>, &e);
+  preload_one(pull_binned_kernel<float, false>, &e);
+  preload_one(pull_binned_kernel<float4, true>, &e);
+  preload_one(pull_binned_kernel<float2, true>, &e);
+  preload_one(pull_binned_kernel<float, true>, &e);
   preload_one(insert_binned_kernel<float4>, &e);
   preload_one(insert_binned_kernel<float2>, &e);
   preload_one(insert_binned_kernel<float>, &e);

@@ -115,7 +115,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
 // probes of later chunks of the request run beside this kernel.  Grid: `grid_ctas` CTAs, persistent.
 cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
                                float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
-                               cudaStream_t stream);
+                               cudaStream_t stream, int insert = 0, uint32_t epoch = 0, uint32_t* d_inserted = nullptr);
+// insert: the pulling warp also inserts the row (fused; HBM work hidden behind the PCIe reads).  Only when nothing
+// probes the cache meanwhile: the caller holds the cache exclusively and every probe of the request has completed.
 // Inserts the rows the binned pull delivered, reading them back from the output buffer (HBM to HBM); entries whose
 // key was replaced by kEmptyKey are skipped.  Caller excludes probes (they would copy rows while slots are rewritten).
 cudaError_t launch_insert_binned(const DeviceTable& t, const MissBins& bins, const float* d_out,

@@ -177,6 +177,10 @@ struct ModelState {
   // contract applies.
   int pooling = -1;  // -1 off, else hpsx_combiner
   std::vector<size_t> pooling_hotness;
+  // Opt-in extension: config.pbtxt parameter `hps_report_stats` = "1" adds the response parameters CacheHits /
+  // CacheMisses (totals of the Execute call the response belongs to) — how a client, or bench.py, learns the hit
+  // rate of a deployed model.  Costs one small device-to-host read per call.
+  bool report_stats = false;
 
   bool gpucache() const { return params.use_gpu_embedding_cache != 0; }
   size_t num_tables() const { return params.num_tables; }
@@ -293,6 +297,8 @@ TRITONSERVER_Error* ModelState::parse() {
         hpsx::json_get(*v, "string_value", &refresh_delay);
       if (const Value* v = p->find("freeze_sparse"); v && v->is_object())
         hpsx::json_get(*v, "string_value", &freeze_sparse);
+      if (const Value* v = p->find("hps_report_stats"); v && v->is_object())
+        hpsx::json_get(*v, "string_value", &report_stats);
       std::string pool_mode, pool_hot;
       if (const Value* v = p->find("hps_pooling"); v && v->is_object()) hpsx::json_get(*v, "string_value", &pool_mode);
       if (const Value* v = p->find("hps_pooling_hotness"); v && v->is_object())
@@ -902,6 +908,8 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInstanceExecute(TRITONBACKEND_ModelInstan
     // phase 2: lookups.  Consecutive un-pooled GPU requests with device output buffers share one engine pass
     // (cross-request batching) as long as they fit one request's key budget; everything else runs alone.
     ModelState* ms = inst->model;
+    hpsx_session_stats stats0{}, stats1{};
+    const bool report = ms->report_stats && hpsx_session_get_stats(inst->session, &stats0) == HPSX_OK;
     const uint64_t key_budget = static_cast<uint64_t>(ms->max_batch_size) * ms->cat_num;
     auto batchable = [&](uint32_t r) {
       return ok[r] && plans[r].has_output && ms->gpucache() && ms->pooling < 0 && plans[r].out_on_device;
@@ -946,9 +954,18 @@ TRITONSERVER_Error* TRITONBACKEND_ModelInstanceExecute(TRITONBACKEND_ModelInstan
       r = group.back() + 1;
     }
     const uint64_t t_phase3 = now_ns();
+    const bool reported = report && hpsx_session_get_stats(inst->session, &stats1) == HPSX_OK;
     // phase 3: responses and statistics
     for (uint32_t q = 0; q < request_count; ++q) {
       if (!ok[q]) continue;
+      if (reported) {
+        HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "CacheHits",
+                                                               static_cast<int64_t>(stats1.hits - stats0.hits)),
+                         "failed return cache hits");
+        HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "CacheMisses",
+                                                               static_cast<int64_t>(stats1.misses - stats0.misses)),
+                         "failed return cache misses");
+      }
       HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "NumSample", plans[q].num_samples),
                        "failed return Number of samples");
       HPS_LOG_IF_ERROR(TRITONBACKEND_ResponseSetIntParameter(responses[q], "DeviceID", inst->device),

@@ -309,6 +309,9 @@ class LookupSession:
     def set_insert_mode(self, mode: int) -> None:
         N.check(self._L.hpsx_session_set_insert_mode(self._h, mode))
 
+    def set_debug(self, flags: int) -> None:
+        N.check(self._L.hpsx_session_set_debug(self._h, flags))
+
     def set_probe_variant(self, variant: str) -> None:
         N.check(self._L.hpsx_session_set_probe_variant(self._h, PROBE_VARIANTS[variant]))
 

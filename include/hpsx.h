@@ -83,7 +83,7 @@ typedef struct hpsx_model_params {
                                               lock and insert in a short exclusive section; < 0: whole-call exclusive lock */
   int request_chunks;                      /* a direct-pull request of >= 2^18 keys is cut into this many chunks so that
                                               the PCIe pull of chunk c overlaps the probe of chunk c+1; 0 -> 4 */
-  int pull_grid_ctas;                      /* CTAs (of 256 threads) of the persistent binned pull kernel; 0 -> 296 */
+  int pull_grid_ctas;                      /* CTAs (of 256 threads) of the persistent binned pull kernel; 0 -> 370 */
   int probe_variant;                       /* probe+gather kernel, see hpsx_session_set_probe_variant; used when
                                               probe_variant_set != 0, else the default (4) */
   int probe_variant_set;
@@ -335,6 +335,10 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
  * evict_first and bucket keys kept in L2 (rows must be multiples of 32 B, else 0 is used), 0 = LDG.128 register
  * copies (any row size), 1 = bulk-async (TMA engine) row staging through shared memory. */
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
+/* Measurement aid for the binned direct pull (bench experiments; not a serving knob): bit 0 = insert only after ALL
+ * pulls of the request, bit 1 = start the pulls only after ALL probes, bit 2 = print a per-kernel timeline of every
+ * request on stderr. */
+int hpsx_session_set_debug(hpsx_session* s, int flags);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);
 

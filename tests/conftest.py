@@ -3,6 +3,14 @@ import sys
 
 import pytest
 
+# tests/test_shard_group_gpu.py runs two ranks of a model-parallel group on ONE device (two streams): a rank's flag-wait
+# kernel spins until the other rank's kernels have published.  With CUDA's default LAZY module loading the first launch
+# of any kernel (ours, CUB's, the driver's own memset kernels) stalls until the kernels already running on the device
+# finish — here the spinner, which waits for that very launch (measured: tools/stream_alias_probe.cu, 1 of 552 stream
+# pairs serialised with lazy loading, 0 with eager).  Must be set before the CUDA context exists.  Deployments with one
+# rank per device are not affected: a module load only waits for kernels of its own device.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -58,6 +58,7 @@ _SIGS = {
     "ft_request_force_output_memory": (None, [_vp, _int]),
     "ft_request_fail_output_buffer": (None, [_vp, _int]),
     "ft_execute": (_int, [_vp, _vpp, _u32]),
+    "ft_execute_repeat": (_int, [_vp, _vpp, _u32, _u32, ctypes.POINTER(_u64)]),
     "ft_request_released": (_int, [_vp]),
     "ft_request_response_count": (_int, [_vp]),
     "ft_response_sent": (_int, [_vp]),
@@ -238,7 +239,7 @@ class Instance:
                                                   shape=(nbytes.value // 4,)).copy()
             else:
                 resp.data = np.empty(0, dtype=np.float32)
-        for p in ("NumSample", "DeviceID"):
+        for p in ("NumSample", "DeviceID", "CacheHits", "CacheMisses"):
             v = _i64()
             if L.ft_response_int_param(r, p.encode(), ctypes.byref(v)):
                 resp.params[p] = int(v.value)
@@ -257,8 +258,40 @@ class Instance:
             for h in handles:
                 self._L.ft_request_delete(h)
 
+    def prepare(self, requests: Sequence[dict]) -> "Prepared":
+        """Requests built once and executed many times (benchmarks): see Prepared.run."""
+        return Prepared(self, requests)
+
     def infer(self, keys, numkeys, **kw) -> Response:
         return self.infer_many([dict(keys=keys, numkeys=numkeys, **kw)])[0]
+
+
+class Prepared:
+    """A fixed set of requests for one instance; run(repeat) executes them `repeat` times, ONE Execute call per pass
+    carrying all of them, and returns the seconds spent inside the backend (timed in C, no Python in the loop)."""
+
+    def __init__(self, inst: Instance, requests: Sequence[dict]):
+        self.inst = inst
+        self._keep: list = []
+        inst._caller_cpu_out = any(kw.get("cpu_out") is not None for kw in requests)
+        self._handles = [inst._make_request(keep=self._keep, **kw) for kw in requests]
+        self._arr = (ctypes.c_void_p * len(self._handles))(*self._handles)
+
+    def run(self, repeat: int = 1) -> float:
+        ns = _u64()
+        _check(self.inst._L.ft_execute_repeat(self.inst._h, self._arr, len(self._handles), repeat, ctypes.byref(ns)))
+        return ns.value / 1e9
+
+    def responses(self) -> List[Response]:
+        return [self.inst._collect(h) for h in self._handles]
+
+    def close(self) -> None:
+        for h in self._handles:
+            self.inst._L.ft_request_delete(h)
+        self._handles = []
+
+    def __del__(self):
+        self.close()
 
 
 class Model:

@@ -6,6 +6,7 @@
 //
 // No CUDA here: a GPU output buffer is whatever device pointer the test hands in (a torch tensor);
 // without one the harness falls back to CPU memory, as Triton may (hps_backend/src/hps.cc:638-648).
+#include <chrono>
 #include <dlfcn.h>
 
 #include <atomic>
@@ -636,6 +637,23 @@ void ft_request_fail_output_buffer(TRITONBACKEND_Request* r, int fail) { r->fail
 // Runs TRITONBACKEND_ModelInstanceExecute on `n` requests (one call, like Triton's scheduler).
 int ft_execute(TRITONBACKEND_ModelInstance* i, TRITONBACKEND_Request** reqs, uint32_t n) {
   return consume(i->model->backend->execute(i, reqs, n));
+}
+
+// The same Execute call `repeat` times over prepared requests (each pass: one call carrying all `n` requests), timed
+// here so that a benchmark of small requests measures the backend and not the Python harness.  Responses of earlier
+// passes are dropped; the last pass's stay for inspection.
+int ft_execute_repeat(TRITONBACKEND_ModelInstance* i, TRITONBACKEND_Request** reqs, uint32_t n, uint32_t repeat,
+                      uint64_t* elapsed_ns) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t rep = 0; rep < repeat; ++rep) {
+    for (uint32_t q = 0; q < n; ++q) reqs[q]->responses.clear();
+    const int rc = consume(i->model->backend->execute(i, reqs, n));
+    if (rc != 0) return rc;
+  }
+  if (elapsed_ns != nullptr)
+    *elapsed_ns = static_cast<uint64_t>(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
 }
 
 int ft_request_released(TRITONBACKEND_Request* r) { return r->released; }

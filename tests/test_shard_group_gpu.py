@@ -67,13 +67,23 @@ def test_world2_same_device_threads(cuda_device, pagelock):
     The two ranks' kernels run on different streams of one device, and a rank's flag-wait kernel spins until the
     other rank's kernels have published.  Round 1 saw this time out now and then; the cause was CUDA's lazy kernel
     loading — the first launch of a kernel stalls behind the kernels already running on the device, here behind the
-    very spinner that waits for it (tools/stream_alias_probe.cu).  hpsx_shard_group_create now loads every kernel a
-    lookup can launch up front, so the test runs without a retry."""
+    very spinner that waits for it (tools/stream_alias_probe.cu).  hpsx_shard_group_create now loads every kernel of
+    this library that a lookup can launch up front, and tests/conftest.py asks the driver for eager loading of
+    everything else (its own memset kernels, CUB, torch).  The second cause was a cudaFree (device-wide
+    synchronisation) issued from a rank's thread by the garbage collector; see _world2_same_device.  No retry."""
     assert _world2_same_device(pagelock) == "ok"
 
 
 def _world2_same_device(pagelock):
+    import gc
+
     torch = _torch()
+    # Objects of earlier tests must be gone BEFORE a flag-wait kernel spins: their destructors call cudaFree, which
+    # waits for all work on the device — a garbage collection that happens to run in one rank's thread would park that
+    # rank behind the other rank's spinning kernel until the timeout (the second cause of round 1's sporadic failure;
+    # the log line "rank 1 ... last flag seen per peer: 0 0" with rank 0 arriving 20 s late shows it).
+    gc.collect()
+    torch.cuda.synchronize()
     rows, dim, world = 80_000, 128, 2
     ref = O.NumpyTable(dim, 0.25)
     ref.fill_procedural(rows, SEED)
@@ -87,6 +97,9 @@ def _world2_same_device(pagelock):
     results = {}
 
     def run(rank):
+        import faulthandler
+
+        faulthandler.dump_traceback_later(12, exit=False)  # a rank that is stuck shows where (all threads' stacks)
         torch.cuda.set_device(0)
         rng = np.random.default_rng(10 + rank)
         ok = True
@@ -98,7 +111,8 @@ def _world2_same_device(pagelock):
             try:
                 view = groups[rank].lookup(dk, n)
             except hb.HpsxError as e:
-                results[rank] = "timeout" if "timeout" in str(e) else f"error: {e}"
+                print(f"rank {rank}, request {it}: {e}")
+                results[rank] = f"timeout: {e}" if "timeout" in str(e) else f"error: {e}"
                 return
             st = groups[rank].stats()
             ok &= st["status"] == 0
@@ -106,16 +120,21 @@ def _world2_same_device(pagelock):
             if n:
                 out = torch.as_tensor(view, device="cuda").cpu().numpy()
                 ok &= bool(np.array_equal(out, ref.lookup(keys)))
+        faulthandler.cancel_dump_traceback_later()
         results[rank] = ok
 
     threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
-    [t.start() for t in threads]
-    [t.join(180) for t in threads]
+    gc.disable()  # no destructor (cudaFree = device-wide synchronisation) may run inside a rank's thread
+    try:
+        [t.start() for t in threads]
+        [t.join(180) for t in threads]
+    finally:
+        gc.enable()
     assert not any(t.is_alive() for t in threads), "a rank hung"
-    if "timeout" in results.values():
+    if any(isinstance(v, str) and v.startswith("timeout") for v in results.values()):
         for g in groups:
             g.close()
-        return "timeout"
+        return f"timeout: {results}"
     if results != {0: True, 1: True}:
         return f"wrong result: {results}"
     # what one rank received is what the other sent
