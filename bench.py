@@ -59,7 +59,8 @@ def parse_args():
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
     ap.add_argument("--variant", default="v8", choices=["ldg", "tma", "v8"])
     ap.add_argument("--chunks", type=int, default=0, help="request_chunks of the model (0: engine default 4)")
-    ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 370)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 148)")
+    ap.add_argument("--window-mb", type=int, default=0, help="pull_window of the parameter server in MiB (0: engine default 16)")
     ap.add_argument("--value-only", action="store_true", help="device-resident arm only (kernel experiments)")
     ap.add_argument("--debug-flags", type=int, default=0, help="hpsx_session_set_debug bits 0-1 for the timed arm (experiments)")
     ap.add_argument("--workload", default="dcn", choices=["dcn", "c4"],
@@ -652,7 +653,7 @@ def run_ours(a):
 
     # ---- server: host table + HBM cache ------------------------------------------------------------
     t0 = time.perf_counter()
-    hps = hb.HPS(num_partitions=16)
+    hps = hb.HPS(num_partitions=16, pull_window_mb=a.window_mb)
     hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
                                  cache_size_percentage=a.gpucacheper, deployed_devices=[local],
                                  cache_load_factor=a.load_factor, enable_pagelock=(a.miss_path == "direct"),

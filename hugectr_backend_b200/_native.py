@@ -53,6 +53,7 @@ class VolatileParamsC(ctypes.Structure):
         ("allocation_rate", ctypes.c_size_t),
         ("initial_cache_rate", ctypes.c_double),
         ("num_threads", ctypes.c_size_t),
+        ("pull_window_bytes", ctypes.c_size_t),
     ]
 
 

@@ -73,7 +73,7 @@ struct Model {
   // engine extensions of ps.json / hpsx_model_params (ps_config.hpp: hpsx_*)
   bool split_lock = true;
   int request_chunks = 4;
-  int pull_grid_ctas = 370;
+  int pull_grid_ctas = 148;
   int probe_variant = kProbeV8;
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
@@ -113,8 +113,9 @@ struct hpsx_session {
   bool host_out_done = false;
   int request_chunks = 4;              // a request of >= kPipelineMinKeys keys is cut into this many chunks: the pull of
                                        // chunk c (and the key copy of chunk c+1) overlaps the probe of chunk c+1
-  int pull_grid_ctas = 370;            // CTAs of the persistent binned pull kernel (2.5 per SM: the measured optimum is
-                                       // 370-444, 48.7-49.1 GB/s fused; 518 falls off a cliff to 42 GB/s)
+  int pull_grid_ctas = 148;            // CTAs of the persistent binned pull kernel.  One per SM: on a 10 M-row table 148-444
+                                       // CTAs all give 48-49 GB/s (518: 42), on a 100 M-row table 148 give 43 GB/s, 222
+                                       // 35 and 370 32 — the more reads are in flight, the wider they spread over host memory
   int debug_flags = 0;                 // hpsx_session_set_debug: 1 inserts after ALL pulls, 2 pulls after ALL probes, 4 timeline
   std::vector<cudaEvent_t> ev_trace;   // timing events of the timeline
   // binned miss lists (MissBins) of the groups of one request

@@ -127,12 +127,14 @@ void ThreadPool::post(std::function<void()> job) {
 // ------------------------------------------------------------------------------------------------
 // HostTable
 // ------------------------------------------------------------------------------------------------
-HostTable::HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate)
+HostTable::HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate, size_t pull_window_bytes)
     : dim_(dim), default_value_(default_value) {
   if (dim == 0) throw std::invalid_argument("embedding vector size must be > 0");
   if (num_partitions == 0) num_partitions = 1;
   requested_partitions_ = num_partitions;
   if (allocation_rate == 0) allocation_rate = 256ull << 20;
+  allocation_rate_ = allocation_rate;
+  if (pull_window_bytes != 0) pull_window_bytes_ = std::max<size_t>(pull_window_bytes, 1u << 20);
   const size_t row_bytes = dim * sizeof(float);
   size_t rows_per_slab = std::max<size_t>(1, allocation_rate / row_bytes);
   slab_shift_ = 0;
@@ -295,9 +297,23 @@ void HostTable::repartition_for(size_t expected_rows) {
   // caller holds rw_ exclusively
   if (partitions_sized_ || rows_.load(std::memory_order_relaxed) != 0) return;
   partitions_sized_ = true;  // the first bulk load (or reserve) decides
-  const size_t bytes = expected_rows * dim_ * sizeof(float);
-  size_t want = std::max(requested_partitions_, (bytes + kPullWindowBytes - 1) / kPullWindowBytes);
-  want = std::min<size_t>(std::max<size_t>(want, 1), 4096);
+  const size_t row_bytes = dim_ * sizeof(float);
+  const size_t bytes = expected_rows * row_bytes;
+  // partitions of ~80 % of a window, so that the usual +-10 % spread of a hash partition still fits ONE slab
+  const size_t fill = pull_window_bytes_ - pull_window_bytes_ / 5;
+  size_t want = std::max(requested_partitions_, (bytes + fill - 1) / fill);
+  want = std::min<size_t>(std::max<size_t>(want, 1), kMaxPartitions);
+  // slabs of one window (a power of two of rows), never larger than allocation_rate: a partition allocates a second
+  // slab only when it outgrows the first
+  {
+    const size_t per_part = (bytes + want - 1) / want;
+    const size_t target = std::min(allocation_rate_, std::max<size_t>(pull_window_bytes_, per_part + per_part / 4));
+    const size_t rows_per_slab = std::max<size_t>(1, target / row_bytes);
+    slab_shift_ = 0;
+    while ((1ull << slab_shift_) < rows_per_slab) ++slab_shift_;
+    while (slab_shift_ > 0 && (1ull << slab_shift_) * row_bytes > allocation_rate_) --slab_shift_;
+    slab_mask_ = (1ull << slab_shift_) - 1;
+  }
   if (want == parts_.size()) return;
   parts_.clear();
   for (size_t p = 0; p < want; ++p) {

@@ -59,7 +59,7 @@ class ThreadPool {
 // One embedding table in host DRAM.
 class HostTable {
  public:
-  HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate);
+  HostTable(size_t dim, float default_value, size_t num_partitions, size_t allocation_rate, size_t pull_window_bytes = 0);
   ~HostTable();
   HostTable(const HostTable&) = delete;
   HostTable& operator=(const HostTable&) = delete;
@@ -87,11 +87,15 @@ class HostTable {
   // partition's rows fill at most kPullWindowBytes of host memory (see below).
   void reserve(size_t rows);
 
-  // Direct pull reads rows over PCIe at 39 GB/s when the rows in flight are spread over the whole table and at
-  // 51 GB/s when they stay inside a window of <= 256 MiB (tools/pcie_probe2.cu, profiles/pcie_probe2_r02.txt).
-  // A partition therefore doubles as a locality bin: its rows live in slabs of its own, partition_of(key) needs
-  // no memory access, and the probe kernel appends a missed key straight to its partition's miss list.
-  static constexpr size_t kPullWindowBytes = 192ull << 20;
+  // Direct pull reads rows over PCIe faster the closer together the rows in flight lie in host memory
+  // (tools/pcie_probe2.cu; profiles/pcie_probe2_r02.txt, pcie_probe2_48g_r02.txt): a 5 GiB table gives 39 GB/s in
+  // random order and 51 GB/s inside windows of <= 256 MiB; a 48 GiB table gives 25 GB/s random, 41 GB/s inside
+  // 64-256 MiB windows, 45.5 GB/s inside 8-16 MiB windows and 46 GB/s fully sorted.  A partition therefore doubles
+  // as a locality bin: its rows live in slabs of its own (one window), partition_of(key) needs no memory access, and
+  // the probe kernel appends a missed key straight to its partition's miss list.  Default window: 16 MiB
+  // (volatile_db "hpsx_pull_window_mb" / hpsx_volatile_params.pull_window_bytes); at most kMaxPartitions partitions.
+  static constexpr size_t kDefaultPullWindowBytes = 16ull << 20;
+  static constexpr size_t kMaxPartitions = 4096;
 
   // enable_pagelock (reference key: src/backend.cpp:506-511): page-lock the used part of every value
   // slab and map it into the CUDA address space, so kernels can read rows straight from host DRAM
@@ -151,6 +155,8 @@ class HostTable {
   size_t dim_;
   float default_value_;
   size_t requested_partitions_ = 1;
+  size_t allocation_rate_ = 256ull << 20;
+  size_t pull_window_bytes_ = kDefaultPullWindowBytes;
   bool partitions_sized_ = false;
   std::vector<std::unique_ptr<Partition>> parts_;
   size_t slab_shift_;  // rows per slab = 1 << slab_shift_

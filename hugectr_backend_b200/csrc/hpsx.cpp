@@ -1309,6 +1309,7 @@ int hpsx_ps_create(const hpsx_volatile_params* vdb, hpsx_ps** out) {
   if (vdb) {
     ps->vdb.num_partitions = vdb->num_partitions;
     if (vdb->allocation_rate) ps->vdb.allocation_rate = vdb->allocation_rate;
+    ps->vdb.hpsx_pull_window_mb = vdb->pull_window_bytes >> 20;
     if (vdb->initial_cache_rate > 0) ps->vdb.initial_cache_rate = vdb->initial_cache_rate;
     threads = vdb->num_threads;
   }
@@ -1361,14 +1362,14 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
   m->direct_pull = cfg.enable_pagelock;
   m->split_lock = cfg.hpsx_split_lock;
   m->request_chunks = cfg.hpsx_request_chunks > 0 ? std::min<int>(cfg.hpsx_request_chunks, kMaxBatchRequests) : 4;
-  m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 370;
+  m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 148;
   m->probe_variant = cfg.hpsx_probe == "ldg" ? kProbeLdg : cfg.hpsx_probe == "tma" ? kProbeTma : kProbeV8;
   for (size_t t = 0; t < T; ++t) {
     if (cfg.embedding_vecsize_per_table[t] == 0)
       return fail(HPSX_ERR_INVALID_ARG, "embedding_vecsize_per_table must be > 0");
     m->tables.emplace_back(new HostTable(cfg.embedding_vecsize_per_table[t],
                                          cfg.default_value_for_each_table[t], ps->vdb.num_partitions,
-                                         ps->vdb.allocation_rate));
+                                         ps->vdb.allocation_rate, ps->vdb.hpsx_pull_window_mb << 20));
   }
   for (size_t t = 0; t < T && t < cfg.sparse_files.size(); ++t) {
     if (cfg.sparse_files[t].empty()) continue;
@@ -1450,6 +1451,7 @@ int hpsx_ps_create_from_json(const char* ps_json_path, hpsx_ps** out) {
   hpsx_volatile_params vp{};
   vp.num_partitions = cfg.volatile_db.num_partitions;
   vp.allocation_rate = cfg.volatile_db.allocation_rate;
+  vp.pull_window_bytes = cfg.volatile_db.hpsx_pull_window_mb << 20;
   vp.initial_cache_rate = cfg.volatile_db.initial_cache_rate;
   hpsx_ps* ps = nullptr;
   int rc = hpsx_ps_create(&vp, &ps);

@@ -243,6 +243,7 @@ void parse_volatile(const json::Value& j, VolatileDbConfig* p) {
   need(j, "password", &p->password, false);
   need(j, "num_partitions", &p->num_partitions, false);
   need(j, "allocation_rate", &p->allocation_rate, false);
+  need(j, "hpsx_pull_window_mb", &p->hpsx_pull_window_mb, false);
   need(j, "max_batch_size", &p->max_batch_size, false);
   need(j, "overflow_margin", &p->overflow_margin, false);
   get_enum(j, "overflow_policy", &p->overflow_policy, parse_overflow_policy,

@@ -22,6 +22,7 @@ struct VolatileDbConfig {
   std::string address = "127.0.0.1:7000", user_name = "default", password;
   size_t num_partitions = 0;  // 0 -> min(cores, 16)
   size_t allocation_rate = 256ull << 20;
+  size_t hpsx_pull_window_mb = 0;  // engine extension: locality window of the direct pull (host_ps.hpp); 0 -> 16
   size_t max_batch_size = 65536;
   size_t overflow_margin = SIZE_MAX;
   OverflowPolicy overflow_policy = OverflowPolicy::EvictRandom;

@@ -84,13 +84,13 @@ class HPS:
     """The parameter server: host database + per-(model, device) HBM embedding caches."""
 
     def __init__(self, ps_json: Optional[str] = None, num_partitions: int = 0, num_threads: int = 0,
-                 allocation_rate: int = 0):
+                 allocation_rate: int = 0, pull_window_mb: int = 0):
         self._L = N.lib()
         h = ctypes.c_void_p()
         if ps_json is not None:
             N.check(self._L.hpsx_ps_create_from_json(ps_json.encode(), ctypes.byref(h)))
         else:
-            vp = N.VolatileParamsC(num_partitions, allocation_rate, 1.0, num_threads)
+            vp = N.VolatileParamsC(num_partitions, allocation_rate, 1.0, num_threads, pull_window_mb << 20)
             N.check(self._L.hpsx_ps_create(ctypes.byref(vp), ctypes.byref(h)))
         self._h = h
         self._dims = {}

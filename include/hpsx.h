@@ -83,7 +83,7 @@ typedef struct hpsx_model_params {
                                               lock and insert in a short exclusive section; < 0: whole-call exclusive lock */
   int request_chunks;                      /* a direct-pull request of >= 2^18 keys is cut into this many chunks so that
                                               the PCIe pull of chunk c overlaps the probe of chunk c+1; 0 -> 4 */
-  int pull_grid_ctas;                      /* CTAs (of 256 threads) of the persistent binned pull kernel; 0 -> 370 */
+  int pull_grid_ctas;                      /* CTAs (of 256 threads) of the persistent binned pull kernel; 0 -> 148 */
   int probe_variant;                       /* probe+gather kernel, see hpsx_session_set_probe_variant; used when
                                               probe_variant_set != 0, else the default (4) */
   int probe_variant_set;
@@ -95,6 +95,8 @@ typedef struct hpsx_volatile_params {
   size_t allocation_rate;    /* "allocation_rate" :161-165; 0 -> 256 MiB */
   double initial_cache_rate; /* "initial_cache_rate" :194-198; <=0 -> 1.0 */
   size_t num_threads;        /* worker pool; 0 -> HCTR_DEFAULT_CONCURRENCY or hardware_concurrency (src/thread_pool.cpp:25-41) */
+  size_t pull_window_bytes;  /* engine extension (ps.json: volatile_db "hpsx_pull_window_mb"): host-memory window one
+                                partition of a table — one bin of the direct-pull miss lists — should fit; 0 -> 16 MiB */
 } hpsx_volatile_params;
 
 /* Counters of one lookup session, cumulative since creation / last reset. */

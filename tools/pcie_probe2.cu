@@ -163,7 +163,8 @@ int main(int argc, char** argv) {
   CK(cudaFuncSetAttribute(gather_bulk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CK(cudaFuncSetAttribute(gather_bulk<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 
-  for (int mem_mode = 0; mem_mode < 3; ++mem_mode) {
+  const int mem_modes = argc > 3 ? atoi(argv[3]) : 3;
+  for (int mem_mode = 0; mem_mode < mem_modes; ++mem_mode) {
     const char* mem_name[] = {"registered 256-MiB slabs (4K-aligned malloc)", "registered 256-MiB slabs, 2M-aligned + MADV_HUGEPAGE",
                               "one cudaHostAlloc"};
     Table t;
@@ -201,7 +202,7 @@ int main(int argc, char** argv) {
     std::vector<size_t> rows(n);
     for (auto& r : rows) r = rnd() % t.rows;
     // orders: -1 random, 0 fully sorted, else bin shift (rows random inside a window of 2^shift bytes)
-    for (int shift : {-1, 0, 26, 28, 30}) {
+    for (int shift : {-1, 0, 23, 24, 25, 26, 28, 30}) {
       if (mem_mode != 0 && shift > 0) continue;
       std::vector<size_t> ord = rows;
       if (shift == 0) {
@@ -217,7 +218,7 @@ int main(int argc, char** argv) {
       else if (shift == 0) snprintf(oname, 64, "sorted");
       else snprintf(oname, 64, "bins of %d MiB", 1 << (shift - 20));
       for (int cps : {1, 2, 4, 8}) {
-        if ((shift > 0 || mem_mode != 0) && cps != 1 && cps != 8) continue;
+        if ((shift > 0 || mem_mode != 0) && cps != 1 && cps != 2 && cps != 8) continue;
         const double g16 = time_it([&] { gather_ld16<<<148 * cps, 256>>>(d_addr, n, reinterpret_cast<float4*>(d_out)); });
         const double g32 = time_it([&] { gather_ld32<<<148 * cps, 256>>>(d_addr, n, reinterpret_cast<V8*>(d_out)); });
         printf("   %-16s %d CTA/SM: ld16 %5.1f GB/s | ld32 %5.1f GB/s", oname, cps, g16, g32);
