@@ -7,7 +7,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 CSRC      := hugectr_backend_b200/csrc
 LIBDIR    := hugectr_backend_b200/lib
 NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wextra,-pthread -Iinclude
-ENGINE_SRC := $(CSRC)/kernels.cu $(CSRC)/shard_kernels.cu $(CSRC)/dense_mlp.cu $(CSRC)/hpsx.cpp $(CSRC)/shard_group.cpp $(CSRC)/mlp_abi.cpp $(CSRC)/host_ps.cpp $(CSRC)/ps_config.cpp
+ENGINE_SRC := $(CSRC)/kernels.cu $(CSRC)/shard_kernels.cu $(CSRC)/dense_mlp.cu $(CSRC)/hpsx.cpp $(CSRC)/shard_group.cpp $(CSRC)/peer_tier.cpp $(CSRC)/mlp_abi.cpp $(CSRC)/host_ps.cpp $(CSRC)/ps_config.cpp
 ENGINE_HDR := $(wildcard $(CSRC)/*.h $(CSRC)/*.hpp $(CSRC)/*.cuh include/*.h)
 
 all: $(LIBDIR)/libhpsx.so $(LIBDIR)/libtriton_hps.so tests/fake_triton/libfake_triton.so oracle

@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-tier", action="store_true",
+                    help="N > 1: replicas only, every cache miss goes to host memory over PCIe (the reference's behaviour); default "
+                         "with N > 1 is the NVLink tier: the host table sharded over the GPUs' HBM, misses read from the owner's shard")
     ap.add_argument("--zipf", type=float, default=0.0,
                     help="> 1: draw keys Zipf(alpha)-distributed over the rows instead of the hot/cold mixture (popular rows are the "
                          "warmed ones); config.unique_over_keys reports the duplication U/N of a request")
@@ -381,6 +384,92 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
             "verified_rows": verified}
 
 
+def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
+    """N > 1 end-to-end arm: ONE server process (fake Triton + libtriton_hps.so) with the model deployed on all `world` GPUs,
+    one instance per GPU, "hpsx_peer_tier": true — the reference's multi-GPU deployment (one tritonserver, one cache per
+    device, hps_backend/src/model_state.cpp:395-419) with this engine's NVLink tier.  Every instance serves its own stream of
+    distinct requests from its own thread: host KEYS -> GPU OUTPUT0 on its device.  Wall clock over all threads."""
+    import tempfile
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_triton as FT
+
+    devs = list(range(world))
+    m = _ps_model("dcn", a.rows, SEED, a.dim, a.slots, a.batch, 0, gpucacheper=a.gpucacheper)
+    m["deployed_device_list"] = devs
+    m["hpsx_peer_tier"] = True
+    steps = a.steps
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ps_one_server.json")
+        with open(path, "w") as f:
+            json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16}, "models": [m]}, f)
+        t0 = time.perf_counter()
+        with FT.Backend(path) as be:
+            model = be.model("dcn", FT.model_config("dcn", gpus=devs, max_batch_size=a.batch))
+            insts = [model.instance(name=f"dcn_{d}", kind=FT.KIND_GPU, device=d) for d in devs]
+            setup_s = time.perf_counter() - t0
+            numkeys = np.array([[n]], dtype=np.int32)
+            pre = make_requests(a, hot, warm_rows, a.prefill, SEED + 4000)
+            work = []
+            for d, inst in enumerate(insts):
+                out = torch.empty(n * a.dim, device=f"cuda:{d}", dtype=torch.float32)
+                reqs = make_requests(a, hot, warm_rows, a.warmup + steps, SEED + 5000 + d)
+                prepared = [inst.prepare([dict(keys=k, numkeys=numkeys, gpu_out=out, out_device=d)]) for k in reqs]
+                work.append((d, inst, out, reqs, prepared))
+            errors = []
+
+            def serve(item, lo, hi, pre_keys):
+                d, inst, out, reqs, prepared = item
+                torch.cuda.set_device(d)
+                for k in pre_keys:
+                    r = inst.infer(k, numkeys, gpu_out=out, out_device=d)
+                    if r.error_code is not None:
+                        errors.append((d, r.error_message))
+                        return
+                for p in prepared[lo:hi]:
+                    p.run(1)
+                    r = p.responses()[0]
+                    if r.error_code is not None or r.params.get("NumSample") != a.batch:
+                        errors.append((d, r.error_message))
+                        return
+
+            def run_all(lo, hi, pre_keys=()):
+                th = [threading.Thread(target=serve, args=(item, lo, hi, pre_keys)) for item in work]
+                t = time.perf_counter()
+                [x.start() for x in th]
+                [x.join() for x in th]
+                for d in devs:
+                    torch.cuda.synchronize(d)
+                return time.perf_counter() - t
+
+            run_all(0, a.warmup, pre)  # untimed: prefill (cache reaches steady state) + warm-up
+            assert not errors, errors
+            samplers = [sampler_cls(d) for d in devs]
+            [s.start() for s in samplers]
+            wall = run_all(a.warmup, a.warmup + steps)
+            clocks = [s.stop() for s in samplers]
+            assert not errors, errors
+            verified = 0
+            for d, inst, out, reqs, prepared in work:
+                with torch.cuda.device(d):
+                    verified += verify_rows(torch, torch.from_numpy(reqs[-1]).cuda(), out.view(n, a.dim), a.dim, SEED,
+                                            f"one-server Triton arm, GPU {d}")
+            for d, inst, out, reqs, prepared in work:
+                for p in prepared:
+                    p.close()
+                inst.close()
+            model.close()
+    return {"value": world * steps * n / wall, "unit": UNIT, "ms_per_step": wall / steps * 1e3,
+            "call": f"TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so), ONE server process, {world} instances (one per GPU, one "
+                    "thread each): host KEYS/NUMKEYS -> GPU OUTPUT0 on the instance's device; hpsx_peer_tier on",
+            "timer": "host wall clock from the start of all instance threads to the last device synchronised",
+            "output": "device memory (Triton GPU output buffer contract)", "verified_rows": verified, "setup_s": setup_s,
+            "h2d_bytes_per_step": n * 8.0, "d2h_bytes_per_step": 16.0,
+            "bytes_note": "per instance: KEYS copied H2D (8 B/key) + counters D2H; the rows of missed keys come from the NVLink "
+                          "tier, not over PCIe",
+            "clocks_per_gpu": clocks}
+
+
 def _ps_model(name, rows, seed, dim, slots, batch, device, *, gpucache=True, gpucacheper=0.2, pagelock=True, instances=1):
     return {"model": name, "sparse_files": [f"synthetic:rows={rows},seed={seed}"], "num_of_worker_buffer_in_pool": instances,
             "embedding_vecsize_per_table": [dim], "maxnum_catfeature_query_per_table_per_sample": [slots],
@@ -661,6 +750,27 @@ def run_ours(a):
     hps.load_table_procedural("dcn", 0, a.rows, SEED)
     hps.create_embedding_cache("dcn")
     setup_s = time.perf_counter() - t0
+    # N > 1: the replicas' cache misses leave the host fabric (29 GB/s per GPU at N=4, 21-37 at N=8 against 49-55 at
+    # N=1: profiles/pcie_conc_r02.txt) for the NVLink tier — one process per GPU, shards mapped over CUDA IPC
+    use_tier = world > 1 and not a.no_peer_tier and a.miss_path == "direct"
+    tier_info = None
+    if use_tier:
+        def gather(obj):
+            got = [None] * world
+            dist.all_gather_object(got, obj)
+            return got
+
+        t1 = time.perf_counter()
+        tier_info = hps.peer_tier_connect_distributed("dcn", local, rank, world, 1, gather)
+        tier_info["setup_s"] = time.perf_counter() - t1
+
+    def tier_teardown():
+        if use_tier:
+            torch.cuda.synchronize()
+            dist.barrier()  # nobody reads a shard any more
+            hps.peer_tier_detach("dcn", local)
+            dist.barrier()  # every rank has unmapped its peers before any shard is freed
+
     hot = hps.cache_keys("dcn", local, 0)
     warm_rows = int(np.ceil(a.gpucacheper * a.rows))
     # every request is distinct (fresh cold keys each step): [prefill | device arm | e2e arm]
@@ -762,7 +872,10 @@ def run_ours(a):
                               "misses": miss_per, "chunks": a.chunks, "pull_ctas": a.pull_ctas, "verified_rows": verified_rows,
                               "all_hit_kernel_ms": st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches),
                               "all_hit_frac": (n * (8 + 8 * a.dim)) / (st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches) / 1e3) / 1e9 / peak_gbs,
+                              "tier_gbs": (st.tier_bytes / a.steps) / (max(st.pull_kernel_ms, 1e-9) / a.steps / 1e3) / 1e9,
                               "all_hit_step_ms": ms_h / a.steps}), flush=True)
+        del sess
+        tier_teardown()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -775,6 +888,16 @@ def run_ours(a):
     link_gbs = measure_host_link_gbs(torch)
     pull_ms = (st.pull_kernel_ms if st.pull_kernel_ms > 0 else st.insert_kernel_ms) / a.steps  # first pull start -> last pull end
     miss_bytes = (st.h2d_bytes - 0) / a.steps  # device-key arm: every H2D byte is a missed row crossing PCIe
+    roofline_tier = None
+    if use_tier:
+        tier_b = st.tier_bytes / a.steps
+        roofline_tier = {"bound": "nvlink", "kernel": "pull_binned (rows read from the owners' HBM shards)",
+                         "achieved": tier_b / (pull_ms / 1e3) / 1e9 if pull_ms > 0 else 0.0, "peak": 900.0,
+                         "peak_source": "NVLink 5 nominal, one direction; (world-1)/world of the bytes cross it, the rest is local HBM",
+                         "unit": "GB/s", "frac": (tier_b / (pull_ms / 1e3) / 1e9 / 900.0) if pull_ms > 0 else 0.0,
+                         "avg_ms_per_step": pull_ms, "algorithmic_bytes_per_step": tier_b,
+                         "bytes_over_nvlink_per_step": tier_b * (world - 1) / world,
+                         "share_of_step": pull_ms / (ms_serial / a.steps)}
     roofline_host_link = {"bound": "pcie", "kernel": "pull_misses" if a.miss_path == "direct" else "host gather + cudaMemcpyAsync + insert_merge",
                           "achieved": miss_bytes / (pull_ms / 1e3) / 1e9 if pull_ms > 0 else 0.0, "peak": link_gbs,
                           "peak_source": "pinned 128 MiB cudaMemcpyAsync H2D measured in this run", "unit": "GB/s",
@@ -798,7 +921,8 @@ def run_ours(a):
     # ---- end-to-end arm 2 (headline e2e): the reference-facing plugin call ------------------------------
     # TRITONBACKEND_ModelInstanceExecute of libtriton_hps.so, driven by the fake-Triton harness: KEYS/NUMKEYS in
     # host memory, OUTPUT0 in a GPU buffer (what Triton hands a gpucache model, hps.cc:638-642).
-    if a.skip_triton_arm:
+    one_server = use_tier and not a.skip_triton_arm  # N > 1: ONE server process drives all GPUs (arm at the end, rank 0)
+    if a.skip_triton_arm or one_server:
         e2e = dict(e2e_session)
         e2e["note"] = "--skip-triton-arm: session-level end-to-end arm reported"
     else:
@@ -995,6 +1119,33 @@ def run_ours(a):
                       "cublas_note": "torch bf16 matmul + relu of the three GEMM layers on pre-converted operands (no input conversion, no last layer)"}
         mlp.close()
 
+    if use_tier:
+        del sess
+        tier_teardown()
+    if one_server:
+        # The reference's multi-GPU deployment is ONE tritonserver process with one cache per device
+        # (hps_backend/src/model_state.cpp:395-419): rank 0 plays that server for all N GPUs, with the NVLink tier switched
+        # on in ps.json; the other ranks have released their GPUs' memory and wait.
+        import gc
+
+        del hps, out, d_reqs, h_reqs, hit_reqs
+        gc.collect()
+        torch.cuda.empty_cache()
+        dist.barrier()
+        self_check_failed = None
+        if rank == 0:
+            try:
+                e2e_srv = triton_arm_one_server(a, world, hot, warm_rows, n, torch, ClockSampler)
+                e2e_srv["session_level"] = {k: e2e_session[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+                e2e = e2e_srv
+            except SystemExit as ex:  # wrong rows: fail the run, but only after the other ranks have been released
+                self_check_failed = ex
+            except Exception as ex:  # keep the line: the session-level arm stands in, and the failure is named
+                print(f"[bench] one-server Triton arm FAILED: {ex!r}", file=sys.stderr)
+                e2e["note"] = f"one-server Triton arm failed ({ex!r}); session-level end-to-end arm reported"
+        dist.barrier()
+        if self_check_failed is not None:
+            raise self_check_failed
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1013,7 +1164,7 @@ def run_ours(a):
         import gc
         import tempfile
 
-        del sess, hps, out, d_reqs, h_reqs, hit_reqs
+        del sess, hps, out, d_reqs, h_reqs, hit_reqs  # (world == 1: nothing was released above)
         gc.collect()
         torch.cuda.empty_cache()
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -1049,7 +1200,11 @@ def run_ours(a):
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches per arm",
                    "hot_draw_probability": a.hit, "prefill_requests": a.prefill,
                    "load_factor": a.load_factor, "miss_path": a.miss_path,
-                   "parallelism": f"replica x{world}", "setup_s": setup_s, "host_cores": os.cpu_count()},
+                   "parallelism": f"replica x{world}" + (" + NVLink tier: the host table also sharded over the GPUs' HBM "
+                                                         "(1/N per GPU), cache misses read from the owner's shard by the "
+                                                         "pull kernel instead of over PCIe" if use_tier else ""),
+                   "setup_s": setup_s, "host_cores": os.cpu_count()},
+        "peer_tier": tier_info, "roofline_nvlink_tier": roofline_tier,
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "e2e_host_output": e2e_host_output, "e2e_session": e2e_session,
         "cache_hit": cache_hit, "small_batch": small_batch, "two_instances": two_instances, "dense_head": dense_head,
@@ -1058,7 +1213,7 @@ def run_ours(a):
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,
                       "insert_phase_ms_per_step": st.insert_kernel_ms / a.steps,
-                      "h2d_bytes_per_step": st.h2d_bytes / a.steps},
+                      "h2d_bytes_per_step": st.h2d_bytes / a.steps, "tier_bytes_per_step": st.tier_bytes / a.steps},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

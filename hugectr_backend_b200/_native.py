@@ -44,6 +44,7 @@ class ModelParamsC(ctypes.Structure):
         ("pull_grid_ctas", ctypes.c_int),
         ("probe_variant", ctypes.c_int),
         ("probe_variant_set", ctypes.c_int),
+        ("peer_tier", ctypes.c_int),
     ]
 
 
@@ -74,6 +75,18 @@ class SessionStatsC(ctypes.Structure):
         ("insert_kernel_ms", ctypes.c_double),
         ("host_gather_ms", ctypes.c_double),
         ("pull_kernel_ms", ctypes.c_double),
+        ("tier_bytes", ctypes.c_uint64),
+    ]
+
+
+class PeerTierInfoC(ctypes.Structure):
+    _fields_ = [
+        ("rank", ctypes.c_uint32),
+        ("world", ctypes.c_uint32),
+        ("committed", ctypes.c_int),
+        ("own_rows", ctypes.c_uint64),
+        ("own_bytes", ctypes.c_uint64),
+        ("index_entries_in_tier", ctypes.c_uint64),
     ]
 
 
@@ -123,6 +136,14 @@ SYMBOLS = {
     "hpsx_shard_group_capacity": (_int, [_vp, c_size_p]),
     "hpsx_shard_group_set_timeout_ms": (_int, [_vp, ctypes.c_uint64]),
     "hpsx_shard_group_destroy": (_int, [_vp]),
+    "hpsx_cache_peer_tier_build": (_int, [_vp, ctypes.c_uint32, ctypes.c_uint32]),
+    "hpsx_cache_peer_tier_export": (_int, [_vp, _sz, _vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "hpsx_cache_peer_tier_attach_ipc": (_int, [_vp, _sz, ctypes.c_uint32, _vp, ctypes.c_uint64, ctypes.c_uint64]),
+    "hpsx_cache_peer_tier_attach_local": (_int, [_vp, ctypes.c_uint32, _vp]),
+    "hpsx_cache_peer_tier_commit": (_int, [_vp]),
+    "hpsx_cache_peer_tier_detach": (_int, [_vp]),
+    "hpsx_cache_peer_tier_info": (_int, [_vp, ctypes.POINTER(PeerTierInfoC)]),
+    "hpsx_ps_peer_tier_connect_local": (_int, [_vp, _cp]),
     "hpsx_copy_to_host": (_int, [_int, _vp, _vp, _sz]),
     "hpsx_session_lookup_ex": (_int, [_vp, _vpp, _int, _vpp, _int, c_size_p, _sz]),
     "hpsx_session_lookup_batch": (_int, [_vp, _sz, _vpp, _int, _vpp, _int, c_size_p]),

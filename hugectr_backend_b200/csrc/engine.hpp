@@ -31,6 +31,24 @@ struct Model;
 
 }  // namespace hpsx
 
+namespace hpsx {
+// NVLink tier of one cache (kernels.h launch_tier_fill / launch_index_repoint; include/hpsx.h hpsx_cache_peer_tier_*).
+struct PeerTier {
+  struct Shard {
+    unsigned char* base = nullptr;  // [int64 keys[cap] | pad to 512 B | float rows[cap][dim]], one cudaMalloc
+    uint64_t cap = 0, rows = 0;
+    bool ipc = false;               // mapped with cudaIpcOpenMemHandle (closed, not freed, on release)
+    static size_t rows_offset(uint64_t cap) { return (static_cast<size_t>(cap) * sizeof(int64_t) + 511) & ~static_cast<size_t>(511); }
+    static size_t bytes(uint64_t cap, size_t dim) { return rows_offset(cap) + static_cast<size_t>(cap) * dim * sizeof(float); }
+  };
+  uint32_t rank = 0, world = 0;            // world == 0: no tier
+  std::vector<Shard> own;                  // [T]
+  std::vector<std::vector<Shard>> peers;   // [T][world]; entry [t][rank] aliases own[t]
+  bool committed = false;                  // the direct-pull index points at the shards
+  uint64_t repointed = 0;                  // index entries that point into a shard (all tables)
+};
+}  // namespace hpsx
+
 // One HBM embedding cache: all tables of one model on one device.
 struct hpsx_cache {
   hpsx::Model* model = nullptr;
@@ -49,6 +67,7 @@ struct hpsx_cache {
   // call (also where they run outside `rw`), a database reload holds it exclusively while it rewrites rows,
   // re-registers slabs and rebuilds the index.  Lock order: async_mu, pull_rw, rw.
   std::shared_mutex pull_rw;
+  hpsx::PeerTier tier;                  // guarded by pull_rw (exclusive to change, shared while kernels read through it)
   // asynchronous insertion (hit_rate >= hit_rate_threshold): one workspace, jobs serialised
   std::mutex async_mu;
   std::condition_variable async_cv;
@@ -75,6 +94,7 @@ struct Model {
   int request_chunks = 4;
   int pull_grid_ctas = 148;
   int probe_variant = kProbeV8;
+  bool peer_tier = false;
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
   std::vector<std::string> table_names;

@@ -59,6 +59,15 @@ int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, floa
 int ensure_pool_stage(hpsx_session* s, size_t m);
 int ensure_sort_workspace(hpsx_session* s);
 size_t pull_sort_min();
+int sync_direct_pull_index(hpsx_cache* c, cudaStream_t stream);
+
+// peer_tier.cpp — callers hold c->async_mu, c->pull_rw and c->rw exclusively (or the cache is not published yet)
+int tier_build_locked(hpsx_cache* c, uint32_t rank, uint32_t world);
+int tier_attach_local_locked(hpsx_cache* c, size_t table, uint32_t peer, hpsx_cache* peer_cache);
+int tier_commit_locked(hpsx_cache* c);
+void tier_release(hpsx_cache* c);  // unmaps the peers' shards and frees the own ones
+// every cache of `m` in this process becomes one rank of a tier (ranks in ascending device order)
+int tier_connect_local_locked(hpsx::Model* m, const std::vector<hpsx_cache*>& caches);
 
 }  // namespace eng
 }  // namespace hpsx

@@ -192,7 +192,7 @@ int insert_rows_from_host(hpsx_ps* ps, hpsx_cache* c, size_t t, const int64_t* k
 // and again after the host tables changed (update_database): registers the new slab ranges, re-allocates an
 // index that became too small and rebuilds it.  The caller excludes lookups (c->rw exclusive, or the cache is
 // not published yet) and has the device selected.
-int sync_direct_pull_index(hpsx_cache* c, cudaStream_t stream) {
+int sync_direct_pull_index_impl(hpsx_cache* c, cudaStream_t stream) {
   Model* model = c->model;
   const size_t T = model->tables.size();
   int64_t* d_ikeys = nullptr;
@@ -312,7 +312,7 @@ int build_cache(hpsx_ps* ps, Model* model, int device, std::unique_ptr<hpsx_cach
     }
   }
   if (rc == HPSX_OK && model->direct_pull) {
-    rc = sync_direct_pull_index(c.get(), stream);
+    rc = sync_direct_pull_index_impl(c.get(), stream);
     c->direct_pull = rc == HPSX_OK;
   }
   cudaFree(d_inserted);
@@ -394,6 +394,8 @@ void* bf16_dst(const hpsx_session* s, size_t t, size_t row_off, size_t dim) {
 
 namespace hpsx {
 namespace eng {
+
+int sync_direct_pull_index(hpsx_cache* c, cudaStream_t stream) { return sync_direct_pull_index_impl(c, stream); }
 
 int stream_miss_rows(hpsx_session* s, size_t t, size_t key_off, uint32_t m, float* d_out, bool insert,
                      uint32_t epoch, float* d_all_stage, std::unique_lock<std::shared_mutex>* wlock,
@@ -740,6 +742,8 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
   const bool overlap = host_out;  // pull of group g on stream B beside the probes of group g+1
   const bool fused = !c->is_static && !split && !overlap;
   cudaStream_t P = overlap ? B : A;  // where the pulls run
+  // NVLink reads need ~2 MB in flight (latency x 700 GB/s) where PCIe needs ~130 KB: four CTAs per SM instead of one
+  const int pull_ctas = c->tier.committed ? std::max(s->pull_grid_ctas, 148 * 4) : s->pull_grid_ctas;
   size_t li = 0;
   for (size_t g = 0; g < G; ++g) {
     const BinGroup& grp = groups[g];
@@ -766,7 +770,7 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
     if (g == 0) HPSX_CU(cudaEventRecord(s->ev_pull[0], P));
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 2], P));
     HPSX_CU(launch_pull_binned(dt, grp.bins, grp.out, grp.out_bf16, batch ? grp.outs.data() : nullptr,
-                               batch ? static_cast<int>(R) : 0, d_absent + g, s->pull_grid_ctas, P,
+                               batch ? static_cast<int>(R) : 0, d_absent + g, pull_ctas, P,
                                fused ? ((s->debug_flags & 8) ? 2 : 1) : 0, epoch, d_inserted + g));
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 3], P));
     HPSX_CU(cudaEventRecord(ev_pulled[g], P));
@@ -839,7 +843,8 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
     const uint32_t absent = s->h_counters[2 * s->vt + g];
     s->stats.hits += grp.n - m;
     s->stats.misses += m;
-    s->stats.h2d_bytes += (m - absent) * c->tables[grp.table].dim * sizeof(float);  // rows pulled over PCIe by the kernel
+    // rows pulled by the kernel: over PCIe from host memory, or from the NVLink tier's shards
+    (c->tier.committed ? s->stats.tier_bytes : s->stats.h2d_bytes) += (m - absent) * c->tables[grp.table].dim * sizeof(float);
     s->stats.default_filled += absent;
     total_keys += grp.n;
     total_miss += m;
@@ -1001,7 +1006,7 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
     s->stats.misses += m;
     const size_t row_bytes = s->model->tables[t % T]->dim() * sizeof(float);
     const uint32_t absent = s->h_counters[2 * s->vt + t];
-    s->stats.h2d_bytes += static_cast<uint64_t>(m - absent) * row_bytes;  // rows pulled over PCIe by the kernel
+    (c->tier.committed ? s->stats.tier_bytes : s->stats.h2d_bytes) += static_cast<uint64_t>(m - absent) * row_bytes;  // rows pulled by the kernel (PCIe, or the NVLink tier)
     s->stats.default_filled += (m != 0 && !decide_sync(s, n, m)) ? m : absent;
     s->miss_ratio = 0.5 * s->miss_ratio + 0.5 * static_cast<double>(m) / static_cast<double>(n);
     if (trace_on()) {
@@ -1237,6 +1242,7 @@ hpsx_cache::~hpsx_cache() {
       if (t.buckets) cudaFree(t.buckets);
       if (t.values) cudaFree(t.values);
     }
+    hpsx::eng::tier_release(this);
     for (hpsx::IndexSlot* ix : indexes) cudaFree(ix);
     if (async_d_keys) cudaFree(async_d_keys);
     if (async_d_stage) cudaFree(async_d_stage);
@@ -1364,6 +1370,7 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
   m->request_chunks = cfg.hpsx_request_chunks > 0 ? std::min<int>(cfg.hpsx_request_chunks, kMaxBatchRequests) : 4;
   m->pull_grid_ctas = cfg.hpsx_pull_grid_ctas > 0 ? std::min(cfg.hpsx_pull_grid_ctas, 148 * 8) : 148;
   m->probe_variant = cfg.hpsx_probe == "ldg" ? kProbeLdg : cfg.hpsx_probe == "tma" ? kProbeTma : kProbeV8;
+  m->peer_tier = cfg.hpsx_peer_tier;
   for (size_t t = 0; t < T; ++t) {
     if (cfg.embedding_vecsize_per_table[t] == 0)
       return fail(HPSX_ERR_INVALID_ARG, "embedding_vecsize_per_table must be > 0");
@@ -1426,6 +1433,7 @@ int hpsx_ps_add_model(hpsx_ps* ps, const hpsx_model_params* p) {
   cfg.hpsx_request_chunks = p->request_chunks;
   cfg.hpsx_pull_grid_ctas = p->pull_grid_ctas;
   cfg.hpsx_probe = p->probe_variant == kProbeLdg && p->probe_variant_set ? "ldg" : p->probe_variant == kProbeTma ? "tma" : "";
+  cfg.hpsx_peer_tier = p->peer_tier != 0;
   return add_model_cfg(ps, cfg, p->cache_load_factor);
   HPSX_GUARD_END
 }
@@ -1543,6 +1551,7 @@ int hpsx_ps_get_model_params(hpsx_ps* ps, const char* model, hpsx_model_params* 
   out->pull_grid_ctas = m->pull_grid_ctas;
   out->probe_variant = m->probe_variant;
   out->probe_variant_set = 1;
+  out->peer_tier = m->peer_tier ? 1 : 0;
   return HPSX_OK;
 }
 
@@ -1604,6 +1613,11 @@ int hpsx_ps_create_embedding_cache_per_model(hpsx_ps* ps, const char* model) {
     std::lock_guard<std::mutex> lk(m->mu);
     m->caches[dev] = std::move(c);
   }
+  if (m->peer_tier) {
+    if (!m->direct_pull)
+      return fail(HPSX_ERR_INVALID_ARG, "model '" + m->cfg.model_name + "': hpsx_peer_tier needs enable_pagelock");
+    if (m->cfg.deployed_devices.size() >= 2) return hpsx_ps_peer_tier_connect_local(ps, model);
+  }
   return HPSX_OK;
   HPSX_GUARD_END
 }
@@ -1652,8 +1666,16 @@ int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model) {
     if (!c->direct_pull) continue;
     DeviceGuard guard(c->device);
     if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
-    const int rc = sync_direct_pull_index(c, c->async_stream);
+    const int rc = sync_direct_pull_index_impl(c, c->async_stream);
     if (rc != HPSX_OK) return rc;
+    c->tier.committed = false;  // the index holds host addresses again
+    c->tier.repointed = 0;
+  }
+  if (m->peer_tier) {
+    std::vector<hpsx_cache*> dp;
+    for (hpsx_cache* c : caches)
+      if (c->direct_pull) dp.push_back(c);
+    if (dp.size() >= 2) return tier_connect_local_locked(m, dp);
   }
   return HPSX_OK;
   HPSX_GUARD_END

@@ -595,6 +595,63 @@ __global__ void __launch_bounds__(kBlock) index_build_kernel(IndexSlot* slots, u
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// NVLink tier (kernels.h): the rows of the page-locked host table sharded over the HBM of the GPUs of one box.
+// ------------------------------------------------------------------------------------------------
+// One warp per (key, host row address) pair: the pairs this rank owns are appended to its shard, the row is copied
+// out of mapped host memory (zero-copy PCIe reads, once, at build time).  Pairs past `cap` stay host-only.
+__global__ void __launch_bounds__(kBlock) tier_fill_kernel(const int64_t* __restrict__ keys,
+                                                           const uint64_t* __restrict__ addrs, size_t n, uint32_t rank,
+                                                           uint32_t world, uint32_t dim, int64_t* shard_keys,
+                                                           float* shard_rows, unsigned long long cap,
+                                                           unsigned long long* count) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const size_t warp = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
+  const size_t nwarps = (static_cast<size_t>(gridDim.x) * kBlock) >> 5;
+  for (size_t i = warp; i < n; i += nwarps) {
+    const int64_t key = keys[i];
+    if (key == kEmptyKey || owner_of(key, world) != rank) continue;
+    unsigned long long j = 0;
+    if (lane == 0) j = atomicAdd(count, 1ull);
+    j = __shfl_sync(kFull, j, 0);
+    if (j >= cap) continue;
+    const float* src = reinterpret_cast<const float*>(addrs[i]);
+    float* dst = shard_rows + j * dim;
+    if ((dim & 3u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(dst);
+      for (uint32_t v = lane; v < dim / 4u; v += 32u) d4[v] = s4[v];
+    } else {
+      for (uint32_t v = lane; v < dim; v += 32u) dst[v] = src[v];
+    }
+    if (lane == 0) shard_keys[j] = key;
+  }
+}
+
+// Points the direct-pull index at a shard: entry i of the shard (key shard_keys[i], possibly read over NVLink from
+// the owner's HBM) lives at shard_rows + i * dim.  Keys that are not in this rank's index are left alone (the index
+// is the host table's: a key the host table does not have keeps answering with the default vector).
+__global__ void __launch_bounds__(kBlock) index_repoint_kernel(IndexSlot* slots, uint64_t mask,
+                                                               const int64_t* __restrict__ shard_keys,
+                                                               const float* shard_rows, unsigned long long n,
+                                                               uint32_t dim, unsigned long long* repointed) {
+  const unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const int64_t key = shard_keys[i];
+  if (key == kEmptyKey) return;
+  uint64_t slot = mix64(static_cast<uint64_t>(key)) & mask;
+  while (true) {
+    const int64_t k = __ldcg(reinterpret_cast<const long long*>(&slots[slot].key));
+    if (k == key) {
+      slots[slot].row = shard_rows + i * dim;
+      if (repointed != nullptr) atomicAdd(repointed, 1ull);
+      return;
+    }
+    if (k == kEmptyKey) return;
+    slot = (slot + 1) & mask;
+  }
+}
+
 // Warp-cooperative index lookup: 8 lanes read 8 consecutive slots (one 128-B line), the first match
 // before the first empty slot wins.  Returns the host row address or nullptr (key not in the table).
 __device__ __forceinline__ const float* index_find(const IndexSlot* __restrict__ index, uint64_t mask,
@@ -1653,6 +1710,25 @@ cudaError_t preload_miss_path_kernels() {
 cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t stream) {
   if (capacity == 0) return cudaSuccess;
   index_clear_kernel<<<grid_for(capacity), kBlock, 0, stream>>>(slots, capacity);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tier_fill(const int64_t* d_keys, const uint64_t* d_row_addrs, size_t n, uint32_t rank, uint32_t world,
+                             size_t dim, int64_t* shard_keys, float* shard_rows, unsigned long long cap,
+                             unsigned long long* d_count, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  if (world == 0 || rank >= world || dim == 0 || dim > 0xFFFFFFFFull) return cudaErrorInvalidValue;
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n * 32 + kBlock - 1) / kBlock, 148u * 16u));
+  tier_fill_kernel<<<grid, kBlock, 0, stream>>>(d_keys, d_row_addrs, n, rank, world, static_cast<uint32_t>(dim), shard_keys,
+                                                shard_rows, cap, d_count);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_index_repoint(IndexSlot* slots, uint64_t mask, const int64_t* shard_keys, const float* shard_rows,
+                                 unsigned long long n, size_t dim, unsigned long long* d_repointed, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  index_repoint_kernel<<<grid_for(n), kBlock, 0, stream>>>(slots, mask, shard_keys, shard_rows, n, static_cast<uint32_t>(dim),
+                                                           d_repointed);
   return cudaGetLastError();
 }
 

@@ -140,6 +140,22 @@ cudaError_t launch_index_clear(IndexSlot* slots, uint64_t capacity, cudaStream_t
 cudaError_t launch_index_build(IndexSlot* slots, uint64_t mask, const int64_t* d_keys,
                                const uint64_t* d_row_addrs, size_t n, cudaStream_t stream);
 
+// NVLink tier: with several GPUs in the box the rows of a page-locked host table are also kept
+// SHARDED over the GPUs' HBM — rank r holds the rows with owner_of(key, world) == r as [keys | rows] in one
+// allocation that every rank maps (peer access / CUDA IPC) — and the direct-pull index of every rank points at
+// those copies instead of at host memory.  The pull kernels are unchanged: a missed row is read with the same
+// loads, over NVLink from the owner's HBM (or from local HBM) instead of over PCIe from host DRAM.  One-sided: the
+// owner's SMs, streams and locks are not involved, replicas stay independent (no collective, no flags).
+// launch_tier_fill: of n (key, device-visible host row address) pairs append those owned by `rank` to the shard
+// (*d_count = entries so far, may run past `cap`: the excess stays host-only).
+cudaError_t launch_tier_fill(const int64_t* d_keys, const uint64_t* d_row_addrs, size_t n, uint32_t rank, uint32_t world,
+                             size_t dim, int64_t* shard_keys, float* shard_rows, unsigned long long cap,
+                             unsigned long long* d_count, cudaStream_t stream);
+// launch_index_repoint: index[shard_keys[i]].row = shard_rows + i * dim for the keys the index already holds;
+// shard_keys / shard_rows may be a peer's memory.  *d_repointed (nullable) counts the entries changed.
+cudaError_t launch_index_repoint(IndexSlot* slots, uint64_t mask, const int64_t* shard_keys, const float* shard_rows,
+                                 unsigned long long n, size_t dim, unsigned long long* d_repointed, cudaStream_t stream);
+
 // a8: pooled[b*dim..) = sum_{j<hotness} row(src[b*hotness+j]) (mean: / hotness), ascending j, fp32.
 // Rows come from the cache slab or (kSrcMissBit) from the staged miss rows.
 cudaError_t launch_pooled_gather(const DeviceTable& t, const uint32_t* d_src, const float* d_stage,

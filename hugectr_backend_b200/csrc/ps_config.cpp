@@ -317,6 +317,7 @@ void parse_model(const json::Value& j, bool i64, ModelConfig* m) {
   need(j, "hpsx_request_chunks", &m->hpsx_request_chunks, false);
   need(j, "hpsx_pull_grid_ctas", &m->hpsx_pull_grid_ctas, false);
   need(j, "hpsx_probe", &m->hpsx_probe, false);
+  need(j, "hpsx_peer_tier", &m->hpsx_peer_tier, false);
   m->hpsx_probe = lower(m->hpsx_probe);
   if (!m->hpsx_probe.empty() && m->hpsx_probe != "v8" && m->hpsx_probe != "ldg" && m->hpsx_probe != "tma")
     throw std::invalid_argument("The parameter 'hpsx_probe' of model '" + m->model_name + "' must be v8, ldg or tma.");

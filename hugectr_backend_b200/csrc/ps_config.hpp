@@ -85,6 +85,7 @@ struct ModelConfig {
   int hpsx_request_chunks = 0;
   int hpsx_pull_grid_ctas = 0;
   std::string hpsx_probe;  // "", "v8", "ldg", "tma"
+  bool hpsx_peer_tier = false;  // NVLink tier over the deployed devices (needs enable_pagelock and >= 2 devices)
   // refresh knobs: carried for the Triton shell (model_state.cpp:312-335)
   float refresh_delay = 0.0f, refresh_interval = 0.0f;
 };

@@ -59,6 +59,7 @@ class ModelParams:
     request_chunks: int = 0
     pull_grid_ctas: int = 0
     probe_variant: Optional[str] = None  # "v8" (default), "ldg", "tma"
+    peer_tier: bool = False  # NVLink tier over the deployed devices of this process (needs enable_pagelock)
 
 
 @dataclass
@@ -78,6 +79,7 @@ class SessionStats:
     insert_kernel_ms: float
     host_gather_ms: float
     pull_kernel_ms: float = 0.0
+    tier_bytes: int = 0
 
 
 class HPS:
@@ -156,6 +158,7 @@ class HPS:
         c.pull_grid_ctas = int(p.pull_grid_ctas)
         c.probe_variant_set = 0 if p.probe_variant is None else 1
         c.probe_variant = PROBE_VARIANTS[p.probe_variant] if p.probe_variant is not None else 0
+        c.peer_tier = 1 if p.peer_tier else 0
         N.check(self._L.hpsx_ps_add_model(self._h, ctypes.byref(c)))
         self._dims[p.model_name] = [int(v) for v in p.embedding_vecsize_per_table]
 
@@ -223,6 +226,55 @@ class HPS:
         n = ctypes.c_size_t()
         N.check(self._L.hpsx_cache_dump_keys(self._cache(model, device), table, _addr(out), cap, ctypes.byref(n)))
         return out[: n.value].copy()
+
+    # ---- NVLink tier (include/hpsx.h hpsx_cache_peer_tier_*) ----
+    def peer_tier_connect_local(self, model: str) -> None:
+        """Every cache of `model` in this process becomes one rank of a tier."""
+        N.check(self._L.hpsx_ps_peer_tier_connect_local(self._h, model.encode()))
+
+    def peer_tier_build(self, model: str, device: int, rank: int, world: int) -> None:
+        N.check(self._L.hpsx_cache_peer_tier_build(self._cache(model, device), rank, world))
+
+    def peer_tier_export(self, model: str, device: int, table: int):
+        """-> (64-byte CUDA IPC handle, rows, capacity) of this rank's shard of `table`."""
+        h = (ctypes.c_ubyte * 64)()
+        rows, cap = ctypes.c_uint64(), ctypes.c_uint64()
+        N.check(self._L.hpsx_cache_peer_tier_export(self._cache(model, device), table, h, ctypes.byref(rows), ctypes.byref(cap)))
+        return bytes(h), int(rows.value), int(cap.value)
+
+    def peer_tier_attach_ipc(self, model: str, device: int, table: int, peer: int, handle: bytes, rows: int, cap: int) -> None:
+        buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+        N.check(self._L.hpsx_cache_peer_tier_attach_ipc(self._cache(model, device), table, peer, buf, rows, cap))
+
+    def peer_tier_attach_local(self, model: str, device: int, peer: int, peer_hps: "HPS", peer_model: str, peer_device: int) -> None:
+        N.check(self._L.hpsx_cache_peer_tier_attach_local(self._cache(model, device), peer, peer_hps._cache(peer_model, peer_device)))
+
+    def peer_tier_commit(self, model: str, device: int) -> None:
+        N.check(self._L.hpsx_cache_peer_tier_commit(self._cache(model, device)))
+
+    def peer_tier_detach(self, model: str, device: int) -> None:
+        N.check(self._L.hpsx_cache_peer_tier_detach(self._cache(model, device)))
+
+    def peer_tier_info(self, model: str, device: int) -> dict:
+        info = N.PeerTierInfoC()
+        N.check(self._L.hpsx_cache_peer_tier_info(self._cache(model, device), ctypes.byref(info)))
+        return {f[0]: int(getattr(info, f[0])) for f in N.PeerTierInfoC._fields_}
+
+    def peer_tier_connect_distributed(self, model: str, device: int, rank: int, world: int, num_tables: int, all_gather_object) -> dict:
+        """One process per GPU: build this rank's shards, exchange the CUDA IPC handles with
+        `all_gather_object(obj) -> list of world objs` (e.g. a torch.distributed wrapper), map the peers' shards and
+        point the direct-pull index at them.  Collective over the ranks; call peer_tier_detach on every rank (and
+        synchronise) before any rank destroys its cache."""
+        self.peer_tier_build(model, device, rank, world)
+        mine = [self.peer_tier_export(model, device, t) for t in range(num_tables)]
+        everyone = all_gather_object(mine)
+        for p, shards in enumerate(everyone):
+            if p == rank:
+                continue
+            for t, (handle, rows, cap) in enumerate(shards):
+                self.peer_tier_attach_ipc(model, device, t, p, handle, rows, cap)
+        self.peer_tier_commit(model, device)
+        return self.peer_tier_info(model, device)
 
     def drain_async(self, model: str, device: int) -> None:
         N.check(self._L.hpsx_cache_drain_async(self._cache(model, device)))

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define HPSX_ABI_VERSION 4
+#define HPSX_ABI_VERSION 5
 
 typedef enum hpsx_status {
   HPSX_OK = 0,
@@ -87,6 +87,9 @@ typedef struct hpsx_model_params {
   int probe_variant;                       /* probe+gather kernel, see hpsx_session_set_probe_variant; used when
                                               probe_variant_set != 0, else the default (4) */
   int probe_variant_set;
+  int peer_tier;                           /* "hpsx_peer_tier": with enable_pagelock and >= 2 deployed devices, the rows of
+                                              the host tables are also kept sharded over the devices' HBM and cache misses
+                                              are read over NVLink instead of PCIe (hpsx_cache_peer_tier_*) */
 } hpsx_model_params;
 
 /* ~ HugeCTR::VolatileDatabaseParams, hash_map / parallel_hash_map only (src/backend.cpp:129-216). */
@@ -117,6 +120,8 @@ typedef struct hpsx_session_stats {
   double host_gather_ms;       /* wall time spent in the host parameter-server gather */
   double pull_kernel_ms;       /* binned direct pull: first pull kernel start to last pull kernel end (sum); the pulls of a
                                   chunked request run beside the probes of its later chunks */
+  uint64_t tier_bytes;         /* bytes of missed rows read from the NVLink tier (peer or local HBM) instead of over PCIe;
+                                  not part of h2d_bytes */
 } hpsx_session_stats;
 
 /* ---------------------------------------------------------------------------------------------
@@ -308,6 +313,42 @@ int hpsx_shard_group_get_stats(const hpsx_shard_group* g, hpsx_shard_stats* out)
 int hpsx_shard_group_capacity(const hpsx_shard_group* g, size_t* rows);
 int hpsx_shard_group_set_timeout_ms(hpsx_shard_group* g, uint64_t ms);
 int hpsx_shard_group_destroy(hpsx_shard_group* g);
+
+/* ---------------------------------------------------------------------------------------------
+ * NVLink tier (engine extension; ps.json model key "hpsx_peer_tier").  The reference deploys one full cache per
+ * device and every device's cache misses go to the one host parameter server (src/model_state.cpp:395-419,
+ * include/backend.hpp:70-74) — over a host fabric that, measured on this pool, gives eight GPUs less than half the
+ * per-GPU rate it gives one.  With the tier the rows of a page-locked (enable_pagelock) host table are ALSO kept
+ * sharded over the HBM of the box's GPUs: rank r holds the rows with hpsx_owner(key, world) == r, every rank maps every
+ * shard (peer access inside one process, CUDA IPC between processes), and the key -> row-address index the
+ * direct-pull kernels use points into the shards.  A cache miss is then read over NVLink from its owner's HBM (or from
+ * local HBM) by the same kernels, one-sidedly: no collective, no flag, the owner's SMs are not involved.  Values are
+ * those of the host table at build time; hpsx_ps_update_database_per_model points the index back at host memory
+ * (and, for a model with "hpsx_peer_tier", rebuilds the tier of all its caches in this process).
+ *   one process, several devices:  hpsx_ps_peer_tier_connect_local (automatic for "hpsx_peer_tier": true)
+ *   one process per device:        build -> export (every table) -> exchange handles -> attach_ipc (every peer and
+ *                                  table) -> commit; detach on every rank before any rank destroys its cache.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct hpsx_peer_tier_info {
+  uint32_t rank, world;           /* world == 0: no tier */
+  int committed;                  /* the index points at the shards */
+  uint64_t own_rows;              /* rows in this rank's shards (all tables) */
+  uint64_t own_bytes;             /* HBM the shards occupy */
+  uint64_t index_entries_in_tier; /* keys whose misses are served from a shard (all tables) */
+} hpsx_peer_tier_info;
+int hpsx_cache_peer_tier_build(hpsx_cache* cache, uint32_t rank, uint32_t world);
+/* handle64: HPSX_SHARD_HANDLE_BYTES; rows / cap: what the importing rank passes to attach_ipc */
+int hpsx_cache_peer_tier_export(hpsx_cache* cache, size_t table, void* handle64, uint64_t* rows, uint64_t* cap);
+int hpsx_cache_peer_tier_attach_ipc(hpsx_cache* cache, size_t table, uint32_t peer, const void* handle64, uint64_t rows,
+                                    uint64_t cap);
+/* same process (all tables of `peer_cache`, which was built as rank `peer` of the same world) */
+int hpsx_cache_peer_tier_attach_local(hpsx_cache* cache, uint32_t peer, hpsx_cache* peer_cache);
+int hpsx_cache_peer_tier_commit(hpsx_cache* cache);
+/* Index back to host memory, peers unmapped, own shards freed (other ranks must have detached first). */
+int hpsx_cache_peer_tier_detach(hpsx_cache* cache);
+int hpsx_cache_peer_tier_info(hpsx_cache* cache, hpsx_peer_tier_info* out);
+/* Every cache of `model` in this process becomes one rank of a tier (ranks in ascending device order). */
+int hpsx_ps_peer_tier_connect_local(hpsx_ps* ps, const char* model);
 
 /* Blocking device -> host copy on `device` (small control tensors such as NUMKEYS that Triton
  * delivered in GPU memory). */

@@ -120,7 +120,7 @@ def test_numpy_and_c_oracle_agree_on_random_tables():
 # ------------------------------------------------------------------------------------------------
 def test_abi_library_exports_every_declared_symbol():
     L = hb.lib()
-    assert L.hpsx_abi_version() == 4
+    assert L.hpsx_abi_version() == 5
     header = open(os.path.join(ROOT, "include", "hpsx.h")).read()
     declared = set(re.findall(r"\b(hpsx_[a-z0-9_]+)\s*\(", header))
     declared -= {"hpsx_status"}

@@ -71,3 +71,77 @@ def test_sharded_lookup_nccl(cuda_device, pagelock, mode):
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert all(ret[r] for r in range(world))
+
+
+def _tier_worker(rank, world, port, rows, dim, seed, ret):
+    """One replica per GPU (the reference's multi-GPU mode) + the NVLink tier between them over CUDA IPC."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    import hugectr_backend_b200 as hb
+    from oracle import hps_oracle as O
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        hps = hb.HPS(num_partitions=8, num_threads=4)
+        hps.add_model(hb.ModelParams("dcn", 1 << 16, [dim], [1], [0.25], cache_size_percentage=0.1,
+                                     hit_rate_threshold=1.0, deployed_devices=[rank], enable_pagelock=True))
+        # every replica holds the whole table, but with its OWN values: a returned row names the rank that served it
+        hps.load_table_procedural("dcn", 0, rows, seed + rank)
+        hps.create_embedding_cache("dcn")
+        refs = []
+        for r in range(world):
+            t = O.NumpyTable(dim, 0.25)
+            t.fill_procedural(rows, seed + r)
+            refs.append(t)
+
+        def gather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        info = hps.peer_tier_connect_distributed("dcn", rank, rank, world, 1, gather)
+        ok = info["committed"] == 1 and info["index_entries_in_tier"] == rows
+        s = hps.session("dcn", rank)
+        rng = np.random.default_rng(200 + rank)
+        warm = rows // 10
+        for n in (1, 4097, 60000, 60000):
+            keys = rng.integers(warm, rows + 5, size=n)
+            out = torch.full((n, dim), float("nan"), device="cuda")
+            s.lookup([keys], [out], [n])
+            own = O.owner(keys, world)
+            exp = refs[rank].lookup(keys)  # default vector for keys past the table
+            for r in range(world):
+                sel = (own == r) & (keys < rows)
+                exp[sel] = refs[r].lookup(keys[sel])
+            ok &= bool(np.array_equal(out.cpu().numpy(), exp))
+        st = s.stats()
+        ok &= st.tier_bytes > 0 and st.h2d_bytes == (1 + 4097 + 60000 + 60000) * 8
+        del s
+        dist.barrier()  # nobody reads a shard any more
+        hps.peer_tier_detach("dcn", rank)
+        dist.barrier()  # every rank has unmapped its peers before any shard is freed with its cache
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_tier_over_cuda_ipc(cuda_device):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    rows, dim, seed = 300_000, 128, 77
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    procs = [ctx.Process(target=_tier_worker, args=(r, world, port, rows, dim, seed, ret)) for r in range(world)]
+    [p.start() for p in procs]
+    [p.join(300) for p in procs]
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert all(ret[r] for r in range(world))
