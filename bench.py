@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--local-tier", action="store_true",
+                    help="experiment (N = 1): a world-1 tier — the whole host table also in local HBM, misses pulled from it")
     ap.add_argument("--no-peer-tier", action="store_true",
                     help="N > 1: replicas only, every cache miss goes to host memory over PCIe (the reference's behaviour); default "
                          "with N > 1 is the NVLink tier: the host table sharded over the GPUs' HBM, misses read from the owner's shard")
@@ -414,12 +416,13 @@ def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
             for d, inst in enumerate(insts):
                 out = torch.empty(n * a.dim, device=f"cuda:{d}", dtype=torch.float32)
                 reqs = make_requests(a, hot, warm_rows, a.warmup + steps, SEED + 5000 + d)
-                prepared = [inst.prepare([dict(keys=k, numkeys=numkeys, gpu_out=out, out_device=d)]) for k in reqs]
-                work.append((d, inst, out, reqs, prepared))
+                pinned = [torch.from_numpy(k).pin_memory() for k in reqs]  # Triton hands the backend pinned input buffers
+                prepared = [inst.prepare([dict(keys=t.numpy(), numkeys=numkeys, gpu_out=out, out_device=d)]) for t in pinned]
+                work.append((d, inst, out, reqs, prepared, pinned))
             errors = []
 
             def serve(item, lo, hi, pre_keys):
-                d, inst, out, reqs, prepared = item
+                d, inst, out, reqs, prepared, _pinned = item
                 torch.cuda.set_device(d)
                 for k in pre_keys:
                     r = inst.infer(k, numkeys, gpu_out=out, out_device=d)
@@ -450,11 +453,11 @@ def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
             clocks = [s.stop() for s in samplers]
             assert not errors, errors
             verified = 0
-            for d, inst, out, reqs, prepared in work:
+            for d, inst, out, reqs, prepared, _pinned in work:
                 with torch.cuda.device(d):
                     verified += verify_rows(torch, torch.from_numpy(reqs[-1]).cuda(), out.view(n, a.dim), a.dim, SEED,
                                             f"one-server Triton arm, GPU {d}")
-            for d, inst, out, reqs, prepared in work:
+            for d, inst, out, reqs, prepared, _pinned in work:
                 for p in prepared:
                     p.close()
                 inst.close()
@@ -752,12 +755,15 @@ def run_ours(a):
     setup_s = time.perf_counter() - t0
     # N > 1: the replicas' cache misses leave the host fabric (29 GB/s per GPU at N=4, 21-37 at N=8 against 49-55 at
     # N=1: profiles/pcie_conc_r02.txt) for the NVLink tier — one process per GPU, shards mapped over CUDA IPC
-    use_tier = world > 1 and not a.no_peer_tier and a.miss_path == "direct"
+    use_tier = (world > 1 or a.local_tier) and not a.no_peer_tier and a.miss_path == "direct"
     tier_info = None
     if use_tier:
         def gather(obj):
             got = [None] * world
-            dist.all_gather_object(got, obj)
+            if world > 1:
+                dist.all_gather_object(got, obj)
+            else:
+                got[0] = obj
             return got
 
         t1 = time.perf_counter()
@@ -767,9 +773,11 @@ def run_ours(a):
     def tier_teardown():
         if use_tier:
             torch.cuda.synchronize()
-            dist.barrier()  # nobody reads a shard any more
+            if world > 1:
+                dist.barrier()  # nobody reads a shard any more
             hps.peer_tier_detach("dcn", local)
-            dist.barrier()  # every rank has unmapped its peers before any shard is freed
+            if world > 1:
+                dist.barrier()  # every rank has unmapped its peers before any shard is freed
 
     hot = hps.cache_keys("dcn", local, 0)
     warm_rows = int(np.ceil(a.gpucacheper * a.rows))
@@ -921,7 +929,7 @@ def run_ours(a):
     # ---- end-to-end arm 2 (headline e2e): the reference-facing plugin call ------------------------------
     # TRITONBACKEND_ModelInstanceExecute of libtriton_hps.so, driven by the fake-Triton harness: KEYS/NUMKEYS in
     # host memory, OUTPUT0 in a GPU buffer (what Triton hands a gpucache model, hps.cc:638-642).
-    one_server = use_tier and not a.skip_triton_arm  # N > 1: ONE server process drives all GPUs (arm at the end, rank 0)
+    one_server = use_tier and world > 1 and not a.skip_triton_arm  # N > 1: ONE server process drives all GPUs (arm at the end, rank 0)
     if a.skip_triton_arm or one_server:
         e2e = dict(e2e_session)
         e2e["note"] = "--skip-triton-arm: session-level end-to-end arm reported"

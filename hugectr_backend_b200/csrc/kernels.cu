@@ -430,29 +430,36 @@ struct InsertArgs {
 
 // Claims the cache slot for `key`.  Called by a whole warp.  Both candidate buckets (primary and second
 // choice) are locked in ascending index order, so concurrent inserts can neither deadlock nor place one key
-// twice; returns with the locks HELD (release_claim() must follow).  Result: slot index to write, or
-// kMissSlot when the key is already resident (LRU refreshed) or nothing may be evicted (all 16 ways were
-// touched in this very epoch).  Placement: a free way of the primary bucket, else a free way of the second
-// choice, else the way with the oldest stamp of the 16 (primary wins ties).
-struct Claim {
-  Bucket* lo;
-  Bucket* hi;  // nullptr when both choices are the same bucket
-};
-
+// twice.  Result: slot index to write, or kMissSlot when the key is already resident (LRU refreshed) or nothing
+// may be evicted (all 16 ways were touched in this very epoch).  Placement: a free way of the primary bucket,
+// else a free way of the second choice, else the way with the oldest stamp of the 16 (primary wins ties).
+//
+// The critical section covers the bucket's keys and stamps only, and the locks are RELEASED before this returns:
+// the caller then writes the row without any lock.  That is safe because a way claimed in this epoch carries
+// stamp == epoch and is never evicted by another claim of the same kernel, a second claim of the same key finds
+// it present and writes nothing, and rows are read only by probes, which never run beside an inserting kernel
+// (host lock of the cache).  The chain per insert is lock -> load -> store + release, without waiting for the
+// row (which may still be on its way over PCIe or NVLink) — a per-row fence used to cost several microseconds.
 __device__ __forceinline__ void lock_bucket(Bucket* B) {
-  while (atomicCAS(&B->lock, 0u, 1u) != 0u) __nanosleep(32);
+  uint32_t old;
+  do {
+    asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(&B->lock) : "memory");
+    if (old != 0u) __nanosleep(32);
+  } while (old != 0u);
+}
+__device__ __forceinline__ void unlock_bucket(Bucket* B) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&B->lock), "r"(0u) : "memory");
 }
 
 __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buckets, int64_t key, uint32_t epoch,
-                                               uint32_t lane, Claim* claim) {
+                                               uint32_t lane) {
   const uint32_t b1 = bucket_of(key, num_buckets);
   const uint32_t b2 = bucket2_of(key, num_buckets);
-  claim->lo = &buckets[min(b1, b2)];
-  claim->hi = b1 == b2 ? nullptr : &buckets[max(b1, b2)];
+  Bucket* lo = &buckets[min(b1, b2)];
+  Bucket* hi = b1 == b2 ? nullptr : &buckets[max(b1, b2)];
   if (lane == 0) {
-    lock_bucket(claim->lo);
-    if (claim->hi != nullptr) lock_bucket(claim->hi);
-    __threadfence();
+    lock_bucket(lo);
+    if (hi != nullptr) lock_bucket(hi);
   }
   __syncwarp();
   // lanes 0-7: ways of the primary bucket, lanes 8-15: ways of the second choice
@@ -467,45 +474,44 @@ __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buc
   }
   const unsigned present = __ballot_sync(kFull, lane < nways && k == key);
   int pick = -1;  // lane index of the chosen way
+  bool fresh = false;
   if (present != 0u) {
-    if (lane == __ffs(present) - 1) buckets[my_b].stamp[my_w] = epoch;  // already cached: refresh LRU only
-    return kMissSlot;
-  }
-  const unsigned empties = __ballot_sync(kFull, lane < nways && k == kEmptyKey);
-  if (empties != 0u) {
-    pick = __ffs(empties) - 1;  // primary ways come first
+    pick = __ffs(present) - 1;  // already cached: refresh LRU only
   } else {
-    // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted.  Instances that share the
-    // cache run with interleaved epochs: a stamp NEWER than this call's epoch is age 0 too (signed difference),
-    // not a huge unsigned age that would make the most recently used rows the first victims.
-    const int32_t diff = static_cast<int32_t>(epoch - st);
-    const uint32_t age = (lane < nways && diff > 0) ? static_cast<uint32_t>(diff) : 0u;
-    unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
+    const unsigned empties = __ballot_sync(kFull, lane < nways && k == kEmptyKey);
+    if (empties != 0u) {
+      pick = __ffs(empties) - 1;  // primary ways come first
+      fresh = true;
+    } else {
+      // oldest stamp wins; ways touched in this very epoch (age 0) are never evicted.  Instances that share the
+      // cache run with interleaved epochs: a stamp NEWER than this call's epoch is age 0 too (signed difference),
+      // not a huge unsigned age that would make the most recently used rows the first victims.
+      const int32_t diff = static_cast<int32_t>(epoch - st);
+      const uint32_t age = (lane < nways && diff > 0) ? static_cast<uint32_t>(diff) : 0u;
+      unsigned long long packed = (static_cast<unsigned long long>(age) << 8) | (255u - lane);
 #pragma unroll
-    for (int off = 8; off > 0; off >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
-      packed = o > packed ? o : packed;
+      for (int off = 8; off > 0; off >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
+        packed = o > packed ? o : packed;
+      }
+      packed = __shfl_sync(kFull, packed, 0);
+      if ((packed >> 8) != 0ull) {
+        pick = 255 - static_cast<int>(packed & 255ull);
+        fresh = true;
+      }
     }
-    packed = __shfl_sync(kFull, packed, 0);
-    if ((packed >> 8) != 0ull) pick = 255 - static_cast<int>(packed & 255ull);
   }
-  if (pick < 0) return kMissSlot;
   const uint32_t pb = pick < kWays ? b1 : b2;
-  const uint32_t pw = static_cast<uint32_t>(pick) & (kWays - 1);
+  const uint32_t pw = static_cast<uint32_t>(pick < 0 ? 0 : pick) & (kWays - 1);
   if (lane == 0) {
-    buckets[pb].keys[pw] = key;
-    buckets[pb].stamp[pw] = epoch;
+    if (pick >= 0) {
+      if (fresh) buckets[pb].keys[pw] = key;
+      buckets[pb].stamp[pw] = epoch;
+    }
+    if (hi != nullptr) unlock_bucket(hi);
+    unlock_bucket(lo);
   }
-  return pb * kWays + pw;
-}
-
-__device__ __forceinline__ void release_claim(const Claim& c, uint32_t lane) {
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) {
-    if (c.hi != nullptr) atomicExch(&c.hi->lock, 0u);
-    atomicExch(&c.lo->lock, 0u);
-  }
+  return fresh ? pb * kWays + pw : kMissSlot;
 }
 
 template <typename VecT>
@@ -523,9 +529,8 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
                         ? reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(a.miss_pos[i]) * V
                         : nullptr;
     VecT* dst_slab = nullptr;
-    Claim claim{nullptr, nullptr};
     if (a.insert && key != kEmptyKey) {
-      const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+      const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane);
       if (slot != kMissSlot) dst_slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
     }
     for (uint32_t v = lane; v < V; v += 32u) {
@@ -536,10 +541,7 @@ __global__ void __launch_bounds__(kBlock) insert_merge_kernel(const InsertArgs a
         if (dst_out && a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(a.miss_pos[i]) * V + v) * 4u, x);
       }
     }
-    if (claim.lo != nullptr) {
-      release_claim(claim, lane);
-      if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
-    }
+    if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
   }
 }
 
@@ -831,9 +833,8 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
       }
       VecT* dst_stage = a.stage ? reinterpret_cast<VecT*>(a.stage) + i * V : nullptr;
       VecT* dst_slab = nullptr;
-      Claim claim{nullptr, nullptr};
       if (a.insert && src[r] != nullptr && key[r] != kEmptyKey) {
-        const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key[r], a.epoch, lane, &claim);
+        const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key[r], a.epoch, lane);
         if (slot != kMissSlot) dst_slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
       }
       for (uint32_t v = lane; v < V; v += 32u) {
@@ -851,10 +852,7 @@ __global__ void __launch_bounds__(kBlock) pull_misses_kernel(const PullArgs a) {
           if (dst_out && a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(a.miss_pos[i]) * V + v) * 4u, x);
         }
       }
-      if (claim.lo != nullptr) {
-        release_claim(claim, lane);
-        if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
-      }
+      if (lane == 0 && dst_slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
       if (lane == 0 && src[r] == nullptr) {
         if (a.absent != nullptr) atomicAdd(a.absent, 1u);
         if (a.mark_absent != nullptr) a.mark_absent[i] = kEmptyKey;
@@ -933,10 +931,47 @@ struct PullBinnedArgs {
   uint32_t num_buckets;
   uint32_t epoch;
   uint32_t* inserted;
-  int claim_first;  // experiment: claim the slot before the PCIe reads are issued instead of while they are in flight
 };
 
-template <typename VecT, bool kInsert>
+// Group form of index_find: the warp resolves FOUR keys at once, 8 lanes (one 128-B index line) per key.  Lanes
+// 8g..8g+7 work on key[g]; returns, in every lane, the row address of the key of ITS group (nullptr: not in the table).
+__device__ __forceinline__ const float* index_find4(const IndexSlot* __restrict__ index, uint64_t mask, int64_t key,
+                                                    bool active, uint32_t lane) {
+  const uint32_t sub = lane & 7u, shift = lane & ~7u;
+  uint64_t base = mix64(static_cast<uint64_t>(key)) & mask;
+  const float* found = nullptr;
+  bool done = !active;
+  while (__any_sync(kFull, !done)) {
+    int64_t k = kEmptyKey;
+    unsigned long long row = 0;
+    if (!done) {
+      const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(&index[(base + sub) & mask]));
+      k = static_cast<int64_t>((static_cast<unsigned long long>(raw.y) << 32) | raw.x);
+      row = (static_cast<unsigned long long>(raw.w) << 32) | raw.z;
+    }
+    const unsigned hit = (__ballot_sync(kFull, !done && k == key) >> shift) & 0xffu;
+    const unsigned empty = (__ballot_sync(kFull, !done && k == kEmptyKey) >> shift) & 0xffu;
+    const bool is_hit = hit != 0u && (empty == 0u || __ffs(hit) < __ffs(empty));
+    const unsigned long long r = __shfl_sync(kFull, row, shift + (is_hit ? __ffs(hit) - 1 : 0));
+    if (!done) {
+      if (is_hit) {
+        found = reinterpret_cast<const float*>(r);
+        done = true;
+      } else if (empty != 0u) {
+        done = true;
+      } else {
+        base = (base + 8) & mask;
+      }
+    }
+  }
+  return found;
+}
+
+// kRows = 1: one row per warp at a time — the host link needs few bytes in flight, and the closer together they lie
+// in host memory the faster it runs (engine.hpp pull_grid_ctas).  kRows = 4 (rows of <= 32 vectors; NVLink tier):
+// four entries per warp iteration — their index lines are read together (8 lanes each), then all four rows are
+// in flight before the first is stored: NVLink / HBM want megabytes in flight, not locality.
+template <typename VecT, bool kInsert, int kRows>
 __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArgs a) {
   __shared__ uint32_t prefix[kMaxBins + 2];
   __shared__ uint32_t warp_sums[kBlock / 32];
@@ -946,6 +981,64 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
   const uint32_t nwarps = (gridDim.x * kBlock) >> 5;
   const uint32_t V = a.dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
   const VecT defv = splat<VecT>(a.default_value);
+  if constexpr (kRows == 4) {
+    const uint32_t g = lane >> 3;  // the entry of the quad whose index line this lane reads
+    for (uint32_t i0 = warp * 4u; i0 < total; i0 += nwarps * 4u) {
+      // lane 8e reads entry e's key and position; the other lanes get them by shuffle
+      int64_t my_key = kEmptyKey;
+      uint32_t my_pos = 0;
+      size_t my_r = 0;
+      const bool have = i0 + g < total;
+      if (have) {
+        my_r = bin_entry(a.bins, prefix, i0 + g);
+        my_key = a.bins.keys[my_r];
+        my_pos = a.bins.pos[my_r];
+      }
+      const float* my_row = index_find4(a.index, a.index_mask, my_key, have && my_key != kEmptyKey, lane);
+      if (have && my_key == kEmptyKey) my_row = a.sentinel_row;
+      int64_t key[4];
+      uint32_t pos[4];
+      const VecT* src[4];
+      VecT x[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        key[e] = __shfl_sync(kFull, my_key, 8 * e);
+        pos[e] = __shfl_sync(kFull, my_pos, 8 * e);
+        src[e] = reinterpret_cast<const VecT*>(
+            __shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), 8 * e));
+        x[e] = defv;
+        if (src[e] != nullptr && lane < V) x[e] = src[e][lane];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (i0 + e >= total) break;
+        VecT* dst = a.batch ? reinterpret_cast<VecT*>(a.batch_out[pos[e] >> kShardPosBits]) +
+                                  static_cast<size_t>(pos[e] & ((1u << kShardPosBits) - 1u)) * V
+                            : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(pos[e]) * V;
+        VecT* slab = nullptr;
+        if constexpr (kInsert) {
+          if (src[e] != nullptr && key[e] != kEmptyKey) {
+            const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key[e], a.epoch, lane);
+            if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
+          }
+        }
+        if (lane < V) {
+          st_stream(dst + lane, x[e]);
+          if (kInsert && slab != nullptr) slab[lane] = x[e];
+          if constexpr (sizeof(VecT) == 16) {
+            if (a.out_bf16) st_bf16x4(a.out_bf16 + (static_cast<size_t>(pos[e]) * V + lane) * 4u, x[e]);
+          }
+        }
+        if (lane == 0) {
+          if (kInsert && slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+          if (src[e] == nullptr) {
+            atomicAdd(a.absent, 1u);
+            a.bins.keys[bin_entry(a.bins, prefix, i0 + e)] = kEmptyKey;  // the insert pass skips it
+          }
+        }
+      }
+    }
+  } else {
   for (uint32_t i = warp; i < total; i += nwarps) {
     const size_t r = bin_entry(a.bins, prefix, i);
     const int64_t key = a.bins.keys[r];
@@ -955,15 +1048,8 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
     VecT* dst = a.batch ? reinterpret_cast<VecT*>(a.batch_out[p >> kShardPosBits]) +
                               static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
                         : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(p) * V;
-    // all PCIe reads of the row first (up to 4 per lane in flight); the slot claim runs while they are in flight
+    // all reads of the row first (up to 4 per lane in flight); the slot claim runs while they are in flight
     VecT* slab = nullptr;
-    Claim claim{nullptr, nullptr};
-    if constexpr (kInsert) {
-      if (a.claim_first && src != nullptr && key != kEmptyKey) {
-        const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
-        if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
-      }
-    }
     for (uint32_t v0 = 0; v0 < V; v0 += 128u) {
       VecT x[4];
 #pragma unroll
@@ -973,8 +1059,8 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
         if (src != nullptr && v < V) x[u] = src[v];
       }
       if constexpr (kInsert) {
-        if (!a.claim_first && v0 == 0 && src != nullptr && key != kEmptyKey) {
-          const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+        if (v0 == 0 && src != nullptr && key != kEmptyKey) {
+          const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane);
           if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
         }
       }
@@ -990,16 +1076,14 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
         }
       }
     }
-    if constexpr (kInsert) {
-      if (claim.lo != nullptr) {
-        release_claim(claim, lane);
-        if (lane == 0 && slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+    if (lane == 0) {
+      if (kInsert && slab != nullptr && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
+      if (src == nullptr) {
+        atomicAdd(a.absent, 1u);
+        a.bins.keys[r] = kEmptyKey;  // the insert pass skips it
       }
     }
-    if (lane == 0 && src == nullptr) {
-      atomicAdd(a.absent, 1u);
-      a.bins.keys[r] = kEmptyKey;  // the insert pass skips it
-    }
+  }
   }
 }
 
@@ -1033,13 +1117,11 @@ __global__ void __launch_bounds__(kBlock) insert_binned_kernel(const InsertBinne
     const VecT* src = a.batch ? reinterpret_cast<const VecT*>(a.batch_out[p >> kShardPosBits]) +
                                     static_cast<size_t>(p & ((1u << kShardPosBits) - 1u)) * V
                               : reinterpret_cast<const VecT*>(a.out) + static_cast<size_t>(p) * V;
-    Claim claim{nullptr, nullptr};
-    const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane, &claim);
+    const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key, a.epoch, lane);
     if (slot != kMissSlot) {
       VecT* dst = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
       for (uint32_t v = lane; v < V; v += 32u) dst[v] = ld_stream(src + v);
     }
-    release_claim(claim, lane);
     if (lane == 0 && slot != kMissSlot && a.inserted != nullptr) atomicAdd(a.inserted, 1u);
   }
 }
@@ -1619,7 +1701,7 @@ cudaError_t launch_resolve_and_sort_misses(const DeviceTable& t, const int64_t* 
 
 cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
                                float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
-                               cudaStream_t stream, int insert, uint32_t epoch, uint32_t* d_inserted) {
+                               cudaStream_t stream, int insert, uint32_t epoch, uint32_t* d_inserted, int rows_in_flight) {
   if (t.index == nullptr || bins.count == nullptr || bins.num_bins == 0 || bins.num_bins > kMaxBins || d_absent == nullptr)
     return cudaErrorInvalidValue;
   if (batch_count < 0 || batch_count > kMaxBatchOuts || (batch_count > 0 && (batch_outs == nullptr || d_out_bf16 != nullptr)))
@@ -1640,7 +1722,6 @@ cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float
   a.num_buckets = t.num_buckets;
   a.epoch = epoch;
   a.inserted = d_inserted;
-  a.claim_first = insert == 2;
   uintptr_t bits = reinterpret_cast<uintptr_t>(d_out) | (insert ? reinterpret_cast<uintptr_t>(t.values) : 0);
   for (int r = 0; r < batch_count; ++r) {
     a.batch_out[r] = batch_outs[r];
@@ -1652,19 +1733,25 @@ cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float
   const unsigned grid = static_cast<unsigned>(std::max(1, std::min(grid_ctas, 148 * 8)));
   const int vb = vec_bytes(t.dim, reinterpret_cast<const void*>(bits & 15u));
   if (d_out_bf16 != nullptr && (vb != 16 || (reinterpret_cast<uintptr_t>(d_out_bf16) & 7u) != 0)) return cudaErrorNotSupported;
-  // host rows: slabs are 4096-B aligned and rows dim*4 apart, so the row alignment is that of dim*4
-  if (vb == 16 && insert)
-    pull_binned_kernel<float4, true><<<grid, kBlock, 0, stream>>>(a);
+  // host rows: slabs are 4096-B aligned and rows dim*4 apart, so the row alignment is that of dim*4 (tier shards: 512-B
+  // aligned row arrays)
+  const bool quad = rows_in_flight >= 4 && t.dim / (vb / 4) <= 32;
+  if (vb == 16 && insert && quad)
+    pull_binned_kernel<float4, true, 4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 16 && quad)
+    pull_binned_kernel<float4, false, 4><<<grid, kBlock, 0, stream>>>(a);
+  else if (vb == 16 && insert)
+    pull_binned_kernel<float4, true, 1><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 16)
-    pull_binned_kernel<float4, false><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float4, false, 1><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 8 && insert)
-    pull_binned_kernel<float2, true><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float2, true, 1><<<grid, kBlock, 0, stream>>>(a);
   else if (vb == 8)
-    pull_binned_kernel<float2, false><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float2, false, 1><<<grid, kBlock, 0, stream>>>(a);
   else if (insert)
-    pull_binned_kernel<float, true><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float, true, 1><<<grid, kBlock, 0, stream>>>(a);
   else
-    pull_binned_kernel<float, false><<<grid, kBlock, 0, stream>>>(a);
+    pull_binned_kernel<float, false, 1><<<grid, kBlock, 0, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -1717,12 +1804,14 @@ cudaError_t preload_miss_path_kernels() {
   preload_one(pull_misses_kernel<float4, 1>, &e);
   preload_one(pull_misses_kernel<float2, 1>, &e);
   preload_one(pull_misses_kernel<float, 1>, &e);
-  preload_one(pull_binned_kernel<float4, false>, &e);
-  preload_one(pull_binned_kernel<float2, false>, &e);
-  preload_one(pull_binned_kernel<float, false>, &e);
-  preload_one(pull_binned_kernel<float4, true>, &e);
-  preload_one(pull_binned_kernel<float2, true>, &e);
-  preload_one(pull_binned_kernel<float, true>, &e);
+  preload_one(pull_binned_kernel<float4, false, 1>, &e);
+  preload_one(pull_binned_kernel<float2, false, 1>, &e);
+  preload_one(pull_binned_kernel<float, false, 1>, &e);
+  preload_one(pull_binned_kernel<float4, true, 1>, &e);
+  preload_one(pull_binned_kernel<float2, true, 1>, &e);
+  preload_one(pull_binned_kernel<float, true, 1>, &e);
+  preload_one(pull_binned_kernel<float4, false, 4>, &e);
+  preload_one(pull_binned_kernel<float4, true, 4>, &e);
   preload_one(insert_binned_kernel<float4>, &e);
   preload_one(insert_binned_kernel<float2>, &e);
   preload_one(insert_binned_kernel<float>, &e);

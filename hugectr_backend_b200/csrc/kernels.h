@@ -118,7 +118,9 @@ cudaError_t launch_pull_misses(const DeviceTable& t, const int64_t* d_miss_keys,
 // probes of later chunks of the request run beside this kernel.  Grid: `grid_ctas` CTAs, persistent.
 cudaError_t launch_pull_binned(const DeviceTable& t, const MissBins& bins, float* d_out, void* d_out_bf16,
                                float* const* batch_outs, int batch_count, uint32_t* d_absent, int grid_ctas,
-                               cudaStream_t stream, int insert = 0, uint32_t epoch = 0, uint32_t* d_inserted = nullptr);
+                               cudaStream_t stream, int insert = 0, uint32_t epoch = 0, uint32_t* d_inserted = nullptr,
+                               int rows_in_flight = 1);
+// rows_in_flight >= 4 (NVLink tier; rows of <= 32 vectors): every warp keeps four rows in flight instead of one.
 // insert: the pulling warp also inserts the row (fused; HBM work hidden behind the PCIe reads).  Only when nothing
 // probes the cache meanwhile: the caller holds the cache exclusively and every probe of the request has completed.
 // Inserts the rows the binned pull delivered, reading them back from the output buffer (HBM to HBM); entries whose
