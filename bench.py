@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--static-cache", action="store_true",
+                    help="experiment: embedding_cache_type static (no insertion, no LRU stamps): what the LRU touch costs the probe kernel")
     ap.add_argument("--local-tier", action="store_true",
                     help="experiment (N = 1): a world-1 tier — the whole host table also in local HBM, misses pulled from it")
     ap.add_argument("--no-peer-tier", action="store_true",
@@ -749,7 +751,8 @@ def run_ours(a):
     hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
                                  cache_size_percentage=a.gpucacheper, deployed_devices=[local],
                                  cache_load_factor=a.load_factor, enable_pagelock=(a.miss_path == "direct"),
-                                 request_chunks=a.chunks, pull_grid_ctas=a.pull_ctas))
+                                 request_chunks=a.chunks, pull_grid_ctas=a.pull_ctas,
+                                 embedding_cache_type="static" if a.static_cache else "dynamic"))
     hps.load_table_procedural("dcn", 0, a.rows, SEED)
     hps.create_embedding_cache("dcn")
     setup_s = time.perf_counter() - t0

@@ -95,6 +95,14 @@ struct Model {
   int pull_grid_ctas = 148;
   int probe_variant = kProbeV8;
   bool peer_tier = false;
+  // sparse_files entry "synthetic_device:rows=<N>,seed=<S>": table t has NO host rows; its rows (keys [0, N), synth_value)
+  // are generated on the devices, sharded by owner_of over the NVLink tier, which is then the only copy
+  std::vector<unsigned long long> device_rows, device_seed;  // [T], rows == 0: an ordinary table
+  bool tier_only() const {
+    for (unsigned long long r : device_rows)
+      if (r == 0) return false;
+    return !device_rows.empty();
+  }
   // C views of cfg for hpsx_ps_get_model_params (built once in add_model_cfg)
   std::vector<const char*> c_sparse_files, c_table_names;
   std::vector<std::string> table_names;

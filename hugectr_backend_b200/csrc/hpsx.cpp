@@ -888,6 +888,49 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
   std::unique_lock<std::shared_mutex> wlock(c->rw, std::defer_lock);
   std::shared_lock<std::shared_mutex> rlock(c->rw, std::defer_lock);
 
+  if (s->model->tier_only() && pos_per_table == nullptr) {
+    // Tables that live in the NVLink tier only (model-parallel rows, "synthetic_device:" tables): no local cache to
+    // probe and nothing to insert — one gather kernel per table reads every row from its owner's shard.
+    if (!c->tier.committed)
+      return fail(HPSX_ERR_UNSUPPORTED, "model '" + s->model->cfg.model_name + "': its tables live in the NVLink tier, which is not attached");
+    uint32_t* d_absent = s->d_counters + 2 * s->vt;
+    if (num_tables > s->vt) return fail(HPSX_ERR_INTERNAL, "tier lookup: more tables than counters");
+    HPSX_CU(cudaMemsetAsync(d_absent, 0, num_tables * sizeof(uint32_t), s->stream));
+    HPSX_CU(cudaEventRecord(s->ev_pull[0], s->stream));
+    size_t off = 0;
+    for (size_t t = 0; t < num_tables; ++t) {
+      const size_t n = n_per_table[t];
+      if (n == 0) continue;
+      const int64_t* d_keys = static_cast<const int64_t*>(keys_per_table[t]);
+      if (!keys_on_device) {
+        HPSX_CU(cudaMemcpyAsync(s->d_keys + off, keys_per_table[t], n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+        s->stats.h2d_bytes += n * sizeof(int64_t);
+        d_keys = s->d_keys + off;
+      }
+      HPSX_CU(launch_tier_gather(c->tables[t % T], d_keys, n, out_per_table[t], d_absent + t, s->stream));
+      ++s->stats.kernel_launches;
+      off += n;
+    }
+    HPSX_CU(cudaEventRecord(s->ev_pull[1], s->stream));
+    HPSX_CU(cudaMemcpyAsync(s->h_counters + 2 * s->vt, d_absent, num_tables * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    HPSX_CU(cudaStreamSynchronize(s->stream));
+    s->stats.d2h_bytes += num_tables * sizeof(uint32_t);
+    for (size_t t = 0; t < num_tables; ++t) {
+      const size_t n = n_per_table[t];
+      if (n == 0) continue;
+      const uint32_t absent = s->h_counters[2 * s->vt + t];
+      s->stats.misses += n;  // of the (absent) local cache: every key is served by the tier
+      s->stats.default_filled += absent;
+      s->stats.tier_bytes += (n - absent) * c->tables[t % T].dim * sizeof(float);
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s->ev_pull[0], s->ev_pull[1]) == cudaSuccess) {
+      s->stats.insert_kernel_ms += ms;
+      s->stats.pull_kernel_ms += ms;
+    }
+    return HPSX_OK;
+  }
+
   if (binned_path_applies(s, n_per_table, num_tables, pos_per_table)) {
     // The insert pass rewrites cache slots: exclusive unless the cache is static (never inserts).  When several
     // instances share the cache (include/model_state.hpp:76-84) the call splits instead: probes and pulls under
@@ -1378,8 +1421,22 @@ static int add_model_cfg(hpsx_ps* ps, const ModelConfig& cfg, float load_factor)
                                          cfg.default_value_for_each_table[t], ps->vdb.num_partitions,
                                          ps->vdb.allocation_rate, ps->vdb.hpsx_pull_window_mb << 20));
   }
+  m->device_rows.assign(T, 0);
+  m->device_seed.assign(T, 0);
   for (size_t t = 0; t < T && t < cfg.sparse_files.size(); ++t) {
     if (cfg.sparse_files[t].empty()) continue;
+    if (cfg.sparse_files[t].rfind("synthetic_device:", 0) == 0) {
+      unsigned long long rows = 0, seed = 0;
+      if (std::sscanf(cfg.sparse_files[t].c_str(), "synthetic_device:rows=%llu,seed=%llu", &rows, &seed) != 2 || rows == 0)
+        return fail(HPSX_ERR_INVALID_ARG, "malformed table spec '" + cfg.sparse_files[t] +
+                                              "' (want synthetic_device:rows=<N>,seed=<S>)");
+      if (!cfg.hpsx_peer_tier || !cfg.enable_pagelock || !cfg.use_gpu_embedding_cache)
+        return fail(HPSX_ERR_INVALID_ARG, "model '" + cfg.model_name + "': a synthetic_device table lives in the NVLink tier only; "
+                                              "it needs gpucache, enable_pagelock and hpsx_peer_tier");
+      m->device_rows[t] = rows;
+      m->device_seed[t] = seed;
+      continue;
+    }
     const int rc = load_sparse_dir(ps, m->tables[t].get(), cfg.sparse_files[t]);
     if (rc != HPSX_OK) return rc;
   }
@@ -1520,7 +1577,7 @@ int hpsx_ps_table_rows(const hpsx_ps* ps, const char* model, size_t table, size_
   Model* m = find_model(const_cast<hpsx_ps*>(ps), model);
   if (!m || !out) return fail(HPSX_ERR_NOT_FOUND, "unknown model");
   if (table >= m->tables.size()) return fail(HPSX_ERR_NOT_FOUND, "table index out of range");
-  *out = m->tables[table]->rows();
+  *out = m->device_rows[table] != 0 ? static_cast<size_t>(m->device_rows[table]) : m->tables[table]->rows();
   return HPSX_OK;
 }
 
@@ -1616,7 +1673,7 @@ int hpsx_ps_create_embedding_cache_per_model(hpsx_ps* ps, const char* model) {
   if (m->peer_tier) {
     if (!m->direct_pull)
       return fail(HPSX_ERR_INVALID_ARG, "model '" + m->cfg.model_name + "': hpsx_peer_tier needs enable_pagelock");
-    if (m->cfg.deployed_devices.size() >= 2) return hpsx_ps_peer_tier_connect_local(ps, model);
+    if (m->cfg.deployed_devices.size() >= 2 || m->tier_only()) return hpsx_ps_peer_tier_connect_local(ps, model);
   }
   return HPSX_OK;
   HPSX_GUARD_END
@@ -1658,7 +1715,7 @@ int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model) {
   for (hpsx_cache* c : caches)
     if (c->direct_pull) held.emplace_back(c->rw);
   for (size_t t = 0; t < m->tables.size() && t < m->cfg.sparse_files.size(); ++t) {
-    if (m->cfg.sparse_files[t].empty()) continue;
+    if (m->cfg.sparse_files[t].empty() || m->device_rows[t] != 0) continue;
     const int rc = load_sparse_dir(ps, m->tables[t].get(), m->cfg.sparse_files[t]);
     if (rc != HPSX_OK) return rc;
   }
@@ -1675,7 +1732,7 @@ int hpsx_ps_update_database_per_model(hpsx_ps* ps, const char* model) {
     std::vector<hpsx_cache*> dp;
     for (hpsx_cache* c : caches)
       if (c->direct_pull) dp.push_back(c);
-    if (dp.size() >= 2) return tier_connect_local_locked(m, dp);
+    if (dp.size() >= 2 || m->tier_only()) return tier_connect_local_locked(m, dp);
   }
   return HPSX_OK;
   HPSX_GUARD_END

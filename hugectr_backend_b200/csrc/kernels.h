@@ -161,6 +161,19 @@ cudaError_t launch_tier_fill(const int64_t* d_keys, const uint64_t* d_row_addrs,
 cudaError_t launch_index_repoint(IndexSlot* slots, uint64_t mask, const int64_t* shard_keys, const float* shard_rows,
                                  unsigned long long n, size_t dim, unsigned long long* d_repointed, cudaStream_t stream);
 
+// Tables that exist ONLY in the tier (model-parallel rows: no host copy, no local cache — BASELINE configs[3]):
+// launch_tier_fill_procedural generates the shard on the device (keys [0, num_rows) owned by `rank`, synth_value rows),
+// launch_index_insert_shard enters a shard's keys into the index (insert or overwrite), and launch_tier_gather serves a
+// request: d_out[i] = row(d_keys[i]) read from the owner's shard (NVLink or local HBM), default vector + *d_absent
+// (nullable) for keys in no shard.
+cudaError_t launch_tier_fill_procedural(unsigned long long num_rows, unsigned long long seed, uint32_t rank, uint32_t world,
+                                        size_t dim, int64_t* shard_keys, float* shard_rows, unsigned long long cap,
+                                        unsigned long long* d_count, cudaStream_t stream);
+cudaError_t launch_index_insert_shard(IndexSlot* slots, uint64_t mask, const int64_t* shard_keys, const float* shard_rows,
+                                      unsigned long long n, size_t dim, cudaStream_t stream);
+cudaError_t launch_tier_gather(const DeviceTable& t, const int64_t* d_keys, size_t n, float* d_out, uint32_t* d_absent,
+                               cudaStream_t stream);
+
 // a8: pooled[b*dim..) = sum_{j<hotness} row(src[b*hotness+j]) (mean: / hotness), ascending j, fp32.
 // Rows come from the cache slab or (kSrcMissBit) from the staged miss rows.
 cudaError_t launch_pooled_gather(const DeviceTable& t, const uint32_t* d_src, const float* d_stage,

@@ -92,7 +92,8 @@ int tier_build_locked(hpsx_cache* c, uint32_t rank, uint32_t world) {
   for (size_t t = 0; t < T && rc == HPSX_OK; ++t) {
     const HostTable& ht = *model->tables[t];
     const size_t dim = ht.dim();
-    const uint64_t cap = shard_capacity(ht.rows(), world);
+    const unsigned long long device_rows = model->device_rows[t];  // != 0: generated here, no host copy
+    const uint64_t cap = shard_capacity(device_rows != 0 ? static_cast<size_t>(device_rows) : ht.rows(), world);
     PeerTier::Shard& own = tr.own[t];
     cudaError_t ce = cudaSuccess;
     if (own.base == nullptr || own.cap < cap) {
@@ -104,7 +105,10 @@ int tier_build_locked(hpsx_cache* c, uint32_t rank, uint32_t world) {
     int64_t* shard_keys = reinterpret_cast<int64_t*>(own.base);
     float* shard_rows = reinterpret_cast<float*>(own.base + PeerTier::Shard::rows_offset(own.cap));
     if (ce == cudaSuccess) ce = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), stream);
-    if (ce == cudaSuccess) {
+    if (ce == cudaSuccess && device_rows != 0) {
+      ce = launch_tier_fill_procedural(device_rows, model->device_seed[t], rank, world, dim, shard_keys, shard_rows, own.cap,
+                                       d_count, stream);
+    } else if (ce == cudaSuccess) {
       ht.export_rows(kChunk, [&](const int64_t* k, const uint64_t* a, size_t n) {
         if (ce != cudaSuccess) return;
         ce = cudaMemcpyAsync(d_keys, k, n * sizeof(int64_t), cudaMemcpyHostToDevice, stream);
@@ -172,13 +176,35 @@ int tier_commit_locked(hpsx_cache* c) {
   HPSX_CU(cudaMalloc(&d_n, sizeof(unsigned long long)));
   cudaStream_t stream = c->async_stream;
   cudaError_t ce = cudaMemsetAsync(d_n, 0, sizeof(unsigned long long), stream);
+  unsigned long long inserted = 0;
   for (size_t t = 0; t < tr.peers.size() && ce == cudaSuccess; ++t) {
     const size_t dim = c->tables[t].dim;
+    const bool device_table = c->model->device_rows[t] != 0;
+    if (device_table) {
+      // no host table behind it: the index is built from the shards themselves
+      unsigned long long total = 0;
+      for (uint32_t p = 0; p < tr.world; ++p) total += tr.peers[t][p].rows;
+      uint64_t cap = 1024;
+      while (cap < 2 * total) cap <<= 1;
+      if (c->indexes.size() <= t) c->indexes.resize(t + 1, nullptr);
+      if (c->indexes[t] == nullptr || c->tables[t].index_mask + 1 != cap) {
+        if (c->indexes[t] != nullptr) cudaFree(c->indexes[t]);
+        c->indexes[t] = nullptr;
+        c->tables[t].index = nullptr;
+        ce = cudaMalloc(&c->indexes[t], cap * sizeof(IndexSlot));
+        if (ce != cudaSuccess) break;
+      }
+      c->tables[t].index = c->indexes[t];
+      c->tables[t].index_mask = cap - 1;
+      ce = launch_index_clear(c->indexes[t], cap, stream);
+      inserted += total;
+    }
     for (uint32_t p = 0; p < tr.world && ce == cudaSuccess; ++p) {
       const PeerTier::Shard& s = tr.peers[t][p];
-      ce = launch_index_repoint(c->indexes[t], c->tables[t].index_mask, reinterpret_cast<const int64_t*>(s.base),
-                                reinterpret_cast<const float*>(s.base + PeerTier::Shard::rows_offset(s.cap)), s.rows, dim, d_n,
-                                stream);
+      const int64_t* keys = reinterpret_cast<const int64_t*>(s.base);
+      const float* rows = reinterpret_cast<const float*>(s.base + PeerTier::Shard::rows_offset(s.cap));
+      ce = device_table ? launch_index_insert_shard(c->indexes[t], c->tables[t].index_mask, keys, rows, s.rows, dim, stream)
+                        : launch_index_repoint(c->indexes[t], c->tables[t].index_mask, keys, rows, s.rows, dim, d_n, stream);
     }
   }
   unsigned long long n = 0;
@@ -186,7 +212,7 @@ int tier_commit_locked(hpsx_cache* c) {
   if (ce == cudaSuccess) ce = cudaMemcpy(&n, d_n, sizeof(n), cudaMemcpyDeviceToHost);
   cudaFree(d_n);
   if (ce != cudaSuccess) return fail(HPSX_ERR_CUDA, std::string("peer tier commit: ") + cudaGetErrorString(ce));
-  tr.repointed = n;
+  tr.repointed = n + inserted;
   tr.committed = true;
   return HPSX_OK;
 }

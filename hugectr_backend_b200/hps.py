@@ -326,6 +326,13 @@ class LookupSession:
         k, o, n, T = self._arrays(d_keys_per_table, d_vectors_per_table, num_keys_per_table)
         N.check(self._L.hpsx_session_lookup_device_keys(self._h, k, o, n, T))
 
+    def lookup_ex(self, keys_per_table, vectors_per_table, num_keys_per_table, key_memory: str = "host",
+                  vector_memory: str = "device") -> None:
+        """General form (what the Triton shell calls): keys and vectors each in "host" or "device" memory."""
+        K, O_, Nn, T = self._arrays(keys_per_table, vectors_per_table, num_keys_per_table)
+        N.check(self._L.hpsx_session_lookup_ex(self._h, K, 1 if key_memory == "device" else 0, O_,
+                                               1 if vector_memory == "device" else 0, Nn, T))
+
     def lookup_batch(self, requests, device_keys: bool = False, device_vectors: bool = True) -> None:
         """``requests``: list of (keys_per_table, vectors_per_table, num_keys_per_table), served in one pass."""
         k, o, n = [], [], []

@@ -166,3 +166,76 @@ def test_batched_and_large_requests_through_the_tier(cuda_device):
     for keys_l, out_l, _ in reqs:
         assert np.array_equal(out_l[0].cpu().numpy(), exp_for(keys_l[0]))
     del s, ranks
+
+
+# ------------------------------------------------------------------------------------------------
+# tables that live in the tier only ("synthetic_device:" — model-parallel rows without a host copy, BASELINE configs[3])
+# ------------------------------------------------------------------------------------------------
+def make_device_table_rank(rows, dim, seed, *, default=0.25, max_batch=8192):
+    hps = hb.HPS(num_partitions=8)
+    hps.add_model(hb.ModelParams("mp", max_batch, [dim], [1], [default], hit_rate_threshold=1.0, cache_size_percentage=0.0,
+                                 enable_pagelock=True, embedding_cache_type="static", peer_tier=True,
+                                 sparse_files=[f"synthetic_device:rows={rows},seed={seed}"]))
+    return hps
+
+
+@pytest.mark.parametrize("dim", [128, 32, 20])
+def test_device_table_single_rank(cuda_device, dim):
+    """One device: create_embedding_cache builds the world-1 tier by itself (the table has no other copy)."""
+    torch = _torch()
+    rows, n, seed = 150_000, 8192, 0xB2000020
+    hps = make_device_table_rank(rows, dim, seed)
+    hps.create_embedding_cache("mp")
+    assert hps.table_rows("mp", 0) == rows
+    info = hps.peer_tier_info("mp", 0)
+    assert info["world"] == 1 and info["committed"] == 1 and info["own_rows"] == rows and info["index_entries_in_tier"] == rows
+    ref = O.NumpyTable(dim, 0.25)
+    ref.fill_procedural(rows, seed)
+    s = hps.session("mp", 0)
+    rng = np.random.default_rng(17)
+    for n_req in (n, 1, 4097, 3):
+        keys = rng.integers(-3, rows + 300, size=n_req)
+        out = torch.full((n_req, dim), float("nan"), device="cuda")
+        s.lookup([keys], [out], [n_req])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
+        d_keys = torch.from_numpy(keys).cuda()
+        out2 = torch.full((n_req, dim), float("nan"), device="cuda")
+        s.lookup_device_keys([d_keys], [out2], [n_req])
+        assert torch.equal(out, out2)
+    st = s.stats()
+    assert st.hits == 0 and st.default_filled > 0 and st.tier_bytes == (st.misses - st.default_filled) * dim * 4
+    # host output (Triton may hand back CPU memory)
+    keys = rng.integers(0, rows, size=1000)
+    h_out = np.full((1000, dim), np.nan, dtype=np.float32)
+    s.lookup_ex([keys], [h_out], [1000], key_memory="host", vector_memory="host")
+    assert np.array_equal(h_out, ref.lookup(keys))
+
+
+def test_device_table_two_ranks_on_one_device(cuda_device):
+    """Two ranks (two servers on one device): every rank generates only the rows it owns, maps the other's shard and
+    builds its index from both; each serves the whole key range."""
+    torch = _torch()
+    rows, dim, n, seed = 300_000, 128, 8192, 0xB2000021
+    ranks = [make_device_table_rank(rows, dim, seed) for _ in range(2)]
+    for r, hps in enumerate(ranks):
+        # deployed on one device the cache creation builds a world-1 tier; rebuild it as rank r of 2
+        hps.create_embedding_cache("mp")
+        hps.peer_tier_build("mp", 0, r, 2)
+    own = [hps.peer_tier_info("mp", 0)["own_rows"] for hps in ranks]
+    assert sum(own) == rows and all(abs(o - rows / 2) < 8 * np.sqrt(rows / 2) + 8 for o in own)
+    for r, hps in enumerate(ranks):
+        hps.peer_tier_attach_local("mp", 0, 1 - r, ranks[1 - r], "mp", 0)
+        hps.peer_tier_commit("mp", 0)
+        assert hps.peer_tier_info("mp", 0)["index_entries_in_tier"] == rows
+    ref = O.NumpyTable(dim, 0.25)
+    ref.fill_procedural(rows, seed)
+    rng = np.random.default_rng(23)
+    for hps in ranks:
+        s = hps.session("mp", 0)
+        keys = rng.integers(-3, rows + 300, size=n)
+        out = torch.full((n, dim), float("nan"), device="cuda")
+        s.lookup([keys], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
+        del s
+    for hps in ranks:
+        hps.peer_tier_detach("mp", 0)
