@@ -72,6 +72,9 @@ def parse_args():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="c4 only: p2p = fused exchange over NVLink peer memory (hpsx_shard_group); nccl = all-to-all-v of keys and rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--c4-rows-per-gpu", type=int, default=125_000_000,
+                    help="rows per GPU of the model-parallel table of the c4 arm (configs[3]: 1 B rows / 8 GPUs)")
+    ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--static-cache", action="store_true",
                     help="experiment: embedding_cache_type static (no insertion, no LRU stamps): what the LRU touch costs the probe kernel")
     ap.add_argument("--local-tier", action="store_true",
@@ -388,91 +391,119 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
             "verified_rows": verified}
 
 
-def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
-    """N > 1 end-to-end arm: ONE server process (fake Triton + libtriton_hps.so) with the model deployed on all `world` GPUs,
-    one instance per GPU, "hpsx_peer_tier": true — the reference's multi-GPU deployment (one tritonserver, one cache per
-    device, hps_backend/src/model_state.cpp:395-419) with this engine's NVLink tier.  Every instance serves its own stream of
-    distinct requests from its own thread: host KEYS -> GPU OUTPUT0 on its device.  Wall clock over all threads."""
+def _one_server(a, world, model_json, name, batch_per_instance, seed, make_instance_requests, prefill, torch, sampler_cls):
+    """ONE server process (fake Triton + libtriton_hps.so) with model `name` deployed on all `world` GPUs, one instance per
+    GPU — the reference's multi-GPU deployment (one tritonserver, one cache per device, hps_backend/src/model_state.cpp:
+    395-419).  Every instance serves its own stream of distinct requests (host KEYS in pinned memory -> GPU OUTPUT0 on its
+    device); the streams run at once, one C++ thread per instance inside the harness (no Python in the timed region)."""
     import tempfile
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import fake_triton as FT
 
     devs = list(range(world))
-    m = _ps_model("dcn", a.rows, SEED, a.dim, a.slots, a.batch, 0, gpucacheper=a.gpucacheper)
-    m["deployed_device_list"] = devs
-    m["hpsx_peer_tier"] = True
+    n = batch_per_instance * a.slots
     steps = a.steps
     with tempfile.TemporaryDirectory() as tmp:
-        path = os.path.join(tmp, "ps_one_server.json")
+        path = os.path.join(tmp, f"ps_{name}.json")
         with open(path, "w") as f:
-            json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16}, "models": [m]}, f)
+            json.dump({"supportlonglong": True, "volatile_db": {"type": "parallel_hash_map", "num_partitions": 16},
+                       "models": [model_json]}, f)
         t0 = time.perf_counter()
         with FT.Backend(path) as be:
-            model = be.model("dcn", FT.model_config("dcn", gpus=devs, max_batch_size=a.batch))
-            insts = [model.instance(name=f"dcn_{d}", kind=FT.KIND_GPU, device=d) for d in devs]
+            model = be.model(name, FT.model_config(name, gpus=devs, max_batch_size=batch_per_instance))
+            insts = [model.instance(name=f"{name}_{d}", kind=FT.KIND_GPU, device=d) for d in devs]
             setup_s = time.perf_counter() - t0
             numkeys = np.array([[n]], dtype=np.int32)
-            pre = make_requests(a, hot, warm_rows, a.prefill, SEED + 4000)
-            work = []
+            outs, all_reqs, keep, prepared = [], [], [], []
             for d, inst in enumerate(insts):
                 out = torch.empty(n * a.dim, device=f"cuda:{d}", dtype=torch.float32)
-                reqs = make_requests(a, hot, warm_rows, a.warmup + steps, SEED + 5000 + d)
+                reqs = list(prefill) + make_instance_requests(d, a.warmup + steps)
                 pinned = [torch.from_numpy(k).pin_memory() for k in reqs]  # Triton hands the backend pinned input buffers
-                prepared = [inst.prepare([dict(keys=t.numpy(), numkeys=numkeys, gpu_out=out, out_device=d)]) for t in pinned]
-                work.append((d, inst, out, reqs, prepared, pinned))
-            errors = []
-
-            def serve(item, lo, hi, pre_keys):
-                d, inst, out, reqs, prepared, _pinned = item
-                torch.cuda.set_device(d)
-                for k in pre_keys:
-                    r = inst.infer(k, numkeys, gpu_out=out, out_device=d)
-                    if r.error_code is not None:
-                        errors.append((d, r.error_message))
-                        return
-                for p in prepared[lo:hi]:
-                    p.run(1)
-                    r = p.responses()[0]
-                    if r.error_code is not None or r.params.get("NumSample") != a.batch:
-                        errors.append((d, r.error_message))
-                        return
-
-            def run_all(lo, hi, pre_keys=()):
-                th = [threading.Thread(target=serve, args=(item, lo, hi, pre_keys)) for item in work]
-                t = time.perf_counter()
-                [x.start() for x in th]
-                [x.join() for x in th]
-                for d in devs:
-                    torch.cuda.synchronize(d)
-                return time.perf_counter() - t
-
-            run_all(0, a.warmup, pre)  # untimed: prefill (cache reaches steady state) + warm-up
-            assert not errors, errors
+                prepared.append(inst.prepare([dict(keys=t.numpy(), numkeys=numkeys, gpu_out=out, out_device=d) for t in pinned]))
+                outs.append(out)
+                all_reqs.append(reqs)
+                keep.append(pinned)
+            P = len(prefill)
+            FT.run_sequences_parallel(prepared, 0, P + a.warmup)  # untimed: prefill (cache reaches steady state) + warm-up
+            for d in devs:
+                torch.cuda.synchronize(d)
             samplers = [sampler_cls(d) for d in devs]
             [s.start() for s in samplers]
-            wall = run_all(a.warmup, a.warmup + steps)
+            wall = FT.run_sequences_parallel(prepared, P + a.warmup, P + a.warmup + steps)
+            for d in devs:
+                torch.cuda.synchronize(d)
             clocks = [s.stop() for s in samplers]
-            assert not errors, errors
             verified = 0
-            for d, inst, out, reqs, prepared, _pinned in work:
+            for d, p in enumerate(prepared):
+                r = p.responses()[-1]
+                assert r.error_code is None and r.params.get("NumSample") == batch_per_instance, (d, r.error_message)
                 with torch.cuda.device(d):
-                    verified += verify_rows(torch, torch.from_numpy(reqs[-1]).cuda(), out.view(n, a.dim), a.dim, SEED,
-                                            f"one-server Triton arm, GPU {d}")
-            for d, inst, out, reqs, prepared, _pinned in work:
-                for p in prepared:
-                    p.close()
+                    verified += verify_rows(torch, torch.from_numpy(all_reqs[d][-1]).cuda(), outs[d].view(n, a.dim), a.dim, seed,
+                                            f"one-server arm {name}, GPU {d}")
+            for p in prepared:
+                p.close()
+            for inst in insts:
                 inst.close()
             model.close()
-    return {"value": world * steps * n / wall, "unit": UNIT, "ms_per_step": wall / steps * 1e3,
-            "call": f"TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so), ONE server process, {world} instances (one per GPU, one "
-                    "thread each): host KEYS/NUMKEYS -> GPU OUTPUT0 on the instance's device; hpsx_peer_tier on",
-            "timer": "host wall clock from the start of all instance threads to the last device synchronised",
+    return {"value": world * steps * n / wall, "unit": UNIT, "ms_per_step": wall / steps * 1e3, "steps": steps,
+            "timer": "host wall clock (C++, inside the harness) from the common start of the instance threads to the end of the last",
             "output": "device memory (Triton GPU output buffer contract)", "verified_rows": verified, "setup_s": setup_s,
-            "h2d_bytes_per_step": n * 8.0, "d2h_bytes_per_step": 16.0,
-            "bytes_note": "per instance: KEYS copied H2D (8 B/key) + counters D2H; the rows of missed keys come from the NVLink "
-                          "tier, not over PCIe",
-            "clocks_per_gpu": clocks}
+            "h2d_bytes_per_step": n * 8.0, "d2h_bytes_per_step": 16.0, "clocks_per_gpu": clocks}
+
+
+def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
+    """N > 1 end-to-end arm of the headline workload: the DCN model on all GPUs of one server, "hpsx_peer_tier": true."""
+    m = _ps_model("dcn", a.rows, SEED, a.dim, a.slots, a.batch, 0, gpucacheper=a.gpucacheper)
+    m["deployed_device_list"] = list(range(world))
+    m["hpsx_peer_tier"] = True
+    pre = make_requests(a, hot, warm_rows, a.prefill, SEED + 4000)
+    r = _one_server(a, world, m, "dcn", a.batch, SEED, lambda d, count: make_requests(a, hot, warm_rows, count, SEED + 5000 + d),
+                    pre, torch, sampler_cls)
+    r["call"] = (f"TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so), ONE server process, {world} instances (one per GPU, one "
+                 "thread each): host KEYS/NUMKEYS -> GPU OUTPUT0 on the instance's device; hpsx_peer_tier on")
+    r["bytes_note"] = ("per instance: KEYS copied H2D (8 B/key) + counters D2H; the rows of missed keys come from the NVLink "
+                       "tier, not over PCIe")
+    return r
+
+
+def config_c4(a, world, torch, sampler_cls, peak_nvlink=900.0):
+    """BASELINE configs[3]: DLRM-shaped model-parallel table — 1 B rows x dim 128 over 8 GPUs (125 M rows = 64 GB of HBM per
+    GPU; scaled as 125 M x N on fewer GPUs), global batch 131072 x 26 keys, no host copy, no local cache.  The reference has
+    no such mode (one full cache per device, hps_backend/src/model_state.cpp:395-419); here the table lives in the NVLink
+    tier only: every GPU generates the rows it owns, maps its peers' shards, and serves its share of the batch with ONE
+    gather kernel that reads each row from its owner's HBM (one-sided NVLink reads; no all-to-all, no flags).  Served through
+    TRITONBACKEND_ModelInstanceExecute of one server process, one instance per GPU."""
+    rows = a.c4_rows_per_gpu * world
+    seed = 0xB2000000 + 44
+    batch = 131072 // world
+    m = {"model": "dlrm", "sparse_files": [f"synthetic_device:rows={rows},seed={seed}"], "num_of_worker_buffer_in_pool": 1,
+         "embedding_vecsize_per_table": [a.dim], "maxnum_catfeature_query_per_table_per_sample": [a.slots],
+         "default_value_for_each_table": [0.0], "deployed_device_list": list(range(world)), "max_batch_size": batch,
+         "hit_rate_threshold": 1.0, "gpucacheper": 0.0, "gpucache": True, "enable_pagelock": True, "hpsx_peer_tier": True,
+         "embedding_cache_type": "static"}
+    n = batch * a.slots
+
+    def reqs(d, count):
+        rng = np.random.default_rng(seed + 100 + d)
+        return [rng.integers(0, rows, size=n, dtype=np.int64) for _ in range(count)]
+
+    r = _one_server(a, world, m, "dlrm", batch, seed, reqs, [], torch, sampler_cls)
+    step_s = r["ms_per_step"] / 1e3
+    row_bytes = a.dim * 4
+    ingress = n * row_bytes * (world - 1) / world / step_s / 1e9  # per GPU
+    r.update({
+        "workload": f"configs[3]: model-parallel table, {rows / 1e6:.0f} M rows x dim {a.dim} over {world} GPUs "
+                    f"({a.c4_rows_per_gpu / 1e6:.0f} M rows = {a.c4_rows_per_gpu * row_bytes / 1e9:.0f} GB per GPU), global batch "
+                    f"{batch * world} x {a.slots} keys, uniform keys, rows generated on the devices (no host copy), no local cache",
+        "rows": rows, "global_keys_per_step": world * n,
+        "call": f"TRITONBACKEND_ModelInstanceExecute, ONE server process, {world} instances: host KEYS -> GPU OUTPUT0; "
+                "tier_gather kernel reads every row from its owner's shard",
+        "roofline_nvlink": {"bound": "nvlink", "kernel": "tier_gather", "achieved": ingress, "peak": peak_nvlink,
+                            "unit": "GB/s", "frac": ingress / peak_nvlink,
+                            "note": "NVLink ingress per GPU over the WHOLE step (wall clock incl. key copy and host overhead): "
+                                    "(N-1)/N of the rows x 512 B; peak = NVLink 5 nominal, one direction"}})
+    return r
 
 
 def _ps_model(name, rows, seed, dim, slots, batch, device, *, gpucache=True, gpucacheper=0.2, pagelock=True, instances=1):
@@ -932,6 +963,7 @@ def run_ours(a):
     # ---- end-to-end arm 2 (headline e2e): the reference-facing plugin call ------------------------------
     # TRITONBACKEND_ModelInstanceExecute of libtriton_hps.so, driven by the fake-Triton harness: KEYS/NUMKEYS in
     # host memory, OUTPUT0 in a GPU buffer (what Triton hands a gpucache model, hps.cc:638-642).
+    c4 = None
     one_server = use_tier and world > 1 and not a.skip_triton_arm  # N > 1: ONE server process drives all GPUs (arm at the end, rank 0)
     if a.skip_triton_arm or one_server:
         e2e = dict(e2e_session)
@@ -1144,6 +1176,7 @@ def run_ours(a):
         torch.cuda.empty_cache()
         dist.barrier()
         self_check_failed = None
+        c4 = None
         if rank == 0:
             try:
                 e2e_srv = triton_arm_one_server(a, world, hot, warm_rows, n, torch, ClockSampler)
@@ -1154,6 +1187,18 @@ def run_ours(a):
             except Exception as ex:  # keep the line: the session-level arm stands in, and the failure is named
                 print(f"[bench] one-server Triton arm FAILED: {ex!r}", file=sys.stderr)
                 e2e["note"] = f"one-server Triton arm failed ({ex!r}); session-level end-to-end arm reported"
+            if not a.skip_c4:
+                gc.collect()
+                torch.cuda.empty_cache()
+                t_c4 = time.perf_counter()
+                try:
+                    c4 = config_c4(a, world, torch, ClockSampler)
+                    c4["arm_wall_s"] = time.perf_counter() - t_c4
+                except SystemExit as ex:
+                    self_check_failed = ex
+                except Exception as ex:
+                    print(f"[bench] configuration c4 FAILED: {ex!r}", file=sys.stderr)
+                    c4 = {"error": repr(ex)}
         dist.barrier()
         if self_check_failed is not None:
             raise self_check_failed
@@ -1219,7 +1264,7 @@ def run_ours(a):
         "roofline": roofline, "roofline_host_link": roofline_host_link, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "e2e_host_output": e2e_host_output, "e2e_session": e2e_session,
         "cache_hit": cache_hit, "small_batch": small_batch, "two_instances": two_instances, "dense_head": dense_head,
-        "c1": extra.get("c1"), "c5": extra.get("c5"), "c3": extra.get("c3"),
+        "c1": extra.get("c1"), "c5": extra.get("c5"), "c3": extra.get("c3"), "c4": c4,
         "gpu_launches": int(st_pipe.kernel_launches), "clocks": clocks, "verified_rows": verified_rows,
         "wall_ms_per_step": wall / a.steps * 1e3,
         "miss_path": {"misses_per_step": miss_per, "host_gather_ms_per_step": st.host_gather_ms / a.steps,

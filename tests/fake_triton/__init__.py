@@ -59,6 +59,8 @@ _SIGS = {
     "ft_request_fail_output_buffer": (None, [_vp, _int]),
     "ft_execute": (_int, [_vp, _vpp, _u32]),
     "ft_execute_repeat": (_int, [_vp, _vpp, _u32, _u32, ctypes.POINTER(_u64)]),
+    "ft_execute_sequence": (_int, [_vp, _vpp, _u32, ctypes.POINTER(_u64)]),
+    "ft_execute_sequences_parallel": (_int, [_vpp, _u32, _vpp, ctypes.POINTER(_u32), ctypes.POINTER(_u64)]),
     "ft_request_released": (_int, [_vp]),
     "ft_request_response_count": (_int, [_vp]),
     "ft_response_sent": (_int, [_vp]),
@@ -282,6 +284,12 @@ class Prepared:
         _check(self.inst._L.ft_execute_repeat(self.inst._h, self._arr, len(self._handles), repeat, ctypes.byref(ns)))
         return ns.value / 1e9
 
+    def run_sequence(self) -> float:
+        """One Execute call PER request, in order (a stream of distinct requests); seconds, timed in C."""
+        ns = _u64()
+        _check(self.inst._L.ft_execute_sequence(self.inst._h, self._arr, len(self._handles), ctypes.byref(ns)))
+        return ns.value / 1e9
+
     def responses(self) -> List[Response]:
         return [self.inst._collect(h) for h in self._handles]
 
@@ -292,6 +300,24 @@ class Prepared:
 
     def __del__(self):
         self.close()
+
+
+def run_sequences_parallel(prepared: Sequence[Prepared], lo: int = 0, hi: Optional[int] = None) -> float:
+    """Requests [lo, hi) of every Prepared as one stream per instance, all instances at once, one C++ thread each (a
+    server process driving several GPUs; no Python in the timed region).  Returns the wall seconds of the whole pass."""
+    L = prepared[0].inst._L
+    k = len(prepared)
+    insts = (ctypes.c_void_p * k)(*[p.inst._h for p in prepared])
+    handles, counts = [], []
+    for p in prepared:
+        part = p._handles[lo:hi]
+        handles += part
+        counts.append(len(part))
+    arr = (ctypes.c_void_p * len(handles))(*handles)
+    cnt = (_u32 * k)(*counts)
+    ns = _u64()
+    _check(L.ft_execute_sequences_parallel(insts, k, arr, cnt, ctypes.byref(ns)))
+    return ns.value / 1e9
 
 
 class Model:

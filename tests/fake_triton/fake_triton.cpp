@@ -16,6 +16,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -653,6 +654,56 @@ int ft_execute_repeat(TRITONBACKEND_ModelInstance* i, TRITONBACKEND_Request** re
   if (elapsed_ns != nullptr)
     *elapsed_ns = static_cast<uint64_t>(
         std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
+}
+
+// A stream of DISTINCT requests on one instance: one Execute call per request, in order, timed here.
+int ft_execute_sequence(TRITONBACKEND_ModelInstance* i, TRITONBACKEND_Request** reqs, uint32_t n, uint64_t* elapsed_ns) {
+  const auto t0 = std::chrono::steady_clock::now();
+  for (uint32_t q = 0; q < n; ++q) {
+    reqs[q]->responses.clear();
+    const int rc = consume(i->model->backend->execute(i, reqs + q, 1));
+    if (rc != 0) return rc;
+  }
+  if (elapsed_ns != nullptr)
+    *elapsed_ns = static_cast<uint64_t>(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+  return 0;
+}
+
+// The same for `k` instances at once, one thread per instance — a server process driving several GPUs.  `reqs` is the
+// concatenation of the instances' sequences (counts[j] requests for instance j).  *elapsed_ns = wall time from the
+// common start to the end of the last thread; returns the first non-zero thread result.
+int ft_execute_sequences_parallel(TRITONBACKEND_ModelInstance** insts, uint32_t k, TRITONBACKEND_Request** reqs,
+                                  const uint32_t* counts, uint64_t* elapsed_ns) {
+  std::vector<int> rcs(k, 0);
+  std::vector<std::string> errs(k);
+  std::vector<std::thread> threads;
+  std::atomic<uint32_t> ready{0};
+  std::atomic<bool> go{false};
+  uint32_t off = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    TRITONBACKEND_Request** mine = reqs + off;
+    off += counts[j];
+    threads.emplace_back([&, j, mine] {
+      ready.fetch_add(1);
+      while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+      rcs[j] = ft_execute_sequence(insts[j], mine, counts[j], nullptr);
+      if (rcs[j] != 0) errs[j] = g_ft_error;
+    });
+  }
+  while (ready.load() < k) std::this_thread::yield();
+  const auto t0 = std::chrono::steady_clock::now();
+  go.store(true, std::memory_order_release);
+  for (std::thread& t : threads) t.join();
+  if (elapsed_ns != nullptr)
+    *elapsed_ns = static_cast<uint64_t>(
+        std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+  for (uint32_t j = 0; j < k; ++j)
+    if (rcs[j] != 0) {
+      g_ft_error = errs[j];
+      return rcs[j];
+    }
   return 0;
 }
 
