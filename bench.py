@@ -871,6 +871,14 @@ def run_ours(a):
 
     st = st_pipe
     ms_serial = ms
+    # How much would de-duplicating the miss list save?  Misses of the next request against the cache as it is now.
+    resident_now = hps.cache_keys("dcn", local, 0)
+    nxt = reqs[a.steps % R]
+    miss_now = nxt[~np.isin(nxt, resident_now)]
+    miss_dup = {"misses": int(len(miss_now)), "unique_misses": int(len(np.unique(miss_now))),
+                "duplicate_fraction": float(1.0 - len(np.unique(miss_now)) / max(1, len(miss_now))),
+                "note": "keys of one request that are not resident before it: occurrences vs distinct keys — the share of the "
+                        "pulled rows a de-duplicated miss list would save"}
 
     probe_ms = st.probe_kernel_ms / max(1, st.probe_kernel_launches)
     hits_per, miss_per = st.hits / a.steps, st.misses / a.steps
@@ -1251,7 +1259,7 @@ def run_ours(a):
         "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim,
                    "gpucacheper": a.gpucacheper, "hit_rate_measured": st_pipe.hits / max(1, st_pipe.keys),
                    "request_chunks": a.chunks or 4,
-                   "unique_over_keys": float(len(np.unique(reqs[0])) / n),
+                   "unique_over_keys": float(len(np.unique(reqs[0])) / n), "miss_duplicates": miss_dup,
                    "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
                    "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per step, {R} distinct key batches per arm",
                    "hot_draw_probability": a.hit, "prefill_requests": a.prefill,

@@ -447,6 +447,11 @@ __device__ __forceinline__ void lock_bucket(Bucket* B) {
     if (old != 0u) __nanosleep(32);
   } while (old != 0u);
 }
+__device__ __forceinline__ bool try_lock_bucket(Bucket* B) {
+  uint32_t old;
+  asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(&B->lock) : "memory");
+  return old == 0u;
+}
 __device__ __forceinline__ void unlock_bucket(Bucket* B) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&B->lock), "r"(0u) : "memory");
 }
@@ -504,6 +509,107 @@ __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buc
   const uint32_t pb = pick < kWays ? b1 : b2;
   const uint32_t pw = static_cast<uint32_t>(pick < 0 ? 0 : pick) & (kWays - 1);
   if (lane == 0) {
+    if (pick >= 0) {
+      if (fresh) buckets[pb].keys[pw] = key;
+      buckets[pb].stamp[pw] = epoch;
+    }
+    if (hi != nullptr) unlock_bucket(hi);
+    unlock_bucket(lo);
+  }
+  return fresh ? pb * kWays + pw : kMissSlot;
+}
+
+// Four claims at once (quad form of the tier pull): lanes 8e..8e+7 work on key[e] — lane 8e takes the locks, lane
+// 8e+w looks at way w of both candidate buckets.  The lock / load / store chain, a handful of dependent L2 round trips,
+// is paid once per quad instead of once per row.  Entries of one quad that share a bucket (the same key twice, or a
+// bucket collision) cannot hold their locks side by side: every entry that shares a bucket with a LOWER entry of the
+// quad is left to the caller (returned in *deferred as a bit mask) to claim one by one with claim_slot.  The locks of
+// a quad are only TRIED: a warp that waited for one lock while its other lanes hold theirs would break the ascending
+// lock order that keeps the blocking form deadlock-free (warp A holds 100 and waits for 50, warp B holds 50 and waits
+// for 100); an entry whose try fails gives back what it took and is deferred as well.
+// `want`: this lane's entry is to be claimed (uniform within its 8-lane group).  Returns the slot of this lane's entry.
+__device__ __forceinline__ uint32_t claim_slot4(Bucket* buckets, uint32_t num_buckets, int64_t key, bool want, uint32_t epoch,
+                                                uint32_t lane, unsigned* deferred) {
+  const uint32_t sub = lane & 7u, shift = lane & ~7u, e = lane >> 3;
+  const uint32_t b1 = bucket_of(key, num_buckets);
+  const uint32_t b2 = bucket2_of(key, num_buckets);
+  // conflicts with lower entries of the quad
+  bool conflict = false;
+#pragma unroll
+  for (int o = 0; o < 3; ++o) {
+    const uint32_t ob1 = __shfl_sync(kFull, b1, 8 * o), ob2 = __shfl_sync(kFull, b2, 8 * o);
+    const bool owant = __shfl_sync(kFull, want ? 1 : 0, 8 * o) != 0;
+    if (static_cast<uint32_t>(o) < e && owant && (ob1 == b1 || ob1 == b2 || ob2 == b1 || ob2 == b2)) conflict = true;
+  }
+  const unsigned conflict_lanes = __ballot_sync(kFull, want && conflict);
+  *deferred = ((conflict_lanes >> 0) & 1u) | (((conflict_lanes >> 8) & 1u) << 1) | (((conflict_lanes >> 16) & 1u) << 2) |
+              (((conflict_lanes >> 24) & 1u) << 3);
+  Bucket* lo = &buckets[min(b1, b2)];
+  Bucket* hi = b1 == b2 ? nullptr : &buckets[max(b1, b2)];
+  bool got = false;
+  if (want && !conflict && sub == 0) {
+    got = try_lock_bucket(lo);
+    if (got && hi != nullptr && !try_lock_bucket(hi)) {
+      unlock_bucket(lo);
+      got = false;
+    }
+  }
+  got = __shfl_sync(kFull, got ? 1 : 0, shift) != 0;  // the lead lane's result, for its whole group
+  __syncwarp();
+  const unsigned busy_lanes = __ballot_sync(kFull, want && !conflict && !got);
+  *deferred |= ((busy_lanes >> 0) & 1u) | (((busy_lanes >> 8) & 1u) << 1) | (((busy_lanes >> 16) & 1u) << 2) |
+               (((busy_lanes >> 24) & 1u) << 3);
+  const bool active = want && !conflict && got;
+  int64_t k1 = kEmptyKey, k2 = kEmptyKey;
+  uint32_t s1 = epoch, s2 = epoch;
+  const bool two = b1 != b2;
+  if (active) {
+    k1 = __ldcg(reinterpret_cast<const long long*>(&buckets[b1].keys[sub]));
+    s1 = __ldcg(&buckets[b1].stamp[sub]);
+    if (two) {
+      k2 = __ldcg(reinterpret_cast<const long long*>(&buckets[b2].keys[sub]));
+      s2 = __ldcg(&buckets[b2].stamp[sub]);
+    }
+  }
+  const unsigned p1 = (__ballot_sync(kFull, active && k1 == key) >> shift) & 0xffu;
+  const unsigned p2 = (__ballot_sync(kFull, active && two && k2 == key) >> shift) & 0xffu;
+  const unsigned e1 = (__ballot_sync(kFull, active && k1 == kEmptyKey) >> shift) & 0xffu;
+  const unsigned e2 = (__ballot_sync(kFull, active && two && k2 == kEmptyKey) >> shift) & 0xffu;
+  // oldest stamp of the 16 ways (primary wins ties, lower way wins ties): same order as claim_slot
+  const int32_t d1 = static_cast<int32_t>(epoch - s1), d2 = static_cast<int32_t>(epoch - s2);
+  const uint32_t a1 = (active && d1 > 0) ? static_cast<uint32_t>(d1) : 0u;
+  const uint32_t a2 = (active && two && d2 > 0) ? static_cast<uint32_t>(d2) : 0u;
+  unsigned long long packed1 = (static_cast<unsigned long long>(a1) << 8) | (255u - sub);
+  unsigned long long packed2 = (static_cast<unsigned long long>(a2) << 8) | (255u - (8u + sub));
+  unsigned long long packed = packed1 > packed2 ? packed1 : packed2;
+#pragma unroll
+  for (int off = 4; off > 0; off >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(kFull, packed, off);
+    packed = o > packed ? o : packed;
+  }
+  int pick = -1;  // 0-7: way of the primary, 8-15: way of the second choice
+  bool fresh = false;
+  if (p1 != 0u) {
+    pick = __ffs(p1) - 1;
+  } else if (p2 != 0u) {
+    pick = 8 + __ffs(p2) - 1;
+  } else if (e1 != 0u) {
+    pick = __ffs(e1) - 1;
+    fresh = true;
+  } else if (e2 != 0u) {
+    pick = 8 + __ffs(e2) - 1;
+    fresh = true;
+  } else if ((packed >> 8) != 0ull) {
+    pick = 255 - static_cast<int>(packed & 255ull);
+    fresh = true;
+  }
+  if (!active) {
+    pick = -1;
+    fresh = false;
+  }
+  const uint32_t pb = pick < kWays ? b1 : b2;
+  const uint32_t pw = static_cast<uint32_t>(pick < 0 ? 0 : pick) & (kWays - 1);
+  if (active && sub == 0) {
     if (pick >= 0) {
       if (fresh) buckets[pb].keys[pw] = key;
       buckets[pb].stamp[pw] = epoch;
@@ -1016,6 +1122,18 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
         x[e] = defv;
         if (src[e] != nullptr && lane < V) x[e] = src[e][lane];
       }
+      // the four slot claims together, while the rows are in flight
+      uint32_t slot4[4] = {kMissSlot, kMissSlot, kMissSlot, kMissSlot};
+      if constexpr (kInsert) {
+        unsigned deferred = 0;
+        const uint32_t my_slot = claim_slot4(a.buckets, a.num_buckets, my_key, have && my_row != nullptr && my_key != kEmptyKey,
+                                             a.epoch, lane, &deferred);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          slot4[e] = __shfl_sync(kFull, my_slot, 8 * e);
+          if ((deferred >> e) & 1u) slot4[e] = claim_slot(a.buckets, a.num_buckets, key[e], a.epoch, lane);
+        }
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (i0 + e >= total) break;
@@ -1024,10 +1142,7 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
                             : reinterpret_cast<VecT*>(a.out) + static_cast<size_t>(pos[e]) * V;
         VecT* slab = nullptr;
         if constexpr (kInsert) {
-          if (src[e] != nullptr && key[e] != kEmptyKey) {
-            const uint32_t slot = claim_slot(a.buckets, a.num_buckets, key[e], a.epoch, lane);
-            if (slot != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot) * V;
-          }
+          if (slot4[e] != kMissSlot) slab = reinterpret_cast<VecT*>(a.values) + static_cast<size_t>(slot4[e]) * V;
         }
         if (lane < V) {
           st_stream(dst + lane, x[e]);

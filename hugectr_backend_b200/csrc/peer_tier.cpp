@@ -119,6 +119,8 @@ int tier_build_locked(hpsx_cache* c, uint32_t rank, uint32_t world) {
       });
     }
     unsigned long long count = 0;
+    // (the stream is non-blocking: a plain cudaMemcpy would not wait for the fill kernel)
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
     if (ce == cudaSuccess) ce = cudaMemcpy(&count, d_count, sizeof(count), cudaMemcpyDeviceToHost);
     if (ce != cudaSuccess) {
       rc = fail(HPSX_ERR_CUDA, std::string("building the NVLink tier shard: ") + cudaGetErrorString(ce));

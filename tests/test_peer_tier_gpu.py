@@ -101,6 +101,32 @@ def test_two_ranks_on_one_device_serve_each_others_misses(cuda_device, dim):
         del s
 
 
+def test_tier_pull_with_heavy_key_duplication(cuda_device):
+    """Quads of the tier pull whose entries share buckets (the same missing key many times in one request) are claimed
+    one by one; nothing may hang and every occurrence gets its row."""
+    torch = _torch()
+    rows, dim, n = 60000, 128, 8192
+    hps, ref = make_rank(rows, dim, SEEDS[0], cache_pct=0.05)
+    hps.peer_tier_build("m", 0, 0, 1)
+    hps.peer_tier_commit("m", 0)
+    s = hps.session("m", 0)
+    rng = np.random.default_rng(29)
+    for distinct in (1, 3, 40, 500):
+        pool = rng.integers(rows // 2, rows, size=distinct)
+        keys = pool[rng.integers(0, distinct, size=n)]
+        out = torch.full((n, dim), float("nan"), device="cuda")
+        s.lookup([keys], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
+    # cache pressure: far more distinct missing keys than slots, several rounds (evictions under the quad claims)
+    for _ in range(6):
+        keys = rng.integers(rows // 20, rows, size=n)
+        out = torch.full((n, dim), float("nan"), device="cuda")
+        s.lookup([keys], [out], [n])
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys))
+    resident = hps.cache_keys("m", 0, 0)
+    assert len(np.unique(resident)) == len(resident)  # no key was placed twice
+
+
 def test_world_one_tier_is_the_whole_table_in_hbm(cuda_device):
     torch = _torch()
     rows, dim, n = 30000, 128, 4096
