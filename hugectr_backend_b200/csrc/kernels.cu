@@ -1119,10 +1119,9 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
         pos[e] = __shfl_sync(kFull, my_pos, 8 * e);
         src[e] = reinterpret_cast<const VecT*>(
             __shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), 8 * e));
-        x[e] = defv;
-        if (src[e] != nullptr && lane < V) x[e] = src[e][lane];
       }
-      // the four slot claims together, while the rows are in flight
+      // The four slot claims together, BEFORE the rows are requested: releasing a bucket lock is a MEMBAR that waits
+      // for every memory operation the thread has in flight — with the row loads outstanding it would wait for NVLink.
       uint32_t slot4[4] = {kMissSlot, kMissSlot, kMissSlot, kMissSlot};
       if constexpr (kInsert) {
         unsigned deferred = 0;
@@ -1133,6 +1132,11 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
           slot4[e] = __shfl_sync(kFull, my_slot, 8 * e);
           if ((deferred >> e) & 1u) slot4[e] = claim_slot(a.buckets, a.num_buckets, key[e], a.epoch, lane);
         }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[e] = defv;
+        if (src[e] != nullptr && lane < V) x[e] = src[e][lane];
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
