@@ -452,16 +452,16 @@ def _one_server(a, world, model_json, name, batch_per_instance, seed, make_insta
             "h2d_bytes_per_step": n * 8.0, "d2h_bytes_per_step": 16.0, "clocks_per_gpu": clocks}
 
 
-def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls):
+def triton_arm_one_server(a, world, hot, warm_rows, n, torch, sampler_cls, tier=True):
     """N > 1 end-to-end arm of the headline workload: the DCN model on all GPUs of one server, "hpsx_peer_tier": true."""
     m = _ps_model("dcn", a.rows, SEED, a.dim, a.slots, a.batch, 0, gpucacheper=a.gpucacheper)
     m["deployed_device_list"] = list(range(world))
-    m["hpsx_peer_tier"] = True
+    m["hpsx_peer_tier"] = bool(tier)
     pre = make_requests(a, hot, warm_rows, a.prefill, SEED + 4000)
     r = _one_server(a, world, m, "dcn", a.batch, SEED, lambda d, count: make_requests(a, hot, warm_rows, count, SEED + 5000 + d),
                     pre, torch, sampler_cls)
     r["call"] = (f"TRITONBACKEND_ModelInstanceExecute (libtriton_hps.so), ONE server process, {world} instances (one per GPU, one "
-                 "thread each): host KEYS/NUMKEYS -> GPU OUTPUT0 on the instance's device; hpsx_peer_tier on")
+                 "thread each): host KEYS/NUMKEYS -> GPU OUTPUT0 on the instance's device; hpsx_peer_tier " + ("on" if tier else "off"))
     r["bytes_note"] = ("per instance: KEYS copied H2D (8 B/key) + counters D2H; the rows of missed keys come from the NVLink "
                        "tier, not over PCIe")
     return r
@@ -765,8 +765,12 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         with stdout_to_stderr():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if os.environ.get("HPSX_BENCH_BACKEND", "nccl") == "gloo":  # experiment: no NCCL communicator in the process
+                dist.init_process_group("gloo")
+            else:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             dist.barrier()
+    red_dev = "cpu" if os.environ.get("HPSX_BENCH_BACKEND", "nccl") == "gloo" else "cuda"
 
     n = a.batch * a.slots
     peaks = {}
@@ -801,7 +805,12 @@ def run_ours(a):
             return got
 
         t1 = time.perf_counter()
-        tier_info = hps.peer_tier_connect_distributed("dcn", local, rank, world, 1, gather)
+        if a.local_tier:  # every rank its own world-1 tier: no peer mapping at all
+            hps.peer_tier_build("dcn", local, 0, 1)
+            hps.peer_tier_commit("dcn", local)
+            tier_info = hps.peer_tier_info("dcn", local)
+        else:
+            tier_info = hps.peer_tier_connect_distributed("dcn", local, rank, world, 1, gather)
         tier_info["setup_s"] = time.perf_counter() - t1
 
     def tier_teardown():
@@ -842,14 +851,15 @@ def run_ours(a):
         e0.record(ext)
         w0 = time.perf_counter()
         for i in range(steps):
-            fn(i)
+            if rank == 0 or not os.environ.get("HPSX_BENCH_IDLE_RANKS"):  # experiment: only rank 0 works, the others idle
+                fn(i)
         e1.record(ext)
         torch.cuda.synchronize()
         wall = time.perf_counter() - w0
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms, wall * 1e3], device="cuda", dtype=torch.float64)
+            t = torch.tensor([ms, wall * 1e3], device=red_dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall
@@ -866,6 +876,8 @@ def run_ours(a):
     sampler.start()
     ms, wall = timed(dev_step, a.steps)
     st_pipe = sess.stats()
+    print(f"[bench] rank {rank}: pull {st_pipe.pull_kernel_ms / a.steps:.3f} ms/step, probe "
+          f"{st_pipe.probe_kernel_ms / max(1, st_pipe.probe_kernel_launches):.3f} ms, misses {st_pipe.misses // a.steps}", file=sys.stderr)
     value = world * a.steps * n / (ms / 1e3)
     verified_rows = verify_rows(torch, d_reqs[(a.steps - 1) % R], out, a.dim, SEED, "value arm")
 
@@ -972,7 +984,7 @@ def run_ours(a):
     # TRITONBACKEND_ModelInstanceExecute of libtriton_hps.so, driven by the fake-Triton harness: KEYS/NUMKEYS in
     # host memory, OUTPUT0 in a GPU buffer (what Triton hands a gpucache model, hps.cc:638-642).
     c4 = None
-    one_server = use_tier and world > 1 and not a.skip_triton_arm  # N > 1: ONE server process drives all GPUs (arm at the end, rank 0)
+    one_server = False  # (N > 1 is run_server's job: ONE server process drives all GPUs)
     if a.skip_triton_arm or one_server:
         e2e = dict(e2e_session)
         e2e["note"] = "--skip-triton-arm: session-level end-to-end arm reported"
@@ -1284,6 +1296,266 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_server(a):
+    """N > 1 (torchrun, one rank per GPU): the reference deploys ONE tritonserver process with one embedding cache per device
+    (hps_backend/src/model_state.cpp:395-419) and ONE host parameter server behind them (include/backend.hpp:70-74) — rank 0
+    plays that server for all N GPUs: one parameter server, N caches, N lookup sessions, the NVLink tier between the caches
+    ("hpsx_peer_tier"), every GPU serving its own stream of distinct requests at the same time.  Ranks 1..N-1 keep the
+    rendezvous and wait on a CPU (gloo) barrier: a rank spinning in an NCCL barrier would time-slice its GPU with the server's
+    kernels.  No data-path collective (SURVEY.md §8e mode 1): the only cross-GPU traffic is the one-sided NVLink reads of the
+    miss kernels.  `--no-peer-tier`: the same server without the tier (every miss over PCIe, the reference's behaviour).
+    (One process per GPU with the shards mapped over CUDA IPC is supported — hpsx_cache_peer_tier_export/attach_ipc,
+    tests/test_sharded_gpu.py — but is not what is measured here.)"""
+    import gc
+
+    import torch
+    import torch.distributed as dist
+
+    import hugectr_backend_b200 as hb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the lookup path has no CPU fallback")
+    torch.cuda.set_device(local)
+    with stdout_to_stderr():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+        cpu_group = dist.new_group(backend="gloo")
+    if rank != 0:
+        dist.barrier(group=cpu_group)  # until the server is done; no GPU work meanwhile
+        dist.destroy_process_group()
+        return
+
+    devs = list(range(world))
+    n = a.batch * a.slots
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_gbs, peak_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    use_tier = not a.no_peer_tier and a.miss_path == "direct"
+    line, failed = None, None
+    try:
+        t0 = time.perf_counter()
+        hps = hb.HPS(num_partitions=16, pull_window_mb=a.window_mb)
+        hps.add_model(hb.ModelParams("dcn", a.batch, [a.dim], [a.slots], [0.0], hit_rate_threshold=1.0,
+                                     cache_size_percentage=a.gpucacheper, deployed_devices=devs, cache_load_factor=a.load_factor,
+                                     enable_pagelock=(a.miss_path == "direct"), request_chunks=a.chunks,
+                                     pull_grid_ctas=a.pull_ctas, peer_tier=use_tier))
+        hps.load_table_procedural("dcn", 0, a.rows, SEED)
+        hps.create_embedding_cache("dcn")  # N caches + (hpsx_peer_tier) the shards and the re-pointed indexes
+        setup_s = time.perf_counter() - t0
+        tier_info = hps.peer_tier_info("dcn", 0) if use_tier else None
+        hot = hps.cache_keys("dcn", 0, 0)
+        warm_rows = int(np.ceil(a.gpucacheper * a.rows))
+        R = a.distinct if a.distinct > 0 else min(32, a.steps + a.warmup)
+        pre_reqs = make_requests(a, hot, warm_rows, a.prefill, SEED + 4000)
+        sess, d_reqs, h_reqs, outs, exts = [], [], [], [], []
+        for d in devs:
+            reqs = make_requests(a, hot, warm_rows, 2 * R, SEED + 100 * d)
+            with torch.cuda.device(d):
+                s = hps.session("dcn", d)
+                s.set_probe_variant(a.variant)
+                sess.append(s)
+                d_reqs.append([torch.from_numpy(k).cuda() for k in reqs[:R]])
+                h_reqs.append([torch.from_numpy(k).pin_memory() for k in reqs[R:]])
+                outs.append(torch.empty((n, a.dim), device="cuda", dtype=torch.float32))
+                exts.append(torch.cuda.ExternalStream(s.stream, device=d))
+
+        def on_all(fn):
+            """fn(d) on one thread per GPU, all at once; returns the wall seconds of the whole pass."""
+            err = []
+
+            def body(d):
+                try:
+                    torch.cuda.set_device(d)
+                    fn(d)
+                except BaseException as ex:  # noqa: BLE001 — re-raised below
+                    err.append(ex)
+
+            th = [threading.Thread(target=body, args=(d,)) for d in devs]
+            t = time.perf_counter()
+            [x.start() for x in th]
+            [x.join() for x in th]
+            for d in devs:
+                torch.cuda.synchronize(d)
+            if err:
+                raise err[0]
+            return time.perf_counter() - t
+
+        def timed(step, steps):
+            """K steps per GPU, all GPUs at once; device time = max over GPUs of the CUDA-event time on the GPU's session stream."""
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in devs]
+
+            def body(d):
+                ev[d][0].record(exts[d])
+                for i in range(steps):
+                    step(d, i)
+                ev[d][1].record(exts[d])
+
+            wall = on_all(body)
+            return max(e0.elapsed_time(e1) for e0, e1 in ev), wall
+
+        on_all(lambda d: [sess[d].lookup([k], [outs[d]], [n]) for k in pre_reqs])  # untimed: caches reach steady state
+        dev_step = lambda d, i: sess[d].lookup_device_keys([d_reqs[d][i % R]], [outs[d]], [n])
+        e2e_step = lambda d, i: sess[d].lookup([h_reqs[d][i % R].numpy()], [outs[d]], [n])
+
+        # ---- device-resident arm (value)
+        timed(dev_step, a.warmup)
+        [s.reset_stats() for s in sess]
+        samplers = [ClockSampler(d) for d in devs]
+        [x.start() for x in samplers]
+        ms, wall = timed(dev_step, a.steps)
+        stats = [s.stats() for s in sess]
+        value = world * a.steps * n / (ms / 1e3)
+        verified_rows = 0
+        for d in devs:
+            with torch.cuda.device(d):
+                verified_rows += verify_rows(torch, d_reqs[d][(a.steps - 1) % R], outs[d], a.dim, SEED, f"value arm, GPU {d}")
+        st = stats[0]
+        probe_ms = st.probe_kernel_ms / max(1, st.probe_kernel_launches)
+        hits_per, miss_per = st.hits / a.steps, st.misses / a.steps
+        alg_bytes = hits_per * (8 + 8 * a.dim) + miss_per * 8
+        achieved = alg_bytes / (probe_ms / 1e3) / 1e9 if probe_ms > 0 else 0.0
+        traffic, traffic_src = None, None
+        try:
+            import glob
+            tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_traffic_*.json")))[-1]))
+            k = tr[f"probe_gather_{a.variant}"]
+            traffic, traffic_src = k["dram_bytes_read"] + k["dram_bytes_write"], tr["source"]
+        except (OSError, KeyError, ValueError):
+            pass
+        step_ms = ms / a.steps
+        roofline = {"bound": "hbm", "kernel": f"probe_gather_{a.variant}", "achieved": achieved, "peak": peak_gbs,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": traffic,
+                    "traffic_source": traffic_src, "avg_launch_ms": probe_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "share_of_step": probe_ms / step_ms, "gpu": 0,
+                    "step_fraction_of_hbm_roofline": (n * (8 + 8 * a.dim) / (step_ms / 1e3) / 1e9) / peak_gbs,
+                    "note": "GPU 0's probe+gather kernel; the rest of the step is the miss kernel, see roofline_nvlink_tier / "
+                            "roofline_host_link"}
+        pull_ms = max((x.pull_kernel_ms if x.pull_kernel_ms > 0 else x.insert_kernel_ms) for x in stats) / a.steps
+        tier_b = sum(x.tier_bytes for x in stats) / a.steps / world
+        link_b = sum(x.h2d_bytes for x in stats) / a.steps / world
+        roofline_tier = None
+        if use_tier:
+            roofline_tier = {"bound": "nvlink", "kernel": "pull_binned (quad form): rows read from the owners' HBM shards",
+                             "achieved": tier_b * (world - 1) / world / (pull_ms / 1e3) / 1e9, "peak": 900.0,
+                             "peak_source": "NVLink 5 nominal, one direction (measured with SM loads of random 512-B rows: 765 GB/s, "
+                                            "profiles/nvlink_read_probe_r02.txt)",
+                             "unit": "GB/s", "avg_ms_per_step": pull_ms, "rows_bytes_per_gpu_per_step": tier_b,
+                             "bytes_over_nvlink_per_gpu_per_step": tier_b * (world - 1) / world,
+                             "share_of_step": pull_ms / step_ms,
+                             "note": "per GPU, slowest GPU's miss phase; the kernel is bound by its slot-claim chain (locks, "
+                                     "MEMBAR), not by the link: see DESIGN.md §3"}
+            roofline_tier["frac"] = roofline_tier["achieved"] / 900.0
+        roofline_host_link = {"bound": "pcie", "kernel": "pull_binned", "achieved": link_b / (pull_ms / 1e3) / 1e9 if pull_ms > 0 else 0.0,
+                              "unit": "GB/s", "avg_ms_per_step": pull_ms, "algorithmic_bytes_per_step": link_b,
+                              "note": "bytes of missed rows that crossed PCIe, per GPU per step (0 with the tier)"}
+
+        # ---- end-to-end, session level: pinned host keys -> device vectors on every GPU
+        timed(e2e_step, a.warmup)
+        [s.reset_stats() for s in sess]
+        ms_e, wall_e = timed(e2e_step, a.steps)
+        st_e = [s.stats() for s in sess]
+        ver_e = 0
+        for d in devs:
+            with torch.cuda.device(d):
+                ver_e += verify_rows(torch, h_reqs[d][(a.steps - 1) % R].cuda(), outs[d], a.dim, SEED, f"e2e session arm, GPU {d}")
+        e2e_session = {"value": world * a.steps * n / (ms_e / 1e3), "unit": UNIT, "ms_per_step": ms_e / a.steps,
+                       "h2d_bytes_per_step": sum(x.h2d_bytes for x in st_e) / a.steps / world,
+                       "d2h_bytes_per_step": sum(x.d2h_bytes for x in st_e) / a.steps / world,
+                       "hit_rate": sum(x.hits for x in st_e) / max(1, sum(x.keys for x in st_e)), "verified_rows": ver_e,
+                       "call": "hpsx_session_lookup (host keys -> device vectors) on every GPU at once, CUDA events per GPU, max"}
+        clocks_all = [x.stop() for x in samplers]
+        clocks = dict(clocks_all[0])
+        clocks["per_gpu"] = clocks_all
+
+        # ---- all-hit pass on every GPU
+        rng = np.random.default_rng(SEED + 77)
+        hit_reqs = []
+        for d in devs:
+            hot_now = hps.cache_keys("dcn", d, 0)
+            with torch.cuda.device(d):
+                hit_reqs.append([torch.from_numpy(hot_now[rng.integers(0, len(hot_now), size=n)]).cuda() for _ in range(4)])
+        hit_step = lambda d, i: sess[d].lookup_device_keys([hit_reqs[d][i % 4]], [outs[d]], [n])
+        timed(hit_step, a.warmup)
+        [s.reset_stats() for s in sess]
+        ms_h, _ = timed(hit_step, a.steps)
+        st_h = sess[0].stats()
+        probe_h = st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches)
+        cache_hit = {"vectors_per_s": world * a.steps * n / (ms_h / 1e3), "ms_per_step": ms_h / a.steps, "kernel_ms": probe_h,
+                     "hbm_gbs": n * (8 + 8 * a.dim) / (probe_h / 1e3) / 1e9 if probe_h > 0 else 0.0,
+                     "hit_rate": st_h.hits / max(1, st_h.keys)}
+        cache_hit["frac_of_peak"] = cache_hit["hbm_gbs"] / peak_gbs
+        hit_rate = sum(x.hits for x in stats) / max(1, sum(x.keys for x in stats))
+        launches = int(sum(x.kernel_launches for x in stats))
+        miss_path = {"misses_per_step": sum(x.misses for x in stats) / a.steps / world, "insert_phase_ms_per_step": pull_ms,
+                     "insert_phase_ms_per_step_per_gpu": [(x.pull_kernel_ms if x.pull_kernel_ms > 0 else x.insert_kernel_ms) / a.steps for x in stats],
+                     "h2d_bytes_per_step": link_b, "tier_bytes_per_step": tier_b}
+        del sess, hps, outs, d_reqs, h_reqs, hit_reqs, exts
+        gc.collect()
+        for d in devs:
+            with torch.cuda.device(d):
+                torch.cuda.empty_cache()
+
+        # ---- end-to-end through the plugin call (headline e2e) and the model-parallel configuration
+        e2e, c4 = dict(e2e_session), None
+        if not a.skip_triton_arm:
+            try:
+                e2e = triton_arm_one_server(a, world, hot, warm_rows, n, torch, ClockSampler, tier=use_tier)
+                e2e["session_level"] = {k: e2e_session[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
+            except SystemExit as ex:
+                failed = ex
+            except Exception as ex:  # keep the line: the session-level arm stands in, and the failure is named
+                print(f"[bench] one-server Triton arm FAILED: {ex!r}", file=sys.stderr)
+                e2e["note"] = f"one-server Triton arm failed ({ex!r}); session-level end-to-end arm reported"
+        else:
+            e2e["note"] = "--skip-triton-arm: session-level end-to-end arm reported"
+        if not a.skip_c4 and failed is None:
+            gc.collect()
+            t_c4 = time.perf_counter()
+            try:
+                c4 = config_c4(a, world, torch, ClockSampler)
+                c4["arm_wall_s"] = time.perf_counter() - t_c4
+            except SystemExit as ex:
+                failed = ex
+            except Exception as ex:
+                print(f"[bench] configuration c4 FAILED: {ex!r}", file=sys.stderr)
+                c4 = {"error": repr(ex)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "keys_per_step": n, "keys_per_step_all_gpus": world * n, "rows": a.rows,
+                       "dim": a.dim, "gpucacheper": a.gpucacheper, "hit_rate_measured": hit_rate,
+                       "insert": "synchronous (hit_rate_threshold 1.0)", "probe_variant": a.variant,
+                       "l2": f"inputs exceed L2: 13.6 MB keys + 872 MB output + >1 GB cache slab per GPU per step, {R} distinct key "
+                             "batches per GPU and arm",
+                       "hot_draw_probability": a.hit, "prefill_requests": a.prefill, "load_factor": a.load_factor,
+                       "miss_path": a.miss_path,
+                       "parallelism": f"replica x{world}: ONE server process (rank 0) with one cache and one lookup session per GPU and "
+                                      "one host parameter server, as the reference deploys it; every GPU serves its own request "
+                                      "stream" + ("; NVLink tier on: the host table is also sharded over the GPUs' HBM (1/N per GPU) and "
+                                                  "cache misses are read from the owner's shard instead of over PCIe" if use_tier else
+                                                  "; no tier: every cache miss crosses PCIe"),
+                       "setup_s": setup_s, "host_cores": os.cpu_count()},
+            "peer_tier": tier_info, "roofline_nvlink_tier": roofline_tier, "roofline": roofline,
+            "roofline_host_link": roofline_host_link, "cpu_baseline": None, "e2e": e2e, "e2e_session": e2e_session,
+            "cache_hit": cache_hit, "c4": c4, "gpu_launches": launches, "clocks": clocks, "verified_rows": verified_rows,
+            "wall_ms_per_step": wall / a.steps * 1e3, "miss_path": miss_path,
+        }
+    finally:
+        dist.barrier(group=cpu_group)  # release the waiting ranks whatever happened
+    if failed is not None:
+        raise failed
+    print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def run_sharded(a):
     """configs[3]-shaped: one table sharded by owner(key) over the ranks, every rank serves its slice of the global
     batch, every key is HBM-resident at its owner.  value = keys of ALL ranks / max-over-ranks device time."""
@@ -1420,8 +1692,10 @@ def main():
         run_reference(a)
     elif a.workload == "c4":
         run_sharded(a)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and not a.value_only and not os.environ.get("HPSX_BENCH_REPLICA_PROCESSES"):
+        run_server(a)
     else:
-        run_ours(a)
+        run_ours(a)  # N = 1; also (HPSX_BENCH_REPLICA_PROCESSES=1 / --value-only) one replica process per GPU over CUDA IPC
 
 
 if __name__ == "__main__":

@@ -1136,7 +1136,7 @@ __global__ void __launch_bounds__(kBlock) pull_binned_kernel(const PullBinnedArg
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         x[e] = defv;
-        if (src[e] != nullptr && lane < V) x[e] = src[e][lane];
+        if (src[e] != nullptr && lane < V) x[e] = ld_stream(src[e] + lane);  // rows are read-only while lookups run
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
