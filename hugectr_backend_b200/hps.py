@@ -326,6 +326,21 @@ class LookupSession:
         k, o, n, T = self._arrays(d_keys_per_table, d_vectors_per_table, num_keys_per_table)
         N.check(self._L.hpsx_session_lookup_device_keys(self._h, k, o, n, T))
 
+    def bind(self, keys_per_table, vectors_per_table, num_keys_per_table, device_keys: bool = False):
+        """A lookup with its argument arrays built once: returns a callable that only makes the C call (benchmarks that
+        drive several GPUs from Python threads keep the interpreter's share of a sub-millisecond step small)."""
+        K, O_, Nn, T = self._arrays(keys_per_table, vectors_per_table, num_keys_per_table)
+        fn = self._L.hpsx_session_lookup_device_keys if device_keys else self._L.hpsx_session_lookup
+        h, keep = self._h, (keys_per_table, vectors_per_table)
+
+        def call():
+            rc = fn(h, K, O_, Nn, T)
+            if rc != 0:
+                N.check(rc)
+            return keep is None
+
+        return call
+
     def lookup_ex(self, keys_per_table, vectors_per_table, num_keys_per_table, key_memory: str = "host",
                   vector_memory: str = "device") -> None:
         """General form (what the Triton shell calls): keys and vectors each in "host" or "device" memory."""
