@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--c4-rows-per-gpu", type=int, default=125_000_000,
                     help="rows per GPU of the model-parallel table of the c4 arm (configs[3]: 1 B rows / 8 GPUs)")
+    ap.add_argument("--c4-instances-per-gpu", type=int, default=2)
     ap.add_argument("--skip-c4", action="store_true")
     ap.add_argument("--static-cache", action="store_true",
                     help="experiment: embedding_cache_type static (no insertion, no LRU stamps): what the LRU touch costs the probe kernel")
@@ -391,11 +392,13 @@ def triton_arm(a, local, world, h_keys, pre_reqs, out, n, barrier):
             "verified_rows": verified}
 
 
-def _one_server(a, world, model_json, name, batch_per_instance, seed, make_instance_requests, prefill, torch, sampler_cls):
-    """ONE server process (fake Triton + libtriton_hps.so) with model `name` deployed on all `world` GPUs, one instance per
-    GPU — the reference's multi-GPU deployment (one tritonserver, one cache per device, hps_backend/src/model_state.cpp:
-    395-419).  Every instance serves its own stream of distinct requests (host KEYS in pinned memory -> GPU OUTPUT0 on its
-    device); the streams run at once, one C++ thread per instance inside the harness (no Python in the timed region)."""
+def _one_server(a, world, model_json, name, batch_per_instance, seed, make_instance_requests, prefill, torch, sampler_cls,
+                instances_per_gpu=1):
+    """ONE server process (fake Triton + libtriton_hps.so) with model `name` deployed on all `world` GPUs,
+    `instances_per_gpu` instances per GPU (instance_group count) — the reference's multi-GPU deployment (one tritonserver, one
+    cache per device, hps_backend/src/model_state.cpp:395-419).  Every instance serves its own stream of distinct requests (host
+    KEYS in pinned memory -> GPU OUTPUT0 on its device); the streams run at once, one C++ thread per instance inside the harness
+    (no Python in the timed region)."""
     import tempfile
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -411,14 +414,14 @@ def _one_server(a, world, model_json, name, batch_per_instance, seed, make_insta
                        "models": [model_json]}, f)
         t0 = time.perf_counter()
         with FT.Backend(path) as be:
-            model = be.model(name, FT.model_config(name, gpus=devs, max_batch_size=batch_per_instance))
-            insts = [model.instance(name=f"{name}_{d}", kind=FT.KIND_GPU, device=d) for d in devs]
+            model = be.model(name, FT.model_config(name, gpus=devs, max_batch_size=batch_per_instance, count=instances_per_gpu))
+            insts = [(d, model.instance(name=f"{name}_{d}_{j}", kind=FT.KIND_GPU, device=d)) for d in devs for j in range(instances_per_gpu)]
             setup_s = time.perf_counter() - t0
             numkeys = np.array([[n]], dtype=np.int32)
             outs, all_reqs, keep, prepared = [], [], [], []
-            for d, inst in enumerate(insts):
+            for w, (d, inst) in enumerate(insts):
                 out = torch.empty(n * a.dim, device=f"cuda:{d}", dtype=torch.float32)
-                reqs = list(prefill) + make_instance_requests(d, a.warmup + steps)
+                reqs = list(prefill) + make_instance_requests(w, a.warmup + steps)
                 pinned = [torch.from_numpy(k).pin_memory() for k in reqs]  # Triton hands the backend pinned input buffers
                 prepared.append(inst.prepare([dict(keys=t.numpy(), numkeys=numkeys, gpu_out=out, out_device=d) for t in pinned]))
                 outs.append(out)
@@ -435,18 +438,19 @@ def _one_server(a, world, model_json, name, batch_per_instance, seed, make_insta
                 torch.cuda.synchronize(d)
             clocks = [s.stop() for s in samplers]
             verified = 0
-            for d, p in enumerate(prepared):
-                r = p.responses()[-1]
+            for w, (d, inst) in enumerate(insts):
+                r = prepared[w].responses()[-1]
                 assert r.error_code is None and r.params.get("NumSample") == batch_per_instance, (d, r.error_message)
                 with torch.cuda.device(d):
-                    verified += verify_rows(torch, torch.from_numpy(all_reqs[d][-1]).cuda(), outs[d].view(n, a.dim), a.dim, seed,
+                    verified += verify_rows(torch, torch.from_numpy(all_reqs[w][-1]).cuda(), outs[w].view(n, a.dim), a.dim, seed,
                                             f"one-server arm {name}, GPU {d}")
             for p in prepared:
                 p.close()
-            for inst in insts:
+            for d, inst in insts:
                 inst.close()
             model.close()
-    return {"value": world * steps * n / wall, "unit": UNIT, "ms_per_step": wall / steps * 1e3, "steps": steps,
+    return {"value": len(insts) * steps * n / wall, "unit": UNIT, "ms_per_step": wall / steps * 1e3, "steps": steps,
+            "instances_per_gpu": instances_per_gpu,
             "timer": "host wall clock (C++, inside the harness) from the common start of the instance threads to the end of the last",
             "output": "device memory (Triton GPU output buffer contract)", "verified_rows": verified, "setup_s": setup_s,
             "h2d_bytes_per_step": n * 8.0, "d2h_bytes_per_step": 16.0, "clocks_per_gpu": clocks}
@@ -476,8 +480,9 @@ def config_c4(a, world, torch, sampler_cls, peak_nvlink=900.0):
     TRITONBACKEND_ModelInstanceExecute of one server process, one instance per GPU."""
     rows = a.c4_rows_per_gpu * world
     seed = 0xB2000000 + 44
+    ipg = max(1, a.c4_instances_per_gpu)  # instance_group count: one instance's key copy and host work overlap the other's gather
     batch = 131072 // world
-    m = {"model": "dlrm", "sparse_files": [f"synthetic_device:rows={rows},seed={seed}"], "num_of_worker_buffer_in_pool": 1,
+    m = {"model": "dlrm", "sparse_files": [f"synthetic_device:rows={rows},seed={seed}"], "num_of_worker_buffer_in_pool": ipg,
          "embedding_vecsize_per_table": [a.dim], "maxnum_catfeature_query_per_table_per_sample": [a.slots],
          "default_value_for_each_table": [0.0], "deployed_device_list": list(range(world)), "max_batch_size": batch,
          "hit_rate_threshold": 1.0, "gpucacheper": 0.0, "gpucache": True, "enable_pagelock": True, "hpsx_peer_tier": True,
@@ -488,16 +493,17 @@ def config_c4(a, world, torch, sampler_cls, peak_nvlink=900.0):
         rng = np.random.default_rng(seed + 100 + d)
         return [rng.integers(0, rows, size=n, dtype=np.int64) for _ in range(count)]
 
-    r = _one_server(a, world, m, "dlrm", batch, seed, reqs, [], torch, sampler_cls)
+    r = _one_server(a, world, m, "dlrm", batch, seed, reqs, [], torch, sampler_cls, instances_per_gpu=ipg)
     step_s = r["ms_per_step"] / 1e3
     row_bytes = a.dim * 4
-    ingress = n * row_bytes * (world - 1) / world / step_s / 1e9  # per GPU
+    ingress = ipg * n * row_bytes * (world - 1) / world / step_s / 1e9  # per GPU
     r.update({
         "workload": f"configs[3]: model-parallel table, {rows / 1e6:.0f} M rows x dim {a.dim} over {world} GPUs "
                     f"({a.c4_rows_per_gpu / 1e6:.0f} M rows = {a.c4_rows_per_gpu * row_bytes / 1e9:.0f} GB per GPU), global batch "
                     f"{batch * world} x {a.slots} keys, uniform keys, rows generated on the devices (no host copy), no local cache",
-        "rows": rows, "global_keys_per_step": world * n,
-        "call": f"TRITONBACKEND_ModelInstanceExecute, ONE server process, {world} instances: host KEYS -> GPU OUTPUT0; "
+        "rows": rows, "keys_per_request": n, "requests_in_flight": world * ipg,
+        "call": f"TRITONBACKEND_ModelInstanceExecute, ONE server process, {world} GPUs x {ipg} instance(s): every request is one "
+                f"GPU's share ({batch} samples) of a global batch of 131072; host KEYS -> GPU OUTPUT0; "
                 "tier_gather kernel reads every row from its owner's shard",
         "roofline_nvlink": {"bound": "nvlink", "kernel": "tier_gather", "achieved": ingress, "peak": peak_nvlink,
                             "unit": "GB/s", "frac": ingress / peak_nvlink,

@@ -903,9 +903,18 @@ int gpu_lookup_direct(hpsx_session* s, const void* const* keys_per_table, bool k
       if (n == 0) continue;
       const int64_t* d_keys = static_cast<const int64_t*>(keys_per_table[t]);
       if (!keys_on_device) {
-        HPSX_CU(cudaMemcpyAsync(s->d_keys + off, keys_per_table[t], n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+        // pinned host keys (what Triton hands a backend) are read in place by the gather kernel, 256 B per warp tile
+        // over PCIe while other warps' rows are in flight; pageable keys are staged first
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, keys_per_table[t]) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+            at.devicePointer != nullptr) {
+          d_keys = static_cast<const int64_t*>(at.devicePointer);
+        } else {
+          cudaGetLastError();
+          HPSX_CU(cudaMemcpyAsync(s->d_keys + off, keys_per_table[t], n * sizeof(int64_t), cudaMemcpyHostToDevice, s->stream));
+          d_keys = s->d_keys + off;
+        }
         s->stats.h2d_bytes += n * sizeof(int64_t);
-        d_keys = s->d_keys + off;
       }
       HPSX_CU(launch_tier_gather(c->tables[t % T], d_keys, n, out_per_table[t], d_absent + t, s->stream));
       ++s->stats.kernel_launches;

@@ -1223,37 +1223,45 @@ __global__ void __launch_bounds__(kBlock) tier_gather_kernel(const int64_t* __re
                                                              const IndexSlot* __restrict__ index, uint64_t mask,
                                                              uint32_t dim, float default_value, float* out,
                                                              uint32_t* absent) {
+  // A warp owns a tile of 32 consecutive keys (one coalesced 256-B load — also when `keys` is the caller's pinned host
+  // buffer, read in place over PCIe) and serves it quad by quad.
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
   const uint32_t nwarps = (gridDim.x * kBlock) >> 5;
   const uint32_t V = dim / static_cast<uint32_t>(sizeof(VecT) / sizeof(float));
   const VecT defv = splat<VecT>(default_value);
   const uint32_t g = lane >> 3;
-  for (uint32_t i0 = warp * 4u; i0 < n; i0 += nwarps * 4u) {
-    const bool have = i0 + g < n;
-    const int64_t my_key = have ? keys[i0 + g] : kEmptyKey;
-    const float* my_row = index_find4(index, mask, my_key, have && my_key != kEmptyKey, lane);
-    const VecT* src[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      src[e] = reinterpret_cast<const VecT*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), 8 * e));
-    uint32_t missing = 0;
-    for (uint32_t v0 = 0; v0 < V; v0 += 32u) {
-      const uint32_t v = v0 + lane;
-      VecT x[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        x[e] = defv;
-        if (src[e] != nullptr && v < V) x[e] = ld_stream(src[e] + v);
-      }
+  uint32_t missing = 0;
+  for (uint32_t t0 = warp * 32u; t0 < n; t0 += nwarps * 32u) {
+    const int64_t tile_key = t0 + lane < n ? keys[t0 + lane] : kEmptyKey;
+#pragma unroll 2
+    for (uint32_t q = 0; q < 8u; ++q) {
+      const uint32_t i0 = t0 + 4u * q;
+      if (i0 >= n) break;
+      const bool have = i0 + g < n;
+      const int64_t my_key = __shfl_sync(kFull, tile_key, 4u * q + g);
+      const float* my_row = index_find4(index, mask, my_key, have && my_key != kEmptyKey, lane);
+      const VecT* src[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (i0 + e < n && v < V) st_stream(reinterpret_cast<VecT*>(out) + static_cast<size_t>(i0 + e) * V + v, x[e]);
-    }
+        src[e] = reinterpret_cast<const VecT*>(__shfl_sync(kFull, reinterpret_cast<unsigned long long>(my_row), 8 * e));
+      for (uint32_t v0 = 0; v0 < V; v0 += 32u) {
+        const uint32_t v = v0 + lane;
+        VecT x[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) missing += (i0 + e < n && src[e] == nullptr) ? 1u : 0u;
-    if (lane == 0 && missing != 0u && absent != nullptr) atomicAdd(absent, missing);
+        for (int e = 0; e < 4; ++e) {
+          x[e] = defv;
+          if (src[e] != nullptr && v < V) x[e] = ld_stream(src[e] + v);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < n && v < V) st_stream(reinterpret_cast<VecT*>(out) + static_cast<size_t>(i0 + e) * V + v, x[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) missing += (i0 + e < n && src[e] == nullptr) ? 1u : 0u;
+    }
   }
+  if (lane == 0 && missing != 0u && absent != nullptr) atomicAdd(absent, missing);
 }
 
 // Synthetic shard (tables too large for a host copy): of the keys [key_lo, key_hi) append those this rank owns, with
@@ -2090,7 +2098,7 @@ cudaError_t launch_tier_gather(const DeviceTable& t, const int64_t* d_keys, size
                                cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   if (t.index == nullptr || n > 0xFFFFFFFFull) return cudaErrorInvalidValue;
-  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + 31) / 32, 148u * 16u));  // 8 warps x 4 keys per CTA pass
+  const unsigned grid = static_cast<unsigned>(std::min<size_t>((n + kBlock - 1) / kBlock, 148u * 16u));  // a warp per 32-key tile
   const int vb = vec_bytes(t.dim, d_out);
   if (vb == 16)
     tier_gather_kernel<float4><<<grid, kBlock, 0, stream>>>(d_keys, static_cast<uint32_t>(n), t.index, t.index_mask, t.dim,
