@@ -179,6 +179,12 @@ class HPS:
         N.check(self._L.hpsx_ps_table_rows(self._h, model.encode(), table, ctypes.byref(n)))
         return n.value
 
+    def request_capacity(self, model: str, table: int) -> int:
+        """Keys of `table` one request of the model may hold: max_batch_size x maxnum_catfeature_query_per_table_per_sample."""
+        p = N.ModelParamsC()
+        N.check(self._L.hpsx_ps_get_model_params(self._h, model.encode(), ctypes.byref(p)))
+        return int(p.max_batch_size) * int(p.maxnum_catfeature_query_per_table_per_sample[table])
+
     def lookup(self, keys: np.ndarray, model: str, table: int, dim: Optional[int] = None) -> np.ndarray:
         """CPU parameter-server lookup (gpucache = false path).  ~ ``HPS.lookup(key, model_name, table_id)``."""
         keys = np.ascontiguousarray(keys, dtype=np.int64).ravel()

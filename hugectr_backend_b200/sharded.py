@@ -146,15 +146,26 @@ class ShardedLookup:
         rows = torch.empty((m, self.dim), dtype=torch.float32, device=keys.device)
         if m == 0:
             return rows
-        T = self.table + 1
-        k = [None] * self.table + [keys if self.on_gpu else keys.numpy()]
-        o = [None] * self.table + [rows if self.on_gpu else rows.numpy()]
-        c = [0] * self.table + [m]
-        if self.on_gpu:
-            self.session.lookup_device_keys(k, o, c)
-        else:
-            self.session.lookup(k, o, c)
+        # Skewed ownership can hand one rank more keys than a request of the session may hold (max_batch_size x
+        # maxnum_catfeature): serve them in pieces instead of failing between the two all-to-alls, where the other
+        # ranks would be left waiting in the row exchange.
+        cap = self._capacity()
+        for lo in range(0, m, cap):
+            hi = min(m, lo + cap)
+            kk, rr = keys[lo:hi], rows[lo:hi]
+            k = [None] * self.table + [kk if self.on_gpu else kk.numpy()]
+            o = [None] * self.table + [rr if self.on_gpu else rr.numpy()]
+            c = [0] * self.table + [hi - lo]
+            if self.on_gpu:
+                self.session.lookup_device_keys(k, o, c)
+            else:
+                self.session.lookup(k, o, c)
         return rows
+
+    def _capacity(self) -> int:
+        if getattr(self, "_cap", None) is None:
+            self._cap = max(1, int(self.hps.request_capacity(self.model, self.table)))
+        return self._cap
 
     def lookup(self, keys, out: Optional["object"] = None):
         """keys: int64 tensor [n] of THIS rank's request (CUDA tensor for a GPU session, CPU tensor otherwise).

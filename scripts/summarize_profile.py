@@ -96,7 +96,7 @@ def main():
         if not os.path.exists(p) or os.path.getsize(p) == 0:
             continue
         shutil.copy(p, os.path.join(DST, f"bench_{tag}{suffix}.json"))
-        d = json.load(open(p))
+        d = json.loads(open(p).read().strip().splitlines()[-1])
         rf, hl = d.get("roofline"), d.get("roofline_host_link")
         lines.append("| %s | %.1f | %.3f | %.1f | %s | %s | %s |" % (
             label, d["value"] / 1e6, d["ms_per_step"], d["e2e"]["value"] / 1e6,
@@ -142,8 +142,18 @@ def main():
             json.dump(traffic, f, indent=1)
     # extra passes: the single-GPU form of the model-parallel workload and the dense head
     for suffix, title in (("_c4", "model-parallel workload on one GPU (`bench.py --workload c4 --gpus 1`)"),
+                          ("_tier", "NVLink tier with one rank: misses pulled from the local shard (`bench.py --value-only --local-tier`)"),
+                          ("_gather", "tier-only table, 125 M rows, 1.7 M keys per request (`scripts/c4_repro.py`)"),
                           ("_mlp", "dense head, Criteo shape (`scripts/mlp_profile_driver.py`)")):
         if not os.path.exists(os.path.join(SRC, f"launches_{tag}{suffix}.csv")):
+            for c in full_capture(tag, suffix):
+                lines.append(f"**{c['kernel']}** (`ncu --set full`) — {title}\n")
+                lines.append("| metric | value | unit |")
+                lines.append("|---|---|---|")
+                for m in METRICS:
+                    if m in c:
+                        lines.append(f"| `{m}` | {c[m][0]} | {c[m][1]} |")
+                lines.append("")
             continue
         agg2, total2 = launch_list(tag, suffix)
         shutil.copy(os.path.join(SRC, f"launches_{tag}{suffix}.csv"), os.path.join(DST, f"launches_{tag}{suffix}.csv"))

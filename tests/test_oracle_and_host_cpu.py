@@ -277,3 +277,22 @@ def test_model_params_round_trip_through_the_abi(tmp_path):
     assert p.number_of_worker_buffers_in_pool == 3 and p.num_deployed_devices == 2 and p.deployed_devices[1] == 0
     assert p.table_names[0] == b"emb" and p.enable_pagelock == 1
     assert p.sparse_files[0].decode().endswith("sparse_d4")
+
+
+def test_tier_only_table_spec_is_validated_on_the_host():
+    """sparse_files entry "synthetic_device:rows=N,seed=S" (a table that lives in the NVLink tier only, include/hpsx.h):
+    needs gpucache + enable_pagelock + hpsx_peer_tier; has no host rows (the CPU path answers with the default vector)."""
+    hps = hb.HPS(num_partitions=2)
+    with pytest.raises(Exception, match="NVLink tier"):
+        hps.add_model(hb.ModelParams("a", 64, [8], [1], [0.5], enable_pagelock=True,
+                                     sparse_files=["synthetic_device:rows=100,seed=3"]))
+    with pytest.raises(Exception, match="malformed"):
+        hps.add_model(hb.ModelParams("b", 64, [8], [1], [0.5], enable_pagelock=True, peer_tier=True,
+                                     sparse_files=["synthetic_device:rows=abc"]))
+    hps.add_model(hb.ModelParams("c", 64, [8], [1], [0.5], enable_pagelock=True, peer_tier=True, embedding_cache_type="static",
+                                 cache_size_percentage=0.0, sparse_files=["synthetic_device:rows=100,seed=3"]))
+    assert hps.table_rows("c", 0) == 100
+    assert np.array_equal(hps.lookup(np.arange(5), "c", 0), np.full((5, 8), 0.5, dtype=np.float32))
+    if hb.lib().hpsx_device_count() == 0:
+        with pytest.raises(Exception):  # no CUDA device: the GPU entry points fail, nothing falls back to the CPU
+            hps.create_embedding_cache("c")
