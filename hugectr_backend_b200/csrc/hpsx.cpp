@@ -771,7 +771,7 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 2], P));
     HPSX_CU(launch_pull_binned(dt, grp.bins, grp.out, grp.out_bf16, batch ? grp.outs.data() : nullptr,
                                batch ? static_cast<int>(R) : 0, d_absent + g, pull_ctas, P,
-                               fused ? 1 : 0, epoch, d_inserted + g, c->tier.committed ? 4 : 1));
+                               fused ? 1 : 0, epoch, d_inserted + g, (c->tier.committed || (s->debug_flags & 8)) ? 4 : 1));
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 3], P));
     HPSX_CU(cudaEventRecord(ev_pulled[g], P));
     ++s->stats.kernel_launches;

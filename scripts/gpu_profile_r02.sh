@@ -12,6 +12,11 @@ timeout 900 python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_$
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2> gpurun_out/bench_${TAG}_reference.err
 timeout 300 python bench.py --value-only --zipf 1.05 --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_zipf105.json 2> gpurun_out/bench_${TAG}_zipf105.err
 timeout 300 python bench.py --value-only --local-tier --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${TAG}_local_tier.json 2> gpurun_out/bench_${TAG}_local_tier.err
+: > gpurun_out/sweep_${TAG}_quad_pcie.jsonl
+for ctas in 37 74 148; do
+  echo "{\"cfg\": \"quad pull over PCIe, $ctas CTAs\"}" >> gpurun_out/sweep_${TAG}_quad_pcie.jsonl
+  timeout 200 python bench.py --value-only --debug-flags 8 --pull-ctas $ctas --steps 20 --warmup 3 --no-cpu-baseline >> gpurun_out/sweep_${TAG}_quad_pcie.jsonl 2>> gpurun_out/sweep_${TAG}_quad_pcie.err
+done
 NCU="ncu --clock-control none"
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 700 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --steps 2 --warmup 3 --prefill 2 --no-cpu-baseline --core-arms-only --skip-extra > gpurun_out/ncu_bench.log 2>&1
@@ -33,4 +38,5 @@ for k in ('c1','c5','c3'):
 print('miss dup', d['config'].get('miss_duplicates'))
 PY
 cut -c1-300 gpurun_out/bench_${TAG}_zipf105.json; cut -c1-300 gpurun_out/bench_${TAG}_local_tier.json
+cut -c1-260 gpurun_out/sweep_${TAG}_quad_pcie.jsonl
 ls -la gpurun_out/*.ncu-rep | tail -4
