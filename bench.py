@@ -938,6 +938,8 @@ def run_ours(a):
                               "pull_ms": st.pull_kernel_ms / a.steps, "miss_phase_ms": st.insert_kernel_ms / a.steps,
                               "link_gbs": (st.h2d_bytes / a.steps) / (max(st.pull_kernel_ms, 1e-9) / a.steps / 1e3) / 1e9,
                               "misses": miss_per, "chunks": a.chunks, "pull_ctas": a.pull_ctas, "verified_rows": verified_rows,
+                              "miss_duplicates": miss_dup, "hit_rate_measured": st.hits / max(1, st.keys),
+                              "unique_over_keys": float(len(np.unique(reqs[0])) / n),
                               "all_hit_kernel_ms": st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches),
                               "all_hit_frac": (n * (8 + 8 * a.dim)) / (st_h.probe_kernel_ms / max(1, st_h.probe_kernel_launches) / 1e3) / 1e9 / peak_gbs,
                               "tier_gbs": (st.tier_bytes / a.steps) / (max(st.pull_kernel_ms, 1e-9) / a.steps / 1e3) / 1e9,

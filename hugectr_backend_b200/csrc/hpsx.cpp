@@ -744,6 +744,12 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
   cudaStream_t P = overlap ? B : A;  // where the pulls run
   // NVLink reads need ~2 MB in flight (latency x 700 GB/s) where PCIe needs ~130 KB: four CTAs per SM instead of one
   const int pull_ctas = c->tier.committed ? std::max(s->pull_grid_ctas, 148 * 4) : s->pull_grid_ctas;
+  // Rows over PCIe: on a host table of a few GB the quad form of the pull kernel (four rows in flight per warp, half the
+  // CTAs) reaches 50.2 GB/s where the one-row form reaches 48.5 (profiles/r02_summary.md); on tens of GB more rows in flight
+  // spread the reads over more host memory and lose (engine.hpp pull_grid_ctas), so large tables keep the one-row form.
+  auto small_host_table = [&](size_t t) {
+    return s->model->tables[t]->rows() * s->model->tables[t]->dim() * sizeof(float) <= (8ull << 30);
+  };
   size_t li = 0;
   for (size_t g = 0; g < G; ++g) {
     const BinGroup& grp = groups[g];
@@ -769,9 +775,10 @@ int gpu_lookup_direct_binned(hpsx_session* s, const void* const* keys_v, bool ke
     if (overlap) HPSX_CU(cudaStreamWaitEvent(P, ev_probe[g], 0));
     if (g == 0) HPSX_CU(cudaEventRecord(s->ev_pull[0], P));
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 2], P));
+    const bool quad_pcie = !c->tier.committed && !(s->debug_flags & 8) && small_host_table(grp.table);
     HPSX_CU(launch_pull_binned(dt, grp.bins, grp.out, grp.out_bf16, batch ? grp.outs.data() : nullptr,
-                               batch ? static_cast<int>(R) : 0, d_absent + g, pull_ctas, P,
-                               fused ? 1 : 0, epoch, d_inserted + g, (c->tier.committed || (s->debug_flags & 8)) ? 4 : 1));
+                               batch ? static_cast<int>(R) : 0, d_absent + g, quad_pcie ? std::max(1, pull_ctas / 2) : pull_ctas, P,
+                               fused ? 1 : 0, epoch, d_inserted + g, (c->tier.committed || quad_pcie) ? 4 : 1));
     if (timeline) HPSX_CU(cudaEventRecord(s->ev_trace[6 * g + 3], P));
     HPSX_CU(cudaEventRecord(ev_pulled[g], P));
     ++s->stats.kernel_launches;

@@ -380,7 +380,7 @@ int hpsx_session_set_insert_mode(hpsx_session* s, int mode);
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant);
 /* Measurement aid for the binned direct pull (bench experiments; not a serving knob): bit 0 = insert only after ALL
  * pulls of the request, bit 1 = start the pulls only after ALL probes, bit 2 = print a per-kernel timeline of every
- * request on stderr, bit 3 = four rows in flight per warp in the pull kernel also when the rows come over PCIe. */
+ * request on stderr, bit 3 = the one-row form of the pull kernel also on small host tables (default there: four rows in flight per warp). */
 int hpsx_session_set_debug(hpsx_session* s, int flags);
 /* Block until background (asynchronous) insertions queued by this session's cache are done. */
 int hpsx_cache_drain_async(hpsx_cache* cache);
