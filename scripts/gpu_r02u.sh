@@ -4,13 +4,13 @@
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo_8.txt 2>&1
 timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 \
-    bench.py --gpus 8 > gpurun_out/bench_r02u.json 2> gpurun_out/bench_r02u.err
+    bench.py --gpus 8 > gpurun_out/bench_r02w.json 2> gpurun_out/bench_r02w.err
 echo "bench exit $?"
-grep -v "^\*\*\*\|OMP_NUM_THREADS\|^$" gpurun_out/bench_r02u.err | tail -n 8
+grep -v "^\*\*\*\|OMP_NUM_THREADS\|^$" gpurun_out/bench_r02w.err | tail -n 8
 python - <<'PY'
 import json
 try:
-    d=json.loads(open('gpurun_out/bench_r02u.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/bench_r02w.json').read().strip().splitlines()[-1])
     print({k:d[k] for k in ('value','ms_per_step','verified_rows','n_gpus','wall_ms_per_step')})
     print('  e2e',{k:v for k,v in d['e2e'].items() if k in ('value','ms_per_step','verified_rows','note','setup_s')})
     print('  e2e_session',{k:v for k,v in d['e2e_session'].items() if k in ('value','ms_per_step')})
