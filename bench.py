@@ -1188,6 +1188,21 @@ def run_ours(a):
                       "includes": "fp32 -> bf16 conversion of the lookup output (0.87 GB read), 3 tcgen05 GEMM layers with fused bias+ReLU, final dot-product layer",
                       "cublas_bf16_gemms_ms": ms_lib,
                       "cublas_note": "torch bf16 matmul + relu of the three GEMM layers on pre-converted operands (no input conversion, no last layer)"}
+        # TF32 head: the reference's dense model is fp32; weights and activations stay fp32, the lookup output is read in place
+        mlp32 = hb.DenseMlp(local, weights, [np.zeros(d, np.float32) for d in dims[1:]], [1, 1, 1, 0], precision="tf32")
+        for _ in range(3):
+            mlp32.forward(out, a.batch, logit, stream=cur.cuda_stream)
+        ev0.record()
+        for _ in range(a.steps):
+            mlp32.forward(out, a.batch, logit, stream=cur.cuda_stream)
+        ev1.record()
+        ev1.synchronize()
+        ms_tf32 = ev0.elapsed_time(ev1) / a.steps
+        dense_head["tf32"] = {"head_ms_per_step": ms_tf32, "head_tflops": flops / (ms_tf32 / 1e3) / 1e12,
+                              "frac_of_half_the_bf16_peak": flops / (ms_tf32 / 1e3) / 1e12 / (peak_tf / 2),
+                              "note": "hpsx_mlp_create_ex(HPSX_MLP_TF32): no conversion pass, fp32 hidden activations; within 1e-3 of a "
+                                      "pure fp32 model (tests/test_dense_mlp_gpu.py); TF32 tensor-core rate is half the bf16 rate"}
+        mlp32.close()
         mlp.close()
 
     if use_tier:

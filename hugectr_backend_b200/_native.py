@@ -174,6 +174,7 @@ SYMBOLS = {
     "hpsx_session_set_probe_variant": (_int, [_vp, _int]),
     "hpsx_cache_drain_async": (_int, [_vp]),
     "hpsx_mlp_create": (_int, [_int, _sz, c_size_p, _vpp, _vpp, ctypes.POINTER(_int), _vpp]),
+    "hpsx_mlp_create_ex": (_int, [_int, _sz, c_size_p, _vpp, _vpp, ctypes.POINTER(_int), _int, _vpp]),
     "hpsx_mlp_forward": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "hpsx_mlp_forward_bf16": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "hpsx_mlp_destroy": (_int, [_vp]),

@@ -3,7 +3,12 @@
 // reshaped LOOKUP_VECTORS; 02_model_inference_hps_tf_ensemble.ipynb:336-395).  It is the only true contraction next to
 // the lookup path, so it runs on the 5th-generation tensor cores:
 //
-//   Y[M,N] = act(X[M,K] . W[N,K]^T + b)      bf16 operands, fp32 accumulation in TMEM
+//   Y[M,N] = act(X[M,K] . W[N,K]^T + b)      bf16 operands (default) or TF32 operands, fp32 accumulation in TMEM
+//
+// TF32 mode (mlp_create precision 1; the reference's dense model is fp32, 01_model_training.ipynb cells 7,11): X and W stay
+// fp32 in memory — the lookup's OUTPUT0 is read by TMA as it is, no conversion pass and no bf16 mirror — the tensor
+// cores round the operands to TF32 (10-bit mantissa) and accumulate in fp32, hidden activations are stored as fp32.
+// Same tile shape: a 128-byte swizzle row holds 32 fp32 instead of 64 bf16, K per instruction is 8 instead of 16.
 //
 //   warp 0  (one elected lane)  TMA producer: cp.async.bulk.tensor 2-D tiles of X and W into a 128B-swizzled
 //                               shared-memory ring, completion on mbarriers
@@ -32,7 +37,9 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockN = 256;  // one tcgen05.mma covers the whole 128 x 256 tile: half the operand bytes per flop of 128 x 128
 constexpr int kBlockK = 64;   // 64 bf16 = 128 B = one swizzle row
-constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit operands
+// K per tcgen05.mma: 16 for 16-bit operands, 8 for TF32 — 32 bytes of a swizzle row either way (kUmmaKBytes)
+constexpr int kBlockK32 = 32; // TF32 mode: 32 fp32 = 128 B = one swizzle row (same tile bytes)
+constexpr int kUmmaKBytes = 32;  // K bytes per tcgen05.mma inside a swizzle row: 16 x 2 B = 8 x 4 B
 constexpr int kStages = 4;
 constexpr int kAccStages = 2;  // accumulators in TMEM: the epilogue of tile i overlaps the MMAs of tile i+1
 constexpr int kThreads = 192;  // 6 warps
@@ -86,9 +93,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// tcgen05 instruction descriptor: D fp32, A/B bf16, both K-major, M x N tile.
-__device__ __forceinline__ uint32_t make_instr_desc(uint32_t m, uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+// tcgen05 instruction descriptor: D fp32, A/B bf16 (format 1; kind::f16) or TF32 (format 2; kind::tf32), both K-major.
+__device__ __forceinline__ uint32_t make_instr_desc(uint32_t m, uint32_t n, bool tf32) {
+  const uint32_t fmt = tf32 ? 2u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -97,6 +105,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
@@ -126,8 +144,10 @@ struct GemmArgs {
 };
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ... (n fastest, so concurrently running CTAs share X rows in L2).
+template <bool kTf32>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const GemmArgs g) {
+  constexpr int kBK = kTf32 ? kBlockK32 : kBlockK;  // elements of K per ring stage (128 bytes either way)
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* tiles = smem;
@@ -139,7 +159,7 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  const int num_k_blocks = (g.K + kBlockK - 1) / kBlockK;
+  const int num_k_blocks = (g.K + kBK - 1) / kBK;
   const int num_n = (g.N + kBlockN - 1) / kBlockN;
   const int num_m = (g.M + kBlockM - 1) / kBlockM;
   const int num_tiles = num_n * num_m;
@@ -181,15 +201,15 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           unsigned char* a_tile = tiles + s * kStageBytes;
           unsigned char* b_tile = a_tile + kTileABytes;
           mbar_expect_tx(&full_bar[s], kStageBytes);
-          tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &full_bar[s]);
-          tma_load_2d(b_tile, &map_w, kb * kBlockK, n0, &full_bar[s]);
+          tma_load_2d(a_tile, &map_x, kb * kBK, m0, &full_bar[s]);
+          tma_load_2d(b_tile, &map_w, kb * kBK, n0, &full_bar[s]);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc = make_instr_desc(kBlockM, kBlockN);
+      const uint32_t idesc = make_instr_desc(kBlockM, kBlockN, kTf32);
       uint32_t it = 0, t = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
         const uint32_t acc = t % kAccStages;
@@ -205,10 +225,13 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
           const uint32_t a_addr = smem_addr(tiles + s * kStageBytes);
           const uint32_t b_addr = a_addr + kTileABytes;
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t da = make_smem_desc(a_addr + k * kUmmaK * 2);
-            const uint64_t db = make_smem_desc(b_addr + k * kUmmaK * 2);
-            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 128 / kUmmaKBytes; ++k) {
+            const uint64_t da = make_smem_desc(a_addr + k * kUmmaKBytes);
+            const uint64_t db = make_smem_desc(b_addr + k * kUmmaKBytes);
+            if constexpr (kTf32)
+              umma_tf32(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);  // the ring slot is free once these MMAs have read it
         }
@@ -268,13 +291,27 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
             }
           } else {
             float* dst = g.out_f32 + static_cast<size_t>(m) * g.N + n_base;
+            if (n_base + 32 <= g.N && (g.N & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n_base + j < g.N) {
-                float x = __uint_as_float(v[j]);
-                if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
-                if (g.relu) x = fmaxf(x, 0.f);
-                dst[j] = x;
+              for (int j = 0; j < 32; j += 4) {
+                float x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  x[q] = __uint_as_float(v[j + q]);
+                  if (g.bias != nullptr) x[q] += __ldg(g.bias + n_base + j + q);
+                  if (g.relu) x[q] = fmaxf(x[q], 0.f);
+                }
+                *reinterpret_cast<float4*>(dst + j) = make_float4(x[0], x[1], x[2], x[3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (n_base + j < g.N) {
+                  float x = __uint_as_float(v[j]);
+                  if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
+                  if (g.relu) x = fmaxf(x, 0.f);
+                  dst[j] = x;
+                }
               }
             }
           }
@@ -329,6 +366,24 @@ __global__ void __launch_bounds__(256) mlp_dot_kernel(const __nv_bfloat16* __res
   }
 }
 
+__global__ void __launch_bounds__(256) mlp_dot_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int M, int K, int relu,
+                                                          float* __restrict__ out) {
+  const int row = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<size_t>(row) * K;
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) acc += xr[k] * w[k];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    if (bias != nullptr) acc += bias[0];
+    if (relu) acc = fmaxf(acc, 0.f);
+    out[row] = acc;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -345,15 +400,16 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// bf16 matrix [rows, cols] row-major (cols contiguous): box = 64 columns x box_rows rows, 128-byte swizzle.
-bool make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols, uint32_t box_rows) {
+// bf16 (or, TF32 mode, fp32) matrix [rows, cols] row-major (cols contiguous): box = 128 bytes of columns x box_rows rows,
+// 128-byte swizzle.
+bool make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols, uint32_t box_rows, bool f32 = false) {
   EncodeTiledFn fn = encode_tiled();
   if (fn == nullptr) return false;
   const cuuint64_t dims[2] = {cols, rows};
-  const cuuint64_t strides[1] = {cols * sizeof(__nv_bfloat16)};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  const cuuint64_t strides[1] = {cols * (f32 ? sizeof(float) : sizeof(__nv_bfloat16))};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(f32 ? kBlockK32 : kBlockK), box_rows};
   const cuuint32_t elem[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
+  return fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -363,6 +419,9 @@ bool make_map(CUtensorMap* map, const void* base, size_t rows, size_t cols, uint
 struct DenseMlp {
   int device = 0;
   std::vector<size_t> dims;  // [L+1]
+  int tf32 = 0;                   // precision 1: fp32 weights and activations, TF32 tensor-core arithmetic
+  std::vector<float*> w32;        // [L] device, [out, in] fp32 (TF32 mode)
+  float* act32[2] = {nullptr, nullptr};
   std::vector<__nv_bfloat16*> w;  // [L] device, [out, in] bf16
   std::vector<float*> b;          // [L] device or nullptr
   std::vector<int> relu;
@@ -382,7 +441,7 @@ static cudaError_t fail_cuda(cudaError_t e, const char* what) {
 }
 
 cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const float* const* weights,
-                       const float* const* biases, const int* relu, DenseMlp** out) {
+                       const float* const* biases, const int* relu, DenseMlp** out, int precision) {
   if (num_layers == 0 || !dims || !weights || !out) {
     g_mlp_err = "null argument";
     return cudaErrorInvalidValue;
@@ -396,12 +455,15 @@ cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const 
   if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
   static bool attr_set = false;
   if (!attr_set) {
-    e = cudaFuncSetAttribute(mlp_gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+    e = cudaFuncSetAttribute(mlp_gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mlp_gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes));
     if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute");
     attr_set = true;
   }
   DenseMlp* m = new DenseMlp();
   m->device = device;
+  m->tf32 = precision == 1 ? 1 : 0;
   cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
   if (m->num_sms <= 0) m->num_sms = 148;
   m->dims.assign(dims, dims + num_layers + 1);
@@ -411,15 +473,21 @@ cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const 
     float* tmp = nullptr;
     __nv_bfloat16* w = nullptr;
     e = cudaMalloc(&tmp, n * k * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&w, n * k * sizeof(__nv_bfloat16));
     if (e == cudaSuccess) e = cudaMemcpy(tmp, weights[l], n * k * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-      const size_t n8 = n * k / 8;
-      to_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256>>>(tmp, w, n8);
-      e = cudaDeviceSynchronize();
+    if (m->tf32) {
+      m->w32.push_back(tmp);  // kept as fp32
+      m->w.push_back(nullptr);
+    } else {
+      if (e == cudaSuccess) e = cudaMalloc(&w, n * k * sizeof(__nv_bfloat16));
+      if (e == cudaSuccess) {
+        const size_t n8 = n * k / 8;
+        to_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256>>>(tmp, w, n8);
+        e = cudaDeviceSynchronize();
+      }
+      cudaFree(tmp);
+      m->w.push_back(w);
+      m->w32.push_back(nullptr);
     }
-    cudaFree(tmp);
-    m->w.push_back(w);
     float* b = nullptr;
     if (e == cudaSuccess && biases && biases[l]) {
       e = cudaMalloc(&b, n * sizeof(float));
@@ -441,9 +509,12 @@ void mlp_destroy(DenseMlp* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   for (auto* p : m->w) cudaFree(p);
+  for (auto* p : m->w32) cudaFree(p);
   for (auto* p : m->b) cudaFree(p);
   cudaFree(m->act[0]);
   cudaFree(m->act[1]);
+  cudaFree(m->act32[0]);
+  cudaFree(m->act32[1]);
   delete m;
 }
 
@@ -456,6 +527,65 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
   if (batch == 0) return cudaSuccess;
   cudaError_t e = cudaSetDevice(m->device);
   if (e != cudaSuccess) return fail_cuda(e, "cudaSetDevice");
+  const size_t L = m->w.size();
+  if (m->tf32) {
+    // TF32 mode: fp32 end to end in memory; layer 0 reads d_in (the lookup's OUTPUT0) in place
+    if (d_in == nullptr) {
+      g_mlp_err = "a TF32 head takes the fp32 vectors (hpsx_mlp_forward), not the bf16 mirror";
+      return cudaErrorInvalidValue;
+    }
+    size_t hidden = 0;
+    for (size_t l = 1; l < L; ++l) hidden = m->dims[l] > hidden ? m->dims[l] : hidden;
+    if (m->act_rows < batch && hidden != 0) {
+      for (int i = 0; i < 2; ++i) {
+        cudaFree(m->act32[i]);
+        m->act32[i] = nullptr;
+        e = cudaMalloc(&m->act32[i], batch * hidden * sizeof(float));
+        if (e != cudaSuccess) return fail_cuda(e, "allocating activations");
+      }
+      m->act_rows = batch;
+    }
+    int cur32 = 0;
+    const float* x_in = d_in;
+    for (size_t l = 0; l < L; ++l) {
+      const size_t K = m->dims[l], N = m->dims[l + 1];
+      const bool last = l + 1 == L;
+      if (N == 1) {
+        if (!last) {
+          g_mlp_err = "a layer with one output unit must be the last layer";
+          return cudaErrorInvalidValue;
+        }
+        mlp_dot_f32_kernel<<<static_cast<unsigned>((batch * 32 + 255) / 256), 256, 0, stream>>>(
+            x_in, m->w32[l], m->b[l], static_cast<int>(batch), static_cast<int>(K), m->relu[l], d_out);
+        continue;
+      }
+      if ((reinterpret_cast<uintptr_t>(x_in) & 15u) != 0) {
+        g_mlp_err = "the fp32 input must be 16-byte aligned";
+        return cudaErrorInvalidValue;
+      }
+      CUtensorMap map_x, map_w;
+      if (!make_map(&map_x, x_in, batch, K, kBlockM, true) || !make_map(&map_w, m->w32[l], N, K, kBlockN, true)) {
+        g_mlp_err = "cuTensorMapEncodeTiled failed";
+        return cudaErrorInvalidValue;
+      }
+      GemmArgs g{};
+      g.M = static_cast<int>(batch);
+      g.N = static_cast<int>(N);
+      g.K = static_cast<int>(K);
+      g.bias = m->b[l];
+      g.relu = m->relu[l];
+      g.out_bf16 = nullptr;
+      g.out_f32 = last ? d_out : m->act32[cur32];
+      const size_t tiles = ((N + kBlockN - 1) / kBlockN) * ((batch + kBlockM - 1) / kBlockM);
+      const unsigned grid = static_cast<unsigned>(tiles < static_cast<size_t>(m->num_sms) ? tiles : m->num_sms);
+      mlp_gemm_tcgen05_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, g);
+      x_in = g.out_f32;
+      cur32 ^= 1;
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail_cuda(e, "launching the MLP kernels");
+    return cudaSuccess;
+  }
   if (m->act_rows < batch) {
     for (int i = 0; i < 2; ++i) {
       cudaFree(m->act[i]);
@@ -465,7 +595,6 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
     }
     m->act_rows = batch;
   }
-  const size_t L = m->w.size();
   // input fp32 (the lookup's output) -> bf16, unless the lookup already wrote a bf16 mirror
   if (d_in_bf16 == nullptr) {
     const size_t n = batch * m->dims[0], n8 = n / 8;
@@ -507,7 +636,7 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
     g.out_f32 = last ? d_out : nullptr;
     const size_t tiles = ((N + kBlockN - 1) / kBlockN) * ((batch + kBlockM - 1) / kBlockM);
     const unsigned grid = static_cast<unsigned>(tiles < static_cast<size_t>(m->num_sms) ? tiles : m->num_sms);
-    mlp_gemm_tcgen05_kernel<<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, g);
+    mlp_gemm_tcgen05_kernel<false><<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, g);
     cur ^= 1;
   }
   e = cudaGetLastError();

@@ -16,12 +16,18 @@ struct hpsx_mlp {
 
 int hpsx_mlp_create(int device, size_t num_layers, const size_t* dims, const float* const* weights,
                     const float* const* biases, const int* relu, hpsx_mlp** out) {
+  return hpsx_mlp_create_ex(device, num_layers, dims, weights, biases, relu, HPSX_MLP_BF16, out);
+}
+
+int hpsx_mlp_create_ex(int device, size_t num_layers, const size_t* dims, const float* const* weights,
+                       const float* const* biases, const int* relu, int precision, hpsx_mlp** out) {
   HPSX_GUARD_BEGIN
   if (!out) return fail(HPSX_ERR_INVALID_ARG, "null output handle");
+  if (precision != HPSX_MLP_BF16 && precision != HPSX_MLP_TF32) return fail(HPSX_ERR_INVALID_ARG, "unknown MLP precision");
   DeviceGuard guard(device);
   if (!guard.ok) return fail(HPSX_ERR_CUDA, "cudaSetDevice failed");
   hpsx::DenseMlp* impl = nullptr;
-  const cudaError_t e = hpsx::mlp_create(device, num_layers, dims, weights, biases, relu, &impl);
+  const cudaError_t e = hpsx::mlp_create(device, num_layers, dims, weights, biases, relu, &impl, precision);
   if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? HPSX_ERR_INVALID_ARG : HPSX_ERR_CUDA, hpsx::mlp_last_error());
   hpsx_mlp* m = new hpsx_mlp();
   m->impl = impl;

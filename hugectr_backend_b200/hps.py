@@ -469,8 +469,10 @@ class DenseMlp:
     """~ the dense model of the reference's ensembles (hps-triton-ensemble/01_model_training.ipynb cells 7,11) on the
     tcgen05 tensor cores.  ``weights[l]``: float32 [out, in]; ``biases[l]``: float32 [out] or None."""
 
-    def __init__(self, device: int, weights, biases=None, relu=None):
+    def __init__(self, device: int, weights, biases=None, relu=None, precision: str = "bf16"):
+        """precision "bf16" (default) or "tf32" (weights and activations stay fp32; ≤1e-3 of an fp32 model)."""
         self._L = N.lib()
+        self.precision = precision
         L = len(weights)
         ws = [np.ascontiguousarray(w, dtype=np.float32) for w in weights]
         dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
@@ -484,7 +486,7 @@ class DenseMlp:
         B = (ctypes.c_void_p * L)(*[_addr(b) for b in bs])
         R = (ctypes.c_int * L)(*[int(bool(r)) for r in (relu or [0] * L)])
         h = ctypes.c_void_p()
-        N.check(self._L.hpsx_mlp_create(device, L, D, W, B, R, ctypes.byref(h)))
+        N.check(self._L.hpsx_mlp_create_ex(device, L, D, W, B, R, {"bf16": 0, "tf32": 1}[precision], ctypes.byref(h)))
         self._h = h
 
     def forward(self, d_in, batch: int, d_out, stream: int = 0) -> None:

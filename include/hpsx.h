@@ -398,6 +398,14 @@ typedef struct hpsx_mlp hpsx_mlp;
  * sample).  Every dims[l] (layer input width) must be a multiple of 8; a layer with one output unit must be last. */
 int hpsx_mlp_create(int device, size_t num_layers, const size_t* dims, const float* const* weights,
                     const float* const* biases, const int* relu, hpsx_mlp** out);
+/* Same with the arithmetic chosen: HPSX_MLP_BF16 (above), or HPSX_MLP_TF32 — weights and activations stay fp32 in
+ * memory, hpsx_mlp_forward reads the lookup's fp32 vectors in place (no conversion pass), the tensor cores round the
+ * operands to TF32 and accumulate in fp32: within 1e-3 (relative to the output's scale) of a pure fp32 model, tested
+ * (tests/test_dense_mlp_gpu.py); the reference's dense model is fp32 (01_model_training.ipynb cells 7,11).
+ * hpsx_mlp_forward_bf16 is not available on a TF32 head. */
+typedef enum hpsx_mlp_precision { HPSX_MLP_BF16 = 0, HPSX_MLP_TF32 = 1 } hpsx_mlp_precision;
+int hpsx_mlp_create_ex(int device, size_t num_layers, const size_t* dims, const float* const* weights,
+                       const float* const* biases, const int* relu, int precision, hpsx_mlp** out);
 /* d_in: device fp32 [batch, dims[0]]; d_out: device fp32 [batch, dims[num_layers]].  Asynchronous on `stream`
  * (a cudaStream_t, NULL = default stream). */
 int hpsx_mlp_forward(hpsx_mlp* m, const float* d_in, size_t batch, float* d_out, void* stream);

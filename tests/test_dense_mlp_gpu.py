@@ -134,3 +134,54 @@ def test_bf16_mirror_is_the_rounded_fp32_output_and_feeds_the_head(cuda_device, 
         mlp.forward_bf16(mirror, batch, b)
         torch.cuda.synchronize()
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# TF32 mode: against a PURE fp32 model (no operand rounding in the reference).  The reference's dense model is fp32
+# (01_model_training.ipynb cells 7,11); TF32 keeps 10 mantissa bits per operand and accumulates in fp32.
+# Tolerance: 1e-3 of the output's scale (max |y| of the fp32 model), stated by the verdict of round 1.
+# ------------------------------------------------------------------------------------------------
+def fp32_model(torch, x, weights, biases, relu):
+    h = x.double()
+    for l, w in enumerate(weights):
+        h = h @ torch.from_numpy(w).cuda().double().t()
+        if biases[l] is not None:
+            h = h + torch.from_numpy(biases[l]).cuda().double()
+        if relu[l]:
+            h = torch.relu(h)
+    return h
+
+
+@pytest.mark.parametrize("batch,dims,relu", [
+    (128, [32, 128], [0]),                       # one tile, one k-block of 32 fp32
+    (128, [256, 128], [0]),                      # ring wrap-around (8 k-blocks, 4 stages)
+    (1000, [48, 256, 128, 1], [0, 0, 0]),        # the sample's dense model, ragged batch
+    (4096, [3328, 1024, 512, 256, 1], [1, 1, 1, 0]),  # Criteo-shape head
+    (333, [136, 200, 72], [1, 0]),               # N and K tails
+])
+def test_tf32_mlp_is_within_1e3_of_a_pure_fp32_model(cuda_device, batch, dims, relu):
+    torch = _torch()
+    rng = np.random.default_rng(7 * batch + len(dims))
+    weights = [(rng.standard_normal((dims[l + 1], dims[l])) / np.sqrt(dims[l])).astype(np.float32) for l in range(len(dims) - 1)]
+    biases = [rng.standard_normal(dims[l + 1]).astype(np.float32) * 0.1 if l % 2 == 0 else None for l in range(len(dims) - 1)]
+    mlp = hb.DenseMlp(0, weights, biases, relu, precision="tf32")
+    x = torch.from_numpy(rng.standard_normal((batch, dims[0])).astype(np.float32)).cuda()
+    out = torch.full((batch, dims[-1]), float("nan"), device="cuda")
+    mlp.forward(x, batch, out)
+    torch.cuda.synchronize()
+    want = fp32_model(torch, x, weights, biases, relu)
+    assert torch.isfinite(out).all()
+    scale = float(want.abs().max())
+    err = float((out.double() - want).abs().max())
+    assert err <= 1e-3 * scale, (err, scale)
+    # and the bf16 head on the same model, for the record: an order of magnitude further away
+    mlp16 = hb.DenseMlp(0, weights, biases, relu)
+    out16 = torch.empty_like(out)
+    mlp16.forward(x, batch, out16)
+    torch.cuda.synchronize()
+    err16 = float((out16.double() - want).abs().max())
+    assert err < err16
+    with pytest.raises(Exception, match="TF32"):
+        mlp.forward_bf16(x.to(torch.bfloat16), batch, out)
+    mlp.close()
+    mlp16.close()
