@@ -231,7 +231,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "keys_per_step": n, "note": "CPU ParameterServer path, rank 0 only"},
+        "config": {"workload": workload_name(a), "keys_per_step": n, "rows": a.rows, "dim": a.dim, "gpucacheper": a.gpucacheper,
+                   "hot_draw_probability": a.hit, "note": "CPU ParameterServer path, rank 0 only"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

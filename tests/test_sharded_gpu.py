@@ -145,3 +145,44 @@ def test_peer_tier_over_cuda_ipc(cuda_device):
     [p.join(300) for p in procs]
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert all(ret[r] for r in range(world))
+
+
+def test_one_server_all_gpus_with_the_tier(tmp_path, cuda_device):
+    """The deployment `bench.py --gpus N` measures: ONE backend process, the model on every GPU of the box with
+    "hpsx_peer_tier": true, one instance per GPU.  The table is loaded from reference-format sparse files; every GPU's
+    responses are bit-exact, and the misses were served from the tier (nothing but keys crossed PCIe is not observable
+    through Triton, so the engine-level twin of this test — tests/test_peer_tier_gpu.py — checks the byte counters)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_triton as FT
+    from oracle import hps_oracle as O
+    from test_triton_backend_cpu import model_entry, ps_json, write_tables
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    devs = list(range(world))
+    dirs, tables = write_tables(str(tmp_path), [(60000, 32)])
+    entry = model_entry("dcn", dirs, [32], [26], gpucache=True, max_batch=512, hit_rate_threshold=1.0, gpucacheper=0.1,
+                        enable_pagelock=True, hpsx_peer_tier=True, devices=devs, workers=1)
+    ps = ps_json(str(tmp_path / "ps.json"), [entry])
+    ref = O.NumpyTable(32, 0.0)
+    ref.insert(*tables[0])
+    rng = np.random.default_rng(9)
+    with FT.Backend(ps) as be:
+        m = be.model("dcn", FT.model_config("dcn", gpus=devs, max_batch_size=512))
+        insts = [m.instance(name=f"dcn_{d}", kind=FT.KIND_GPU, device=d) for d in devs]
+        for it in range(3):
+            for d, inst in enumerate(insts):
+                n = 512 * 26
+                keys = rng.choice(tables[0][0], size=n)
+                keys[::101] = -5  # in no database: default vector
+                out = torch.full((n * 32,), float("nan"), device=f"cuda:{d}")
+                r = inst.infer(keys, np.array([[n]], dtype=np.int32), gpu_out=out, out_device=d)
+                assert r.error_code is None, r.error_message
+                assert r.params["DeviceID"] == d
+                assert np.array_equal(out.cpu().numpy(), ref.lookup(keys).ravel()), (it, d)
+        for inst in insts:
+            inst.close()
+        m.close()

@@ -303,3 +303,64 @@ def test_two_models_with_two_instances_each_run_concurrently(tmp_path, cuda_devi
             x.close()
         ma.close()
         mb.close()
+
+
+def test_tier_only_model_through_execute(tmp_path, cuda_device):
+    """BASELINE configs[3] through the boundary, scaled down: a table given as "synthetic_device:rows=…" lives in the
+    NVLink tier only (generated on the device, no host copy, no local cache) and is served by the same
+    TRITONBACKEND_ModelInstanceExecute call as any other model — here with the one GPU of the test box as a world of 1."""
+    import torch
+    rows, dim, seed = 200_000, 128, 0xB2000031
+    entry = model_entry("dlrm", [f"synthetic_device:rows={rows},seed={seed}"], [dim], [26], gpucache=True, max_batch=256,
+                        hit_rate_threshold=1.0, gpucacheper=0.0, enable_pagelock=True, hpsx_peer_tier=True,
+                        embedding_cache_type="static", workers=2)
+    ps = ps_json(str(tmp_path / "ps.json"), [entry])
+    ref = O.NumpyTable(dim, 0.0)
+    ref.fill_procedural(rows, seed)
+    rng = np.random.default_rng(31)
+    with FT.Backend(ps) as be:
+        m = be.model("dlrm", FT.model_config("dlrm", gpus=[0], count=2, max_batch_size=256))
+        insts = [m.instance(name=f"dlrm_0_{j}", kind=FT.KIND_GPU, device=0) for j in range(2)]
+        for samples in (256, 1, 77):
+            for inst in insts:
+                n = samples * 26
+                keys = rng.integers(-3, rows + 50, size=n)  # a few keys no shard holds -> default vector
+                out = torch.full((n * dim,), float("nan"), device="cuda")
+                r = inst.infer(keys, np.array([[n]], dtype=np.int32), gpu_out=out)
+                assert r.error_code is None, r.error_message
+                assert r.params["NumSample"] == samples
+                assert np.array_equal(out.cpu().numpy(), ref.lookup(keys).ravel())
+        # host output buffer (Triton may hand back CPU memory, hps.cc:682-690)
+        n = 64 * 26
+        keys = rng.integers(0, rows, size=n)
+        h_out = torch.full((n * dim,), float("nan"))
+        r = insts[0].infer(keys, np.array([[n]], dtype=np.int32), cpu_out=h_out)
+        assert r.error_code is None, r.error_message
+        assert np.array_equal(h_out.numpy(), ref.lookup(keys).ravel())
+        for inst in insts:
+            inst.close()
+        m.close()
+
+
+def test_peer_tier_key_with_one_deployed_device_serves_from_the_host(tmp_path, cuda_device):
+    """"hpsx_peer_tier": true needs >= 2 deployed devices to have anything to shard over; with one device the model is
+    served as usual (misses from the page-locked host table) — the key must not break a single-GPU deployment."""
+    import torch
+    dirs, tables = write_tables(str(tmp_path), [(20000, 16)])
+    entry = model_entry("m", dirs, [16], [26], gpucache=True, max_batch=256, hit_rate_threshold=1.0, gpucacheper=0.1,
+                        enable_pagelock=True, hpsx_peer_tier=True)
+    ps = ps_json(str(tmp_path / "ps.json"), [entry])
+    ref = O.NumpyTable(16, 0.0)
+    ref.insert(*tables[0])
+    rng = np.random.default_rng(4)
+    with FT.Backend(ps) as be:
+        m = be.model("m", FT.model_config("m", gpus=[0], max_batch_size=256))
+        inst = m.instance(kind=FT.KIND_GPU, device=0)
+        n = 256 * 26
+        keys = rng.choice(tables[0][0], size=n)
+        out = torch.full((n * 16,), float("nan"), device="cuda")
+        r = inst.infer(keys, np.array([[n]], dtype=np.int32), gpu_out=out)
+        assert r.error_code is None, r.error_message
+        assert np.array_equal(out.cpu().numpy(), ref.lookup(keys).ravel())
+        inst.close()
+        m.close()
