@@ -135,7 +135,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// fp32 -> nearest TF32 value (10 mantissa bits, ties away from zero), still stored as fp32.  The tensor cores TRUNCATE
+// the low 13 bits of an fp32 operand (measured: a three-layer linear model drifts by 1.6e-3 of its output scale, a
+// systematic shrink); operands rounded here first carry an unbiased error of half the size.
+__device__ __forceinline__ float round_tf32(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__global__ void __launch_bounds__(256) round_tf32_kernel(float* w, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * 256 + threadIdx.x;
+  if (i < n) w[i] = round_tf32(w[i]);
+}
+
 struct GemmArgs {
+  int round_out;  // TF32 mode: the output feeds another TF32 GEMM, store it rounded to TF32
   int M, N, K;
   const float* bias;  // [N] or nullptr
   int relu;
@@ -300,6 +312,7 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                   x[q] = __uint_as_float(v[j + q]);
                   if (g.bias != nullptr) x[q] += __ldg(g.bias + n_base + j + q);
                   if (g.relu) x[q] = fmaxf(x[q], 0.f);
+                  if (kTf32 && g.round_out) x[q] = round_tf32(x[q]);
                 }
                 *reinterpret_cast<float4*>(dst + j) = make_float4(x[0], x[1], x[2], x[3]);
               }
@@ -310,6 +323,7 @@ mlp_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_
                   float x = __uint_as_float(v[j]);
                   if (g.bias != nullptr) x += __ldg(g.bias + n_base + j);
                   if (g.relu) x = fmaxf(x, 0.f);
+                  if (kTf32 && g.round_out) x = round_tf32(x);
                   dst[j] = x;
                 }
               }
@@ -475,6 +489,10 @@ cudaError_t mlp_create(int device, size_t num_layers, const size_t* dims, const 
     e = cudaMalloc(&tmp, n * k * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(tmp, weights[l], n * k * sizeof(float), cudaMemcpyHostToDevice);
     if (m->tf32) {
+      if (e == cudaSuccess && n > 1) {  // GEMM layers: weights rounded to TF32 once, here (the dot layer keeps fp32 weights)
+        round_tf32_kernel<<<static_cast<unsigned>((n * k + 255) / 256), 256>>>(tmp, n * k);
+        e = cudaDeviceSynchronize();
+      }
       m->w32.push_back(tmp);  // kept as fp32
       m->w.push_back(nullptr);
     } else {
@@ -576,6 +594,7 @@ cudaError_t mlp_forward(DenseMlp* m, const float* d_in, size_t batch, float* d_o
       g.relu = m->relu[l];
       g.out_bf16 = nullptr;
       g.out_f32 = last ? d_out : m->act32[cur32];
+      g.round_out = (!last && m->dims[l + 2] > 1) ? 1 : 0;
       const size_t tiles = ((N + kBlockN - 1) / kBlockN) * ((batch + kBlockM - 1) / kBlockM);
       const unsigned grid = static_cast<unsigned>(tiles < static_cast<size_t>(m->num_sms) ? tiles : m->num_sms);
       mlp_gemm_tcgen05_kernel<true><<<grid, kThreads, kSmemBytes, stream>>>(map_x, map_w, g);
