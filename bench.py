@@ -687,7 +687,7 @@ def config_c3(a, FT, tmp, local, torch, sampler_cls, link_gbs, peak_gbs):
                    "models": [_ps_model("wdl100m", rows, seed, dim, slots, B, local)]}, f)
     steps, warmup, prefill, R = 6, 2, 26, 8
     rng = np.random.default_rng(seed)
-    reqs = [_mixture(rng, n, rows, warm, p_hot) for _ in range(prefill + R)]
+    reqs = [_mixture(rng, n, rows, warm, p_hot) for _ in range(prefill + 2 * R)]  # prefill | device-key arm | host-key arm
     numkeys = np.array([[n]], dtype=np.int32)
     out = torch.empty(n * dim, device="cuda", dtype=torch.float32)
     t0 = time.perf_counter()
@@ -698,9 +698,9 @@ def config_c3(a, FT, tmp, local, torch, sampler_cls, link_gbs, peak_gbs):
         for k in reqs[:prefill]:  # fills the cache's free half with cold rows: LRU eviction in steady state afterwards
             r = inst.infer(k, numkeys, gpu_out=out, out_device=local)
             assert r.error_code is None, r.error_message
-        timed = reqs[prefill:]
-        d_keys = [torch.from_numpy(k).cuda() for k in timed]
-        pinned = [torch.from_numpy(k).pin_memory() for k in timed]
+        timed, timed_host = reqs[prefill:prefill + R], reqs[prefill + R:]  # every arm its own requests: rows a request brought
+        d_keys = [torch.from_numpy(k).cuda() for k in timed]                 # in are hits for whoever asks again
+        pinned = [torch.from_numpy(k).pin_memory() for k in timed_host]
         dev = [inst.prepare([dict(keys=timed[i], numkeys=numkeys, gpu_out=out, out_device=local, keys_device_ptr=d_keys[i].data_ptr())])
                for i in range(R)]
         host = [inst.prepare([dict(keys=pinned[i].numpy(), numkeys=numkeys, gpu_out=out, out_device=local)]) for i in range(R)]
@@ -718,7 +718,8 @@ def config_c3(a, FT, tmp, local, torch, sampler_cls, link_gbs, peak_gbs):
                 assert r.error_code is None and r.params["NumSample"] == B
                 hm[0] += r.params["CacheHits"]
                 hm[1] += r.params["CacheMisses"]
-            verified = verify_rows(torch, d_keys[(steps - 1) % R], out.view(n, dim), dim, seed, f"C3 {name}")
+            last_keys = d_keys[(steps - 1) % R] if name == "value" else pinned[(steps - 1) % R].cuda()
+            verified = verify_rows(torch, last_keys, out.view(n, dim), dim, seed, f"C3 {name}")
             res[name] = {"value": steps * n / t, "unit": UNIT, "ms_per_step": t / steps * 1e3, "hit_rate_measured": hm[0] / max(1, sum(hm)),
                          "misses_per_step": hm[1] / steps, "verified_rows": verified,
                          "host_link_gbs": hm[1] / steps * dim * 4 / (t / steps) / 1e9}
