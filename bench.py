@@ -271,7 +271,7 @@ def measure_host_link_gbs(torch) -> float:
     src = torch.empty(128 << 20, dtype=torch.uint8).pin_memory()
     dst = torch.empty(128 << 20, dtype=torch.uint8, device="cuda")
     best = 0.0
-    for _ in range(4):
+    for _ in range(10):  # best of ten: single copies scatter by a few GB/s
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         dst.copy_(src, non_blocking=True)
@@ -839,6 +839,8 @@ def run_ours(a):
     sess = hps.session("dcn", local)
     sess.set_probe_variant(a.variant)
     sess.set_debug(a.debug_flags & 11)
+    idle_session = hps.session("dcn", local) if os.environ.get("HPSX_BENCH_SPLIT_FORM") else None  # experiment: a second
+    # session on the cache makes every lookup take the split form: pull without insert, then an insert pass
     ext = torch.cuda.ExternalStream(sess.stream)
 
     d_reqs = [torch.from_numpy(k).cuda() for k in reqs]
@@ -884,7 +886,7 @@ def run_ours(a):
     sampler.start()
     ms, wall = timed(dev_step, a.steps)
     st_pipe = sess.stats()
-    print(f"[bench] rank {rank}: pull {st_pipe.pull_kernel_ms / a.steps:.3f} ms/step, probe "
+    print(f"[bench] rank {rank}: step {ms / a.steps:.3f} ms, pull {st_pipe.pull_kernel_ms / a.steps:.3f} ms/step, probe "
           f"{st_pipe.probe_kernel_ms / max(1, st_pipe.probe_kernel_launches):.3f} ms, misses {st_pipe.misses // a.steps}", file=sys.stderr)
     value = world * a.steps * n / (ms / 1e3)
     verified_rows = verify_rows(torch, d_reqs[(a.steps - 1) % R], out, a.dim, SEED, "value arm")
