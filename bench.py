@@ -770,6 +770,7 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the lookup path has no CPU fallback")
+    local = min(local, torch.cuda.device_count() - 1)  # a launcher may have pinned this rank to one visible GPU
     torch.cuda.set_device(local)
     if world > 1:
         with stdout_to_stderr():
@@ -818,8 +819,20 @@ def run_ours(a):
             hps.peer_tier_commit("dcn", local)
             tier_info = hps.peer_tier_info("dcn", local)
         else:
-            tier_info = hps.peer_tier_connect_distributed("dcn", local, rank, world, 1, gather)
-        tier_info["setup_s"] = time.perf_counter() - t1
+            ok = 1
+            try:
+                tier_info = hps.peer_tier_connect_distributed("dcn", local, rank, world, 1, gather)
+            except Exception as ex:  # e.g. ranks pinned to one visible GPU each: no peer mapping possible
+                print(f"[bench] rank {rank}: NVLink tier unavailable ({ex}); every miss goes over PCIe", file=sys.stderr)
+                ok = 0
+            flag = torch.tensor([ok], device=red_dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 0:  # all ranks or none
+                hps.peer_tier_detach("dcn", local)
+                dist.barrier()
+                use_tier, tier_info = False, None
+        if tier_info is not None:
+            tier_info["setup_s"] = time.perf_counter() - t1
 
     def tier_teardown():
         if use_tier:
@@ -1715,13 +1728,25 @@ def run_sharded(a):
     dist.destroy_process_group()
 
 
+def _visible_gpus() -> int:
+    """GPUs this process can drive (a launcher that pins every rank to its own GPU leaves 1: then the ranks run as replica
+    processes with the tier over CUDA IPC instead of one server process)."""
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:  # noqa: BLE001
+        return 0
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "c4":
         run_sharded(a)
-    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and not a.value_only and not os.environ.get("HPSX_BENCH_REPLICA_PROCESSES"):
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and not a.value_only and not os.environ.get("HPSX_BENCH_REPLICA_PROCESSES") \
+            and _visible_gpus() >= int(os.environ.get("WORLD_SIZE", "1")):
         run_server(a)
     else:
         run_ours(a)  # N = 1; also (HPSX_BENCH_REPLICA_PROCESSES=1 / --value-only) one replica process per GPU over CUDA IPC
