@@ -57,7 +57,7 @@ def parse_args():
                     help="direct: enable_pagelock, kernels pull missing rows from pinned host tables over PCIe; "
                          "staged: CPU gather + cudaMemcpyAsync")
     ap.add_argument("--distinct", type=int, default=0, help="distinct key batches (0: steps+warmup, at most 32)")
-    ap.add_argument("--variant", default="v8", choices=["ldg", "tma", "v8", "v8p1", "v8p2", "v8u8"])
+    ap.add_argument("--variant", default="v8", choices=["ldg", "tma", "v8"])
     ap.add_argument("--chunks", type=int, default=0, help="request_chunks of the model (0: engine default 4)")
     ap.add_argument("--pull-ctas", type=int, default=0, help="pull_grid_ctas of the model (0: engine default 148)")
     ap.add_argument("--window-mb", type=int, default=0, help="pull_window of the parameter server in MiB (0: engine default 16)")

@@ -2347,8 +2347,7 @@ int hpsx_session_set_debug(hpsx_session* s, int flags) {
 
 int hpsx_session_set_probe_variant(hpsx_session* s, int variant) {
   if (!s) return fail(HPSX_ERR_INVALID_ARG, "null session");
-  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbeV8 && variant != kProbeV8P1 && variant != kProbeV8P2 &&
-      variant != kProbeV8U8)
+  if (variant != kProbeLdg && variant != kProbeTma && variant != kProbeV8)
     return fail(HPSX_ERR_INVALID_ARG, "unknown probe variant");
   s->probe_variant = variant;
   return HPSX_OK;

@@ -138,11 +138,11 @@ __device__ __forceinline__ BucketKeys load_bucket_keys_keep(const Bucket* __rest
   return r;
 }
 
-// kPrefetch (experiment, bench --variant v8p1 / v8p2): as soon as a lane knows its slot it asks L2 for the whole row —
-// 1: four `prefetch.global.L2` (one per 128-B line), 2: one `cp.async.bulk.prefetch.L2` of the row.  A prefetch holds no
-// register, so a warp has its whole 16 KB tile in flight instead of 4 KB (kUnroll x 32 B per lane), and the row loads
-// that follow are L2 hits.
-template <int kV8, int kUnroll, bool kMirror = false, int kPrefetch = 0>
+// Measured alternatives that are NOT in the library any more (profiles/probe_experiments_r02.jsonl; the code is in the
+// history: commit "Probe kernel experiments (L2 row prefetch, deeper unroll)"): asking L2 for the whole row right after
+// the probe (`prefetch.global.L2` per line: 0.71 of the HBM peak; one `cp.async.bulk.prefetch.L2` per row: 0.73) and
+// 8 x 32 B per lane in flight (0.64) all lose to this form (0.82).
+template <int kV8, int kUnroll, bool kMirror = false>
 __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs a) {
   const uint32_t lane = threadIdx.x & 31u;
   const size_t tile = (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) >> 5;
@@ -164,16 +164,6 @@ __global__ void __launch_bounds__(kBlock) probe_gather_v8_kernel(const ProbeArgs
       way = match_way(bk, key);
     }
     if (way >= 0) slot = b * kWays + static_cast<uint32_t>(way);
-  }
-  if constexpr (kPrefetch != 0) {
-    if (slot != kMissSlot) {
-      const char* row = reinterpret_cast<const char*>(a.values) + static_cast<size_t>(slot) * V * 32u;
-      if constexpr (kPrefetch == 1) {
-        for (uint32_t o = 0; o < V * 32u; o += 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
-      } else {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(V * 32u) : "memory");
-      }
-    }
   }
   const bool is_miss = valid && slot == kMissSlot;
   unsigned miss_mask = 0;
@@ -1745,18 +1735,9 @@ cudaError_t launch_probe_gather(const DeviceTable& t, const int64_t* d_keys, siz
     if (vb == 8) return launch_probe_ldg_scatter<float2>(a, stream);
     return launch_probe_ldg_scatter<float>(a, stream);
   }
-  if ((variant == kProbeV8 || variant == kProbeV8P1 || variant == kProbeV8P2 || variant == kProbeV8U8) && t.dim % 8 == 0 &&
+  if (variant == kProbeV8 && t.dim % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(t.values)) & 31u) == 0) {
     const unsigned grid = grid_for(n);
-    if (variant != kProbeV8 && a.out_bf16 == nullptr && t.dim == 128) {  // measured alternatives of the default kernel
-      if (variant == kProbeV8P1)
-        probe_gather_v8_kernel<16, 4, false, 1><<<grid, kBlock, 0, stream>>>(a);
-      else if (variant == kProbeV8P2)
-        probe_gather_v8_kernel<16, 4, false, 2><<<grid, kBlock, 0, stream>>>(a);
-      else
-        probe_gather_v8_kernel<16, 8><<<grid, kBlock, 0, stream>>>(a);
-      return cudaGetLastError();
-    }
     if (a.out_bf16 != nullptr) {
       if (t.dim == 128)
         probe_gather_v8_kernel<16, 4, true><<<grid, kBlock, 0, stream>>>(a);

@@ -43,9 +43,6 @@ enum ProbeVariant : int {
   kProbeLdg = 0,  // warp-per-32-keys, LDG.128 row copies through registers (any row size)
   kProbeTma = 1,  // cp.async.bulk row staging through a shared-memory ring (UBLKCP), dim*4 % 16 == 0
   kProbeV8 = 4,   // default: 256-bit row vectors with L2 evict_first, bucket keys kept in L2 (evict_last)
-  kProbeV8P1 = 5, // experiments on the default (dim 128 only, else they run the default): + prefetch.global.L2 per row line
-  kProbeV8P2 = 6, //   + one cp.async.bulk.prefetch.L2 per row
-  kProbeV8U8 = 7, //   8 x 32 B per lane in flight instead of 4
 };
 
 // K2+K3+K6 fused: probe the cache for keys[0..n), copy hit rows to out[i*dim..),

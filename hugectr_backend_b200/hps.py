@@ -34,7 +34,7 @@ def _addr(x) -> int:
     raise TypeError(f"cannot take the address of {type(x)!r}")
 
 
-PROBE_VARIANTS = {"ldg": 0, "tma": 1, "v8": 4, "v8p1": 5, "v8p2": 6, "v8u8": 7}
+PROBE_VARIANTS = {"ldg": 0, "tma": 1, "v8": 4}
 
 
 @dataclass

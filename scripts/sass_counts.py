@@ -9,7 +9,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "hugectr_backend_b200", "lib", "libhpsx.so")
-WANT = [("probe_gather_v8_kernel", "ILi16ELi4ELb0ELi0E"), ("pull_binned_kernel", "I6float4Lb1ELi1E"),
+WANT = [("probe_gather_v8_kernel", "ILi16ELi4ELb0EE"), ("pull_binned_kernel", "I6float4Lb1ELi1E"),
         ("pull_binned_kernel", "I6float4Lb1ELi4E"), ("tier_gather_kernel", "I6float4E"), ("insert_binned_kernel", "I6float4E"),
         ("probe_gather_tma_kernel", ""), ("mlp_gemm_tcgen05_kernel", "")]
 PAT = re.compile(r"^\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)")
