@@ -1008,9 +1008,8 @@ def run_ours(a):
     # ---- end-to-end arm 2 (headline e2e): the reference-facing plugin call ------------------------------
     # TRITONBACKEND_ModelInstanceExecute of libtriton_hps.so, driven by the fake-Triton harness: KEYS/NUMKEYS in
     # host memory, OUTPUT0 in a GPU buffer (what Triton hands a gpucache model, hps.cc:638-642).
-    c4 = None
-    one_server = False  # (N > 1 is run_server's job: ONE server process drives all GPUs)
-    if a.skip_triton_arm or one_server:
+    c4 = None  # (N > 1 with one server process, its Triton arm and c4 are run_server's job)
+    if a.skip_triton_arm:
         e2e = dict(e2e_session)
         e2e["note"] = "--skip-triton-arm: session-level end-to-end arm reported"
     else:
@@ -1225,43 +1224,6 @@ def run_ours(a):
     if use_tier:
         del sess
         tier_teardown()
-    if one_server:
-        # The reference's multi-GPU deployment is ONE tritonserver process with one cache per device
-        # (hps_backend/src/model_state.cpp:395-419): rank 0 plays that server for all N GPUs, with the NVLink tier switched
-        # on in ps.json; the other ranks have released their GPUs' memory and wait.
-        import gc
-
-        del hps, out, d_reqs, h_reqs, hit_reqs
-        gc.collect()
-        torch.cuda.empty_cache()
-        dist.barrier()
-        self_check_failed = None
-        c4 = None
-        if rank == 0:
-            try:
-                e2e_srv = triton_arm_one_server(a, world, hot, warm_rows, n, torch, ClockSampler)
-                e2e_srv["session_level"] = {k: e2e_session[k] for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step")}
-                e2e = e2e_srv
-            except SystemExit as ex:  # wrong rows: fail the run, but only after the other ranks have been released
-                self_check_failed = ex
-            except Exception as ex:  # keep the line: the session-level arm stands in, and the failure is named
-                print(f"[bench] one-server Triton arm FAILED: {ex!r}", file=sys.stderr)
-                e2e["note"] = f"one-server Triton arm failed ({ex!r}); session-level end-to-end arm reported"
-            if not a.skip_c4:
-                gc.collect()
-                torch.cuda.empty_cache()
-                t_c4 = time.perf_counter()
-                try:
-                    c4 = config_c4(a, world, torch, ClockSampler)
-                    c4["arm_wall_s"] = time.perf_counter() - t_c4
-                except SystemExit as ex:
-                    self_check_failed = ex
-                except Exception as ex:
-                    print(f"[bench] configuration c4 FAILED: {ex!r}", file=sys.stderr)
-                    c4 = {"error": repr(ex)}
-        dist.barrier()
-        if self_check_failed is not None:
-            raise self_check_failed
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
