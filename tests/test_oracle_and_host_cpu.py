@@ -267,7 +267,7 @@ def test_model_params_round_trip_through_the_abi(tmp_path):
     cfg = {"supportlonglong": True,
            "models": [_model(model="rt", max_batch_size=99, default_value_for_each_table=[-2.5], gpucache=False,
                              num_of_worker_buffer_in_pool=3, deployed_device_list=[1, 0], embedding_table_names=["emb"],
-                             enable_pagelock=True)]}
+                             enable_pagelock=True, hpsx_peer_tier=True, hpsx_pull_grid_ctas=296, hpsx_request_chunks=2)]}
     hps = _load(tmp_path, cfg)
     p = N.ModelParamsC()
     N.check(hb.lib().hpsx_ps_get_model_params(hps._h, b"rt", ctypes.byref(p)))
@@ -277,6 +277,8 @@ def test_model_params_round_trip_through_the_abi(tmp_path):
     assert p.number_of_worker_buffers_in_pool == 3 and p.num_deployed_devices == 2 and p.deployed_devices[1] == 0
     assert p.table_names[0] == b"emb" and p.enable_pagelock == 1
     assert p.sparse_files[0].decode().endswith("sparse_d4")
+    # engine extensions of ps.json: the NVLink tier switch and the pull tuning
+    assert p.peer_tier == 1 and p.pull_grid_ctas == 296 and p.request_chunks == 2
 
 
 def test_tier_only_table_spec_is_validated_on_the_host():
