@@ -47,6 +47,14 @@ int main() {
     CK(cudaMalloc(&idx, n * 4)); CK(cudaMalloc(&out, (size_t)n * 512));
     CK(cudaMemset(idx, 0, n * 4));
     while (read(to_child[0], &cmd, 1) == 1 && cmd != 'q') {
+      if (cmd == 'o') {  // map the parent's table too: IPC peer mappings in BOTH directions, like two replicas with the tier
+        cudaIpcMemHandle_t ph;
+        if (read(to_child[0], &ph, sizeof(ph)) != (ssize_t)sizeof(ph)) return 1;
+        void* pp = nullptr;
+        CK(cudaIpcOpenMemHandle(&pp, ph, cudaIpcMemLazyEnablePeerAccess));
+        rows_ld<4><<<148, 256>>>(static_cast<const float4*>(pp), idx, 1024, out);  // touch it once
+        CK(cudaDeviceSynchronize());
+      }
       if (cmd == 'b') {  // keep this GPU busy for a while
         for (int r = 0; r < 200; ++r) rows_ld<4><<<148 * 4, 256>>>(t, idx, n, out);
         if (write(to_parent[1], &cmd, 1) != 1) return 1;
@@ -93,6 +101,18 @@ int main() {
   if (write(to_child[1], &c, 1) != 1 || read(to_parent[0], &c, 1) != 1) return 1;
   sweep("IPC-mapped remote table, owner GPU busy with its own gathers");
   if (read(to_parent[0], &c, 1) != 1) return 1;
+  {
+    float4* mine = nullptr;
+    CK(cudaMalloc(&mine, 1ull << 30));
+    CK(cudaMemset(mine, 2, 1ull << 30));
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, mine));
+    c = 'o';
+    if (write(to_child[1], &c, 1) != 1 || write(to_child[1], &mh, sizeof(mh)) != (ssize_t)sizeof(mh)) return 1;
+    if (read(to_parent[0], &c, 1) != 1) return 1;
+    sweep("IPC-mapped remote table, after the owner process mapped one of OUR allocations too (both directions)");
+  }
   c = 'q';
   if (write(to_child[1], &c, 1) != 1) return 1;
   CK(cudaIpcCloseMemHandle(p));
