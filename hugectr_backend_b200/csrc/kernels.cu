@@ -437,13 +437,15 @@ __device__ __forceinline__ void lock_bucket(Bucket* B) {
     if (old != 0u) __nanosleep(32);
   } while (old != 0u);
 }
-__device__ __forceinline__ bool try_lock_bucket(Bucket* B) {
-  uint32_t old;
-  asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(&B->lock) : "memory");
-  return old == 0u;
+// Both locks of a claim with ONE fence (a release store is MEMBAR + store: two of them were a quarter of the quad pull's
+// stall cycles); also gives back a lock that was taken by a failed try (nothing was written under it: no fence at all).
+__device__ __forceinline__ void unlock_bucket_relaxed(Bucket* B) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&B->lock), "r"(0u) : "memory");
 }
-__device__ __forceinline__ void unlock_bucket(Bucket* B) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&B->lock), "r"(0u) : "memory");
+__device__ __forceinline__ void unlock_pair(Bucket* lo, Bucket* hi) {
+  __threadfence();
+  if (hi != nullptr) unlock_bucket_relaxed(hi);
+  unlock_bucket_relaxed(lo);
 }
 
 __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buckets, int64_t key, uint32_t epoch,
@@ -503,8 +505,7 @@ __device__ __forceinline__ uint32_t claim_slot(Bucket* buckets, uint32_t num_buc
       if (fresh) buckets[pb].keys[pw] = key;
       buckets[pb].stamp[pw] = epoch;
     }
-    if (hi != nullptr) unlock_bucket(hi);
-    unlock_bucket(lo);
+    unlock_pair(lo, hi);
   }
   return fresh ? pb * kWays + pw : kMissSlot;
 }
@@ -538,10 +539,14 @@ __device__ __forceinline__ uint32_t claim_slot4(Bucket* buckets, uint32_t num_bu
   Bucket* hi = b1 == b2 ? nullptr : &buckets[max(b1, b2)];
   bool got = false;
   if (want && !conflict && sub == 0) {
-    got = try_lock_bucket(lo);
-    if (got && hi != nullptr && !try_lock_bucket(hi)) {
-      unlock_bucket(lo);
-      got = false;
+    // both tries are issued before either result is looked at: one L2 round trip instead of two
+    uint32_t old_lo = 0, old_hi = 0;
+    asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old_lo) : "l"(&lo->lock) : "memory");
+    if (hi != nullptr) asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], 0, 1;" : "=r"(old_hi) : "l"(&hi->lock) : "memory");
+    got = old_lo == 0u && old_hi == 0u;
+    if (!got) {  // give back whichever was taken; nothing was written under it
+      if (old_lo == 0u) unlock_bucket_relaxed(lo);
+      if (hi != nullptr && old_hi == 0u) unlock_bucket_relaxed(hi);
     }
   }
   got = __shfl_sync(kFull, got ? 1 : 0, shift) != 0;  // the lead lane's result, for its whole group
@@ -604,8 +609,7 @@ __device__ __forceinline__ uint32_t claim_slot4(Bucket* buckets, uint32_t num_bu
       if (fresh) buckets[pb].keys[pw] = key;
       buckets[pb].stamp[pw] = epoch;
     }
-    if (hi != nullptr) unlock_bucket(hi);
-    unlock_bucket(lo);
+    unlock_pair(lo, hi);
   }
   return fresh ? pb * kWays + pw : kMissSlot;
 }
