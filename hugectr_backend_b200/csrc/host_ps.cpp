@@ -429,33 +429,41 @@ void HostTable::fill_procedural(size_t n, uint64_t seed, ThreadPool& pool, uint3
 
 size_t HostTable::fetch_range(const int64_t* keys, size_t begin, size_t end, float* out,
                               size_t stride) const {
-  constexpr size_t kBatch = 16;
+  // Rolling three-stage software pipeline over the keys: key i is hashed and its home slot prefetched, key i - kLag is
+  // resolved (the slot line has arrived) and its row prefetched, key i - 2 kLag is copied (the row has arrived).  Unlike a
+  // batch-at-a-time pipeline there is no drain between batches: ~2 kLag cache misses stay in flight throughout.
+  // kLag = 8 measured best on the build container's cores (1 M x 32 table, requests of 1024 keys: ~50 us against 57-76 us
+  // for the batch-of-16 form and 54-90 us for kLag = 16: a core has about a dozen line-fill buffers, a key needs three lines).
+  constexpr size_t kLag = 8, kRing = 32;
+  static_assert(kRing >= 2 * kLag + 1 && (kRing & (kRing - 1)) == 0, "ring must hold the whole pipeline");
   const size_t row_bytes = dim_ * sizeof(float);
   size_t absent = 0;
-  uint64_t hs[kBatch];
-  const float* rows[kBatch];
-  for (size_t b0 = begin; b0 < end; b0 += kBatch) {
-    const size_t nb = std::min(kBatch, end - b0);
-    // stage 1: hash, prefetch the home slot of every key
-    for (size_t j = 0; j < nb; ++j) {
-      hs[j] = mix64(static_cast<uint64_t>(keys[b0 + j]));
-      const Partition& p = *parts_[partition_of(hs[j])];
-      __builtin_prefetch(&p.slots[hs[j] & (p.slots.size() - 1)], 0, 0);
+  uint64_t hs[kRing];
+  const float* rows[kRing];
+  const size_t n = end - begin;
+  for (size_t i = 0; i < n + 2 * kLag; ++i) {
+    if (i < n) {
+      const uint64_t h = mix64(static_cast<uint64_t>(keys[begin + i]));
+      hs[i & (kRing - 1)] = h;
+      const Partition& p = *parts_[partition_of(h)];
+      __builtin_prefetch(&p.slots[h & (p.slots.size() - 1)], 0, 0);
     }
-    // stage 2: resolve, prefetch the rows
-    for (size_t j = 0; j < nb; ++j) {
-      const Partition& p = *parts_[partition_of(hs[j])];
-      rows[j] = find(p, keys[b0 + j], hs[j]);
-      if (rows[j]) {
-        const char* r = reinterpret_cast<const char*>(rows[j]);
-        for (size_t off = 0; off < row_bytes; off += 64) __builtin_prefetch(r + off, 0, 0);
+    if (i >= kLag && i - kLag < n) {
+      const size_t k = i - kLag;
+      const uint64_t h = hs[k & (kRing - 1)];
+      const float* r = find(*parts_[partition_of(h)], keys[begin + k], h);
+      rows[k & (kRing - 1)] = r;
+      if (r) {
+        const char* c = reinterpret_cast<const char*>(r);
+        for (size_t off = 0; off < row_bytes; off += 64) __builtin_prefetch(c + off, 0, 0);
       }
     }
-    // stage 3: copy
-    for (size_t j = 0; j < nb; ++j) {
-      float* dst = out + (b0 + j) * stride;
-      if (rows[j]) {
-        std::memcpy(dst, rows[j], row_bytes);
+    if (i >= 2 * kLag) {
+      const size_t k = i - 2 * kLag;
+      float* dst = out + (begin + k) * stride;
+      const float* r = rows[k & (kRing - 1)];
+      if (r) {
+        std::memcpy(dst, r, row_bytes);
       } else {
         for (size_t d = 0; d < dim_; ++d) dst[d] = default_value_;
         ++absent;
